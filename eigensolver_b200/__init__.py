@@ -1,0 +1,12 @@
+"""eigensolver_b200 - B200-native dispersion-function sweep for the EIGENSOLVER
+shooting solvers (slab / cylinder flux tubes with non-uniform density).
+
+The numerical path lives in libeigensolver_b200.so (CUDA, sm_100a) behind the C
+ABI of include/eigensolver_b200.h; this package is the thin host side.
+"""
+from ._lib import EsbError, LIB_PATH, load  # noqa: F401
+from .solver import (CYLINDER_CORONAL, CYLINDER_PHOTOSPHERIC, SLAB_CORONAL, SLAB_PHOTOSPHERIC,  # noqa: F401
+                     DispersionSolver, GaussianDensity, Medium, RootTable, bessel_ik_scaled)
+from .reference_api import ReferenceScript  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,319 @@
+// Device core of the dispersion-function hot path: exterior closed forms,
+// per-node ODE coefficients from the staged profile table, fixed-step RK4 / RK8
+// shooting integrator and the matching closures.  One thread evaluates one
+// (k, omega) point.
+//
+// Reference path restated (file:line in /root/reference):
+//   cylinder  Cylinder/Non-uniform density/Coronal/solvers/Density_cylinder.py:694-821
+//   slab      Slab/Non uniform density/Coronal/Solvers/
+//                 multiprocessor_Inhomogeneous_method_coronal.py:461-600
+//
+// What is different from the reference (same mathematics, B200-first mechanics):
+//   * exterior: closed form (cosh/sinh, I_n/K_n) of the reference's own initial-value
+//     problem instead of a 500-point odeint integration;
+//   * interior: the ODE is linear, so the slope that fsolve searches for is obtained
+//     from one integration (cylinder: from the axis outwards, where the end condition
+//     is an initial condition) or two fundamental solutions (slab);
+//   * sympy/lambdify coefficients -> rational expressions of the tabulated profile
+//     (rho, rho') at fixed Runge-Kutta stage nodes, staged in shared memory.
+#pragma once
+#include "bessel.cuh"
+
+namespace esb {
+
+enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1 };
+enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1 };
+enum { OMEGA_SHARED = 0, OMEGA_PHASE_SPEED = 1, OMEGA_PER_K = 2 };
+
+constexpr int TAB_FIELDS = 4;   // doubles per node in the staged table
+
+struct DevModel {
+    int kind, scheme, n_steps, n_nodes;
+    // exterior (uniform) medium
+    double vAe2, ce2, cTe2, se2, rho_e;
+    double ic_v, ic_s;        // exterior initial values
+    double ext_len;           // exterior start = -ext_len / k
+    // interior: c^2 = alpha/rho, vA^2 = beta/rho, cT^2 = tau/rho, S = alpha + beta
+    double alpha, beta, tau, S;
+    double rho_b;             // density at the boundary s_start
+    double s_start;           // boundary position (-1)
+};
+
+// ---------------------------------------------------------------- tableau ----
+constexpr double SQ21 = 4.58257569495584000658804719373;
+constexpr double C8_M = (7.0 - SQ21) / 14.0;
+constexpr double C8_P = (7.0 + SQ21) / 14.0;
+// Cooper-Verner 8th-order, 11 stages (verified to order 8 in tests/test_tableau.py)
+constexpr double a21 = 0.5;
+constexpr double a31 = 0.25, a32 = 0.25;
+constexpr double a41 = 1.0 / 7.0, a42 = (-7.0 - 3.0 * SQ21) / 98.0, a43 = (21.0 + 5.0 * SQ21) / 49.0;
+constexpr double a51 = (11.0 + SQ21) / 84.0, a53 = (18.0 + 4.0 * SQ21) / 63.0, a54 = (21.0 - SQ21) / 252.0;
+constexpr double a61 = (5.0 + SQ21) / 48.0, a63 = (9.0 + SQ21) / 36.0,
+                 a64 = (-231.0 + 14.0 * SQ21) / 360.0, a65 = (63.0 - 7.0 * SQ21) / 80.0;
+constexpr double a71 = (10.0 - SQ21) / 42.0, a73 = (-432.0 + 92.0 * SQ21) / 315.0,
+                 a74 = (633.0 - 145.0 * SQ21) / 90.0, a75 = (-504.0 + 115.0 * SQ21) / 70.0,
+                 a76 = (63.0 - 13.0 * SQ21) / 35.0;
+constexpr double a81 = 1.0 / 14.0, a85 = (14.0 - 3.0 * SQ21) / 126.0, a86 = (13.0 - 3.0 * SQ21) / 63.0,
+                 a87 = 1.0 / 9.0;
+constexpr double a91 = 1.0 / 32.0, a95 = (91.0 - 21.0 * SQ21) / 576.0, a96 = 11.0 / 72.0,
+                 a97 = (-385.0 - 75.0 * SQ21) / 1152.0, a98 = (63.0 + 13.0 * SQ21) / 128.0;
+constexpr double a101 = 1.0 / 14.0, a105 = 1.0 / 9.0, a106 = (-733.0 - 147.0 * SQ21) / 2205.0,
+                 a107 = (515.0 + 111.0 * SQ21) / 504.0, a108 = (-51.0 - 11.0 * SQ21) / 56.0,
+                 a109 = (132.0 + 28.0 * SQ21) / 245.0;
+constexpr double a115 = (-42.0 + 7.0 * SQ21) / 18.0, a116 = (-18.0 + 28.0 * SQ21) / 45.0,
+                 a117 = (-273.0 - 53.0 * SQ21) / 72.0, a118 = (301.0 + 53.0 * SQ21) / 72.0,
+                 a119 = (28.0 - 28.0 * SQ21) / 45.0, a1110 = (49.0 - 7.0 * SQ21) / 18.0;
+constexpr double b8_1 = 1.0 / 20.0, b8_8 = 49.0 / 180.0, b8_9 = 16.0 / 45.0, b8_10 = 49.0 / 180.0,
+                 b8_11 = 1.0 / 20.0;
+
+ESB_HD int nodes_per_step(int scheme) { return scheme == SCHEME_RK8 ? 4 : 2; }
+
+// ------------------------------------------------------------- point data ----
+struct Point {
+    double K, A;       // k^2, omega^2
+    double w;          // omega
+    double m2;         // (azimuthal order)^2, cylinder
+    // products that do not change along the layer
+    double Kalpha, Kbeta, Ktau, SKtau, AKc;
+};
+
+ESB_HD Point make_point(const DevModel& M, double k, double w, int mode) {
+    Point p;
+    p.K = k * k;
+    p.A = w * w;
+    p.w = w;
+    p.m2 = double(mode) * double(mode);
+    p.Kalpha = p.K * M.alpha;
+    p.Kbeta = p.K * M.beta;
+    p.Ktau = p.K * M.tau;
+    p.SKtau = M.S * p.Ktau;
+    p.AKc = -p.A * p.K * (M.tau - M.alpha);
+    return p;
+}
+
+// y'' = a y' + b y  at one staged node (4 doubles f[0..3]).
+//   cylinder: f = {1/r, 1/r^2, rho, rho'}
+//       a = -1/r + rho' w^2/(rho w^2 - k^2 beta)
+//       b = m^2/r^2 + k^2 - (rho w^2)^2/(S (rho w^2 - k^2 tau))
+//     (Density_cylinder.py:742-756 with v_phi = B_phi = v_z = 0, B_i = B_0:
+//      F = r/(rho w^2 - k^2 B_0^2), a = -F'/F, b = g/F.)
+//   slab: f = {rho, rho', -, -}
+//       a = -F'/F = -w^2 k^2 (tau-alpha) rho' / ((k^2 alpha - rho w^2)(k^2 tau - rho w^2))
+//       b = m0^2 = (k^2 alpha - rho w^2)(k^2 beta - rho w^2)/(S (k^2 tau - rho w^2))
+//     (..._coronal.py:222-230.)
+template <int KIND>
+ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, double& a, double& b) {
+    if (KIND == KIND_CYL_DENSITY) {
+        const double invr = f[0], invr2 = f[1], rho = f[2], drho = f[3];
+        const double u = rho * p.A;
+        const double X = u - p.Kbeta;
+        const double Y = fma(M.S, u, -p.SKtau);
+        const double inv = 1.0 / (X * Y);
+        a = fma(drho * p.A * Y, inv, -invr);
+        b = fma(-(u * u) * X, inv, fma(p.m2, invr2, p.K));
+    } else {
+        const double rho = f[0], drho = f[1];
+        const double u = rho * p.A;
+        const double p1 = p.Kalpha - u, p2 = p.Kbeta - u, p3 = p.Ktau - u;
+        const double inv = 1.0 / (p1 * p3);
+        a = p.AKc * drho * inv;
+        b = (p1 * p1) * p2 * inv / M.S;
+    }
+}
+
+// ------------------------------------------------------------- integrator ----
+// State of NS independent solutions: y[s] = value, yp[s] = derivative.
+// ca/cb hold the coefficients at the step's nodes; node 0 is carried over from the
+// previous step (it is that step's end node).
+template <int NS>
+ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[5],
+                     const double (&cb)[5]) {
+    // stage -> node: 1:0  2:2 3:2  4:3 5:3  6:2  7:1 8:1  9:2  10:3  11:4
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const double p = y[s], q = yp[s];
+#define ESB_G(P, Q, n) fma(ca[n], (Q), cb[n] * (P))
+        const double Q1 = q, G1 = ESB_G(p, q, 0);
+        const double P2 = fma(h, a21 * Q1, p), Q2 = fma(h, a21 * G1, q), G2 = ESB_G(P2, Q2, 2);
+        const double P3 = fma(h, fma(a32, Q2, a31 * Q1), p), Q3 = fma(h, fma(a32, G2, a31 * G1), q),
+                     G3 = ESB_G(P3, Q3, 2);
+        const double P4 = fma(h, fma(a43, Q3, fma(a42, Q2, a41 * Q1)), p),
+                     Q4 = fma(h, fma(a43, G3, fma(a42, G2, a41 * G1)), q), G4 = ESB_G(P4, Q4, 3);
+        const double P5 = fma(h, fma(a54, Q4, fma(a53, Q3, a51 * Q1)), p),
+                     Q5 = fma(h, fma(a54, G4, fma(a53, G3, a51 * G1)), q), G5 = ESB_G(P5, Q5, 3);
+        const double P6 = fma(h, fma(a65, Q5, fma(a64, Q4, fma(a63, Q3, a61 * Q1))), p),
+                     Q6 = fma(h, fma(a65, G5, fma(a64, G4, fma(a63, G3, a61 * G1))), q),
+                     G6 = ESB_G(P6, Q6, 2);
+        const double P7 = fma(h, fma(a76, Q6, fma(a75, Q5, fma(a74, Q4, fma(a73, Q3, a71 * Q1)))), p),
+                     Q7 = fma(h, fma(a76, G6, fma(a75, G5, fma(a74, G4, fma(a73, G3, a71 * G1)))), q),
+                     G7 = ESB_G(P7, Q7, 1);
+        const double P8 = fma(h, fma(a87, Q7, fma(a86, Q6, fma(a85, Q5, a81 * Q1))), p),
+                     Q8 = fma(h, fma(a87, G7, fma(a86, G6, fma(a85, G5, a81 * G1))), q),
+                     G8 = ESB_G(P8, Q8, 1);
+        const double P9 = fma(h, fma(a98, Q8, fma(a97, Q7, fma(a96, Q6, fma(a95, Q5, a91 * Q1)))), p),
+                     Q9 = fma(h, fma(a98, G8, fma(a97, G7, fma(a96, G6, fma(a95, G5, a91 * G1)))), q),
+                     G9 = ESB_G(P9, Q9, 2);
+        const double P10 = fma(h, fma(a109, Q9, fma(a108, Q8, fma(a107, Q7, fma(a106, Q6,
+                                  fma(a105, Q5, a101 * Q1))))), p),
+                     Q10 = fma(h, fma(a109, G9, fma(a108, G8, fma(a107, G7, fma(a106, G6,
+                                  fma(a105, G5, a101 * G1))))), q),
+                     G10 = ESB_G(P10, Q10, 3);
+        const double P11 = fma(h, fma(a1110, Q10, fma(a119, Q9, fma(a118, Q8, fma(a117, Q7,
+                                  fma(a116, Q6, a115 * Q5))))), p),
+                     Q11 = fma(h, fma(a1110, G10, fma(a119, G9, fma(a118, G8, fma(a117, G7,
+                                  fma(a116, G6, a115 * G5))))), q),
+                     G11 = ESB_G(P11, Q11, 4);
+        y[s] = fma(h, fma(b8_11, Q11, fma(b8_10, Q10, fma(b8_9, Q9, fma(b8_8, Q8, b8_1 * Q1)))), p);
+        yp[s] = fma(h, fma(b8_11, G11, fma(b8_10, G10, fma(b8_9, G9, fma(b8_8, G8, b8_1 * G1)))), q);
+#undef ESB_G
+    }
+}
+
+template <int NS>
+ESB_HD void rk4_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[3],
+                     const double (&cb)[3]) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const double p = y[s], q = yp[s];
+        const double hh = 0.5 * h;
+        const double G1 = fma(ca[0], q, cb[0] * p);
+        const double P2 = fma(hh, q, p), Q2 = fma(hh, G1, q), G2 = fma(ca[1], Q2, cb[1] * P2);
+        const double P3 = fma(hh, Q2, p), Q3 = fma(hh, G2, q), G3 = fma(ca[1], Q3, cb[1] * P3);
+        const double P4 = fma(h, Q3, p), Q4 = fma(h, G3, q), G4 = fma(ca[2], Q4, cb[2] * P4);
+        const double h6 = h * (1.0 / 6.0);
+        y[s] = fma(h6, q + 2.0 * (Q2 + Q3) + Q4, p);
+        yp[s] = fma(h6, G1 + 2.0 * (G2 + G3) + G4, q);
+    }
+}
+
+// Integrate NS solutions along the staged mesh.  tab: [n_nodes][TAB_FIELDS] then h[n_steps].
+template <int KIND, int SCHEME, int NS>
+ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __restrict__ tab,
+                            double (&y)[NS], double (&yp)[NS]) {
+    const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
+    constexpr int NPS = (SCHEME == SCHEME_RK8) ? 4 : 2;
+    double a0, b0;
+    node_coeffs<KIND>(M, pt, tab, a0, b0);
+    for (int i = 0; i < M.n_steps; ++i) {
+        const double* f = tab + (size_t)(i * NPS) * TAB_FIELDS;
+        const double h = hs[i];
+        if (SCHEME == SCHEME_RK8) {
+            double ca[5], cb[5];
+            ca[0] = a0; cb[0] = b0;
+#pragma unroll
+            for (int n = 1; n <= 4; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n]);
+            rk8_step<NS>(y, yp, h, ca, cb);
+            a0 = ca[4]; b0 = cb[4];
+        } else {
+            double ca[3], cb[3];
+            ca[0] = a0; cb[0] = b0;
+#pragma unroll
+            for (int n = 1; n <= 2; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n]);
+            rk4_step<NS>(y, yp, h, ca, cb);
+            a0 = ca[2]; b0 = cb[2];
+        }
+    }
+}
+
+// --------------------------------------------------------------- exterior ----
+ESB_HD double m_e2(const DevModel& M, double K, double A) {
+    // Density_cylinder.py:699
+    return ((K * M.vAe2 - A) * (K * M.ce2 - A)) / (M.se2 * (K * M.cTe2 - A));
+}
+
+// Exact solution at x = -1 of the reference's exterior initial-value problem.
+// Returns false where the reference skips the point (m_e < 0).
+template <int KIND>
+ESB_HD bool exterior(const DevModel& M, double k, const Point& pt, int mode, double& yb, double& ypb) {
+    const double me = m_e2(M, pt.K, pt.A);
+    if (!(me >= 0.0)) return false;
+    const double kap = sqrt(me);
+    const double x0 = M.ext_len / k;      // |start|
+    if (KIND == KIND_SLAB_DENSITY) {
+        // vx'' = m_e vx   (..._coronal.py:245), from -x0 to -1
+        const double L = x0 - 1.0;
+        if (kap * L < 1e-8) {
+            yb = fma(M.ic_s, L, M.ic_v) + 0.5 * me * L * L * M.ic_v;
+            ypb = M.ic_s + me * L * M.ic_v;
+        } else {
+            const double E = exp(kap * L), Ei = 1.0 / E;
+            const double ch = 0.5 * (E + Ei), sh = 0.5 * (E - Ei);
+            yb = fma(M.ic_v, ch, (M.ic_s / kap) * sh);
+            ypb = fma(M.ic_v * kap, sh, M.ic_s * ch);
+        }
+        return true;
+    } else {
+        // P'' + P'/r - (m_e + n^2/r^2) P = 0   (Density_cylinder.py:765), r from -x0 to -1.
+        // In rho = |r|: P = A I_n(kap rho) + B K_n(kap rho), d/dr = -d/drho.
+        const double z0 = kap * x0, z1 = kap;
+        BesselIK B0, B1;
+        bessel_ik_scaled(mode, z0, B0);
+        bessel_ik_scaled(mode, z1, B1);
+        double I0, dI0, K0, dK0, I1, dI1, K1, dK1;
+        bessel_order(B0, mode, z0, I0, dI0, K0, dK0);
+        bessel_order(B1, mode, z1, I1, dI1, K1, dK1);
+        const double P0 = M.ic_v, dP0 = -M.ic_s / kap;   // d/d(z) at rho0
+        // Wronskian I K' - I' K = -1/z
+        const double As = -z0 * (P0 * dK0 - dP0 * K0);    // true A = As e^{-z0}... (scaled by e^{+z0} K)
+        const double Bs = -z0 * (dP0 * I0 - P0 * dI0);
+        // A I(z1) = As e^{z0}... careful: K0 here is e^{z0} K(z0) so As = A_true e^{z0};
+        // I1 = e^{-z1} I(z1) -> A_true I(z1) = As e^{-z0} e^{z1} I1
+        const double ea = exp(z1 - z0), eb = exp(z0 - z1);
+        yb = As * I1 * ea + Bs * K1 * eb;
+        ypb = -kap * (As * dI1 * ea + Bs * dK1 * eb);
+        return true;
+    }
+}
+
+// ------------------------------------------------------------ full point ----
+// One evaluation of the reference's scan-loop body: (exterior quantity, interior quantity).
+template <int KIND, int SCHEME>
+ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
+                       double& ext_q, double& int_q) {
+    const double nanv = nan("");
+    const Point pt = make_point(M, k, w, mode);
+    double yb, ypb;
+    if (!exterior<KIND>(M, k, pt, mode, yb, ypb)) {
+        ext_q = nanv;
+        int_q = nanv;
+        return;
+    }
+    if (KIND == KIND_CYL_DENSITY) {
+        // xi_e = -P'/(rho_e (k^2 vA_e^2 - w^2))      (Density_cylinder.py:702,773)
+        ext_q = -ypb / (M.rho_e * (pt.K * M.vAe2 - pt.A));
+        // interior from the axis outwards: sausage P'(axis)=0 (:1084), kink/fluting P(axis)=0 (:787)
+        double y[1], yp[1];
+        if (mode == 0) { y[0] = 1.0; yp[0] = 0.0; } else { y[0] = 0.0; yp[0] = 1.0; }
+        integrate_layer<KIND, SCHEME, 1>(M, pt, tab, y, yp);
+        const double slope = yb * yp[0] / y[0];          // dPi that fsolve finds (:790)
+        // xi_i(-1) = (C1 P + D P')/C3 = P'/(rho (w^2 - k^2 vA^2))    (:798)
+        int_q = slope / (M.rho_b * pt.A - pt.Kbeta);
+    } else {
+        // P_e = p_e_const vx'   (..._coronal.py:221,250)
+        const double p_e_const = M.rho_e * M.se2 * (pt.K * M.cTe2 - pt.A) / (w * (pt.K * M.ce2 - pt.A));
+        ext_q = p_e_const * ypb;
+        double y[2] = {1.0, 0.0}, yp[2] = {0.0, 1.0};
+        integrate_layer<KIND, SCHEME, 2>(M, pt, tab, y, yp);
+        // sausage: vx(1) = -vx(-1) (:259); kink: vx(1) = +vx(-1) (:696)
+        const double target = (mode == 0) ? -1.0 : 1.0;
+        const double slope = yb * (target - y[0]) / y[1];
+        // P_i(-1) = P_Ti(-1) vx'(-1)   (:234,267)
+        const double ub = M.rho_b * pt.A;
+        const double P_Ti = M.S * (pt.Ktau - ub) / (w * (pt.Kalpha - ub));
+        int_q = P_Ti * slope;
+    }
+}
+
+// Runtime dispatch on (kind, scheme) to the compiled instantiations.
+ESB_HD void eval_point_rt(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
+                          double& e, double& i) {
+    if (M.kind == KIND_CYL_DENSITY) {
+        if (M.scheme == SCHEME_RK8) eval_point<KIND_CYL_DENSITY, SCHEME_RK8>(M, tab, k, w, mode, e, i);
+        else eval_point<KIND_CYL_DENSITY, SCHEME_RK4>(M, tab, k, w, mode, e, i);
+    } else {
+        if (M.scheme == SCHEME_RK8) eval_point<KIND_SLAB_DENSITY, SCHEME_RK8>(M, tab, k, w, mode, e, i);
+        else eval_point<KIND_SLAB_DENSITY, SCHEME_RK4>(M, tab, k, w, mode, e, i);
+    }
+}
+
+}  // namespace esb

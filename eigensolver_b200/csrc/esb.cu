@@ -1,0 +1,741 @@
+// eigensolver_b200: kernels + C ABI (see include/eigensolver_b200.h).
+//
+// Kernels (all FP64, sm_100a):
+//   grid_kernel      one thread per (k, omega): exterior closed form + RK shooting
+//                    across the layer with the profile table staged in shared memory.
+//   bracket_count /  one warp per k-row: warp-ballot sign-change detection along omega,
+//   bracket_fill     popc prefix -> deterministic, sorted bracket list.
+//   refine_kernel    one thread per bracket: Brent iteration on D(omega), warp-level
+//                    vote (__any_sync) on the convergence flags, acceptance test.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/eigensolver_b200.h"
+#include "core.cuh"
+
+using namespace esb;
+
+// =============================================================== kernels ====
+struct GridArgs {
+    DevModel M;
+    const double* tab;      // global copy of the staged table
+    int tab_doubles;
+    const double* k;
+    const double* w;
+    int nk, nw, layout, mode;
+    double* ext;
+    double* intq;
+};
+
+__device__ __forceinline__ double omega_at(const double* __restrict__ k, const double* __restrict__ w,
+                                           int layout, int nw, int ik, int iw) {
+    if (layout == OMEGA_SHARED) return w[iw];
+    if (layout == OMEGA_PHASE_SPEED) return k[ik] * w[iw];
+    return w[(size_t)ik * nw + iw];
+}
+
+__device__ __forceinline__ void stage_table(const double* __restrict__ g, double* s, int n) {
+    // n is a multiple of 2 doubles; 16-byte vector copies
+    const double2* g2 = reinterpret_cast<const double2*>(g);
+    double2* s2 = reinterpret_cast<double2*>(s);
+    for (int i = threadIdx.x; i < n / 2; i += blockDim.x) s2[i] = g2[i];
+    if ((n & 1) && threadIdx.x == 0) s[n - 1] = g[n - 1];
+    __syncthreads();
+}
+
+template <int KIND, int SCHEME>
+__global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
+    extern __shared__ __align__(16) double stab[];
+    stage_table(g.tab, stab, g.tab_doubles);
+    const int iw = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iw >= g.nw) return;
+    for (int ik = blockIdx.y; ik < g.nk; ik += gridDim.y) {
+        const double k = g.k[ik];
+        const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
+        double e, i;
+        eval_point<KIND, SCHEME>(g.M, stab, k, w, g.mode, e, i);
+        const size_t o = (size_t)ik * g.nw + iw;
+        g.ext[o] = e;
+        g.intq[o] = i;
+    }
+}
+
+// ---- brackets: sign change of D = ext - int between neighbours along omega ----
+__device__ __forceinline__ bool is_bracket(double d0, double d1) {
+    // both evaluated (finite) and strictly opposite signs
+    return isfinite(d0) && isfinite(d1) && ((d0 < 0.0 && d1 > 0.0) || (d0 > 0.0 && d1 < 0.0));
+}
+
+// one warp per row; pass 0 counts, pass 1 fills at row_offset
+__global__ void bracket_kernel(const double* __restrict__ ext, const double* __restrict__ intq, int nk,
+                               int nw, int* __restrict__ row_count, const int* __restrict__ row_offset,
+                               int* __restrict__ bk, int* __restrict__ bw, int capacity, int fill) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= nk) return;
+    const double* e = ext + (size_t)row * nw;
+    const double* q = intq + (size_t)row * nw;
+    int base = fill ? row_offset[row] : 0;
+    int count = 0;
+    for (int j0 = 0; j0 < nw - 1; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        if (j < nw - 1) {
+            const double d0 = e[j] - q[j];
+            // neighbour value: lane+1 holds it except for the last lane of the chunk
+            const double d1 = e[j + 1] - q[j + 1];
+            hit = is_bracket(d0, d1);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (fill && hit) {
+            const int pos = base + count + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < capacity) {
+                bk[pos] = row;
+                bw[pos] = j;
+            }
+        }
+        count += __popc(ballot);
+    }
+    if (!fill && lane == 0) row_count[row] = count;
+}
+
+// exclusive scan of row counts -> offsets[nk+1]; single block
+__global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int n) {
+    __shared__ int carry;
+    __shared__ int warp_sums[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int v = (i < n) ? counts[i] : 0;
+        int x = v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += t;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = (lane < (blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int prefix = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        if (i < n) offsets[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+// ---- refinement ----
+struct RefineArgs {
+    DevModel M;
+    const double* tab;
+    int tab_doubles;
+    const double* k;
+    const double* w;
+    int nk, nw, layout, mode;
+    const int* bk;
+    const int* bw;
+    int n_brackets;
+    double tol_percent;
+    double* omega;
+    double* ext;
+    double* intq;
+    int* accepted;
+    int* iters;
+};
+
+template <int KIND, int SCHEME>
+__global__ void __launch_bounds__(32) refine_kernel(RefineArgs r) {
+    extern __shared__ __align__(16) double stab[];
+    stage_table(r.tab, stab, r.tab_doubles);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < r.n_brackets;
+    const int ik = live ? r.bk[t] : 0;
+    const int jw = live ? r.bw[t] : 0;
+    const double k = r.k[ik];
+    double a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
+    double b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
+    double ea, ia, eb, ib;
+    eval_point<KIND, SCHEME>(r.M, stab, k, a, r.mode, ea, ia);
+    eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, eb, ib);
+    double fa = ea - ia, fb = eb - ib;
+    double c = a, fc = fa, d = b - a, e = d;
+    bool done = !live || !(fa * fb < 0.0);
+    int it = 0;
+    const double eps = 2.220446049250313e-16;
+    // Brent's method; the whole warp iterates until every lane has converged.
+    for (int sweep = 0; sweep < 200 && __any_sync(0xffffffffu, !done); ++sweep) {
+        if (!done) {
+            if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
+                c = a; fc = fa; d = b - a; e = d;
+            }
+            if (fabs(fc) < fabs(fb)) {
+                a = b; b = c; c = a;
+                fa = fb; fb = fc; fc = fa;
+            }
+            const double tol1 = 2.0 * eps * fabs(b);
+            const double xm = 0.5 * (c - b);
+            if (fabs(xm) <= tol1 || fb == 0.0 || !isfinite(fb)) {
+                done = true;
+            } else {
+                if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+                    const double s = fb / fa;
+                    double p, q;
+                    if (a == c) {
+                        p = 2.0 * xm * s;
+                        q = 1.0 - s;
+                    } else {
+                        const double qq = fa / fc, rr = fb / fc;
+                        p = s * (2.0 * xm * qq * (qq - rr) - (b - a) * (rr - 1.0));
+                        q = (qq - 1.0) * (rr - 1.0) * (s - 1.0);
+                    }
+                    if (p > 0.0) q = -q;
+                    p = fabs(p);
+                    const double m1 = 3.0 * xm * q - fabs(tol1 * q);
+                    const double m2 = fabs(e * q);
+                    if (2.0 * p < (m1 < m2 ? m1 : m2)) {
+                        e = d;
+                        d = p / q;
+                    } else {
+                        d = xm;
+                        e = d;
+                    }
+                } else {
+                    d = xm;
+                    e = d;
+                }
+                a = b;
+                fa = fb;
+                b += (fabs(d) > tol1) ? d : (xm > 0.0 ? tol1 : -tol1);
+            }
+        }
+        // evaluation outside the divergent region: every lane runs the integrator together
+        double en, in_;
+        eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, en, in_);
+        if (!done) {
+            fb = en - in_;
+            ++it;
+        }
+    }
+    // b is the best estimate; one more (warp-uniform) evaluation gives both quantities there
+    eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, eb, ib);
+    if (live) {
+        r.omega[t] = b;
+        r.ext[t] = eb;
+        r.intq[t] = ib;
+        r.iters[t] = it;
+        // reference acceptance test (Density_cylinder.py:809)
+        const double mx = fmax(fabs(eb), fabs(ib));
+        const double pct = fabs(eb - ib) * 100.0 / mx;
+        r.accepted[t] = (pct < r.tol_percent) ? 1 : 0;
+    }
+}
+
+// ============================================================ host side ====
+struct esb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool model_set = false;
+    esb_model model{};
+    DevModel dm{};
+    double* d_tab = nullptr;
+    int tab_doubles = 0;
+    // scratch for the host-pointer entry points
+    double *d_k = nullptr, *d_w = nullptr, *d_ext = nullptr, *d_int = nullptr;
+    size_t cap_k = 0, cap_w = 0, cap_grid = 0;
+    int *d_rowcount = nullptr, *d_rowoff = nullptr, *d_bk = nullptr, *d_bw = nullptr;
+    size_t cap_rows = 0, cap_rowoff = 0, cap_br = 0;
+    double *d_ro = nullptr, *d_re = nullptr, *d_ri = nullptr;
+    int *d_racc = nullptr, *d_rit = nullptr;
+    size_t cap_roots = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define CUDA_TRY(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);             \
+            return ESB_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+static int fail(esb_context* c, int code, const char* msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+template <class T>
+static int ensure(esb_context* c, T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return ESB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CUDA_TRY(c, cudaMalloc((void**)&p, need * sizeof(T)));
+    cap = need;
+    return ESB_OK;
+}
+
+// ---- mesh: stage nodes along the direction of integration -------------------
+static double cluster(double t) {   // sin^2(pi t/2): clusters nodes at both ends of [0,1]
+    const double s = sin(0.5 * M_PI * t);
+    return s * s;
+}
+
+static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
+    const int N = m->n_steps;
+    bp.resize(N + 1);
+    if (m->kind == ESB_CYLINDER_DENSITY) {
+        // from the axis end (s_end) out to the boundary (s_start)
+        for (int i = 0; i <= N; ++i) {
+            const double t = double(i) / N;
+            const double f = m->mesh == 1 ? t : cluster(t);
+            bp[i] = m->s_end + (m->s_start - m->s_end) * f;
+        }
+        bp[0] = m->s_end;
+        bp[N] = m->s_start;
+    } else {
+        // slab: boundary -> mid -> far boundary, clustered at the three of them
+        if (N % 2) return ESB_ERR_ARG;
+        const int H = N / 2;
+        const double mid = 0.5 * (m->s_start + m->s_end);
+        for (int i = 0; i <= H; ++i) {
+            const double t = double(i) / H;
+            const double f = m->mesh == 1 ? t : cluster(t);
+            bp[i] = m->s_start + (mid - m->s_start) * f;
+            bp[H + i] = mid + (m->s_end - mid) * f;
+        }
+        bp[0] = m->s_start;
+        bp[H] = mid;
+        bp[N] = m->s_end;
+    }
+    return ESB_OK;
+}
+
+static int check_model(const esb_model* m) {
+    if (!m) return ESB_ERR_ARG;
+    if (m->kind != ESB_SLAB_DENSITY && m->kind != ESB_CYLINDER_DENSITY) return ESB_ERR_ARG;
+    if (m->scheme != ESB_RK4 && m->scheme != ESB_RK8) return ESB_ERR_ARG;
+    if (m->n_steps < 2 || m->n_steps > 8192) return ESB_ERR_ARG;
+    if (m->kind == ESB_SLAB_DENSITY && (m->n_steps % 2)) return ESB_ERR_ARG;
+    return ESB_OK;
+}
+
+extern "C" int esb_version(void) { return ESB_VERSION; }
+
+extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
+    if (!out) return ESB_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    out->kind = kind;
+    out->scheme = ESB_RK8;
+    out->gamma = 5.0 / 3.0;
+    out->rho_i0 = 1.0;
+    out->rho_A = 1.0;
+    out->c_i0 = 1.0;
+    out->ext_wavelengths = 3.0;
+    out->ext_ic_value = 1e-8;
+    out->s_start = -1.0;
+    if (kind == ESB_CYLINDER_DENSITY) {          // Density_cylinder.py:69-72,120,768
+        out->vA_i0 = 2.0; out->vA_e = 5.0; out->c_e = 0.5;
+        out->ext_ic_slope = 1e-15;
+        out->s_end = -0.001;
+        out->n_steps = 256;
+    } else if (kind == ESB_SLAB_DENSITY) {       // ..._coronal.py:69-72,91,247
+        out->vA_i0 = 1.2; out->vA_e = 3.0; out->c_e = 0.4;
+        out->ext_ic_slope = 1e-8;
+        out->s_end = 1.0;
+        out->n_steps = 256;
+    } else {
+        return ESB_ERR_ARG;
+    }
+    return ESB_OK;
+}
+
+extern "C" int esb_mesh_size(const esb_model* m, int32_t* n_nodes) {
+    if (check_model(m) || !n_nodes) return ESB_ERR_ARG;
+    *n_nodes = m->n_steps * nodes_per_step(m->scheme) + 1;
+    return ESB_OK;
+}
+
+static const double* stage_fracs(int scheme, int& n) {
+    static const double f8[4] = {0.0, C8_M, 0.5, C8_P};
+    static const double f4[2] = {0.0, 0.5};
+    if (scheme == ESB_RK8) { n = 4; return f8; }
+    n = 2;
+    return f4;
+}
+
+extern "C" int esb_mesh_nodes(const esb_model* m, double* nodes) {
+    if (check_model(m) || !nodes) return ESB_ERR_ARG;
+    std::vector<double> bp;
+    if (build_breakpoints(m, bp)) return ESB_ERR_ARG;
+    int nf;
+    const double* fr = stage_fracs(m->scheme, nf);
+    const int N = m->n_steps;
+    for (int i = 0; i < N; ++i) {
+        const double h = bp[i + 1] - bp[i];
+        for (int j = 0; j < nf; ++j) nodes[i * nf + j] = bp[i] + fr[j] * h;
+    }
+    nodes[N * nf] = bp[N];
+    return ESB_OK;
+}
+
+extern "C" int esb_create(int32_t device, esb_context** out) {
+    if (!out) return ESB_ERR_ARG;
+    *out = nullptr;
+    esb_context* c = new (std::nothrow) esb_context();
+    if (!c) return ESB_ERR_ALLOC;
+    c->device = device;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device >= n) {
+        // no CPU fallback: the context cannot exist without a device
+        fprintf(stderr, "eigensolver_b200: no usable CUDA device (%s)\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        delete c;
+        return ESB_ERR_CUDA;
+    }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        delete c;
+        return ESB_ERR_CUDA;
+    }
+    *out = c;
+    return ESB_OK;
+}
+
+extern "C" int esb_destroy(esb_context* c) {
+    if (!c) return ESB_OK;
+    cudaSetDevice(c->device);
+    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_rowcount, c->d_rowoff, c->d_bk,
+                    c->d_bw, c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return ESB_OK;
+}
+
+extern "C" const char* esb_last_error(const esb_context* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int64_t esb_launch_count(const esb_context* c) { return c ? c->launches : 0; }
+
+extern "C" double esb_last_kernel_ms(const esb_context* c) {
+    if (!c || !c->timed) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+    return ms;
+}
+
+extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* rho, const double* drho,
+                             int32_t n_nodes, double rho_boundary) {
+    if (!c) return ESB_ERR_ARG;
+    if (check_model(m) || !rho || !drho) return fail(c, ESB_ERR_ARG, "bad model");
+    int32_t need = 0;
+    esb_mesh_size(m, &need);
+    if (n_nodes != need) return fail(c, ESB_ERR_ARG, "n_nodes does not match esb_mesh_size()");
+    std::vector<double> nodes(need);
+    if (esb_mesh_nodes(m, nodes.data())) return fail(c, ESB_ERR_ARG, "mesh");
+    const int N = m->n_steps, nps = nodes_per_step(m->scheme);
+    std::vector<double> tab((size_t)need * TAB_FIELDS + N, 0.0);
+    for (int i = 0; i < need; ++i) {
+        double* f = &tab[(size_t)i * TAB_FIELDS];
+        if (m->kind == ESB_CYLINDER_DENSITY) {
+            const double r = nodes[i];
+            f[0] = 1.0 / r;
+            f[1] = 1.0 / (r * r);
+            f[2] = rho[i];
+            f[3] = drho[i];
+        } else {
+            f[0] = rho[i];
+            f[1] = drho[i];
+        }
+    }
+    for (int i = 0; i < N; ++i) tab[(size_t)need * TAB_FIELDS + i] = nodes[(i + 1) * nps] - nodes[i * nps];
+
+    DevModel& d = c->dm;
+    d.kind = m->kind;
+    d.scheme = m->scheme;
+    d.n_steps = N;
+    d.n_nodes = need;
+    d.vAe2 = m->vA_e * m->vA_e;
+    d.ce2 = m->c_e * m->c_e;
+    d.se2 = d.vAe2 + d.ce2;
+    d.cTe2 = d.ce2 * d.vAe2 / d.se2;
+    const double g = m->gamma;
+    d.rho_e = m->rho_i0 * (m->c_i0 * m->c_i0 + g * 0.5 * m->vA_i0 * m->vA_i0) /
+              (d.ce2 + g * 0.5 * d.vAe2);                    // Density_cylinder.py:80
+    d.ic_v = m->ext_ic_value;
+    d.ic_s = m->ext_ic_slope;
+    d.ext_len = m->ext_wavelengths * 2.0 * M_PI;
+    // c_i^2 = rho_e (c_e^2 + gamma/2 vA_e^2)/rho - gamma/2 vA_i^2   (Density_cylinder.py:210)
+    // cylinder: vA_i^2 = B_0^2/rho = vA_i0^2 rho_i0/rho                (Density_cylinder.py:188-200)
+    // slab:     vA_i^2 = vA_i0^2 rho_i0/profile = vA_i0^2 rho_i0 rho_A/rho   (..._coronal.py:117)
+    d.beta = m->vA_i0 * m->vA_i0 * m->rho_i0 * (m->kind == ESB_SLAB_DENSITY ? m->rho_A : 1.0);
+    d.alpha = d.rho_e * (d.ce2 + 0.5 * g * d.vAe2) - 0.5 * g * d.beta;
+    d.S = d.alpha + d.beta;
+    d.tau = d.alpha * d.beta / d.S;
+    d.rho_b = rho_boundary;
+    d.s_start = m->s_start;
+
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->d_tab) cudaFree(c->d_tab);
+    c->d_tab = nullptr;
+    c->tab_doubles = (int)tab.size();
+    if ((size_t)c->tab_doubles * sizeof(double) > 200 * 1024)
+        return fail(c, ESB_ERR_ARG, "n_steps too large for the shared-memory table (200 KB)");
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_tab, tab.size() * sizeof(double)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->model = *m;
+    c->model_set = true;
+    return ESB_OK;
+}
+
+// ---- launches ---------------------------------------------------------------
+template <int KIND, int SCHEME>
+static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
+    const size_t smem = (size_t)g.tab_doubles * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 block(128);
+    dim3 grid((g.nw + 127) / 128, g.nk < 65535 ? g.nk : 65535);
+    grid_kernel<KIND, SCHEME><<<grid, block, smem, s>>>(g);
+    return cudaGetLastError();
+}
+
+template <int KIND, int SCHEME>
+static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
+    const size_t smem = (size_t)r.tab_doubles * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    refine_kernel<KIND, SCHEME><<<(r.n_brackets + 31) / 32, 32, smem, s>>>(r);
+    return cudaGetLastError();
+}
+
+static int check_mode(const esb_context* c, int mode) {
+    if (c->model.kind == ESB_SLAB_DENSITY) return (mode == 0 || mode == 1) ? 0 : -1;
+    return (mode >= 0 && mode <= ESB_MAX_ORDER) ? 0 : -1;
+}
+
+extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const double* d_k, int32_t nk,
+                                       const double* d_w, int32_t nw, int32_t layout, double* d_ext,
+                                       double* d_int, void* stream) {
+    if (!c) return ESB_ERR_ARG;
+    if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
+    if (nk <= 0 || nw <= 0 || !d_k || !d_w || !d_ext || !d_int || layout < 0 || layout > 2 ||
+        check_mode(c, mode))
+        return fail(c, ESB_ERR_ARG, "bad grid arguments");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    GridArgs g;
+    g.M = c->dm;
+    g.tab = c->d_tab;
+    g.tab_doubles = c->tab_doubles;
+    g.k = d_k; g.w = d_w; g.nk = nk; g.nw = nw; g.layout = layout; g.mode = mode;
+    g.ext = d_ext; g.intq = d_int;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaEventRecord(c->ev0, s));
+    cudaError_t e;
+    if (c->dm.kind == KIND_CYL_DENSITY)
+        e = c->dm.scheme == SCHEME_RK8 ? launch_grid<KIND_CYL_DENSITY, SCHEME_RK8>(g, s)
+                                       : launch_grid<KIND_CYL_DENSITY, SCHEME_RK4>(g, s);
+    else
+        e = c->dm.scheme == SCHEME_RK8 ? launch_grid<KIND_SLAB_DENSITY, SCHEME_RK8>(g, s)
+                                       : launch_grid<KIND_SLAB_DENSITY, SCHEME_RK4>(g, s);
+    CUDA_TRY(c, e);
+    CUDA_TRY(c, cudaEventRecord(c->ev1, s));
+    c->timed = true;
+    c->launches += 1;
+    return ESB_OK;
+}
+
+extern "C" int esb_brackets_dev(esb_context* c, const double* d_ext, const double* d_int, int32_t nk,
+                                int32_t nw, int32_t* d_row_offset, int32_t* d_bk, int32_t* d_bw,
+                                int32_t capacity, int32_t* n_host, void* stream) {
+    if (!c || !d_ext || !d_int || !d_row_offset || nk <= 0 || nw <= 0) return ESB_ERR_ARG;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure(c, c->d_rowcount, c->cap_rows, (size_t)nk + 1);
+    if (rc) return rc;
+    const int threads = 128, rows_per_block = threads / 32;
+    const int blocks = (nk + rows_per_block - 1) / rows_per_block;
+    bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, c->d_rowcount, nullptr, nullptr, nullptr,
+                                              0, 0);
+    CUDA_TRY(c, cudaGetLastError());
+    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, d_row_offset, nk);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches += 2;
+    int total = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&total, d_row_offset + nk, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (n_host) *n_host = total;
+    if (d_bk && d_bw && capacity > 0 && total > 0) {
+        bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, c->d_rowcount, d_row_offset, d_bk,
+                                                  d_bw, capacity, 1);
+        CUDA_TRY(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    return total > capacity && d_bk ? ESB_ERR_CAPACITY : ESB_OK;
+}
+
+static int ensure_grid(esb_context* c, size_t n) {
+    if (c->d_ext && c->d_int && c->cap_grid >= n) return ESB_OK;
+    if (c->d_ext) cudaFree(c->d_ext);
+    if (c->d_int) cudaFree(c->d_int);
+    c->d_ext = c->d_int = nullptr;
+    c->cap_grid = 0;
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_ext, n * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_int, n * sizeof(double)));
+    c->cap_grid = n;
+    return ESB_OK;
+}
+
+static size_t w_len(int layout, int nk, int nw) {
+    return layout == OMEGA_PER_K ? (size_t)nk * nw : (size_t)nw;
+}
+
+static int upload_axes(esb_context* c, const double* k, int nk, const double* w, int nw, int layout) {
+    int rc;
+    if ((rc = ensure(c, c->d_k, c->cap_k, (size_t)nk))) return rc;
+    if ((rc = ensure(c, c->d_w, c->cap_w, w_len(layout, nk, nw)))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_k, k, (size_t)nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_w, w, w_len(layout, nk, nw) * sizeof(double), cudaMemcpyHostToDevice,
+                                c->stream));
+    return ESB_OK;
+}
+
+extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k, int32_t nk,
+                                   const double* w, int32_t nw, int32_t layout, double* ext, double* intq) {
+    if (!c) return ESB_ERR_ARG;
+    if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
+    if (!k || !w || !ext || !intq || nk <= 0 || nw <= 0 || layout < 0 || layout > 2)
+        return fail(c, ESB_ERR_ARG, "bad grid arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload_axes(c, k, nk, w, nw, layout))) return rc;
+    const size_t n = (size_t)nk * nw;
+    if ((rc = ensure_grid(c, n))) return rc;
+    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, nullptr)))
+        return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(ext, c->d_ext, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(intq, c->d_int, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ESB_OK;
+}
+
+extern "C" int esb_find_roots(esb_context* c, int32_t mode, const double* k, int32_t nk, const double* w,
+                              int32_t nw, int32_t layout, double tol_percent, int32_t max_roots,
+                              esb_roots* out, int32_t* n_roots, int32_t* n_brackets) {
+    if (!c) return ESB_ERR_ARG;
+    if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
+    if (!k || !w || !out || !n_roots || nk <= 0 || nw <= 1 || layout < 0 || layout > 2 || max_roots < 0)
+        return fail(c, ESB_ERR_ARG, "bad arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = upload_axes(c, k, nk, w, nw, layout))) return rc;
+    const size_t n = (size_t)nk * nw;
+    if ((rc = ensure_grid(c, n))) return rc;
+    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, nullptr)))
+        return rc;
+    if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, (size_t)nk + 1))) return rc;
+    // pass 1: count
+    int total = 0;
+    rc = esb_brackets_dev(c, c->d_ext, c->d_int, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, nullptr);
+    if (rc) return rc;
+    if (n_brackets) *n_brackets = total;
+    *n_roots = total;
+    if (total == 0) return ESB_OK;
+    if (total > max_roots) return fail(c, ESB_ERR_CAPACITY, "max_roots too small");
+    if (c->cap_br < (size_t)total) {
+        if (c->d_bk) cudaFree(c->d_bk);
+        if (c->d_bw) cudaFree(c->d_bw);
+        c->d_bk = c->d_bw = nullptr;
+        c->cap_br = 0;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_bk, (size_t)total * sizeof(int)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_bw, (size_t)total * sizeof(int)));
+        c->cap_br = total;
+    }
+    if (c->cap_roots < (size_t)total) {
+        void* ps[] = {c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit};
+        for (void* p : ps)
+            if (p) cudaFree(p);
+        c->d_ro = c->d_re = c->d_ri = nullptr;
+        c->d_racc = c->d_rit = nullptr;
+        c->cap_roots = 0;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_ro, (size_t)total * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_re, (size_t)total * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_ri, (size_t)total * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_racc, (size_t)total * sizeof(int)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_rit, (size_t)total * sizeof(int)));
+        c->cap_roots = total;
+    }
+    // pass 2: fill (sorted by row, then omega index)
+    {
+        const int threads = 128, rows_per_block = threads / 32;
+        const int blocks = (nk + rows_per_block - 1) / rows_per_block;
+        bracket_kernel<<<blocks, threads, 0, c->stream>>>(c->d_ext, c->d_int, nk, nw, c->d_rowcount,
+                                                          c->d_rowoff, c->d_bk, c->d_bw, total, 1);
+        CUDA_TRY(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    RefineArgs r;
+    r.M = c->dm;
+    r.tab = c->d_tab;
+    r.tab_doubles = c->tab_doubles;
+    r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout; r.mode = mode;
+    r.bk = c->d_bk; r.bw = c->d_bw; r.n_brackets = total;
+    r.tol_percent = tol_percent;
+    r.omega = c->d_ro; r.ext = c->d_re; r.intq = c->d_ri; r.accepted = c->d_racc; r.iters = c->d_rit;
+    cudaError_t e;
+    if (c->dm.kind == KIND_CYL_DENSITY)
+        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, c->stream)
+                                       : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, c->stream);
+    else
+        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, c->stream)
+                                       : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, c->stream);
+    CUDA_TRY(c, e);
+    c->launches += 1;
+    const size_t nb = (size_t)total;
+    if (out->k_index) CUDA_TRY(c, cudaMemcpyAsync(out->k_index, c->d_bk, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out->w_index) CUDA_TRY(c, cudaMemcpyAsync(out->w_index, c->d_bw, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out->omega) CUDA_TRY(c, cudaMemcpyAsync(out->omega, c->d_ro, nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out->ext) CUDA_TRY(c, cudaMemcpyAsync(out->ext, c->d_re, nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out->intq) CUDA_TRY(c, cudaMemcpyAsync(out->intq, c->d_ri, nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out->accepted) CUDA_TRY(c, cudaMemcpyAsync(out->accepted, c->d_racc, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out->iterations) CUDA_TRY(c, cudaMemcpyAsync(out->iterations, c->d_rit, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ESB_OK;
+}
+
+extern "C" int esb_bessel_ik_scaled(int32_t n, double z, double out[4]) {
+    if (n < 0 || n > ESB_MAX_ORDER || !(z > 0.0) || !out) return ESB_ERR_ARG;
+    BesselIK b;
+    bessel_ik_scaled(n, z, b);
+    bessel_order(b, n, z, out[0], out[1], out[2], out[3]);
+    return ESB_OK;
+}

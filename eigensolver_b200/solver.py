@@ -1,0 +1,236 @@
+"""Host side of the B200 dispersion-function path.
+
+`DispersionSolver` owns one C-ABI context (one GPU).  It takes the reference's
+inputs - the equilibrium speeds, a density profile, a k range and an omega range -
+and returns D(omega,k) grids and per-k root tables.
+
+Reference set-up mirrored here (file:line in /root/reference):
+  equilibrium speeds / rho_e         Density_cylinder.py:69-80
+  inverted-Gaussian density profile  Density_cylinder.py:124-154   (r0, dr)
+                                     ..._coronal.py:93-102          (x0, dx)
+No oracle / CPU code is used on this path; everything numerical happens in
+libeigensolver_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclasses.dataclass(frozen=True)
+class Medium:
+    """Characteristic speeds (Density_cylinder.py:69-72)."""
+    c_i0: float = 1.0
+    vA_i0: float = 2.0
+    vA_e: float = 5.0
+    c_e: float = 0.5
+    gamma: float = 5.0 / 3.0
+    rho_i0: float = 1.0
+
+    @property
+    def rho_e(self):
+        g = self.gamma
+        return self.rho_i0 * (self.c_i0**2 + g * 0.5 * self.vA_i0**2) / (self.c_e**2 + g * 0.5 * self.vA_e**2)
+
+    @property
+    def cT_e(self):
+        return math.sqrt(self.c_e**2 * self.vA_e**2 / (self.c_e**2 + self.vA_e**2))
+
+    @property
+    def cT_i0(self):
+        return math.sqrt(self.c_i0**2 * self.vA_i0**2 / (self.c_i0**2 + self.vA_i0**2))
+
+    @property
+    def c_kink(self):
+        re = self.rho_e
+        return math.sqrt((self.rho_i0 * self.vA_i0**2 + re * self.vA_e**2) / (self.rho_i0 + re))
+
+
+CYLINDER_CORONAL = Medium(1.0, 2.0, 5.0, 0.5)
+CYLINDER_PHOTOSPHERIC = Medium(1.0, 2.0, 0.5, 1.5)
+SLAB_CORONAL = Medium(1.0, 1.2, 3.0, 0.4)
+SLAB_PHOTOSPHERIC = Medium(1.0, 1.9, 0.8, 1.3)
+
+
+@dataclasses.dataclass(frozen=True)
+class GaussianDensity:
+    """rho_e + (rho_i0 - rho_e) exp(-(x-x0)^2/width^2)   (Density_cylinder.py:135)."""
+    width: float = 0.95
+    x0: float = 0.0
+
+    def __call__(self, medium, x):
+        x = np.asarray(x, dtype=np.float64)
+        g = np.exp(-((x - self.x0) ** 2) / self.width**2)
+        rho = medium.rho_e + (medium.rho_i0 - medium.rho_e) * g
+        drho = (medium.rho_i0 - medium.rho_e) * g * (-2.0 * (x - self.x0) / self.width**2)
+        return rho, drho
+
+
+@dataclasses.dataclass
+class RootTable:
+    """Result of a root search.  `k`, `omega` of accepted modes are what the
+    reference stores in sol_ks / sol_omegas."""
+    k_index: np.ndarray
+    w_index: np.ndarray
+    k: np.ndarray
+    omega: np.ndarray
+    ext: np.ndarray
+    intq: np.ndarray
+    accepted: np.ndarray
+    iterations: np.ndarray
+    n_brackets: int = 0
+
+    def modes(self):
+        m = self.accepted.astype(bool)
+        return self.k[m], self.omega[m]
+
+
+_KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY}
+_SCHEMES = {"rk4": L.RK4, "rk8": L.RK8}
+_LAYOUTS = {"shared": L.OMEGA_SHARED, "phase_speed": L.OMEGA_PHASE_SPEED, "per_k": L.OMEGA_PER_K}
+_MODES = {"sausage": 0, "kink": 1, "fluting": 2, "fluting2": 2, "fluting3": 3}
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class DispersionSolver:
+    """One GPU context evaluating D(omega,k) for one equilibrium model."""
+
+    def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh="clustered",
+                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0):
+        self.lib = L.load()
+        self.kind = kind
+        m = L.esb_model()
+        L.check(self.lib, None, self.lib.esb_model_defaults(_KINDS[kind], C.byref(m)), "esb_model_defaults")
+        if medium is None:
+            medium = CYLINDER_CORONAL if kind == "cylinder_density" else SLAB_CORONAL
+        self.medium = medium
+        self.profile = profile if profile is not None else GaussianDensity(
+            0.95 if kind == "cylinder_density" else 0.9)
+        m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
+        m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, rho_A
+        m.scheme = _SCHEMES[scheme]
+        m.mesh = L.MESH_UNIFORM if mesh == "uniform" else L.MESH_CLUSTERED
+        m.ext_wavelengths = ext_wavelengths
+        if n_steps is not None:
+            m.n_steps = int(n_steps)
+        elif scheme == "rk4":
+            m.n_steps = 2048
+        if ext_ic is not None:
+            m.ext_ic_value, m.ext_ic_slope = ext_ic
+        self.model = m
+        n = C.c_int32()
+        L.check(self.lib, None, self.lib.esb_mesh_size(C.byref(m), C.byref(n)), "esb_mesh_size")
+        self.nodes = np.empty(n.value, dtype=np.float64)
+        L.check(self.lib, None, self.lib.esb_mesh_nodes(C.byref(m), _dptr(self.nodes)), "esb_mesh_nodes")
+        rho, drho = self.profile(medium, self.nodes)
+        rho = np.ascontiguousarray(rho * rho_A, dtype=np.float64)
+        drho = np.ascontiguousarray(drho * rho_A, dtype=np.float64)
+        rho_b = float(self.profile(medium, np.array([m.s_start]))[0][0] * rho_A)
+        self.ctx = L._ctx()
+        rc = self.lib.esb_create(int(device), C.byref(self.ctx))
+        if rc != L.ESB_OK:
+            self.ctx = None
+            raise L.EsbError("esb_create failed (status %d): no usable CUDA device %d; "
+                             "eigensolver_b200 has no CPU fallback" % (rc, device))
+        L.check(self.lib, self.ctx,
+                self.lib.esb_set_model(self.ctx, C.byref(m), _dptr(rho), _dptr(drho), n.value, rho_b),
+                "esb_set_model")
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.esb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------
+    @staticmethod
+    def _mode(mode):
+        return _MODES[mode] if isinstance(mode, str) else int(mode)
+
+    def _axes(self, k, w, layout):
+        k = np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        lay = _LAYOUTS[layout]
+        if lay == L.OMEGA_PER_K:
+            assert w.ndim == 2 and w.shape[0] == k.size
+            nw = w.shape[1]
+        else:
+            w = w.reshape(-1)
+            nw = w.size
+        return k, w, lay, nw
+
+    def dispersion_grid(self, mode, k, w, layout="phase_speed"):
+        """(ext, int) arrays of shape (nk, nw); D = ext - int; NaN where m_e < 0."""
+        k, w, lay, nw = self._axes(k, w, layout)
+        ext = np.empty((k.size, nw), dtype=np.float64)
+        inq = np.empty((k.size, nw), dtype=np.float64)
+        rc = self.lib.esb_dispersion_grid(self.ctx, self._mode(mode), _dptr(k), k.size, _dptr(w), nw, lay,
+                                          _dptr(ext), _dptr(inq))
+        L.check(self.lib, self.ctx, rc, "esb_dispersion_grid")
+        return ext, inq
+
+    def D(self, mode, k, w, layout="phase_speed"):
+        e, i = self.dispersion_grid(mode, k, w, layout)
+        return e - i
+
+    def find_roots(self, mode, k, w, layout="phase_speed", tol_percent=1.0, max_roots=None):
+        k, w, lay, nw = self._axes(k, w, layout)
+        cap = int(max_roots) if max_roots else max(1024, 64 * k.size)
+        while True:
+            ki = np.empty(cap, np.int32); wi = np.empty(cap, np.int32)
+            om = np.empty(cap, np.float64); ex = np.empty(cap, np.float64); iq = np.empty(cap, np.float64)
+            ac = np.empty(cap, np.int32); it = np.empty(cap, np.int32)
+            out = L.esb_roots(_iptr(ki), _iptr(wi), _dptr(om), _dptr(ex), _dptr(iq), _iptr(ac), _iptr(it))
+            n = C.c_int32(0)
+            nb = C.c_int32(0)
+            rc = self.lib.esb_find_roots(self.ctx, self._mode(mode), _dptr(k), k.size, _dptr(w), nw, lay,
+                                         float(tol_percent), cap, C.byref(out), C.byref(n), C.byref(nb))
+            if rc == L.ESB_ERR_CAPACITY and max_roots is None:
+                cap = int(n.value)
+                continue
+            L.check(self.lib, self.ctx, rc, "esb_find_roots")
+            break
+        n = n.value
+        return RootTable(ki[:n].copy(), wi[:n].copy(), k[ki[:n]], om[:n].copy(), ex[:n].copy(), iq[:n].copy(),
+                         ac[:n].copy(), it[:n].copy(), nb.value)
+
+    # ------------------------------------------------------------------
+    def last_kernel_ms(self):
+        return float(self.lib.esb_last_kernel_ms(self.ctx))
+
+    def launch_count(self):
+        return int(self.lib.esb_launch_count(self.ctx))
+
+
+def bessel_ik_scaled(n, z):
+    """Host helper: (e^-z I_n, d/dz, e^z K_n, d/dz) from the library's evaluators."""
+    lib = L.load()
+    out = (C.c_double * 4)()
+    rc = lib.esb_bessel_ik_scaled(int(n), float(z), out)
+    if rc != L.ESB_OK:
+        raise L.EsbError("esb_bessel_ik_scaled: bad argument")
+    return tuple(out)

@@ -1,0 +1,156 @@
+/* eigensolver_b200 - C ABI of the B200 dispersion-function hot path.
+ *
+ * Drop-in boundary for the shooting solvers of samuelskirvin/EIGENSOLVER.  Every
+ * reference solver script evaluates, for each (k, omega) of a scan,
+ *
+ *     D(omega, k) = exterior matched quantity - interior matched quantity
+ *
+ * by an exterior ODE integration, an interior shooting integration (odeint +
+ * fsolve) and a subtraction, then bisects sign changes of D along omega:
+ *
+ *   Cylinder/Non-uniform density/Coronal/solvers/Density_cylinder.py
+ *       kink()    :546-824   (scan loop 694-821, bisection locate_kink 548-686)
+ *       sausage() :847-1122  (scan loop 990-1119)
+ *   Slab/Non uniform density/Coronal/Solvers/multiprocessor_Inhomogeneous_method_coronal.py
+ *       sausage() :461-600, kink() :640-790
+ *
+ * This library replaces exactly that: esb_dispersion_grid() is the body of the
+ * scan loop over a whole (k, omega) grid, esb_find_roots() is scan + bracket +
+ * refinement + the reference's acceptance test.  Plain pointers and sizes only;
+ * all "host" entry points take HOST pointers and do their own H2D/D2H copies, the
+ * "_dev" entry points take DEVICE pointers (data already resident in HBM).
+ *
+ * Threading: one esb_context per host thread / per GPU.  All calls return 0 on
+ * success, a negative esb_status otherwise; esb_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute call fails with
+ * ESB_ERR_CUDA.
+ */
+#ifndef EIGENSOLVER_B200_H
+#define EIGENSOLVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESB_VERSION 100
+
+typedef struct esb_context esb_context;
+
+enum esb_status {
+    ESB_OK = 0,
+    ESB_ERR_ARG = -1,      /* bad argument / model not set */
+    ESB_ERR_CUDA = -2,     /* CUDA runtime error (no device, launch failure ...) */
+    ESB_ERR_CAPACITY = -3, /* more roots than max_roots; n_roots holds the needed size */
+    ESB_ERR_ALLOC = -4
+};
+
+/* Solver family = which reference script the model restates. */
+enum esb_model_kind {
+    ESB_SLAB_DENSITY = 0,     /* slab, rho(x)   : ...Inhomogeneous_method_coronal.py        */
+    ESB_CYLINDER_DENSITY = 1  /* cylinder rho(r): Density_cylinder.py                       */
+};
+
+/* Fixed-step integrator used across the layer. */
+enum esb_scheme {
+    ESB_RK4 = 0, /* classical 4-stage, stage nodes c = 0, 1/2, 1                              */
+    ESB_RK8 = 1  /* Cooper-Verner 11-stage 8th order, nodes c = 0, (7-/+sqrt21)/14, 1/2, 1   */
+};
+
+/* How the omega axis is given. */
+enum esb_omega_layout {
+    ESB_OMEGA_SHARED = 0,      /* w[nw]:      omega_ij = w[j]              (same for every k) */
+    ESB_OMEGA_PHASE_SPEED = 1, /* w[nw]:      omega_ij = k[i] * w[j]       (w = omega/k grid,
+                                  what the reference's driver builds: Density_cylinder.py:1145) */
+    ESB_OMEGA_PER_K = 2        /* w[nk*nw]:   omega_ij = w[i*nw + j]                          */
+};
+
+/* Equilibrium + discretisation.  Speeds as in Density_cylinder.py:69-80. */
+typedef struct esb_model {
+    int32_t kind;          /* esb_model_kind */
+    int32_t scheme;        /* esb_scheme */
+    int32_t n_steps;       /* integration steps across the layer */
+    int32_t mesh;          /* 0 = nodes clustered at the layer ends (default), 1 = uniform */
+    double c_i0, vA_i0, vA_e, c_e, gamma, rho_i0;
+    double rho_A;          /* amplitude multiplying the density profile (reference rho_A) */
+    double ext_ic_value;   /* exterior initial values at x = -3*2*pi/k: (1e-8,            */
+    double ext_ic_slope;   /*   1e-8) slab :247, (1e-8, 1e-15) cylinder :768              */
+    double ext_wavelengths;/* exterior domain = ext_wavelengths*2*pi/k  (reference: 3)     */
+    double s_start, s_end; /* layer: boundary and far end: (-1, 1) slab, (-1, -0.001) cyl  */
+} esb_model;
+
+/* Defaults of the reference scripts for `kind` (coronal parameter set). */
+int esb_model_defaults(int32_t kind, esb_model* out);
+
+/* Number of profile sample nodes the chosen scheme needs, and their positions.
+ * The caller samples its density profile (any function) at these nodes:
+ * this is what replaces the reference's sympy `profile(x)` + lambdify.
+ * Nodes are ordered along the direction of integration. */
+int esb_mesh_size(const esb_model* m, int32_t* n_nodes);
+int esb_mesh_nodes(const esb_model* m, double* nodes /* [n_nodes] */);
+
+int esb_create(int32_t device, esb_context** out);
+int esb_destroy(esb_context* ctx);
+const char* esb_last_error(const esb_context* ctx);
+
+/* Upload the model: rho[n_nodes], drho[n_nodes] = profile and its derivative at
+ * esb_mesh_nodes(); rho_b = rho at the boundary s_start. */
+int esb_set_model(esb_context* ctx, const esb_model* m, const double* rho, const double* drho,
+                  int32_t n_nodes, double rho_boundary);
+
+/* D over a grid.  mode: slab 0 = sausage, 1 = kink; cylinder = azimuthal order
+ * 0 (sausage), 1 (kink), 2, 3 (fluting).  ext/intq: [nk*nw] row-major, NaN where the
+ * reference skips the point (m_e < 0).  D = ext - intq. */
+int esb_dispersion_grid(esb_context* ctx, int32_t mode, const double* k, int32_t nk,
+                        const double* w, int32_t nw, int32_t omega_layout, double* ext,
+                        double* intq);
+
+/* Root table: scan + sign-change brackets along omega + Brent refinement + the
+ * reference's acceptance test |ext-int|*100/max(|ext|,|int|) < tol_percent
+ * (Density_cylinder.py:809).  Outputs hold up to max_roots entries, sorted by
+ * (k index, omega index of the bracket); *n_roots = number found. */
+typedef struct esb_roots {
+    int32_t* k_index;     /* [max_roots] row of k[]                                   */
+    int32_t* w_index;     /* [max_roots] bracket = (w_index, w_index+1)                */
+    double* omega;        /* [max_roots] refined root                                  */
+    double* ext;          /* [max_roots] exterior quantity at the root                 */
+    double* intq;         /* [max_roots] interior quantity at the root                 */
+    int32_t* accepted;    /* [max_roots] 1 = passes acceptance test (a mode), 0 = pole */
+    int32_t* iterations;  /* [max_roots] Brent iterations used                         */
+} esb_roots;
+
+int esb_find_roots(esb_context* ctx, int32_t mode, const double* k, int32_t nk, const double* w,
+                   int32_t nw, int32_t omega_layout, double tol_percent, int32_t max_roots,
+                   esb_roots* out, int32_t* n_roots, int32_t* n_brackets);
+
+/* Device-resident variants: all pointers are device pointers, `stream` is a
+ * cudaStream_t (0 = default stream).  Asynchronous; no host synchronisation. */
+int esb_dispersion_grid_dev(esb_context* ctx, int32_t mode, const double* d_k, int32_t nk,
+                            const double* d_w, int32_t nw, int32_t omega_layout, double* d_ext,
+                            double* d_intq, void* stream);
+
+/* Brackets of a device-resident D grid: d_row_count[nk] and, sorted, d_bracket_w[*]
+ * (caller passes capacity; returns total via host int after a stream sync). */
+int esb_brackets_dev(esb_context* ctx, const double* d_ext, const double* d_intq, int32_t nk,
+                     int32_t nw, int32_t* d_row_offset /* [nk+1] */, int32_t* d_bracket_k,
+                     int32_t* d_bracket_w, int32_t capacity, int32_t* n_brackets_host,
+                     void* stream);
+
+/* Host-side helper (no GPU needed): scaled modified Bessel functions used by the
+ * exterior solution, out = {e^-z I_n, d/dz, e^z K_n, d/dz}.  For unit tests. */
+int esb_bessel_ik_scaled(int32_t n, double z, double out[4]);
+
+/* Timing hook for bench.py: device time (ms) of the last grid kernel launch
+ * measured with CUDA events on the launching stream; <0 if none. */
+double esb_last_kernel_ms(const esb_context* ctx);
+/* Number of kernels this context has launched so far. */
+int64_t esb_launch_count(const esb_context* ctx);
+
+int esb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,383 @@
+"""ORACLE (test infrastructure, not product code): CPU restatement of the
+reference's numpy/scipy shooting path for the dispersion function D(omega, k).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import this module; the product path
+(`eigensolver_b200/`) never does.
+
+Parity status: PINNED.  `tests/test_oracle_pinned.py` checks this module against
+  (a) D values produced by executing the reference's own `sausage()` / `kink()`
+      functions in the build container (`tests/golden/make_golden.py`, fixtures
+      `tests/golden/ref_D_*.npz`), and
+  (b) the reference's shipped root tables (`Example data/*.pickle`, converted to
+      `tests/golden/ref_roots_*.npz`).
+
+What the reference does for every (k, omega)  (all four solver families share it):
+  1. m_e(omega,k) < 0  -> the point is skipped (leaky regime, not handled).
+  2. exterior: integrate the uniform-medium ODE from x = -3*2*pi/k to x = -1 with
+     `scipy.integrate.odeint`, initial values (1e-8, 1e-8|1e-15).
+  3. interior: integrate the non-uniform-layer ODE from the boundary (-1) across the
+     layer with initial values (exterior value, s); `fsolve` finds the slope s that
+     satisfies the symmetry condition at the far end (axis / other boundary).
+  4. D = (exterior matched quantity at -1) - (interior matched quantity at -1);
+     a sign change of D along omega brackets a mode, |D|*100/max(|ext|,|int|) < tol
+     accepts it.
+
+Reference sources restated here (file:line refer to /root/reference):
+  cylinder, non-uniform density:
+      Cylinder/Non-uniform density/Coronal/solvers/Density_cylinder.py
+        physics set-up 69-221, kink 546-824 (scan loop 694-821), sausage 847-1122
+      Cylinder/Non-uniform density/Photospheric/Solvers/Density_cylinder_photospheric.py
+  slab, non-uniform density:
+      Slab/Non uniform density/Coronal/Solvers/multiprocessor_Inhomogeneous_method_coronal.py
+        physics set-up 69-185, sausage 461-600 (scan loop), kink 640-790
+      Slab/Non uniform density/Photospheric/Solvers/multiprocessor_Inhomogeneous_method.py
+
+The reference rebuilds every coefficient with sympy (`sym.diff` + `lambdify`) at each
+(k, omega).  Here the same expressions are written in closed form with numpy; the
+pinning test is what shows they are the same functions.
+
+Solver tolerances: `rtol`/`atol`/`xtol` default to None = scipy's defaults
+(1.49e-8), i.e. exactly what the reference runs with.  The GPU parity tests call the
+oracle with tight tolerances (rtol 1e-12, atol 1e-30) so that the comparison is
+against the converged value of the reference's own formulation.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+from scipy.integrate import odeint
+from scipy.optimize import brentq, fsolve
+
+GAMMA = 5.0 / 3.0
+
+
+# --------------------------------------------------------------------------
+# equilibrium models
+# --------------------------------------------------------------------------
+@dataclasses.dataclass
+class Medium:
+    """Characteristic speeds of the reference equilibrium (Density_cylinder.py:69-80)."""
+    c_i0: float = 1.0
+    vA_i0: float = 2.0
+    vA_e: float = 5.0
+    c_e: float = 0.5
+    gamma: float = GAMMA
+    rho_i0: float = 1.0
+
+    @property
+    def rho_e(self):
+        g = self.gamma
+        return self.rho_i0 * (self.c_i0**2 + g * 0.5 * self.vA_i0**2) / (
+            self.c_e**2 + g * 0.5 * self.vA_e**2)
+
+    @property
+    def cT_e(self):
+        return math.sqrt(self.c_e**2 * self.vA_e**2 / (self.c_e**2 + self.vA_e**2))
+
+    @property
+    def cT_i0(self):
+        return math.sqrt(self.c_i0**2 * self.vA_i0**2 / (self.c_i0**2 + self.vA_i0**2))
+
+    @property
+    def B_0(self):
+        return self.vA_i0 * math.sqrt(self.rho_i0)
+
+    def m_e(self, k, w, U_e=0.0):
+        """External m_e^2 (Density_cylinder.py:562 / slab ...coronal.py:172)."""
+        W2 = (w - k * U_e) ** 2
+        K = k * k
+        return ((K * self.vA_e**2 - W2) * (K * self.c_e**2 - W2)) / (
+            (self.vA_e**2 + self.c_e**2) * (K * self.cT_e**2 - W2))
+
+
+# the four parameter sets the reference ships
+CYL_CORONAL = Medium(c_i0=1.0, vA_i0=2.0, vA_e=5.0, c_e=0.5)        # Density_cylinder.py:69-72
+CYL_PHOTOSPHERIC = Medium(c_i0=1.0, vA_i0=2.0, vA_e=0.5, c_e=1.5)    # Density_cylinder_photospheric.py
+SLAB_CORONAL = Medium(c_i0=1.0, vA_i0=1.2, vA_e=3.0, c_e=0.4)        # ...method_coronal.py:69-72
+SLAB_PHOTOSPHERIC = Medium(c_i0=1.0, vA_i0=1.9, vA_e=0.8, c_e=1.3)   # ...Inhomogeneous_method.py
+
+
+@dataclasses.dataclass
+class GaussianDensity:
+    """rho(x) = rho_A*(rho_e + (rho_i0-rho_e) exp(-(x-x0)^2/width^2))  (Density_cylinder.py:135-154)."""
+    medium: Medium
+    width: float = 0.95
+    x0: float = 0.0
+    rho_A: float = 1.0
+    #: True: vA from a constant field B_0 (cylinder script); False: slab script's form
+    const_B: bool = False
+
+    def rho(self, x):
+        m = self.medium
+        return self.rho_A * (m.rho_e + (m.rho_i0 - m.rho_e) * np.exp(-(x - self.x0) ** 2 / self.width**2))
+
+    def drho(self, x):
+        m = self.medium
+        return self.rho_A * (m.rho_i0 - m.rho_e) * np.exp(-(x - self.x0) ** 2 / self.width**2) * (
+            -2.0 * (x - self.x0) / self.width**2)
+
+    # Both density solvers keep total pressure balance with a straight field:
+    #   c_i^2 = rho_e (c_e^2 + gamma/2 vA_e^2)/rho - gamma/2 vA_i^2   (Density_cylinder.py:210)
+    # cylinder: B_i = B_0 const -> vA_i^2 = B_0^2/rho                  (Density_cylinder.py:188-200)
+    # slab:     vA_i = vA_i0 sqrt(rho_i0)/sqrt(profile)                (...coronal.py:117)
+    # With rho_A = 1 (every shipped script) the two coincide; `const_B` selects the
+    # cylinder form when rho_A != 1.
+    def vA2(self, x):
+        m = self.medium
+        prof = self.rho(x) / (1.0 if self.const_B else self.rho_A)
+        return m.vA_i0**2 * m.rho_i0 / prof
+
+    def c2(self, x):
+        m = self.medium
+        return m.rho_e * (m.c_e**2 + 0.5 * m.gamma * m.vA_e**2) / self.rho(x) - 0.5 * m.gamma * self.vA2(x)
+
+    def speeds(self, x):
+        """rho, c^2, vA^2 and their x-derivatives."""
+        m = self.medium
+        rho = self.rho(x)
+        drho = self.drho(x)
+        ra = 1.0 if self.const_B else self.rho_A
+        prof = rho / ra
+        dprof = drho / ra
+        vA2 = m.vA_i0**2 * m.rho_i0 / prof
+        dvA2 = -vA2 * dprof / prof
+        Cc = m.rho_e * (m.c_e**2 + 0.5 * m.gamma * m.vA_e**2)
+        c2 = Cc / rho - 0.5 * m.gamma * vA2
+        dc2 = -Cc * drho / rho**2 - 0.5 * m.gamma * dvA2
+        return rho, drho, c2, dc2, vA2, dvA2
+
+
+# --------------------------------------------------------------------------
+# the four geometry/mode closures
+# --------------------------------------------------------------------------
+class _Base:
+    #: initial values of the exterior integration (value, slope)
+    ext_ic = (1e-8, 1e-15)
+    #: interior integration interval (start at the boundary)
+    s0 = -1.0
+    s1 = 1.0
+    #: reference's fsolve starting guess
+    slope_guess = 1.0
+    n_ext_out = 500
+    n_int_out = 500
+
+    def ext_start(self, k):
+        # "Number of wavelengths/2*pi accomodated in the domain" (Density_cylinder.py:553)
+        return -3.0 * 2.0 * np.pi / k
+
+
+class SlabDensity(_Base):
+    """Slab with non-uniform density, reference
+    Slab/Non uniform density/Coronal/Solvers/multiprocessor_Inhomogeneous_method_coronal.py."""
+    geometry = "slab"
+    ext_ic = (1e-8, 1e-8)          # :247  V0 = [1e-8, 1e-8]
+    s0, s1 = -1.0, 1.0             # :91   ix = linspace(-1, 1, ...)
+    slope_guess = 1.0              # :262  fsolve(objective_dvxi, 1.)
+    n_int_out = 500                # the reference uses 1e6 output points; odeint's
+                                   # steps do not depend on the output grid.
+
+    def __init__(self, profile: GaussianDensity, mode: str):
+        assert mode in ("sausage", "kink")
+        self.profile = profile
+        self.medium = profile.medium
+        self.mode = mode
+
+    # -- exterior ----------------------------------------------------------
+    def ext_rhs(self, k, w):
+        m_e = self.medium.m_e(k, w)
+        return lambda y, x: [y[1], m_e * y[0]]      # dVx_dx_e  :245
+
+    def ext_match(self, k, w, y_b):
+        """-> (value handed to the interior as y(-1), exterior matched quantity)."""
+        m = self.medium
+        K, A = k * k, w * w
+        p_e_const = m.rho_e * (m.vA_e**2 + m.c_e**2) * (K * m.cT_e**2 - A) / (w * (K * m.c_e**2 - A))  # :221
+        return y_b[0], p_e_const * y_b[1]           # left_P_solution = p_e_const*Ls[:,1]  :250
+
+    # -- interior ----------------------------------------------------------
+    def coeffs(self, x, k, w):
+        """y'' = a y' + b y ;  a = -F'/F, b = m0^2   (dVx_dx_i :254)."""
+        K, A = k * k, w * w
+        rho, drho, c2, dc2, vA2, dvA2 = self.profile.speeds(x)
+        s = c2 + vA2
+        ds = dc2 + dvA2
+        cT2 = c2 * vA2 / s
+        dcT2 = (dc2 * vA2 + c2 * dvA2) / s - cT2 * ds / s
+        # F = rho (c^2+vA^2)(k^2 cT^2 - w^2)/(k^2 c^2 - w^2)   :222
+        dlnF = drho / rho + ds / s + K * dcT2 / (K * cT2 - A) - K * dc2 / (K * c2 - A)
+        m0 = (K * c2 - A) * (K * vA2 - A) / (s * (K * cT2 - A))   # :230
+        return -dlnF, m0
+
+    def end_residual(self, y_end, y_start0):
+        # sausage: vx(1) + vx(-1) = 0 (:259), kink: vx(1) - vx(-1) = 0 (:696)
+        return y_end[0] + y_start0 if self.mode == "sausage" else y_end[0] - y_start0
+
+    def end_functional(self):
+        """residual = c0*y(end) + c1*y'(end) + cb*y(start)."""
+        return (1.0, 0.0, 1.0 if self.mode == "sausage" else -1.0)
+
+    def int_match(self, k, w, y0, slope):
+        """interior matched quantity at the boundary: p_i_const[0]*vx'(-1)  (:267)."""
+        K, A = k * k, w * w
+        rho, _, c2, _, vA2, _ = self.profile.speeds(self.s0)
+        cT2 = c2 * vA2 / (c2 + vA2)
+        P_Ti = rho * (vA2 + c2) * (K * cT2 - A) / (w * (K * c2 - A))   # :234
+        return P_Ti * slope
+
+
+class CylinderDensity(_Base):
+    """Cylinder with non-uniform density, reference
+    Cylinder/Non-uniform density/Coronal/solvers/Density_cylinder.py.
+
+    mode: azimuthal wavenumber m (0 sausage, 1 kink, >=2 fluting)."""
+    geometry = "cylinder"
+    ext_ic = (1e-8, 1e-15)         # :768  P0 = [1e-8, 1e-15]
+    s0, s1 = -1.0, -0.001          # :120  ix = linspace(-1., -0.001, 500)
+    slope_guess = -0.001           # :790  fsolve(objective_dPi, -0.001)
+
+    def __init__(self, profile: GaussianDensity, m: int):
+        self.profile = profile
+        self.medium = profile.medium
+        self.m = int(m)
+        self.mode = {0: "sausage", 1: "kink"}.get(self.m, "fluting%d" % self.m)
+
+    def ext_rhs(self, k, w):
+        m_e = self.medium.m_e(k, w)
+        mm = float(self.m * self.m)
+        # dP_dr_e :765 (kink, 1/r^2) and :1061 (sausage, 0/r^2)
+        return lambda y, r: [y[1], -y[1] / r + (m_e + mm / (r * r)) * y[0]]
+
+    def ext_match(self, k, w, y_b):
+        md = self.medium
+        xi_e_const = -1.0 / (md.rho_e * (k * k * md.vA_e**2 - w * w))   # :702
+        return y_b[0], xi_e_const * y_b[1]         # left_xi_solution  :773
+
+    def coeffs(self, r, k, w):
+        """P'' = a P' + b P ; a = -dF/F, b = g/F   (dP_dr_i :782).
+
+        With v_phi = B_phi = v_z = 0 (Density_cylinder.py:97-108) the reference's
+        general coefficients collapse:  Q = T = C1 = 0,  C3 = D rho (w^2 - wA^2),
+        F = r D/C3 = r/(rho w^2 - k^2 B^2),  g = -r C2/D,  and
+        g/F = m^2/r^2 + k^2 - w^4/((c^2+vA^2)(w^2 - k^2 cT^2))."""
+        K, A = k * k, w * w
+        rho, drho, c2, dc2, vA2, dvA2 = self.profile.speeds(r)
+        s = c2 + vA2
+        cT2 = c2 * vA2 / s
+        X = rho * (A - K * vA2)                      # rho (w^2 - wA^2)
+        dX = drho * (A - K * vA2) - rho * K * dvA2
+        dlnF = 1.0 / r - dX / X
+        b = self.m**2 / (r * r) + K - A * A / (s * (A - K * cT2))
+        return -dlnF, b
+
+    def end_functional(self):
+        # kink/fluting: P(axis) = 0 (:787); sausage: P'(axis) = 0 (:1084)
+        return (0.0, 1.0, 0.0) if self.m == 0 else (1.0, 0.0, 0.0)
+
+    def end_residual(self, y_end, y_start0):
+        return y_end[1] if self.m == 0 else y_end[0]
+
+    def int_match(self, k, w, y0, slope):
+        """inside_xi_solution[0] = (C1 P + D P')/C3 at r=-1 (:798) = P'(-1)/(rho (w^2-wA^2))."""
+        rho, _, _, _, vA2, _ = self.profile.speeds(self.s0)
+        return slope / (rho * (w * w - k * k * vA2))
+
+
+# --------------------------------------------------------------------------
+# the dispersion function
+# --------------------------------------------------------------------------
+def _ode_kw(rtol, atol):
+    kw = {}
+    if rtol is not None:
+        kw["rtol"] = rtol
+    if atol is not None:
+        kw["atol"] = atol
+    if rtol is not None and rtol < 1e-9:
+        kw["mxstep"] = 200000
+    return kw
+
+
+def exterior(model, k, w, rtol=None, atol=None):
+    """Step 2: boundary values (y, y') of the exterior solution at x=-1, or None if skipped."""
+    if model.medium.m_e(k, w) < 0:           # "if m_e < 0: pass"  Density_cylinder.py:760
+        return None
+    lx = np.linspace(model.ext_start(k), -1.0, model.n_ext_out)
+    Ls = odeint(model.ext_rhs(k, w), list(model.ext_ic), lx, **_ode_kw(rtol, atol))
+    return Ls[-1]
+
+
+def dispersion(model, k, w, rtol=None, atol=None, xtol=None, shoot="fsolve"):
+    """Steps 1-4 for one (k, w).  Returns (exterior quantity, interior quantity);
+    D = ext - int.  (nan, nan) where the reference skips the point."""
+    yb = exterior(model, k, w, rtol, atol)
+    if yb is None:
+        return float("nan"), float("nan")
+    y0, ext_q = model.ext_match(k, w, yb)
+    ix = np.linspace(model.s0, model.s1, model.n_int_out)
+    okw = _ode_kw(rtol, atol)
+
+    def rhs(y, s):
+        a, b = model.coeffs(s, k, w)
+        return [y[1], a * y[1] + b * y[0]]
+
+    if shoot == "fsolve":
+        def objective(sl):
+            U = odeint(rhs, [y0, float(np.asarray(sl).reshape(-1)[0])], ix, **okw)
+            return model.end_residual(U[-1], y0)
+        fkw = {} if xtol is None else {"xtol": xtol}
+        slope, = fsolve(objective, model.slope_guess, **fkw)
+    else:
+        # the interior ODE is linear, so the residual is affine in the slope:
+        # two integrations give the same slope fsolve converges to.
+        U0 = odeint(rhs, [y0, 0.0], ix, **okw)[-1]
+        U1 = odeint(rhs, [0.0, 1.0], ix, **okw)[-1]
+        r0 = model.end_residual(U0, y0)
+        r1 = model.end_residual(U1, 0.0)
+        slope = -r0 / r1
+    return ext_q, model.int_match(k, w, y0, slope)
+
+
+def D(model, k, w, **kw):
+    e, i = dispersion(model, k, w, **kw)
+    return e - i
+
+
+def mismatch_percent(e, i):
+    """The reference's acceptance test (Density_cylinder.py:809)."""
+    return abs(e - i) * 100.0 / max(abs(e), abs(i))
+
+
+def scan(model, k, freq, **kw):
+    """D over an omega grid at one k -> (ext[], int[]) arrays (nan = skipped)."""
+    out = np.array([dispersion(model, k, w, **kw) for w in freq])
+    return out[:, 0], out[:, 1]
+
+
+def brackets(Dvals):
+    """Indices j with a sign change between grid points j and j+1 (both evaluated)."""
+    d = np.asarray(Dvals)
+    ok = np.isfinite(d[:-1]) & np.isfinite(d[1:])
+    return np.nonzero(ok & (d[:-1] * d[1:] < 0))[0]
+
+
+def refine(model, k, w_lo, w_hi, xtol=1e-14, **kw):
+    """Brent refinement of one bracket; returns (omega, ext, int)."""
+    f = lambda w: D(model, k, w, **kw)
+    w = brentq(f, w_lo, w_hi, xtol=xtol * max(abs(w_lo), abs(w_hi)), rtol=8.9e-16, maxiter=200)
+    e, i = dispersion(model, k, w, **kw)
+    return w, e, i
+
+
+def find_roots(model, k, freq, tol_percent=1.0, **kw):
+    """Reference semantics, restated with a proper root polish:
+    brackets along omega -> refine -> keep those that pass the reference's
+    acceptance test (poles of D change sign too but never pass it)."""
+    e, i = scan(model, k, freq, **kw)
+    roots = []
+    for j in brackets(e - i):
+        w, er, ir = refine(model, k, freq[j], freq[j + 1], **kw)
+        if mismatch_percent(er, ir) < tol_percent:
+            roots.append(w)
+    return np.array(roots)
