@@ -63,6 +63,12 @@ SYMBOLS = {
                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esb_brackets_dev": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, _ip, C.c_void_p]),
+    "esb_upload_axes": (C.c_int, [_ctx, _dp, C.c_int32, _dp, C.c_int32, C.c_int32]),
+    "esb_sweep_resident": (C.c_int, [_ctx, C.c_int32, C.c_double, _ip, _ip]),
+    "esb_download_roots": (C.c_int, [_ctx, C.POINTER(esb_roots), C.c_int32]),
+    "esb_roots_device": (C.c_int, [_ctx, C.POINTER(esb_roots), _ip]),
+    "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "esb_fp64_peak": (C.c_int, [_ctx, _dp]),
     "esb_bessel_ik_scaled": (C.c_int, [C.c_int32, C.c_double, _dp]),
     "esb_last_kernel_ms": (C.c_double, [_ctx]),
     "esb_launch_count": (C.c_int64, [_ctx]),

@@ -5,8 +5,9 @@
 //                    across the layer with the profile table staged in shared memory.
 //   bracket_count /  one warp per k-row: warp-ballot sign-change detection along omega,
 //   bracket_fill     popc prefix -> deterministic, sorted bracket list.
-//   refine_kernel    one thread per bracket: Brent iteration on D(omega), warp-level
-//                    vote (__any_sync) on the convergence flags, acceptance test.
+//   refine_kernel    persistent; one lane per bracket at a time, brackets pulled from a
+//                    queue: Brent iteration on D(omega), warp-level vote (__any_sync) on the
+//                    pending flags, pole early-out, acceptance test.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -150,9 +151,12 @@ struct RefineArgs {
     const double* k;
     const double* w;
     int nk, nw, layout, mode;
+    const double* gext;     // D grid of the scan (end-point values of every bracket)
+    const double* gint;
     const int* bk;
     const int* bw;
     int n_brackets;
+    int* counter;           // work queue head (zeroed before launch)
     double tol_percent;
     double* omega;
     double* ext;
@@ -161,90 +165,113 @@ struct RefineArgs {
     int* iters;
 };
 
+__device__ __forceinline__ double mismatch_pct(double e, double i) {
+    // the reference's acceptance quantity (Density_cylinder.py:809)
+    return fabs(e - i) * 100.0 / fmax(fabs(e), fabs(i));
+}
+
+// Persistent kernel: every lane runs Brent's method on one bracket at a time and pulls
+// the next bracket from a global queue as soon as its own has converged, so a warp
+// never idles behind its slowest lane.  The D evaluation (the expensive part) is executed
+// by all 32 lanes together each round; __any_sync on the "trial pending" flags ends the
+// loop.  End-point values come from the scan grid, not from new evaluations.  A bracket
+// whose best point keeps a mismatch above 50 % while |D| grows or the bracket has shrunk
+// to 1e-7 relative is a pole of D (sign change through infinity): it is reported,
+// unaccepted, without being bisected to machine precision.
 template <int KIND, int SCHEME>
-__global__ void __launch_bounds__(32) refine_kernel(RefineArgs r) {
+__global__ void __launch_bounds__(64) refine_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
     stage_table(r.tab, stab, r.tab_doubles);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t < r.n_brackets;
-    const int ik = live ? r.bk[t] : 0;
-    const int jw = live ? r.bw[t] : 0;
-    const double k = r.k[ik];
-    double a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
-    double b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
-    double ea, ia, eb, ib;
-    eval_point<KIND, SCHEME>(r.M, stab, k, a, r.mode, ea, ia);
-    eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, eb, ib);
-    double fa = ea - ia, fb = eb - ib;
-    double c = a, fc = fa, d = b - a, e = d;
-    bool done = !live || !(fa * fb < 0.0);
-    int it = 0;
     const double eps = 2.220446049250313e-16;
-    // Brent's method; the whole warp iterates until every lane has converged.
-    for (int sweep = 0; sweep < 200 && __any_sync(0xffffffffu, !done); ++sweep) {
-        if (!done) {
+    bool have = false, pending = false, exhausted = false;
+    int t = 0, it = 0;
+    double k = 1.0, a = 0, b = 1.0, c = 0, ea = 0, ia = 0, eb = 0, ib = 0, ec = 0, ic = 0, d = 0, e = 0,
+           f0min = 0;
+    for (;;) {
+        while (!pending && !exhausted) {
+            if (!have) {
+                t = atomicAdd(r.counter, 1);
+                if (t >= r.n_brackets) {
+                    exhausted = true;
+                    break;
+                }
+                const int ik = r.bk[t], jw = r.bw[t];
+                k = r.k[ik];
+                a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
+                b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
+                const size_t o = (size_t)ik * r.nw + jw;
+                ea = r.gext[o]; ia = r.gint[o];
+                eb = r.gext[o + 1]; ib = r.gint[o + 1];
+                c = a; ec = ea; ic = ia;
+                d = b - a; e = d;
+                f0min = fmin(fabs(ea - ia), fabs(eb - ib));
+                it = 0;
+                have = true;
+            }
+            double fa = ea - ia, fb = eb - ib, fc = ec - ic;
             if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
-                c = a; fc = fa; d = b - a; e = d;
+                c = a; ec = ea; ic = ia; fc = fa;
+                d = b - a; e = d;
             }
             if (fabs(fc) < fabs(fb)) {
-                a = b; b = c; c = a;
+                a = b; ea = eb; ia = ib;
+                b = c; eb = ec; ib = ic;
+                c = a; ec = ea; ic = ia;
                 fa = fb; fb = fc; fc = fa;
             }
             const double tol1 = 2.0 * eps * fabs(b);
             const double xm = 0.5 * (c - b);
-            if (fabs(xm) <= tol1 || fb == 0.0 || !isfinite(fb)) {
-                done = true;
-            } else {
-                if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
-                    const double s = fb / fa;
-                    double p, q;
-                    if (a == c) {
-                        p = 2.0 * xm * s;
-                        q = 1.0 - s;
-                    } else {
-                        const double qq = fa / fc, rr = fb / fc;
-                        p = s * (2.0 * xm * qq * (qq - rr) - (b - a) * (rr - 1.0));
-                        q = (qq - 1.0) * (rr - 1.0) * (s - 1.0);
-                    }
-                    if (p > 0.0) q = -q;
-                    p = fabs(p);
-                    const double m1 = 3.0 * xm * q - fabs(tol1 * q);
-                    const double m2 = fabs(e * q);
-                    if (2.0 * p < (m1 < m2 ? m1 : m2)) {
-                        e = d;
-                        d = p / q;
-                    } else {
-                        d = xm;
-                        e = d;
-                    }
+            const bool converged = fabs(xm) <= tol1 || fb == 0.0 || !isfinite(fb) || it >= 120;
+            const bool pole = it >= 2 && mismatch_pct(eb, ib) > 50.0 &&
+                              (fabs(fb) > 4.0 * f0min || fabs(xm) < 1e-7 * fabs(b));
+            if (converged || pole) {
+                r.omega[t] = b;
+                r.ext[t] = eb;
+                r.intq[t] = ib;
+                r.iters[t] = it;
+                r.accepted[t] = (mismatch_pct(eb, ib) < r.tol_percent) ? 1 : 0;
+                have = false;
+                continue;
+            }
+            if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+                const double s = fb / fa;
+                double p, q;
+                if (a == c) {
+                    p = 2.0 * xm * s;
+                    q = 1.0 - s;
+                } else {
+                    const double qq = fa / fc, rr = fb / fc;
+                    p = s * (2.0 * xm * qq * (qq - rr) - (b - a) * (rr - 1.0));
+                    q = (qq - 1.0) * (rr - 1.0) * (s - 1.0);
+                }
+                if (p > 0.0) q = -q;
+                p = fabs(p);
+                const double m1 = 3.0 * xm * q - fabs(tol1 * q);
+                const double m2 = fabs(e * q);
+                if (2.0 * p < (m1 < m2 ? m1 : m2)) {
+                    e = d;
+                    d = p / q;
                 } else {
                     d = xm;
                     e = d;
                 }
-                a = b;
-                fa = fb;
-                b += (fabs(d) > tol1) ? d : (xm > 0.0 ? tol1 : -tol1);
+            } else {
+                d = xm;
+                e = d;
             }
+            a = b; ea = eb; ia = ib;
+            b += (fabs(d) > tol1) ? d : (xm > 0.0 ? tol1 : -tol1);
+            pending = true;
         }
-        // evaluation outside the divergent region: every lane runs the integrator together
+        if (!__any_sync(0xffffffffu, pending)) break;
         double en, in_;
         eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, en, in_);
-        if (!done) {
-            fb = en - in_;
+        if (pending) {
+            eb = en;
+            ib = in_;
             ++it;
+            pending = false;
         }
-    }
-    // b is the best estimate; one more (warp-uniform) evaluation gives both quantities there
-    eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, eb, ib);
-    if (live) {
-        r.omega[t] = b;
-        r.ext[t] = eb;
-        r.intq[t] = ib;
-        r.iters[t] = it;
-        // reference acceptance test (Density_cylinder.py:809)
-        const double mx = fmax(fabs(eb), fabs(ib));
-        const double pct = fabs(eb - ib) * 100.0 / mx;
-        r.accepted[t] = (pct < r.tol_percent) ? 1 : 0;
     }
 }
 
@@ -263,11 +290,16 @@ struct esb_context {
     int *d_rowcount = nullptr, *d_rowoff = nullptr, *d_bk = nullptr, *d_bw = nullptr;
     size_t cap_rows = 0, cap_rowoff = 0, cap_br = 0;
     double *d_ro = nullptr, *d_re = nullptr, *d_ri = nullptr;
-    int *d_racc = nullptr, *d_rit = nullptr;
+    int *d_racc = nullptr, *d_rit = nullptr, *d_counter = nullptr;
+    size_t cap_counter = 0;
     size_t cap_roots = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int64_t launches = 0;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    int ax_nk = 0, ax_nw = 0, ax_layout = 0;
+    int n_roots = 0;
     std::string err;
 };
 
@@ -428,7 +460,7 @@ extern "C" int esb_destroy(esb_context* c) {
     if (!c) return ESB_OK;
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_rowcount, c->d_rowoff, c->d_bk,
-                    c->d_bw, c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit};
+                    c->d_bw, c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit, c->d_counter};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -534,7 +566,10 @@ static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    refine_kernel<KIND, SCHEME><<<(r.n_brackets + 31) / 32, 32, smem, s>>>(r);
+    int blocks = (r.n_brackets + 63) / 64;
+    const int cap = 148 * 8;           // persistent: at most 8 CTAs of 64 threads per SM
+    if (blocks > cap) blocks = cap;
+    refine_kernel<KIND, SCHEME><<<blocks, 64, smem, s>>>(r);
     return cudaGetLastError();
 }
 
@@ -551,7 +586,7 @@ extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const doubl
     if (nk <= 0 || nw <= 0 || !d_k || !d_w || !d_ext || !d_int || layout < 0 || layout > 2 ||
         check_mode(c, mode))
         return fail(c, ESB_ERR_ARG, "bad grid arguments");
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t s = stream ? (cudaStream_t)stream : (c->use_user_stream ? c->user_stream : c->stream);
     GridArgs g;
     g.M = c->dm;
     g.tab = c->d_tab;
@@ -578,7 +613,7 @@ extern "C" int esb_brackets_dev(esb_context* c, const double* d_ext, const doubl
                                 int32_t nw, int32_t* d_row_offset, int32_t* d_bk, int32_t* d_bw,
                                 int32_t capacity, int32_t* n_host, void* stream) {
     if (!c || !d_ext || !d_int || !d_row_offset || nk <= 0 || nw <= 0) return ESB_ERR_ARG;
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t s = stream ? (cudaStream_t)stream : (c->use_user_stream ? c->user_stream : c->stream);
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = ensure(c, c->d_rowcount, c->cap_rows, (size_t)nk + 1);
     if (rc) return rc;
@@ -615,18 +650,11 @@ static int ensure_grid(esb_context* c, size_t n) {
     return ESB_OK;
 }
 
+extern "C" int esb_upload_axes(esb_context* c, const double* k, int32_t nk, const double* w, int32_t nw,
+                               int32_t layout);
+
 static size_t w_len(int layout, int nk, int nw) {
     return layout == OMEGA_PER_K ? (size_t)nk * nw : (size_t)nw;
-}
-
-static int upload_axes(esb_context* c, const double* k, int nk, const double* w, int nw, int layout) {
-    int rc;
-    if ((rc = ensure(c, c->d_k, c->cap_k, (size_t)nk))) return rc;
-    if ((rc = ensure(c, c->d_w, c->cap_w, w_len(layout, nk, nw)))) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_k, k, (size_t)nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_w, w, w_len(layout, nk, nw) * sizeof(double), cudaMemcpyHostToDevice,
-                                c->stream));
-    return ESB_OK;
 }
 
 extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k, int32_t nk,
@@ -637,48 +665,76 @@ extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k
         return fail(c, ESB_ERR_ARG, "bad grid arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc;
-    if ((rc = upload_axes(c, k, nk, w, nw, layout))) return rc;
+    if ((rc = esb_upload_axes(c, k, nk, w, nw, layout))) return rc;
     const size_t n = (size_t)nk * nw;
     if ((rc = ensure_grid(c, n))) return rc;
-    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, nullptr)))
+    cudaStream_t s = c->use_user_stream ? c->user_stream : c->stream;
+    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
         return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(ext, c->d_ext, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(intq, c->d_int, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(ext, c->d_ext, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(intq, c->d_int, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
     return ESB_OK;
 }
 
-extern "C" int esb_find_roots(esb_context* c, int32_t mode, const double* k, int32_t nk, const double* w,
-                              int32_t nw, int32_t layout, double tol_percent, int32_t max_roots,
-                              esb_roots* out, int32_t* n_roots, int32_t* n_brackets) {
+extern "C" int esb_set_stream(esb_context* c, void* stream) {
     if (!c) return ESB_ERR_ARG;
-    if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
-    if (!k || !w || !out || !n_roots || nk <= 0 || nw <= 1 || layout < 0 || layout > 2 || max_roots < 0)
-        return fail(c, ESB_ERR_ARG, "bad arguments");
+    c->user_stream = (cudaStream_t)stream;
+    c->use_user_stream = true;
+    return ESB_OK;
+}
+
+static cudaStream_t cur_stream(esb_context* c) { return c->use_user_stream ? c->user_stream : c->stream; }
+
+extern "C" int esb_upload_axes(esb_context* c, const double* k, int32_t nk, const double* w, int32_t nw,
+                               int32_t layout) {
+    if (!c) return ESB_ERR_ARG;
+    if (!k || !w || nk <= 0 || nw <= 0 || layout < 0 || layout > 2) return fail(c, ESB_ERR_ARG, "bad axes");
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc;
-    if ((rc = upload_axes(c, k, nk, w, nw, layout))) return rc;
+    if ((rc = ensure(c, c->d_k, c->cap_k, (size_t)nk))) return rc;
+    if ((rc = ensure(c, c->d_w, c->cap_w, w_len(layout, nk, nw)))) return rc;
+    cudaStream_t s = cur_stream(c);
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_k, k, (size_t)nk * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_w, w, w_len(layout, nk, nw) * sizeof(double), cudaMemcpyHostToDevice, s));
+    c->ax_nk = nk; c->ax_nw = nw; c->ax_layout = layout;
+    return ESB_OK;
+}
+
+// grid -> brackets -> refine on the axes already resident in HBM; the root table stays
+// on the device (esb_download_roots / esb_roots_device copy it out).
+extern "C" int esb_sweep_resident(esb_context* c, int32_t mode, double tol_percent, int32_t* n_roots,
+                                  int32_t* n_brackets) {
+    if (!c) return ESB_ERR_ARG;
+    if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
+    if (c->ax_nk <= 0 || c->ax_nw <= 1) return fail(c, ESB_ERR_ARG, "axes not uploaded (need nw >= 2)");
+    if (check_mode(c, mode)) return fail(c, ESB_ERR_ARG, "bad mode");
+    const int nk = c->ax_nk, nw = c->ax_nw, layout = c->ax_layout;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = cur_stream(c);
+    int rc;
     const size_t n = (size_t)nk * nw;
     if ((rc = ensure_grid(c, n))) return rc;
-    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, nullptr)))
+    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
         return rc;
     if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, (size_t)nk + 1))) return rc;
-    // pass 1: count
+    // pass 1: count (one 4-byte D2H + sync: the refine launch needs the bracket count)
     int total = 0;
-    rc = esb_brackets_dev(c, c->d_ext, c->d_int, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, nullptr);
+    rc = esb_brackets_dev(c, c->d_ext, c->d_int, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, s);
     if (rc) return rc;
+    c->n_roots = total;
     if (n_brackets) *n_brackets = total;
-    *n_roots = total;
+    if (n_roots) *n_roots = total;
     if (total == 0) return ESB_OK;
-    if (total > max_roots) return fail(c, ESB_ERR_CAPACITY, "max_roots too small");
     if (c->cap_br < (size_t)total) {
         if (c->d_bk) cudaFree(c->d_bk);
         if (c->d_bw) cudaFree(c->d_bw);
         c->d_bk = c->d_bw = nullptr;
         c->cap_br = 0;
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_bk, (size_t)total * sizeof(int)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_bw, (size_t)total * sizeof(int)));
-        c->cap_br = total;
+        const size_t cap = (size_t)total + total / 4 + 64;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_bk, cap * sizeof(int)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_bw, cap * sizeof(int)));
+        c->cap_br = cap;
     }
     if (c->cap_roots < (size_t)total) {
         void* ps[] = {c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit};
@@ -687,19 +743,20 @@ extern "C" int esb_find_roots(esb_context* c, int32_t mode, const double* k, int
         c->d_ro = c->d_re = c->d_ri = nullptr;
         c->d_racc = c->d_rit = nullptr;
         c->cap_roots = 0;
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_ro, (size_t)total * sizeof(double)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_re, (size_t)total * sizeof(double)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_ri, (size_t)total * sizeof(double)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_racc, (size_t)total * sizeof(int)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_rit, (size_t)total * sizeof(int)));
-        c->cap_roots = total;
+        const size_t cap = (size_t)total + total / 4 + 64;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_ro, cap * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_re, cap * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_ri, cap * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_racc, cap * sizeof(int)));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_rit, cap * sizeof(int)));
+        c->cap_roots = cap;
     }
     // pass 2: fill (sorted by row, then omega index)
     {
         const int threads = 128, rows_per_block = threads / 32;
         const int blocks = (nk + rows_per_block - 1) / rows_per_block;
-        bracket_kernel<<<blocks, threads, 0, c->stream>>>(c->d_ext, c->d_int, nk, nw, c->d_rowcount,
-                                                          c->d_rowoff, c->d_bk, c->d_bw, total, 1);
+        bracket_kernel<<<blocks, threads, 0, s>>>(c->d_ext, c->d_int, nk, nw, c->d_rowcount, c->d_rowoff,
+                                                  c->d_bk, c->d_bw, total, 1);
         CUDA_TRY(c, cudaGetLastError());
         c->launches += 1;
     }
@@ -709,26 +766,97 @@ extern "C" int esb_find_roots(esb_context* c, int32_t mode, const double* k, int
     r.tab_doubles = c->tab_doubles;
     r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout; r.mode = mode;
     r.bk = c->d_bk; r.bw = c->d_bw; r.n_brackets = total;
+    r.gext = c->d_ext; r.gint = c->d_int;
+    if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)1))) return rc;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
+    r.counter = c->d_counter;
     r.tol_percent = tol_percent;
     r.omega = c->d_ro; r.ext = c->d_re; r.intq = c->d_ri; r.accepted = c->d_racc; r.iters = c->d_rit;
     cudaError_t e;
     if (c->dm.kind == KIND_CYL_DENSITY)
-        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, c->stream)
-                                       : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, c->stream);
+        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, s)
+                                       : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, s);
     else
-        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, c->stream)
-                                       : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, c->stream);
+        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)
+                                       : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, s);
     CUDA_TRY(c, e);
     c->launches += 1;
-    const size_t nb = (size_t)total;
-    if (out->k_index) CUDA_TRY(c, cudaMemcpyAsync(out->k_index, c->d_bk, nb * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (out->w_index) CUDA_TRY(c, cudaMemcpyAsync(out->w_index, c->d_bw, nb * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (out->omega) CUDA_TRY(c, cudaMemcpyAsync(out->omega, c->d_ro, nb * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (out->ext) CUDA_TRY(c, cudaMemcpyAsync(out->ext, c->d_re, nb * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (out->intq) CUDA_TRY(c, cudaMemcpyAsync(out->intq, c->d_ri, nb * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (out->accepted) CUDA_TRY(c, cudaMemcpyAsync(out->accepted, c->d_racc, nb * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (out->iterations) CUDA_TRY(c, cudaMemcpyAsync(out->iterations, c->d_rit, nb * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ESB_OK;
+}
+
+extern "C" int esb_download_roots(esb_context* c, esb_roots* out, int32_t max_roots) {
+    if (!c || !out) return ESB_ERR_ARG;
+    const size_t nb = (size_t)c->n_roots;
+    if ((int64_t)nb > (int64_t)max_roots) return fail(c, ESB_ERR_CAPACITY, "max_roots too small");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = cur_stream(c);
+    if (nb) {
+        if (out->k_index) CUDA_TRY(c, cudaMemcpyAsync(out->k_index, c->d_bk, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->w_index) CUDA_TRY(c, cudaMemcpyAsync(out->w_index, c->d_bw, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->omega) CUDA_TRY(c, cudaMemcpyAsync(out->omega, c->d_ro, nb * 8, cudaMemcpyDeviceToHost, s));
+        if (out->ext) CUDA_TRY(c, cudaMemcpyAsync(out->ext, c->d_re, nb * 8, cudaMemcpyDeviceToHost, s));
+        if (out->intq) CUDA_TRY(c, cudaMemcpyAsync(out->intq, c->d_ri, nb * 8, cudaMemcpyDeviceToHost, s));
+        if (out->accepted) CUDA_TRY(c, cudaMemcpyAsync(out->accepted, c->d_racc, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->iterations) CUDA_TRY(c, cudaMemcpyAsync(out->iterations, c->d_rit, nb * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    return ESB_OK;
+}
+
+extern "C" int esb_roots_device(esb_context* c, esb_roots* out, int32_t* n_roots) {
+    if (!c || !out) return ESB_ERR_ARG;
+    out->k_index = c->d_bk; out->w_index = c->d_bw; out->omega = c->d_ro; out->ext = c->d_re;
+    out->intq = c->d_ri; out->accepted = c->d_racc; out->iterations = c->d_rit;
+    if (n_roots) *n_roots = c->n_roots;
+    return ESB_OK;
+}
+
+extern "C" int esb_find_roots(esb_context* c, int32_t mode, const double* k, int32_t nk, const double* w,
+                              int32_t nw, int32_t layout, double tol_percent, int32_t max_roots,
+                              esb_roots* out, int32_t* n_roots, int32_t* n_brackets) {
+    if (!c) return ESB_ERR_ARG;
+    if (!out || !n_roots || max_roots < 0) return fail(c, ESB_ERR_ARG, "bad arguments");
+    int rc;
+    if ((rc = esb_upload_axes(c, k, nk, w, nw, layout))) return rc;
+    if ((rc = esb_sweep_resident(c, mode, tol_percent, n_roots, n_brackets))) return rc;
+    return esb_download_roots(c, out, max_roots);
+}
+
+// ---- FP64 pipe peak: the roofline denominator bench.py reports against ----
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int esb_fp64_peak(esb_context* c, double* tflops) {
+    if (!c || !tflops) return ESB_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(c, cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double* d = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaStream_t s = cur_stream(c);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(c->ev0, s);
+        dfma_peak_kernel<<<blocks, threads, 0, s>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(c->ev1, s);
+        cudaError_t e = cudaEventSynchronize(c->ev1);
+        if (e != cudaSuccess) { cudaFree(d); CUDA_TRY(c, e); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    c->timed = false;
+    c->launches += 4;
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) * 1e-12;
     return ESB_OK;
 }
 

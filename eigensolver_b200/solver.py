@@ -198,25 +198,62 @@ class DispersionSolver:
         return e - i
 
     def find_roots(self, mode, k, w, layout="phase_speed", tol_percent=1.0, max_roots=None):
-        k, w, lay, nw = self._axes(k, w, layout)
-        cap = int(max_roots) if max_roots else max(1024, 64 * k.size)
-        while True:
+        """Scan + brackets + refinement; host arrays in, RootTable (host) out."""
+        if max_roots is not None:
+            # single C-ABI call with a caller-sized table (ESB_ERR_CAPACITY if too small)
+            k, w, lay, nw = self._axes(k, w, layout)
+            cap = int(max_roots)
             ki = np.empty(cap, np.int32); wi = np.empty(cap, np.int32)
             om = np.empty(cap, np.float64); ex = np.empty(cap, np.float64); iq = np.empty(cap, np.float64)
             ac = np.empty(cap, np.int32); it = np.empty(cap, np.int32)
             out = L.esb_roots(_iptr(ki), _iptr(wi), _dptr(om), _dptr(ex), _dptr(iq), _iptr(ac), _iptr(it))
-            n = C.c_int32(0)
-            nb = C.c_int32(0)
+            n, nb = C.c_int32(0), C.c_int32(0)
             rc = self.lib.esb_find_roots(self.ctx, self._mode(mode), _dptr(k), k.size, _dptr(w), nw, lay,
                                          float(tol_percent), cap, C.byref(out), C.byref(n), C.byref(nb))
-            if rc == L.ESB_ERR_CAPACITY and max_roots is None:
-                cap = int(n.value)
-                continue
             L.check(self.lib, self.ctx, rc, "esb_find_roots")
-            break
-        n = n.value
-        return RootTable(ki[:n].copy(), wi[:n].copy(), k[ki[:n]], om[:n].copy(), ex[:n].copy(), iq[:n].copy(),
-                         ac[:n].copy(), it[:n].copy(), nb.value)
+            n = n.value
+            return RootTable(ki[:n].copy(), wi[:n].copy(), k[ki[:n]], om[:n].copy(), ex[:n].copy(),
+                             iq[:n].copy(), ac[:n].copy(), it[:n].copy(), nb.value)
+        self.upload_axes(k, w, layout)
+        n, nb = self.sweep_resident(mode, tol_percent)
+        tab = self.download_roots(n)
+        tab.n_brackets = nb
+        return tab
+
+    # -- the same pipeline in three steps (axes stay resident in HBM) -----
+    def upload_axes(self, k, w, layout="phase_speed"):
+        k, w, lay, nw = self._axes(k, w, layout)
+        self._k_host = k
+        L.check(self.lib, self.ctx, self.lib.esb_upload_axes(self.ctx, _dptr(k), k.size, _dptr(w), nw, lay),
+                "esb_upload_axes")
+
+    def sweep_resident(self, mode, tol_percent=1.0):
+        """grid -> brackets -> refinement on the uploaded axes; returns (n_roots, n_brackets);
+        the root table stays on the device."""
+        n, nb = C.c_int32(0), C.c_int32(0)
+        L.check(self.lib, self.ctx,
+                self.lib.esb_sweep_resident(self.ctx, self._mode(mode), float(tol_percent), C.byref(n),
+                                            C.byref(nb)), "esb_sweep_resident")
+        return n.value, nb.value
+
+    def download_roots(self, n):
+        ki = np.empty(n, np.int32); wi = np.empty(n, np.int32)
+        om = np.empty(n, np.float64); ex = np.empty(n, np.float64); iq = np.empty(n, np.float64)
+        ac = np.empty(n, np.int32); it = np.empty(n, np.int32)
+        out = L.esb_roots(_iptr(ki), _iptr(wi), _dptr(om), _dptr(ex), _dptr(iq), _iptr(ac), _iptr(it))
+        L.check(self.lib, self.ctx, self.lib.esb_download_roots(self.ctx, C.byref(out), n),
+                "esb_download_roots")
+        return RootTable(ki, wi, self._k_host[ki], om, ex, iq, ac, it, n)
+
+    def set_stream(self, stream_ptr):
+        """Run this context on an external cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        L.check(self.lib, self.ctx, self.lib.esb_set_stream(self.ctx, C.c_void_p(int(stream_ptr))),
+                "esb_set_stream")
+
+    def fp64_peak_tflops(self):
+        v = C.c_double(0.0)
+        L.check(self.lib, self.ctx, self.lib.esb_fp64_peak(self.ctx, C.byref(v)), "esb_fp64_peak")
+        return v.value
 
     # ------------------------------------------------------------------
     def last_kernel_ms(self):

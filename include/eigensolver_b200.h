@@ -125,6 +125,27 @@ int esb_find_roots(esb_context* ctx, int32_t mode, const double* k, int32_t nk, 
                    int32_t nw, int32_t omega_layout, double tol_percent, int32_t max_roots,
                    esb_roots* out, int32_t* n_roots, int32_t* n_brackets);
 
+/* The same pipeline in three steps, for callers that keep the axes resident in HBM
+ * (bench.py's device-resident timing, multi-GPU gathers):
+ *   esb_upload_axes     H2D copy of k[] and w[] into context-owned buffers
+ *   esb_sweep_resident  grid -> brackets -> refinement, root table left on the device
+ *   esb_download_roots  D2H copy of the root table (synchronises the stream)
+ *   esb_roots_device    device pointers of the root table (valid until the next sweep) */
+int esb_upload_axes(esb_context* ctx, const double* k, int32_t nk, const double* w, int32_t nw,
+                    int32_t omega_layout);
+int esb_sweep_resident(esb_context* ctx, int32_t mode, double tol_percent, int32_t* n_roots,
+                       int32_t* n_brackets);
+int esb_download_roots(esb_context* ctx, esb_roots* out, int32_t max_roots);
+int esb_roots_device(esb_context* ctx, esb_roots* out, int32_t* n_roots);
+
+/* Run every launch and copy of this context on `stream` (a cudaStream_t, e.g. the
+ * caller's torch stream) instead of the context's own stream. */
+int esb_set_stream(esb_context* ctx, void* stream);
+
+/* Measured FP64 FMA throughput of the device (independent DFMA chains, TFLOP/s):
+ * the roofline denominator bench.py quotes the grid kernel against. */
+int esb_fp64_peak(esb_context* ctx, double* tflops);
+
 /* Device-resident variants: all pointers are device pointers, `stream` is a
  * cudaStream_t (0 = default stream).  Asynchronous; no host synchronisation. */
 int esb_dispersion_grid_dev(esb_context* ctx, int32_t mode, const double* d_k, int32_t nk,

@@ -1,0 +1,99 @@
+"""Generate the golden fixtures in tests/golden/ from the reference itself.
+
+Runs ONLY in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Produces
+  ref_D_<solver>.npz      D(omega,k) values obtained by executing the reference's own
+                          sausage()/kink() functions (see run_reference.py) at a set of
+                          (mode, k, omega) points: arrays mode, k, w, D (nan = skipped).
+  ref_scan_<solver>.npz   the reference's own scan + bisection (its `sol_ks`, `sol_omegas`)
+                          over a few (k, frequency-interval) pairs.
+  ref_roots.npz           the root tables the reference ships as "Example data/*.pickle"
+                          ([sausage w, sausage k, kink w, kink k]) for the density solvers,
+                          keyed <family>_<width>_<mode>_{k,w}.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import pickle
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from run_reference import REF_ROOT, ReferenceSolver  # noqa: E402
+
+# phase speeds inside the windows where no Alfven/cusp/sound resonance sits in the layer
+POINTS = {
+    "cylinder_density_coronal": dict(
+        ks=[0.1, 0.5, 1.0, 2.0, 3.2, 4.5],
+        Ws=[0.52, 0.6, 0.75, 0.88, 1.35, 1.6, 1.95, 2.95, 3.3, 4.0, 4.9, 0.45, 5.2],  # last two: skipped / leaky
+    ),
+    "slab_density_coronal": dict(
+        ks=[0.05, 0.3, 0.75, 1.5, 3.0],
+        Ws=[0.42, 0.5, 0.6, 0.74, 1.75, 2.0, 2.5, 2.95, 0.398, 3.1],
+    ),
+}
+
+SCANS = {
+    # (mode, k, W_lo, W_hi, n)  - intervals that contain a mode
+    "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),
+                                 ("kink", 3.0, 0.52, 0.88, 30)],
+    "slab_density_coronal": [("kink", 0.75, 0.42, 0.76, 25), ("sausage", 1.5, 1.75, 2.95, 25)],
+}
+
+PICKLES = {
+    "cyl_coronal": ("Cylinder/Non-uniform density/Coronal/Example data/Cylindrical_coronal_width%s.pickle",
+                    {"09": 0.9, "1": 1.0, "125": 1.25, "15": 1.5, "175": 1.75, "3": 3.0, "1e5": 1e5}),
+    "slab_coronal": ("Slab/Non uniform density/Coronal/Example data/width%s_coronal.pickle",
+                     {"09": 0.9, "15": 1.5, "3": 3.0, "1e5": 1e5}),
+}
+
+
+def main():
+    for name, spec in POINTS.items():
+        t0 = time.time()
+        ref = ReferenceSolver(name)
+        rows = []
+        for mode_id, mode in ((0, "sausage"), (1, "kink")):
+            for k in spec["ks"]:
+                for W in spec["Ws"]:
+                    rows.append((mode_id, k, W * k, ref.D(mode, k, W * k)))
+        a = np.array(rows)
+        np.savez(os.path.join(HERE, "ref_D_%s.npz" % name), mode=a[:, 0].astype(np.int32), k=a[:, 1],
+                 w=a[:, 2], D=a[:, 3])
+        print(name, len(rows), "points in %.0f s" % (time.time() - t0), flush=True)
+        out = {}
+        for n, (mode, k, lo, hi, num) in enumerate(SCANS[name]):
+            freq = np.linspace(lo * k, hi * k, num)
+            ks, ws = ref.roots(mode, k, freq)
+            out["scan%d_mode" % n] = np.array([0 if mode == "sausage" else 1])
+            out["scan%d_k" % n] = np.array([k])
+            out["scan%d_freq" % n] = freq
+            out["scan%d_sol_ks" % n] = ks
+            out["scan%d_sol_ws" % n] = ws
+            print(name, mode, k, "->", ws, flush=True)
+        np.savez(os.path.join(HERE, "ref_scan_%s.npz" % name), **out)
+
+    roots = {}
+    for fam, (pat, widths) in PICKLES.items():
+        for tag, width in widths.items():
+            with open(os.path.join(REF_ROOT, pat % tag), "rb") as fh:
+                sw, sk, kw, kk = pickle.load(fh, encoding="latin1")
+            key = "%s_%s" % (fam, tag)
+            roots[key + "_width"] = np.array([width])
+            roots[key + "_sausage_w"] = np.asarray(sw, dtype=np.float64)
+            roots[key + "_sausage_k"] = np.asarray(sk, dtype=np.float64)
+            roots[key + "_kink_w"] = np.asarray(kw, dtype=np.float64)
+            roots[key + "_kink_k"] = np.asarray(kk, dtype=np.float64)
+    np.savez(os.path.join(HERE, "ref_roots.npz"), **roots)
+    print("ref_roots.npz:", len(roots) // 5, "tables")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol the header declares,
+its host-side helpers are right, and it refuses to compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy import special as sp
+
+import eigensolver_b200 as esb
+from eigensolver_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "eigensolver_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(esb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(esb.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    # and the python binding table covers exactly the header
+    assert sorted(L.SYMBOLS) == names
+
+
+def test_version_and_defaults():
+    lib = esb.load()
+    assert lib.esb_version() == 100
+    m = L.esb_model()
+    assert lib.esb_model_defaults(L.CYLINDER_DENSITY, C.byref(m)) == 0
+    # Density_cylinder.py:69-72,120,768
+    assert (m.c_i0, m.vA_i0, m.vA_e, m.c_e) == (1.0, 2.0, 5.0, 0.5)
+    assert (m.s_start, m.s_end) == (-1.0, -0.001)
+    assert (m.ext_ic_value, m.ext_ic_slope) == (1e-8, 1e-15)
+    assert lib.esb_model_defaults(L.SLAB_DENSITY, C.byref(m)) == 0
+    # ..._coronal.py:69-72,91,247
+    assert (m.c_i0, m.vA_i0, m.vA_e, m.c_e) == (1.0, 1.2, 3.0, 0.4)
+    assert (m.s_start, m.s_end) == (-1.0, 1.0)
+    assert (m.ext_ic_value, m.ext_ic_slope) == (1e-8, 1e-8)
+    assert lib.esb_model_defaults(7, C.byref(m)) == L.ESB_ERR_ARG
+
+
+@pytest.mark.parametrize("kind,scheme,nps", [(L.CYLINDER_DENSITY, L.RK8, 4), (L.SLAB_DENSITY, L.RK8, 4),
+                                             (L.CYLINDER_DENSITY, L.RK4, 2), (L.SLAB_DENSITY, L.RK4, 2)])
+def test_mesh_nodes(kind, scheme, nps):
+    lib = esb.load()
+    m = L.esb_model()
+    lib.esb_model_defaults(kind, C.byref(m))
+    m.scheme = scheme
+    m.n_steps = 64
+    n = C.c_int32()
+    assert lib.esb_mesh_size(C.byref(m), C.byref(n)) == 0
+    assert n.value == 64 * nps + 1
+    x = np.empty(n.value)
+    assert lib.esb_mesh_nodes(C.byref(m), x.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    d = np.diff(x)
+    if kind == L.CYLINDER_DENSITY:       # integrated from the axis out to the boundary
+        assert x[0] == -0.001 and x[-1] == -1.0 and (d < 0).all()
+    else:                                # boundary -> far boundary, through the centre
+        assert x[0] == -1.0 and x[-1] == 1.0 and (d > 0).all()
+        assert x[(n.value - 1) // 2] == 0.0
+    # stage fractions inside each step
+    h = x[nps::nps] - x[:-1:nps]
+    frac = (x[1:nps] - x[0]) / h[0]
+    want = [0.5] if nps == 2 else [(7 - 21**0.5) / 14, 0.5, (7 + 21**0.5) / 14]
+    assert np.allclose(frac, want, rtol=0, atol=1e-12)
+    # odd step count is invalid for the slab (two half-layers)
+    m.n_steps = 63
+    rc = lib.esb_mesh_size(C.byref(m), C.byref(n))
+    assert (rc == L.ESB_ERR_ARG) == (kind == L.SLAB_DENSITY)
+
+
+def test_bessel_helper_matches_scipy():
+    worst = 0.0
+    zs = list(np.logspace(-6, 2.85, 300)) + [1.9999, 2.0, 2.0001, 11.999, 12.0, 12.001, 700.0]
+    for n in range(4):
+        for z in zs:
+            got = esb.bessel_ik_scaled(n, z)
+            want = (sp.ive(n, z), sp.ive(n + 1, z) + n / z * sp.ive(n, z), sp.kve(n, z),
+                    -sp.kve(n + 1, z) + n / z * sp.kve(n, z))
+            worst = max(worst, max(abs(a - b) / abs(b) for a, b in zip(got, want)))
+    assert worst < 5e-14, worst
+    with pytest.raises(esb.EsbError):
+        esb.bessel_ik_scaled(4, 1.0)
+    with pytest.raises(esb.EsbError):
+        esb.bessel_ik_scaled(0, 0.0)
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the CPU."""
+    lib = esb.load()
+    ctx = L._ctx()
+    assert lib.esb_create(0, C.byref(ctx)) == L.ESB_ERR_CUDA
+    assert not ctx.value
+    with pytest.raises(esb.EsbError, match="no CPU fallback"):
+        esb.DispersionSolver("cylinder_density")
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "eigensolver_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "scipy" not in txt, f

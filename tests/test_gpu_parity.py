@@ -1,0 +1,288 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(ctypes -> libeigensolver_b200.so); the oracles are only the checkers.
+
+Tolerances (north_star): bracket indices identical wherever D is above the noise floor
+(= outside the resonant continua, see helpers.continua), refined roots within 1e-9
+relative, D itself within 1e-9 of max(|ext|,|int|).
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import eigensolver_b200 as esb
+from helpers import continua, cyl_profile, regular_mask, slab_profile
+from oracle import reference_path as rp
+from oracle import rk_oracle as ork
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+
+D_TOL = 1e-9       # |D_gpu - D_oracle| / max(|ext|, |int|)
+ROOT_TOL = 1e-9    # relative, refined roots (north_star)
+TIGHT = dict(rtol=1e-12, atol=1e-30, shoot="linear")
+
+CASES = {
+    "cylinder_density": dict(modes=(0, 1, 2), W=(0.40, 5.2), layer=(-1.0, -0.001), slab=False,
+                             prof=cyl_profile),
+    "slab_density": dict(modes=(0, 1), W=(0.30, 3.2), layer=(-1.0, 1.0), slab=True, prof=slab_profile),
+}
+
+
+@pytest.fixture(scope="module")
+def solvers():
+    s = {k: esb.DispersionSolver(k) for k in CASES}
+    yield s
+    for v in s.values():
+        v.close()
+
+
+def _grid_case(kind, nk=20, nw=240):
+    c = CASES[kind]
+    k = np.linspace(0.05, 4.5, nk)
+    W = np.linspace(c["W"][0], c["W"][1], nw)
+    iv = continua(c["prof"](), c["layer"][0], c["layer"][1], c["slab"])
+    return k, W, regular_mask(W, iv, 0.02)
+
+
+@pytest.mark.parametrize("kind", list(CASES))
+def test_grid_brackets_and_roots_match_c_oracle(solvers, kind):
+    s = solvers[kind]
+    model = ork.make_model(kind)
+    k, W, reg = _grid_case(kind)
+    for mode in CASES[kind]["modes"]:
+        ext, inq = s.dispersion_grid(mode, k, W)
+        e0, i0 = ork.grid(model, mode, k, W)
+        # the skip rule (m_e < 0 -> not evaluated) is identical everywhere
+        assert np.array_equal(np.isnan(ext), np.isnan(e0))
+        assert np.array_equal(np.isnan(inq), np.isnan(i0))
+        ok = reg[None, :] & ~np.isnan(e0)
+        assert ok.sum() > 0.4 * ok.size
+        dev = np.abs((ext - inq) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+        assert np.nanmax(dev[ok]) < D_TOL, (mode, np.nanmax(dev[ok]))
+        assert np.nanmax(np.abs(ext - e0)[ok] / np.abs(e0)[ok]) < 1e-10     # closed-form exterior
+        # brackets: identical index sets where both end points are above the noise floor
+        tab = s.find_roots(mode, k, W)
+        gk, gw = ork.brackets(ext - inq)
+        assert np.array_equal(gk, tab.k_index) and np.array_equal(gw, tab.w_index)   # device ballot == numpy
+        ok_iv = reg[:-1] & reg[1:]
+        ok_, ow_ = ork.brackets(e0 - i0)
+        sel_o = ok_iv[ow_]
+        sel_g = ok_iv[tab.w_index]
+        assert np.array_equal(ok_[sel_o], tab.k_index[sel_g])
+        assert np.array_equal(ow_[sel_o], tab.w_index[sel_g])
+        assert sel_g.sum() >= 10
+        # refined roots (accepted modes) vs the oracle's own refinement of the same bracket
+        idx = np.nonzero(sel_g & (tab.accepted == 1))[0]
+        assert len(idx) >= 5
+        for j in idx[:: max(1, len(idx) // 12)]:
+            kk = k[tab.k_index[j]]
+            r, er, ir = ork.refine(model, mode, kk, kk * W[tab.w_index[j]], kk * W[tab.w_index[j] + 1])
+            assert abs(tab.omega[j] - r) <= ROOT_TOL * abs(r), (mode, kk, r, tab.omega[j])
+            assert rp.mismatch_percent(er, ir) < 1.0
+        # poles (sign change through infinity) are found but never accepted
+        for j in np.nonzero(sel_g & (tab.accepted == 0))[0][:20]:
+            assert rp.mismatch_percent(tab.ext[j], tab.intq[j]) >= 1.0
+
+
+def test_roots_match_converged_scipy_reference_path(solvers):
+    """The north_star statement itself: roots within 1e-9 relative of the reference's
+    numpy/scipy path (odeint + shooting, run to convergence) on identical inputs."""
+    s = solvers["cylinder_density"]
+    k = np.array([0.6, 1.0, 2.2, 3.7])
+    W = np.linspace(2.95, 4.95, 60)
+    prof = cyl_profile()
+    n = 0
+    for mode in (0, 1):
+        tab = s.find_roots(mode, k, W)
+        m = rp.CylinderDensity(prof, mode)
+        for j in np.nonzero(tab.accepted == 1)[0]:
+            kk = k[tab.k_index[j]]
+            w, _, _ = rp.refine(m, kk, kk * W[tab.w_index[j]], kk * W[tab.w_index[j] + 1], **TIGHT)
+            assert abs(tab.omega[j] - w) <= ROOT_TOL * abs(w), (mode, kk, w, tab.omega[j])
+            n += 1
+    assert n >= 4
+    s2 = solvers["slab_density"]
+    ks = np.array([0.8, 1.5, 2.6])
+    Ws = np.linspace(1.75, 2.95, 50)
+    tab = s2.find_roots(0, ks, Ws)
+    m = rp.SlabDensity(slab_profile(), "sausage", n_int_out=500)
+    n = 0
+    for j in np.nonzero(tab.accepted == 1)[0]:
+        kk = ks[tab.k_index[j]]
+        w, _, _ = rp.refine(m, kk, kk * Ws[tab.w_index[j]], kk * Ws[tab.w_index[j] + 1], **TIGHT)
+        assert abs(tab.omega[j] - w) <= ROOT_TOL * abs(w)
+        n += 1
+    assert n >= 2
+
+
+@pytest.mark.parametrize("name,kind", [("cylinder_density_coronal", "cylinder_density"),
+                                       ("slab_density_coronal", "slab_density")])
+def test_against_executed_reference_fixture(solvers, golden_dir, name, kind):
+    """Golden D values from the reference's own functions (scipy default tolerances).  The
+    reference's exterior integration starts below its absolute tolerance (|y0| = 1e-8 <
+    atol = 1.5e-8), so its D carries a common amplitude error of 10-25 %; sign, skip pattern
+    and the ext/int ratio are what it determines, and those must agree."""
+    g = np.load(os.path.join(golden_dir, "ref_D_%s.npz" % name))
+    c = CASES[kind]
+    iv = continua(c["prof"](), c["layer"][0], c["layer"][1], c["slab"])
+    s = solvers[kind]
+    n = 0
+    for mode in (0, 1):
+        sel = g["mode"] == mode
+        k, w, Dref = g["k"][sel], g["w"][sel], g["D"][sel]
+        ext, inq = s.dispersion_grid(mode, k, w[:, None], layout="per_k")
+        D = (ext - inq)[:, 0]
+        assert np.array_equal(np.isnan(D), np.isnan(Dref))
+        # W = 2.95 on the slab is inside the reference's absolute-tolerance noise (see test_oracle_pinned)
+        ok = ~np.isnan(Dref) & regular_mask(w / k, iv) & ((w / k < 2.9) | (kind != "slab_density"))
+        assert ok.sum() >= 30
+        assert np.array_equal(np.sign(D[ok]), np.sign(Dref[ok]))
+        ratio = D[ok] / Dref[ok]
+        assert ratio.min() > 0.6 and ratio.max() < 1.4, (ratio.min(), ratio.max())
+        n += ok.sum()
+    assert n >= 60
+
+
+def test_shipped_root_tables(solvers, golden_dir):
+    """The reference's Example data root tables pass its own 1 % acceptance test on the GPU."""
+    g = np.load(os.path.join(golden_dir, "ref_roots.npz"))
+    total = inside = 0
+    for fam, kind in (("cyl_coronal", "cylinder_density"), ("slab_coronal", "slab_density")):
+        c = CASES[kind]
+        tags = sorted(set(f.split("_")[2] for f in g.files if f.startswith(fam)))
+        for tag in tags:
+            width = float(g["%s_%s_width" % (fam, tag)][0])
+            iv = continua(c["prof"](width), c["layer"][0], c["layer"][1], c["slab"])
+            with esb.DispersionSolver(kind, profile=esb.GaussianDensity(width)) as s:
+                for mi, mode in ((0, "sausage"), (1, "kink")):
+                    k = g["%s_%s_%s_k" % (fam, tag, mode)]
+                    w = g["%s_%s_%s_w" % (fam, tag, mode)]
+                    if not len(k):
+                        continue
+                    reg = regular_mask(w / k, iv, 0.0) & (np.abs(w / k) < 6)
+                    k, w = k[reg], w[reg]
+                    e, i = s.dispersion_grid(mi, k, w[:, None], layout="per_k")
+                    pct = np.abs(e - i)[:, 0] * 100 / np.maximum(np.abs(e), np.abs(i))[:, 0]
+                    total += len(pct)
+                    inside += int((pct < 1.5).sum())
+    assert total > 2500 and inside / total > 0.90, (inside, total)
+
+
+def test_reference_api_drop_in(golden_dir):
+    """sausage()/kink() keep the reference's signature and reproduce its own scan result."""
+    g = np.load(os.path.join(golden_dir, "ref_scan_cylinder_density_coronal.npz"))
+
+    class Q:
+        def __init__(self):
+            self.items = []
+
+        def put(self, x):
+            self.items.append(x)
+
+    script = esb.ReferenceScript("cylinder_density")
+    n = 0
+    while "scan%d_k" % n in g.files:
+        mode = int(g["scan%d_mode" % n][0]); k = float(g["scan%d_k" % n][0])
+        freq = g["scan%d_freq" % n]; ws_ref = g["scan%d_sol_ws" % n]
+        ws, ks = Q(), Q()
+        (script.kink if mode == 1 else script.sausage)(k, ws, ks, freq)
+        assert len(ws.items) == 1 and len(ks.items) == 1 and len(ws.items[0]) == len(ks.items[0])
+        assert all(kk == k for kk in ks.items[0])
+        for w in ws_ref:        # the reference stops bisecting once inside its 1 % band
+            assert min(abs(np.array(ws.items[0]) - w)) < 5e-3 * abs(w)
+        n += 1
+    out = script.run(np.linspace(0.5, 4.0, 8), speeds=[2.95, 4.0, 4.95], n_freq=40)
+    assert len(out) == 4 and len(out[0]) == len(out[1]) and len(out[2]) == len(out[3])
+    assert len(out[2]) >= 4 and np.all(out[2] / out[3] > 2.9) and np.all(out[2] / out[3] < 5.0)
+    script.close()
+
+
+def test_edge_cases(solvers):
+    s = solvers["cylinder_density"]
+    # every point skipped (leaky side, W > vA_e): all NaN, no brackets, no roots
+    e, i = s.dispersion_grid(1, [1.0, 2.0], np.linspace(5.1, 6.0, 33))
+    assert np.isnan(e).all() and np.isnan(i).all()
+    tab = s.find_roots(1, [1.0, 2.0], np.linspace(5.1, 6.0, 33))
+    assert len(tab.omega) == 0 and tab.n_brackets == 0
+    # smallest grids, ragged sizes (not multiples of the block / warp size)
+    for nk, nw in ((1, 2), (1, 33), (3, 129), (5, 31)):
+        k = np.linspace(0.7, 2.0, nk); W = np.linspace(3.0, 4.9, nw)
+        e, i = s.dispersion_grid(0, k, W)
+        e0, i0 = ork.grid(ork.make_model("cylinder_density"), 0, k, W)
+        assert np.nanmax(np.abs((e - i) - (e0 - i0)) / np.maximum(abs(e0), abs(i0))) < D_TOL
+        tab = s.find_roots(0, k, W)
+        bk, bw = ork.brackets(e0 - i0)
+        assert np.array_equal(bk, tab.k_index) and np.array_equal(bw, tab.w_index)
+    # a single omega: a grid is fine, a root search needs two points
+    e, i = s.dispersion_grid(1, [1.0], [3.3])
+    assert e.shape == (1, 1) and np.isfinite(e).all()
+    with pytest.raises(esb.EsbError):
+        s.find_roots(1, [1.0], [3.3])
+    # invalid modes / capacity
+    with pytest.raises(esb.EsbError):
+        s.dispersion_grid(4, [1.0], [3.3])
+    with pytest.raises(esb.EsbError):
+        solvers["slab_density"].dispersion_grid(2, [1.0], [0.5])
+    with pytest.raises(esb.EsbError, match="max_roots"):
+        s.find_roots(1, np.linspace(0.5, 4, 16), np.linspace(2.95, 4.95, 64), max_roots=2)
+    # very long exterior domain (tiny k) and the resonance W -> cT_e: finite or NaN, never a crash
+    e, i = s.dispersion_grid(0, [1e-3, 1e-2], np.linspace(0.4976, 0.52, 16))
+    assert e.shape == (2, 16)
+    # omega given directly and per-k agree bit for bit with the phase-speed layout
+    k = np.linspace(0.5, 3.0, 7); W = np.linspace(3.0, 4.9, 50)
+    a = s.dispersion_grid(1, k, W, layout="phase_speed")
+    b = s.dispersion_grid(1, k, k[:, None] * W[None, :], layout="per_k")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    c = s.dispersion_grid(1, k[:1], k[0] * W, layout="shared")
+    assert np.array_equal(a[0][:1], c[0])
+
+
+def test_rk4_and_rk8_agree():
+    k = np.linspace(0.3, 4.0, 6); W = np.linspace(3.0, 4.9, 40)
+    with esb.DispersionSolver("cylinder_density", scheme="rk8") as a, \
+            esb.DispersionSolver("cylinder_density", scheme="rk4", n_steps=2048) as b:
+        ea, ia = a.dispersion_grid(1, k, W)
+        eb, ib = b.dispersion_grid(1, k, W)
+    assert np.array_equal(ea, eb)
+    assert np.max(np.abs(ia - ib) / np.abs(ia)) < 5e-9
+
+
+def test_full_size_properties(solvers):
+    """BASELINE configs[1] size (1000 k x 10000 omega): properties that need no oracle."""
+    s = solvers["cylinder_density"]
+    k = np.linspace(0.01, 4.5, 1000)
+    W = np.linspace(0.40, 5.05, 10000)
+    e1, i1 = s.dispersion_grid(1, k, W)
+    e2, i2 = s.dispersion_grid(1, k, W)
+    assert np.array_equal(e1, e2, equal_nan=True) and np.array_equal(i1, i2, equal_nan=True)   # deterministic
+    # skipped region = exactly where m_e < 0 :  cT_e <= W <= c_e  or  W >= vA_e
+    md = s.medium
+    leaky = ((W > md.cT_e) & (W < md.c_e)) | (W > md.vA_e)
+    assert np.array_equal(np.isnan(e1).all(axis=0), leaky)
+    # D is even in omega for the cylinder (only omega^2 enters)
+    em, im = s.dispersion_grid(1, k[::50], -W[::10])
+    assert np.array_equal(em, e1[::50, ::10], equal_nan=True) and np.array_equal(im, i1[::50, ::10], equal_nan=True)
+    # homogeneity: doubling the exterior initial values doubles D exactly (power of two)
+    with esb.DispersionSolver("cylinder_density", ext_ic=(2e-8, 2e-15)) as s2:
+        e3, i3 = s2.dispersion_grid(1, k[::50], W[::10])
+    assert np.array_equal(e3, 2 * e1[::50, ::10], equal_nan=True)
+    assert np.array_equal(i3, 2 * i1[::50, ::10], equal_nan=True)
+    # root table: count == numpy's on the grid, sorted, inside its bracket, acceptance consistent
+    tab = s.find_roots(1, k, W)
+    bk, bw = ork.brackets(e1 - i1)
+    assert np.array_equal(bk, tab.k_index) and np.array_equal(bw, tab.w_index)
+    key = tab.k_index.astype(np.int64) * len(W) + tab.w_index
+    assert np.all(np.diff(key) > 0)
+    lo = k[tab.k_index] * W[tab.w_index]; hi = k[tab.k_index] * W[tab.w_index + 1]
+    assert np.all((tab.omega >= lo) & (tab.omega <= hi))
+    pct = np.abs(tab.ext - tab.intq) * 100 / np.maximum(np.abs(tab.ext), np.abs(tab.intq))
+    fin = np.isfinite(pct)
+    assert np.array_equal(tab.accepted[fin] == 1, pct[fin] < 1.0)
+    assert tab.accepted.sum() > 2000
+    # sharding the k axis (what the multi-GPU path does) changes nothing
+    lo_half = s.find_roots(1, k[:500], W)
+    hi_half = s.find_roots(1, k[500:], W)
+    assert np.array_equal(np.concatenate([lo_half.omega, hi_half.omega]), tab.omega)
+    assert np.array_equal(np.concatenate([lo_half.k_index, hi_half.k_index + 500]), tab.k_index)
