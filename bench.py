@@ -39,9 +39,12 @@ MODES = (0, 1, 2)
 K_RANGE = (0.01, 4.5)          # Density_cylinder.py:1126  wavenumber = linspace(0.01, 4.5, ...)
 W_RANGE = (0.5, 5.0)           # c_e .. vA_e : the phase-speed window in which m_e >= 0
 N_STEPS = 256
-# algorithmic FP64 flops of one D evaluation (fma = 2, mul/add/div = 1), see DESIGN.md:
-#   per RK8 step: 4 node-coefficient evaluations x 17 + 231 stage arithmetic = 299
+# algorithmic FP64 flops (fma = 2, mul/add/div = 1), see DESIGN.md.  Per RK8 step:
+#   4 node-coefficient evaluations x 15 flop, shared by the modes evaluated together
+#   + per mode: 4 x 2 (b + m^2/r^2) + 231 stage arithmetic
+# one D evaluation alone: 60 + 239 = 299 flop/step; three fused: (60 + 3*239)/3 = 259 flop/step/eval
 FLOPS_PER_EVAL = 299 * N_STEPS + 700
+FLOPS_FUSED_LAUNCH = ((60 + 3 * 239) * N_STEPS + 3 * 500) * NK * NW
 WORKLOAD = "cylinder non-uniform density, n=0,1,2, 1000 k x 10000 omega per GPU"
 
 
@@ -188,24 +191,19 @@ def run_gpu_arm(args):
 
     def step_resident():
         """axes resident in HBM; root tables stay on the device until the gather."""
-        tables, kms = [], []
-        for m in MODES:
-            n, nb = solver.sweep_resident(m)
-            kms.append(solver.last_kernel_ms())
-            tables.append(solver.download_roots(n) if world > 1 else n)
+        ns = solver.sweep_resident_multi(MODES)
+        kms = [solver.last_kernel_ms()]
+        tables = ns
         if world > 1:
+            tables = [solver.download_roots(n, slot) for slot, n in enumerate(ns)]
             gather(tables)
         return kms, tables
 
     def step_e2e():
         """public host API: pinned k/omega in, root tables (host) out, every mode."""
-        h2d = d2h = 0
-        tables = []
-        for m in MODES:
-            t = solver.find_roots(m, k_pin.numpy(), W_pin.numpy())
-            tables.append(t)
-            h2d += k_pin.numel() * 8 + W_pin.numel() * 8
-            d2h += len(t.omega) * (8 * 3 + 4 * 4)
+        tables = solver.find_roots_multi(MODES, k_pin.numpy(), W_pin.numpy())
+        h2d = k_pin.numel() * 8 + W_pin.numel() * 8
+        d2h = sum(len(t.omega) * (8 * 3 + 4 * 4) for t in tables)
         nroots = gather(tables)
         return h2d, d2h, tables, nroots
 
@@ -254,8 +252,8 @@ def run_gpu_arm(args):
     n_brackets = int(sum(len(tb.omega) for tb in tabs))
 
     if rank == 0:
-        kms = float(np.mean(kernel_ms))                      # one grid-kernel launch = NK*NW evals
-        achieved = FLOPS_PER_EVAL * NK * NW / (kms * 1e-3) * 1e-12
+        kms = float(np.mean(kernel_ms))                      # one fused launch = 3 modes x NK*NW evals
+        achieved = FLOPS_FUSED_LAUNCH / (kms * 1e-3) * 1e-12
         nominal = 148 * 64 * 2 * 1.965e9 * 1e-12
         cores = os.cpu_count() or 1
         cpu = None
@@ -281,11 +279,11 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "grid_kernel<cylinder,rk8>", "kernel_ms": kms,
-                         "flops_per_launch": FLOPS_PER_EVAL * NK * NW,
+                         "kernel": "grid_kernel<cylinder,rk8,3 modes fused>", "kernel_ms": kms,
+                         "flops_per_launch": FLOPS_FUSED_LAUNCH,
                          "peak_source": "esb_fp64_peak: DFMA-chain kernel measured in this process "
                                         "(nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s)" % nominal,
-                         "kernel_share_of_step": kms * len(MODES) / (ms / args.steps)},
+                         "kernel_share_of_step": kms / (ms / args.steps)},
             "clocks": sampler.summary(),
         }
         if cpu:

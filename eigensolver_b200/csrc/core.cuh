@@ -72,17 +72,15 @@ ESB_HD int nodes_per_step(int scheme) { return scheme == SCHEME_RK8 ? 4 : 2; }
 struct Point {
     double K, A;       // k^2, omega^2
     double w;          // omega
-    double m2;         // (azimuthal order)^2, cylinder
     // products that do not change along the layer
     double Kalpha, Kbeta, Ktau, SKtau, AKc;
 };
 
-ESB_HD Point make_point(const DevModel& M, double k, double w, int mode) {
+ESB_HD Point make_point(const DevModel& M, double k, double w) {
     Point p;
     p.K = k * k;
     p.A = w * w;
     p.w = w;
-    p.m2 = double(mode) * double(mode);
     p.Kalpha = p.K * M.alpha;
     p.Kbeta = p.K * M.beta;
     p.Ktau = p.K * M.tau;
@@ -101,8 +99,11 @@ ESB_HD Point make_point(const DevModel& M, double k, double w, int mode) {
 //       a = -F'/F = -w^2 k^2 (tau-alpha) rho' / ((k^2 alpha - rho w^2)(k^2 tau - rho w^2))
 //       b = m0^2 = (k^2 alpha - rho w^2)(k^2 beta - rho w^2)/(S (k^2 tau - rho w^2))
 //     (..._coronal.py:222-230.)
+// `b` excludes the azimuthal term; `bm` is its factor: b_total = b + m^2 * bm (bm = 1/r^2 for the
+// cylinder, 0 for the slab), so that several azimuthal orders share one coefficient evaluation.
 template <int KIND>
-ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, double& a, double& b) {
+ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, double& a, double& b,
+                        double& bm) {
     if (KIND == KIND_CYL_DENSITY) {
         const double invr = f[0], invr2 = f[1], rho = f[2], drho = f[3];
         const double u = rho * p.A;
@@ -110,7 +111,8 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
         const double Y = fma(M.S, u, -p.SKtau);
         const double inv = 1.0 / (X * Y);
         a = fma(drho * p.A * Y, inv, -invr);
-        b = fma(-(u * u) * X, inv, fma(p.m2, invr2, p.K));
+        b = fma(-(u * u) * X, inv, p.K);
+        bm = invr2;
     } else {
         const double rho = f[0], drho = f[1];
         const double u = rho * p.A;
@@ -118,6 +120,7 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
         const double inv = 1.0 / (p1 * p3);
         a = p.AKc * drho * inv;
         b = (p1 * p1) * p2 * inv / M.S;
+        bm = 0.0;
     }
 }
 
@@ -127,11 +130,12 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
 // previous step (it is that step's end node).
 template <int NS>
 ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[5],
-                     const double (&cb)[5]) {
+                     const double (&cbs)[NS][5]) {
     // stage -> node: 1:0  2:2 3:2  4:3 5:3  6:2  7:1 8:1  9:2  10:3  11:4
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const double p = y[s], q = yp[s];
+        const double(&cb)[5] = cbs[s];
 #define ESB_G(P, Q, n) fma(ca[n], (Q), cb[n] * (P))
         const double Q1 = q, G1 = ESB_G(p, q, 0);
         const double P2 = fma(h, a21 * Q1, p), Q2 = fma(h, a21 * G1, q), G2 = ESB_G(P2, Q2, 2);
@@ -171,10 +175,11 @@ ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (
 
 template <int NS>
 ESB_HD void rk4_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[3],
-                     const double (&cb)[3]) {
+                     const double (&cbs)[NS][3]) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const double p = y[s], q = yp[s];
+        const double(&cb)[3] = cbs[s];
         const double hh = 0.5 * h;
         const double G1 = fma(ca[0], q, cb[0] * p);
         const double P2 = fma(hh, q, p), Q2 = fma(hh, G1, q), G2 = fma(ca[1], Q2, cb[1] * P2);
@@ -187,31 +192,30 @@ ESB_HD void rk4_step(double (&y)[NS], double (&yp)[NS], double h, const double (
 }
 
 // Integrate NS solutions along the staged mesh.  tab: [n_nodes][TAB_FIELDS] then h[n_steps].
+// m2[s] = (azimuthal order)^2 of solution s (cylinder); the node coefficients are evaluated
+// once per node and shared by all solutions.
 template <int KIND, int SCHEME, int NS>
 ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __restrict__ tab,
-                            double (&y)[NS], double (&yp)[NS]) {
+                            const double (&m2)[NS], double (&y)[NS], double (&yp)[NS]) {
     const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
     constexpr int NPS = (SCHEME == SCHEME_RK8) ? 4 : 2;
-    double a0, b0;
-    node_coeffs<KIND>(M, pt, tab, a0, b0);
+    constexpr int NN = NPS + 1;
+    double a0, b0, bm0;
+    node_coeffs<KIND>(M, pt, tab, a0, b0, bm0);
     for (int i = 0; i < M.n_steps; ++i) {
         const double* f = tab + (size_t)(i * NPS) * TAB_FIELDS;
         const double h = hs[i];
-        if (SCHEME == SCHEME_RK8) {
-            double ca[5], cb[5];
-            ca[0] = a0; cb[0] = b0;
+        double ca[NN], cb[NN], bm[NN], cbs[NS][NN];
+        ca[0] = a0; cb[0] = b0; bm[0] = bm0;
 #pragma unroll
-            for (int n = 1; n <= 4; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n]);
-            rk8_step<NS>(y, yp, h, ca, cb);
-            a0 = ca[4]; b0 = cb[4];
-        } else {
-            double ca[3], cb[3];
-            ca[0] = a0; cb[0] = b0;
+        for (int n = 1; n < NN; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n], bm[n]);
 #pragma unroll
-            for (int n = 1; n <= 2; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n]);
-            rk4_step<NS>(y, yp, h, ca, cb);
-            a0 = ca[2]; b0 = cb[2];
-        }
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int n = 0; n < NN; ++n) cbs[s][n] = (KIND == KIND_CYL_DENSITY) ? fma(m2[s], bm[n], cb[n]) : cb[n];
+        if constexpr (SCHEME == SCHEME_RK8) rk8_step<NS>(y, yp, h, ca, cbs);
+        else rk4_step<NS>(y, yp, h, ca, cbs);
+        a0 = ca[NN - 1]; b0 = cb[NN - 1]; bm0 = bm[NN - 1];
     }
 }
 
@@ -221,99 +225,125 @@ ESB_HD double m_e2(const DevModel& M, double K, double A) {
     return ((K * M.vAe2 - A) * (K * M.ce2 - A)) / (M.se2 * (K * M.cTe2 - A));
 }
 
-// Exact solution at x = -1 of the reference's exterior initial-value problem.
-// Returns false where the reference skips the point (m_e < 0).
-template <int KIND>
-ESB_HD bool exterior(const DevModel& M, double k, const Point& pt, int mode, double& yb, double& ypb) {
-    const double me = m_e2(M, pt.K, pt.A);
-    if (!(me >= 0.0)) return false;
+// Exact solution at x = -1 of the reference's exterior initial-value problem, slab.
+ESB_HD void exterior_slab(const DevModel& M, double k, double me, double& yb, double& ypb) {
+    // vx'' = m_e vx   (..._coronal.py:245), from -x0 to -1
     const double kap = sqrt(me);
-    const double x0 = M.ext_len / k;      // |start|
-    if (KIND == KIND_SLAB_DENSITY) {
-        // vx'' = m_e vx   (..._coronal.py:245), from -x0 to -1
-        const double L = x0 - 1.0;
-        if (kap * L < 1e-8) {
-            yb = fma(M.ic_s, L, M.ic_v) + 0.5 * me * L * L * M.ic_v;
-            ypb = M.ic_s + me * L * M.ic_v;
-        } else {
-            const double E = exp(kap * L), Ei = 1.0 / E;
-            const double ch = 0.5 * (E + Ei), sh = 0.5 * (E - Ei);
-            yb = fma(M.ic_v, ch, (M.ic_s / kap) * sh);
-            ypb = fma(M.ic_v * kap, sh, M.ic_s * ch);
-        }
-        return true;
+    const double L = M.ext_len / k - 1.0;
+    if (kap * L < 1e-8) {
+        yb = fma(M.ic_s, L, M.ic_v) + 0.5 * me * L * L * M.ic_v;
+        ypb = M.ic_s + me * L * M.ic_v;
     } else {
-        // P'' + P'/r - (m_e + n^2/r^2) P = 0   (Density_cylinder.py:765), r from -x0 to -1.
-        // In rho = |r|: P = A I_n(kap rho) + B K_n(kap rho), d/dr = -d/drho.
-        const double z0 = kap * x0, z1 = kap;
-        BesselIK B0, B1;
-        bessel_ik_scaled(mode, z0, B0);
-        bessel_ik_scaled(mode, z1, B1);
-        double I0, dI0, K0, dK0, I1, dI1, K1, dK1;
-        bessel_order(B0, mode, z0, I0, dI0, K0, dK0);
-        bessel_order(B1, mode, z1, I1, dI1, K1, dK1);
-        const double P0 = M.ic_v, dP0 = -M.ic_s / kap;   // d/d(z) at rho0
-        // Wronskian I K' - I' K = -1/z
-        const double As = -z0 * (P0 * dK0 - dP0 * K0);    // true A = As e^{-z0}... (scaled by e^{+z0} K)
-        const double Bs = -z0 * (dP0 * I0 - P0 * dI0);
-        // A I(z1) = As e^{z0}... careful: K0 here is e^{z0} K(z0) so As = A_true e^{z0};
-        // I1 = e^{-z1} I(z1) -> A_true I(z1) = As e^{-z0} e^{z1} I1
-        const double ea = exp(z1 - z0), eb = exp(z0 - z1);
-        yb = As * I1 * ea + Bs * K1 * eb;
-        ypb = -kap * (As * dI1 * ea + Bs * dK1 * eb);
-        return true;
+        const double E = exp(kap * L), Ei = 1.0 / E;
+        const double ch = 0.5 * (E + Ei), sh = 0.5 * (E - Ei);
+        yb = fma(M.ic_v, ch, (M.ic_s / kap) * sh);
+        ypb = fma(M.ic_v * kap, sh, M.ic_s * ch);
     }
+}
+
+// Cylinder: P'' + P'/r - (m_e + n^2/r^2) P = 0   (Density_cylinder.py:765), r from -x0 to -1.
+// In rho = |r|: P = A I_n(kap rho) + B K_n(kap rho), d/dr = -d/drho.  The Bessel sets at the
+// two arguments are computed once (ExtCyl) and serve every azimuthal order.
+struct ExtCyl {
+    BesselIK B0, B1;
+    double kap, z0, ea, eb;
+};
+
+ESB_HD void exterior_cyl_prepare(const DevModel& M, double k, double me, int nmax, ExtCyl& E) {
+    E.kap = sqrt(me);
+    E.z0 = E.kap * (M.ext_len / k);
+    bessel_ik_scaled(nmax, E.z0, E.B0);
+    bessel_ik_scaled(nmax, E.kap, E.B1);
+    E.ea = exp(E.kap - E.z0);
+    E.eb = exp(E.z0 - E.kap);
+}
+
+ESB_HD void exterior_cyl_order(const DevModel& M, const ExtCyl& E, int n, double& yb, double& ypb) {
+    double I0, dI0, K0, dK0, I1, dI1, K1, dK1;
+    bessel_order(E.B0, n, E.z0, I0, dI0, K0, dK0);
+    bessel_order(E.B1, n, E.kap, I1, dI1, K1, dK1);
+    const double P0 = M.ic_v, dP0 = -M.ic_s / E.kap;   // d/dz at rho0 (z = kap rho)
+    // Wronskian I K' - I' K = -1/z.  K0 = e^{z0} K(z0), I0 = e^{-z0} I(z0), hence the e^{+-(z0-z1)}.
+    const double As = -E.z0 * (P0 * dK0 - dP0 * K0);
+    const double Bs = -E.z0 * (dP0 * I0 - P0 * dI0);
+    yb = As * I1 * E.ea + Bs * K1 * E.eb;
+    ypb = -E.kap * (As * dI1 * E.ea + Bs * dK1 * E.eb);
 }
 
 // ------------------------------------------------------------ full point ----
-// One evaluation of the reference's scan-loop body: (exterior quantity, interior quantity).
-template <int KIND, int SCHEME>
-ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
-                       double& ext_q, double& int_q) {
+// NM evaluations of the reference's scan-loop body at one (k, omega), one per requested
+// mode, sharing everything that does not depend on the mode:
+//   cylinder: modes = azimuthal orders; one staged-coefficient evaluation per node and one
+//             Bessel set serve all of them, each order integrates its own solution;
+//   slab:     sausage and kink are two closures of the same two fundamental solutions.
+template <int KIND, int SCHEME, int NM>
+ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, double k, double w,
+                             const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM]) {
     const double nanv = nan("");
-    const Point pt = make_point(M, k, w, mode);
-    double yb, ypb;
-    if (!exterior<KIND>(M, k, pt, mode, yb, ypb)) {
-        ext_q = nanv;
-        int_q = nanv;
+    const Point pt = make_point(M, k, w);
+    const double me = m_e2(M, pt.K, pt.A);
+    if (!(me >= 0.0)) {                       // "if m_e < 0: pass"  (Density_cylinder.py:760)
+#pragma unroll
+        for (int s = 0; s < NM; ++s) { ext_q[s] = nanv; int_q[s] = nanv; }
         return;
     }
     if (KIND == KIND_CYL_DENSITY) {
+        int nmax = 0;
+#pragma unroll
+        for (int s = 0; s < NM; ++s) nmax = modes[s] > nmax ? modes[s] : nmax;
+        ExtCyl E;
+        exterior_cyl_prepare(M, k, me, nmax, E);
+        double yb[NM], y[NM], yp[NM], m2[NM];
         // xi_e = -P'/(rho_e (k^2 vA_e^2 - w^2))      (Density_cylinder.py:702,773)
-        ext_q = -ypb / (M.rho_e * (pt.K * M.vAe2 - pt.A));
-        // interior from the axis outwards: sausage P'(axis)=0 (:1084), kink/fluting P(axis)=0 (:787)
-        double y[1], yp[1];
-        if (mode == 0) { y[0] = 1.0; yp[0] = 0.0; } else { y[0] = 0.0; yp[0] = 1.0; }
-        integrate_layer<KIND, SCHEME, 1>(M, pt, tab, y, yp);
-        const double slope = yb * yp[0] / y[0];          // dPi that fsolve finds (:790)
-        // xi_i(-1) = (C1 P + D P')/C3 = P'/(rho (w^2 - k^2 vA^2))    (:798)
-        int_q = slope / (M.rho_b * pt.A - pt.Kbeta);
+        const double xi_e_const = -1.0 / (M.rho_e * (pt.K * M.vAe2 - pt.A));
+#pragma unroll
+        for (int s = 0; s < NM; ++s) {
+            double ypb;
+            exterior_cyl_order(M, E, modes[s], yb[s], ypb);
+            ext_q[s] = xi_e_const * ypb;
+            // interior from the axis outwards: sausage P'(axis)=0 (:1084), kink/fluting P(axis)=0 (:787)
+            y[s] = modes[s] == 0 ? 1.0 : 0.0;
+            yp[s] = modes[s] == 0 ? 0.0 : 1.0;
+            m2[s] = double(modes[s]) * double(modes[s]);
+        }
+        integrate_layer<KIND, SCHEME, NM>(M, pt, tab, m2, y, yp);
+        const double den = 1.0 / (M.rho_b * pt.A - pt.Kbeta);
+#pragma unroll
+        for (int s = 0; s < NM; ++s) {
+            const double slope = yb[s] * yp[s] / y[s];       // dPi that fsolve finds (:790)
+            // xi_i(-1) = (C1 P + D P')/C3 = P'/(rho (w^2 - k^2 vA^2))    (:798)
+            int_q[s] = slope * den;
+        }
     } else {
+        double yb, ypb;
+        exterior_slab(M, k, me, yb, ypb);
         // P_e = p_e_const vx'   (..._coronal.py:221,250)
         const double p_e_const = M.rho_e * M.se2 * (pt.K * M.cTe2 - pt.A) / (w * (pt.K * M.ce2 - pt.A));
-        ext_q = p_e_const * ypb;
         double y[2] = {1.0, 0.0}, yp[2] = {0.0, 1.0};
-        integrate_layer<KIND, SCHEME, 2>(M, pt, tab, y, yp);
-        // sausage: vx(1) = -vx(-1) (:259); kink: vx(1) = +vx(-1) (:696)
-        const double target = (mode == 0) ? -1.0 : 1.0;
-        const double slope = yb * (target - y[0]) / y[1];
+        const double m2[2] = {0.0, 0.0};
+        integrate_layer<KIND, SCHEME, 2>(M, pt, tab, m2, y, yp);
         // P_i(-1) = P_Ti(-1) vx'(-1)   (:234,267)
         const double ub = M.rho_b * pt.A;
         const double P_Ti = M.S * (pt.Ktau - ub) / (w * (pt.Kalpha - ub));
-        int_q = P_Ti * slope;
+#pragma unroll
+        for (int s = 0; s < NM; ++s) {
+            // sausage: vx(1) = -vx(-1) (:259); kink: vx(1) = +vx(-1) (:696)
+            const double target = (modes[s] == 0) ? -1.0 : 1.0;
+            const double slope = yb * (target - y[0]) / y[1];
+            ext_q[s] = p_e_const * ypb;
+            int_q[s] = P_Ti * slope;
+        }
     }
 }
 
-// Runtime dispatch on (kind, scheme) to the compiled instantiations.
-ESB_HD void eval_point_rt(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
-                          double& e, double& i) {
-    if (M.kind == KIND_CYL_DENSITY) {
-        if (M.scheme == SCHEME_RK8) eval_point<KIND_CYL_DENSITY, SCHEME_RK8>(M, tab, k, w, mode, e, i);
-        else eval_point<KIND_CYL_DENSITY, SCHEME_RK4>(M, tab, k, w, mode, e, i);
-    } else {
-        if (M.scheme == SCHEME_RK8) eval_point<KIND_SLAB_DENSITY, SCHEME_RK8>(M, tab, k, w, mode, e, i);
-        else eval_point<KIND_SLAB_DENSITY, SCHEME_RK4>(M, tab, k, w, mode, e, i);
-    }
+template <int KIND, int SCHEME>
+ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
+                       double& ext_q, double& int_q) {
+    const int modes[1] = {mode};
+    double e[1], i[1];
+    eval_point_multi<KIND, SCHEME, 1>(M, tab, k, w, modes, e, i);
+    ext_q = e[0];
+    int_q = i[0];
 }
 
 }  // namespace esb

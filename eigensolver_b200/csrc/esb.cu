@@ -29,8 +29,10 @@ struct GridArgs {
     int tab_doubles;
     const double* k;
     const double* w;
-    int nk, nw, layout, mode;
-    double* ext;
+    int nk, nw, layout;
+    int n_modes;
+    int modes[4];
+    double* ext;            // [n_modes][nk][nw]
     double* intq;
 };
 
@@ -50,20 +52,29 @@ __device__ __forceinline__ void stage_table(const double* __restrict__ g, double
     __syncthreads();
 }
 
-template <int KIND, int SCHEME>
+// NM modes are evaluated per thread, sharing the staged coefficients (cylinder) or the whole
+// integration (slab); outputs are mode-slot major.
+template <int KIND, int SCHEME, int NM>
 __global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
     if (iw >= g.nw) return;
+    int modes[NM];
+#pragma unroll
+    for (int s = 0; s < NM; ++s) modes[s] = g.modes[s];
+    const size_t plane = (size_t)g.nk * g.nw;
     for (int ik = blockIdx.y; ik < g.nk; ik += gridDim.y) {
         const double k = g.k[ik];
         const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
-        double e, i;
-        eval_point<KIND, SCHEME>(g.M, stab, k, w, g.mode, e, i);
+        double e[NM], i[NM];
+        eval_point_multi<KIND, SCHEME, NM>(g.M, stab, k, w, modes, e, i);
         const size_t o = (size_t)ik * g.nw + iw;
-        g.ext[o] = e;
-        g.intq[o] = i;
+#pragma unroll
+        for (int s = 0; s < NM; ++s) {
+            g.ext[s * plane + o] = e[s];
+            g.intq[s * plane + o] = i[s];
+        }
     }
 }
 
@@ -276,6 +287,8 @@ __global__ void __launch_bounds__(64) refine_kernel(RefineArgs r) {
 }
 
 // ============================================================ host side ====
+#define ESB_MAX_MODES 4
+
 struct esb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -287,19 +300,22 @@ struct esb_context {
     // scratch for the host-pointer entry points
     double *d_k = nullptr, *d_w = nullptr, *d_ext = nullptr, *d_int = nullptr;
     size_t cap_k = 0, cap_w = 0, cap_grid = 0;
-    int *d_rowcount = nullptr, *d_rowoff = nullptr, *d_bk = nullptr, *d_bw = nullptr;
-    size_t cap_rows = 0, cap_rowoff = 0, cap_br = 0;
-    double *d_ro = nullptr, *d_re = nullptr, *d_ri = nullptr;
-    int *d_racc = nullptr, *d_rit = nullptr, *d_counter = nullptr;
+    int *d_rowcount = nullptr, *d_rowoff = nullptr;
+    size_t cap_rows = 0, cap_rowoff = 0;
+    struct RootBuf {
+        int *bk = nullptr, *bw = nullptr, *acc = nullptr, *it = nullptr;
+        double *om = nullptr, *e = nullptr, *i = nullptr;
+        size_t cap = 0;
+        int n = 0;
+    } slots[ESB_MAX_MODES];
+    int* d_counter = nullptr;
     size_t cap_counter = 0;
-    size_t cap_roots = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int64_t launches = 0;
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
     int ax_nk = 0, ax_nw = 0, ax_layout = 0;
-    int n_roots = 0;
     std::string err;
 };
 
@@ -459,10 +475,14 @@ extern "C" int esb_create(int32_t device, esb_context** out) {
 extern "C" int esb_destroy(esb_context* c) {
     if (!c) return ESB_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_rowcount, c->d_rowoff, c->d_bk,
-                    c->d_bw, c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit, c->d_counter};
+    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_rowcount, c->d_rowoff, c->d_counter};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (auto& sl : c->slots) {
+        void* ps[] = {sl.bk, sl.bw, sl.acc, sl.it, sl.om, sl.e, sl.i};
+        for (void* p : ps)
+            if (p) cudaFree(p);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -548,16 +568,26 @@ extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* r
 }
 
 // ---- launches ---------------------------------------------------------------
-template <int KIND, int SCHEME>
-static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
+template <int KIND, int SCHEME, int NM>
+static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s) {
     const size_t smem = (size_t)g.tab_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME>,
+    cudaError_t e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME, NM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 block(128);
     dim3 grid((g.nw + 127) / 128, g.nk < 65535 ? g.nk : 65535);
-    grid_kernel<KIND, SCHEME><<<grid, block, smem, s>>>(g);
+    grid_kernel<KIND, SCHEME, NM><<<grid, block, smem, s>>>(g);
     return cudaGetLastError();
+}
+
+template <int KIND, int SCHEME>
+static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
+    switch (g.n_modes) {
+        case 1: return launch_grid_nm<KIND, SCHEME, 1>(g, s);
+        case 2: return launch_grid_nm<KIND, SCHEME, 2>(g, s);
+        case 3: return launch_grid_nm<KIND, SCHEME, 3>(g, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 template <int KIND, int SCHEME>
@@ -578,20 +608,28 @@ static int check_mode(const esb_context* c, int mode) {
     return (mode >= 0 && mode <= ESB_MAX_ORDER) ? 0 : -1;
 }
 
-extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const double* d_k, int32_t nk,
-                                       const double* d_w, int32_t nw, int32_t layout, double* d_ext,
-                                       double* d_int, void* stream) {
-    if (!c) return ESB_ERR_ARG;
+static int check_modes(const esb_context* c, int n_modes, const int32_t* modes) {
+    if (n_modes < 1 || n_modes > 3 || !modes) return -1;
+    for (int i = 0; i < n_modes; ++i)
+        if (check_mode(c, modes[i])) return -1;
+    return 0;
+}
+
+// one fused launch: every requested mode at every (k, omega); outputs mode-slot major
+static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, const double* d_k, int nk,
+                          const double* d_w, int nw, int layout, double* d_ext, double* d_int,
+                          cudaStream_t s) {
     if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
     if (nk <= 0 || nw <= 0 || !d_k || !d_w || !d_ext || !d_int || layout < 0 || layout > 2 ||
-        check_mode(c, mode))
+        check_modes(c, n_modes, modes))
         return fail(c, ESB_ERR_ARG, "bad grid arguments");
-    cudaStream_t s = stream ? (cudaStream_t)stream : (c->use_user_stream ? c->user_stream : c->stream);
     GridArgs g;
     g.M = c->dm;
     g.tab = c->d_tab;
     g.tab_doubles = c->tab_doubles;
-    g.k = d_k; g.w = d_w; g.nk = nk; g.nw = nw; g.layout = layout; g.mode = mode;
+    g.k = d_k; g.w = d_w; g.nk = nk; g.nw = nw; g.layout = layout;
+    g.n_modes = n_modes;
+    for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
     g.ext = d_ext; g.intq = d_int;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
@@ -607,6 +645,16 @@ extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const doubl
     c->timed = true;
     c->launches += 1;
     return ESB_OK;
+}
+
+static cudaStream_t cur_stream(esb_context* c) { return c->use_user_stream ? c->user_stream : c->stream; }
+
+extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const double* d_k, int32_t nk,
+                                       const double* d_w, int32_t nw, int32_t layout, double* d_ext,
+                                       double* d_int, void* stream) {
+    if (!c) return ESB_ERR_ARG;
+    return grid_dev_multi(c, 1, &mode, d_k, nk, d_w, nw, layout, d_ext, d_int,
+                          stream ? (cudaStream_t)stream : cur_stream(c));
 }
 
 extern "C" int esb_brackets_dev(esb_context* c, const double* d_ext, const double* d_int, int32_t nk,
@@ -657,24 +705,31 @@ static size_t w_len(int layout, int nk, int nw) {
     return layout == OMEGA_PER_K ? (size_t)nk * nw : (size_t)nw;
 }
 
-extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k, int32_t nk,
-                                   const double* w, int32_t nw, int32_t layout, double* ext, double* intq) {
+extern "C" int esb_dispersion_grid_multi(esb_context* c, int32_t n_modes, const int32_t* modes,
+                                         const double* k, int32_t nk, const double* w, int32_t nw,
+                                         int32_t layout, double* ext, double* intq) {
     if (!c) return ESB_ERR_ARG;
     if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
-    if (!k || !w || !ext || !intq || nk <= 0 || nw <= 0 || layout < 0 || layout > 2)
+    if (!k || !w || !ext || !intq || nk <= 0 || nw <= 0 || layout < 0 || layout > 2 ||
+        check_modes(c, n_modes, modes))
         return fail(c, ESB_ERR_ARG, "bad grid arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc;
     if ((rc = esb_upload_axes(c, k, nk, w, nw, layout))) return rc;
-    const size_t n = (size_t)nk * nw;
+    const size_t n = (size_t)nk * nw * n_modes;
     if ((rc = ensure_grid(c, n))) return rc;
-    cudaStream_t s = c->use_user_stream ? c->user_stream : c->stream;
-    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
+    cudaStream_t s = cur_stream(c);
+    if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
         return rc;
     CUDA_TRY(c, cudaMemcpyAsync(ext, c->d_ext, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(c, cudaMemcpyAsync(intq, c->d_int, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(c, cudaStreamSynchronize(s));
     return ESB_OK;
+}
+
+extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k, int32_t nk,
+                                   const double* w, int32_t nw, int32_t layout, double* ext, double* intq) {
+    return esb_dispersion_grid_multi(c, 1, &mode, k, nk, w, nw, layout, ext, intq);
 }
 
 extern "C" int esb_set_stream(esb_context* c, void* stream) {
@@ -683,8 +738,6 @@ extern "C" int esb_set_stream(esb_context* c, void* stream) {
     c->use_user_stream = true;
     return ESB_OK;
 }
-
-static cudaStream_t cur_stream(esb_context* c) { return c->use_user_stream ? c->user_stream : c->stream; }
 
 extern "C" int esb_upload_axes(esb_context* c, const double* k, int32_t nk, const double* w, int32_t nw,
                                int32_t layout) {
@@ -701,113 +754,125 @@ extern "C" int esb_upload_axes(esb_context* c, const double* k, int32_t nk, cons
     return ESB_OK;
 }
 
-// grid -> brackets -> refine on the axes already resident in HBM; the root table stays
-// on the device (esb_download_roots / esb_roots_device copy it out).
-extern "C" int esb_sweep_resident(esb_context* c, int32_t mode, double tol_percent, int32_t* n_roots,
-                                  int32_t* n_brackets) {
+static int ensure_slot(esb_context* c, esb_context::RootBuf& sl, size_t total) {
+    if (sl.cap >= total) return ESB_OK;
+    void* ps[] = {sl.bk, sl.bw, sl.acc, sl.it, sl.om, sl.e, sl.i};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    sl = esb_context::RootBuf();
+    const size_t cap = total + total / 4 + 64;
+    CUDA_TRY(c, cudaMalloc((void**)&sl.bk, cap * sizeof(int)));
+    CUDA_TRY(c, cudaMalloc((void**)&sl.bw, cap * sizeof(int)));
+    CUDA_TRY(c, cudaMalloc((void**)&sl.acc, cap * sizeof(int)));
+    CUDA_TRY(c, cudaMalloc((void**)&sl.it, cap * sizeof(int)));
+    CUDA_TRY(c, cudaMalloc((void**)&sl.om, cap * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc((void**)&sl.e, cap * sizeof(double)));
+    CUDA_TRY(c, cudaMalloc((void**)&sl.i, cap * sizeof(double)));
+    sl.cap = cap;
+    return ESB_OK;
+}
+
+// scan (ONE fused launch for all modes) -> per mode: brackets -> refinement, on the axes
+// already resident in HBM; the root tables stay on the device, one slot per mode
+// (esb_download_roots_slot / esb_roots_device copy them out).
+extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const int32_t* modes,
+                                        double tol_percent, int32_t* n_roots, int32_t* n_brackets) {
     if (!c) return ESB_ERR_ARG;
     if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
     if (c->ax_nk <= 0 || c->ax_nw <= 1) return fail(c, ESB_ERR_ARG, "axes not uploaded (need nw >= 2)");
-    if (check_mode(c, mode)) return fail(c, ESB_ERR_ARG, "bad mode");
+    if (check_modes(c, n_modes, modes)) return fail(c, ESB_ERR_ARG, "bad modes");
     const int nk = c->ax_nk, nw = c->ax_nw, layout = c->ax_layout;
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t s = cur_stream(c);
     int rc;
-    const size_t n = (size_t)nk * nw;
-    if ((rc = ensure_grid(c, n))) return rc;
-    if ((rc = esb_dispersion_grid_dev(c, mode, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
+    const size_t plane = (size_t)nk * nw;
+    if ((rc = ensure_grid(c, plane * n_modes))) return rc;
+    if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
         return rc;
     if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, (size_t)nk + 1))) return rc;
-    // pass 1: count (one 4-byte D2H + sync: the refine launch needs the bracket count)
-    int total = 0;
-    rc = esb_brackets_dev(c, c->d_ext, c->d_int, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, s);
-    if (rc) return rc;
-    c->n_roots = total;
-    if (n_brackets) *n_brackets = total;
-    if (n_roots) *n_roots = total;
-    if (total == 0) return ESB_OK;
-    if (c->cap_br < (size_t)total) {
-        if (c->d_bk) cudaFree(c->d_bk);
-        if (c->d_bw) cudaFree(c->d_bw);
-        c->d_bk = c->d_bw = nullptr;
-        c->cap_br = 0;
-        const size_t cap = (size_t)total + total / 4 + 64;
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_bk, cap * sizeof(int)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_bw, cap * sizeof(int)));
-        c->cap_br = cap;
-    }
-    if (c->cap_roots < (size_t)total) {
-        void* ps[] = {c->d_ro, c->d_re, c->d_ri, c->d_racc, c->d_rit};
-        for (void* p : ps)
-            if (p) cudaFree(p);
-        c->d_ro = c->d_re = c->d_ri = nullptr;
-        c->d_racc = c->d_rit = nullptr;
-        c->cap_roots = 0;
-        const size_t cap = (size_t)total + total / 4 + 64;
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_ro, cap * sizeof(double)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_re, cap * sizeof(double)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_ri, cap * sizeof(double)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_racc, cap * sizeof(int)));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_rit, cap * sizeof(int)));
-        c->cap_roots = cap;
-    }
-    // pass 2: fill (sorted by row, then omega index)
-    {
-        const int threads = 128, rows_per_block = threads / 32;
-        const int blocks = (nk + rows_per_block - 1) / rows_per_block;
-        bracket_kernel<<<blocks, threads, 0, s>>>(c->d_ext, c->d_int, nk, nw, c->d_rowcount, c->d_rowoff,
-                                                  c->d_bk, c->d_bw, total, 1);
-        CUDA_TRY(c, cudaGetLastError());
+    if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)ESB_MAX_MODES))) return rc;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, ESB_MAX_MODES * sizeof(int), s));
+    for (int m = 0; m < n_modes; ++m) {
+        esb_context::RootBuf& sl = c->slots[m];
+        const double* gext = c->d_ext + m * plane;
+        const double* gint = c->d_int + m * plane;
+        // pass 1: count (one 4-byte D2H + sync: the refine launch needs the bracket count)
+        int total = 0;
+        rc = esb_brackets_dev(c, gext, gint, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, s);
+        if (rc) return rc;
+        sl.n = 0;
+        if (n_brackets) n_brackets[m] = total;
+        if (n_roots) n_roots[m] = total;
+        if (total == 0) continue;
+        if ((rc = ensure_slot(c, sl, (size_t)total))) return rc;
+        sl.n = total;
+        // pass 2: fill (sorted by row, then omega index)
+        {
+            const int threads = 128, rows_per_block = threads / 32;
+            const int blocks = (nk + rows_per_block - 1) / rows_per_block;
+            bracket_kernel<<<blocks, threads, 0, s>>>(gext, gint, nk, nw, c->d_rowcount, c->d_rowoff, sl.bk,
+                                                      sl.bw, total, 1);
+            CUDA_TRY(c, cudaGetLastError());
+            c->launches += 1;
+        }
+        RefineArgs r;
+        r.M = c->dm;
+        r.tab = c->d_tab;
+        r.tab_doubles = c->tab_doubles;
+        r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout; r.mode = modes[m];
+        r.gext = gext; r.gint = gint;
+        r.bk = sl.bk; r.bw = sl.bw; r.n_brackets = total;
+        r.counter = c->d_counter + m;
+        r.tol_percent = tol_percent;
+        r.omega = sl.om; r.ext = sl.e; r.intq = sl.i; r.accepted = sl.acc; r.iters = sl.it;
+        cudaError_t e;
+        if (c->dm.kind == KIND_CYL_DENSITY)
+            e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, s)
+                                           : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, s);
+        else
+            e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)
+                                           : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, s);
+        CUDA_TRY(c, e);
         c->launches += 1;
     }
-    RefineArgs r;
-    r.M = c->dm;
-    r.tab = c->d_tab;
-    r.tab_doubles = c->tab_doubles;
-    r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout; r.mode = mode;
-    r.bk = c->d_bk; r.bw = c->d_bw; r.n_brackets = total;
-    r.gext = c->d_ext; r.gint = c->d_int;
-    if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)1))) return rc;
-    CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
-    r.counter = c->d_counter;
-    r.tol_percent = tol_percent;
-    r.omega = c->d_ro; r.ext = c->d_re; r.intq = c->d_ri; r.accepted = c->d_racc; r.iters = c->d_rit;
-    cudaError_t e;
-    if (c->dm.kind == KIND_CYL_DENSITY)
-        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, s)
-                                       : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, s);
-    else
-        e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)
-                                       : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, s);
-    CUDA_TRY(c, e);
-    c->launches += 1;
     return ESB_OK;
 }
 
-extern "C" int esb_download_roots(esb_context* c, esb_roots* out, int32_t max_roots) {
-    if (!c || !out) return ESB_ERR_ARG;
-    const size_t nb = (size_t)c->n_roots;
+extern "C" int esb_sweep_resident(esb_context* c, int32_t mode, double tol_percent, int32_t* n_roots,
+                                  int32_t* n_brackets) {
+    return esb_sweep_resident_multi(c, 1, &mode, tol_percent, n_roots, n_brackets);
+}
+
+extern "C" int esb_download_roots_slot(esb_context* c, int32_t slot, esb_roots* out, int32_t max_roots) {
+    if (!c || !out || slot < 0 || slot >= ESB_MAX_MODES) return ESB_ERR_ARG;
+    const esb_context::RootBuf& sl = c->slots[slot];
+    const size_t nb = (size_t)sl.n;
     if ((int64_t)nb > (int64_t)max_roots) return fail(c, ESB_ERR_CAPACITY, "max_roots too small");
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t s = cur_stream(c);
     if (nb) {
-        if (out->k_index) CUDA_TRY(c, cudaMemcpyAsync(out->k_index, c->d_bk, nb * 4, cudaMemcpyDeviceToHost, s));
-        if (out->w_index) CUDA_TRY(c, cudaMemcpyAsync(out->w_index, c->d_bw, nb * 4, cudaMemcpyDeviceToHost, s));
-        if (out->omega) CUDA_TRY(c, cudaMemcpyAsync(out->omega, c->d_ro, nb * 8, cudaMemcpyDeviceToHost, s));
-        if (out->ext) CUDA_TRY(c, cudaMemcpyAsync(out->ext, c->d_re, nb * 8, cudaMemcpyDeviceToHost, s));
-        if (out->intq) CUDA_TRY(c, cudaMemcpyAsync(out->intq, c->d_ri, nb * 8, cudaMemcpyDeviceToHost, s));
-        if (out->accepted) CUDA_TRY(c, cudaMemcpyAsync(out->accepted, c->d_racc, nb * 4, cudaMemcpyDeviceToHost, s));
-        if (out->iterations) CUDA_TRY(c, cudaMemcpyAsync(out->iterations, c->d_rit, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->k_index) CUDA_TRY(c, cudaMemcpyAsync(out->k_index, sl.bk, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->w_index) CUDA_TRY(c, cudaMemcpyAsync(out->w_index, sl.bw, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->omega) CUDA_TRY(c, cudaMemcpyAsync(out->omega, sl.om, nb * 8, cudaMemcpyDeviceToHost, s));
+        if (out->ext) CUDA_TRY(c, cudaMemcpyAsync(out->ext, sl.e, nb * 8, cudaMemcpyDeviceToHost, s));
+        if (out->intq) CUDA_TRY(c, cudaMemcpyAsync(out->intq, sl.i, nb * 8, cudaMemcpyDeviceToHost, s));
+        if (out->accepted) CUDA_TRY(c, cudaMemcpyAsync(out->accepted, sl.acc, nb * 4, cudaMemcpyDeviceToHost, s));
+        if (out->iterations) CUDA_TRY(c, cudaMemcpyAsync(out->iterations, sl.it, nb * 4, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(c, cudaStreamSynchronize(s));
     return ESB_OK;
 }
 
-extern "C" int esb_roots_device(esb_context* c, esb_roots* out, int32_t* n_roots) {
-    if (!c || !out) return ESB_ERR_ARG;
-    out->k_index = c->d_bk; out->w_index = c->d_bw; out->omega = c->d_ro; out->ext = c->d_re;
-    out->intq = c->d_ri; out->accepted = c->d_racc; out->iterations = c->d_rit;
-    if (n_roots) *n_roots = c->n_roots;
+extern "C" int esb_download_roots(esb_context* c, esb_roots* out, int32_t max_roots) {
+    return esb_download_roots_slot(c, 0, out, max_roots);
+}
+
+extern "C" int esb_roots_device(esb_context* c, int32_t slot, esb_roots* out, int32_t* n_roots) {
+    if (!c || !out || slot < 0 || slot >= ESB_MAX_MODES) return ESB_ERR_ARG;
+    const esb_context::RootBuf& sl = c->slots[slot];
+    out->k_index = sl.bk; out->w_index = sl.bw; out->omega = sl.om; out->ext = sl.e;
+    out->intq = sl.i; out->accepted = sl.acc; out->iterations = sl.it;
+    if (n_roots) *n_roots = sl.n;
     return ESB_OK;
 }
 

@@ -193,6 +193,17 @@ class DispersionSolver:
         L.check(self.lib, self.ctx, rc, "esb_dispersion_grid")
         return ext, inq
 
+    def dispersion_grid_multi(self, modes, k, w, layout="phase_speed"):
+        """Several modes in one fused scan: (ext, int) arrays of shape (n_modes, nk, nw)."""
+        k, w, lay, nw = self._axes(k, w, layout)
+        md = np.array([self._mode(m) for m in modes], dtype=np.int32)
+        ext = np.empty((md.size, k.size, nw), dtype=np.float64)
+        inq = np.empty((md.size, k.size, nw), dtype=np.float64)
+        rc = self.lib.esb_dispersion_grid_multi(self.ctx, md.size, _iptr(md), _dptr(k), k.size, _dptr(w), nw,
+                                                lay, _dptr(ext), _dptr(inq))
+        L.check(self.lib, self.ctx, rc, "esb_dispersion_grid_multi")
+        return ext, inq
+
     def D(self, mode, k, w, layout="phase_speed"):
         e, i = self.dispersion_grid(mode, k, w, layout)
         return e - i
@@ -236,13 +247,30 @@ class DispersionSolver:
                                             C.byref(nb)), "esb_sweep_resident")
         return n.value, nb.value
 
-    def download_roots(self, n):
+    def sweep_resident_multi(self, modes, tol_percent=1.0):
+        """One fused scan for all `modes`, then brackets + refinement per mode.  Returns the
+        per-mode root counts; table m stays on the device in slot m."""
+        md = np.array([self._mode(m) for m in modes], dtype=np.int32)
+        n = np.zeros(md.size, np.int32)
+        nb = np.zeros(md.size, np.int32)
+        L.check(self.lib, self.ctx,
+                self.lib.esb_sweep_resident_multi(self.ctx, md.size, _iptr(md), float(tol_percent), _iptr(n),
+                                                  _iptr(nb)), "esb_sweep_resident_multi")
+        return [int(x) for x in n]
+
+    def find_roots_multi(self, modes, k, w, layout="phase_speed", tol_percent=1.0):
+        """Host arrays in, one RootTable per mode out (one fused scan)."""
+        self.upload_axes(k, w, layout)
+        ns = self.sweep_resident_multi(modes, tol_percent)
+        return [self.download_roots(n, slot) for slot, n in enumerate(ns)]
+
+    def download_roots(self, n, slot=0):
         ki = np.empty(n, np.int32); wi = np.empty(n, np.int32)
         om = np.empty(n, np.float64); ex = np.empty(n, np.float64); iq = np.empty(n, np.float64)
         ac = np.empty(n, np.int32); it = np.empty(n, np.int32)
         out = L.esb_roots(_iptr(ki), _iptr(wi), _dptr(om), _dptr(ex), _dptr(iq), _iptr(ac), _iptr(it))
-        L.check(self.lib, self.ctx, self.lib.esb_download_roots(self.ctx, C.byref(out), n),
-                "esb_download_roots")
+        L.check(self.lib, self.ctx, self.lib.esb_download_roots_slot(self.ctx, int(slot), C.byref(out), n),
+                "esb_download_roots_slot")
         return RootTable(ki, wi, self._k_host[ki], om, ex, iq, ac, it, n)
 
     def set_stream(self, stream_ptr):

@@ -136,7 +136,19 @@ int esb_upload_axes(esb_context* ctx, const double* k, int32_t nk, const double*
 int esb_sweep_resident(esb_context* ctx, int32_t mode, double tol_percent, int32_t* n_roots,
                        int32_t* n_brackets);
 int esb_download_roots(esb_context* ctx, esb_roots* out, int32_t max_roots);
-int esb_roots_device(esb_context* ctx, esb_roots* out, int32_t* n_roots);
+int esb_roots_device(esb_context* ctx, int32_t slot, esb_roots* out, int32_t* n_roots);
+
+/* Several modes in ONE fused scan (n_modes <= 3): cylinder orders share the staged
+ * coefficient evaluation and the Bessel sets, the slab's sausage and kink share the whole
+ * integration.  Grids are mode-slot major: ext[(slot*nk + i)*nw + j].  The sweep keeps one
+ * root table per mode slot on the device. */
+int esb_dispersion_grid_multi(esb_context* ctx, int32_t n_modes, const int32_t* modes, const double* k,
+                              int32_t nk, const double* w, int32_t nw, int32_t omega_layout,
+                              double* ext, double* intq);
+int esb_sweep_resident_multi(esb_context* ctx, int32_t n_modes, const int32_t* modes,
+                             double tol_percent, int32_t* n_roots /* [n_modes] */,
+                             int32_t* n_brackets /* [n_modes] */);
+int esb_download_roots_slot(esb_context* ctx, int32_t slot, esb_roots* out, int32_t max_roots);
 
 /* Run every launch and copy of this context on `stream` (a cudaStream_t, e.g. the
  * caller's torch stream) instead of the context's own stream. */

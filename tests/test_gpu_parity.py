@@ -239,6 +239,37 @@ def test_edge_cases(solvers):
     assert np.array_equal(a[0][:1], c[0])
 
 
+@pytest.mark.parametrize("kind", list(CASES))
+def test_fused_modes_equal_single_mode(solvers, kind):
+    """The multi-mode scan (shared coefficients / shared integration) returns what the
+    single-mode calls return."""
+    s = solvers[kind]
+    k, W, _ = _grid_case(kind, nk=9, nw=150)
+    modes = list(CASES[kind]["modes"])
+    E, I = s.dispersion_grid_multi(modes, k, W)
+    tabs = s.find_roots_multi(modes, k, W)
+    for slot, m in enumerate(modes):
+        e, i = s.dispersion_grid(m, k, W)
+        assert np.array_equal(np.isnan(E[slot]), np.isnan(e))
+        ok = ~np.isnan(e)
+        assert np.max(np.abs(E[slot][ok] - e[ok]) / np.abs(e[ok])) < 1e-13
+        assert np.max(np.abs(I[slot][ok] - i[ok]) / np.abs(i[ok])) < 1e-11
+        t = s.find_roots(m, k, W)
+        same = np.array_equal(t.k_index, tabs[slot].k_index) and np.array_equal(t.w_index, tabs[slot].w_index)
+        if same:
+            acc = (t.accepted == 1) & (tabs[slot].accepted == 1)
+            assert np.max(np.abs(t.omega[acc] - tabs[slot].omega[acc]) / np.abs(t.omega[acc])) < 1e-12
+        else:   # a sign flip of a value at rounding level inside a continuum may move a noise bracket
+            assert abs(len(t.omega) - len(tabs[slot].omega)) <= 0.02 * len(t.omega) + 2
+    if kind == "cylinder_density":
+        # n = 3 (second fluting order) through the single-mode path
+        e3, i3 = s.dispersion_grid(3, k, W)
+        e0, i0 = ork.grid(ork.make_model(kind), 3, k, W)
+        reg = _grid_case(kind, nk=9, nw=150)[2][None, :] & ~np.isnan(e0)
+        dev = np.abs((e3 - i3) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+        assert np.nanmax(dev[reg]) < D_TOL
+
+
 def test_rk4_and_rk8_agree():
     k = np.linspace(0.3, 4.0, 6); W = np.linspace(3.0, 4.9, 40)
     with esb.DispersionSolver("cylinder_density", scheme="rk8") as a, \
