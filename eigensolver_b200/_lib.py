@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeigensolver_b200.so")
 
 ESB_OK, ESB_ERR_ARG, ESB_ERR_CUDA, ESB_ERR_CAPACITY, ESB_ERR_ALLOC = 0, -1, -2, -3, -4
-SLAB_DENSITY, CYLINDER_DENSITY = 0, 1
+SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW = 0, 1, 2
 RK4, RK8 = 0, 1
 OMEGA_SHARED, OMEGA_PHASE_SPEED, OMEGA_PER_K = 0, 1, 2
 MESH_CLUSTERED, MESH_UNIFORM = 0, 1
@@ -29,7 +29,8 @@ class esb_model(C.Structure):
         ("c_i0", C.c_double), ("vA_i0", C.c_double), ("vA_e", C.c_double), ("c_e", C.c_double),
         ("gamma", C.c_double), ("rho_i0", C.c_double), ("rho_A", C.c_double),
         ("ext_ic_value", C.c_double), ("ext_ic_slope", C.c_double), ("ext_wavelengths", C.c_double),
-        ("s_start", C.c_double), ("s_end", C.c_double),
+        ("s_start", C.c_double), ("s_end", C.c_double), ("U_e", C.c_double),
+        ("r_sign", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -56,6 +57,8 @@ SYMBOLS = {
     "esb_destroy": (C.c_int, [_ctx]),
     "esb_last_error": (C.c_char_p, [_ctx]),
     "esb_set_model": (C.c_int, [_ctx, C.POINTER(esb_model), _dp, _dp, C.c_int32, C.c_double]),
+    "esb_set_model_fields": (C.c_int, [_ctx, C.POINTER(esb_model), C.POINTER(_dp), C.c_int32, C.c_int32, _dp,
+                                       C.c_int32]),
     "esb_dispersion_grid": (C.c_int, [_ctx, C.c_int32, _dp, C.c_int32, _dp, C.c_int32, C.c_int32, _dp, _dp]),
     "esb_find_roots": (C.c_int, [_ctx, C.c_int32, _dp, C.c_int32, _dp, C.c_int32, C.c_int32, C.c_double,
                                  C.c_int32, C.POINTER(esb_roots), _ip, _ip]),

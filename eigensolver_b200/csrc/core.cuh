@@ -21,7 +21,7 @@
 
 namespace esb {
 
-enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1 };
+enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1, KIND_SLAB_FLOW = 2 };
 enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1 };
 enum { OMEGA_SHARED = 0, OMEGA_PHASE_SPEED = 1, OMEGA_PER_K = 2 };
 
@@ -37,6 +37,9 @@ struct DevModel {
     double alpha, beta, tau, S;
     double rho_b;             // density at the boundary s_start
     double s_start;           // boundary position (-1)
+    double r_sign;            // cylinder: -1 scripts written in r<0 (coronal), +1 in r>0 (photospheric)
+    // slab with a sheared flow U(x): uniform interior c_i, vA_i, rho_i
+    double ci2, vAi2, cTi2, si, rho_i, U_e, U_b;
 };
 
 // ---------------------------------------------------------------- tableau ----
@@ -71,7 +74,7 @@ ESB_HD int nodes_per_step(int scheme) { return scheme == SCHEME_RK8 ? 4 : 2; }
 // ------------------------------------------------------------- point data ----
 struct Point {
     double K, A;       // k^2, omega^2
-    double w;          // omega
+    double k, w;       // k, omega
     // products that do not change along the layer
     double Kalpha, Kbeta, Ktau, SKtau, AKc;
 };
@@ -80,6 +83,7 @@ ESB_HD Point make_point(const DevModel& M, double k, double w) {
     Point p;
     p.K = k * k;
     p.A = w * w;
+    p.k = k;
     p.w = w;
     p.Kalpha = p.K * M.alpha;
     p.Kbeta = p.K * M.beta;
@@ -113,6 +117,30 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
         a = fma(drho * p.A * Y, inv, -invr);
         b = fma(-(u * u) * X, inv, p.K);
         bm = invr2;
+    } else if (KIND == KIND_SLAB_FLOW) {
+        // f = {U, U', U''}.  vx'' = -D vx' - coeff vx  (flow_multiprocessor_coronal.py:211-219,297):
+        //   Om = w - k U,  t = Om^2 - k^2 cT^2
+        //   m0 = (k^2 c^2 - Om^2)(k^2 vA^2 - Om^2)/(s (k^2 cT^2 - Om^2))
+        //   D  = 2 k U' (t + k^4 cT^2 c^2/(s t)) / (Om (Om^2 - k^2 c^2))
+        //   a = -D,  b = m0 - k U''/Om - k U' D/Om
+        const double U = f[0], dU = f[1], ddU = f[2];
+        const double Om = fma(-p.k, U, p.w);
+        const double O2 = Om * Om;
+        const double t = fma(-p.K, M.cTi2, O2);
+        const double sc = fma(-p.K, M.ci2, O2);          // Om^2 - k^2 c^2
+        const double va = fma(-p.K, M.vAi2, O2);         // Om^2 - k^2 vA^2
+        const double st = M.si * t;
+        // one reciprocal for 1/(s t), 1/(Om sc): inv = 1/(st * Om * sc)
+        const double inv = 1.0 / (st * Om * sc);
+        const double inv_st = inv * (Om * sc);
+        const double inv_osc = inv * st;                 // 1/(Om sc)
+        const double m0 = -(sc * va) * inv_st;           // (Kc^2-O2)(KvA^2-O2)/(s(KcT^2-O2)) = -(sc va)/(s t)
+        const double kdU = p.k * dU;
+        const double Dx = 2.0 * kdU * fma(p.K * p.K * M.cTi2 * M.ci2, inv_st, t) * inv_osc;
+        const double invOm = inv_osc * sc;               // 1/Om
+        a = -Dx;
+        b = m0 - (p.k * ddU + kdU * Dx) * invOm;
+        bm = 0.0;
     } else {
         const double rho = f[0], drho = f[1];
         const double u = rho * p.A;
@@ -262,12 +290,13 @@ ESB_HD void exterior_cyl_order(const DevModel& M, const ExtCyl& E, int n, double
     double I0, dI0, K0, dK0, I1, dI1, K1, dK1;
     bessel_order(E.B0, n, E.z0, I0, dI0, K0, dK0);
     bessel_order(E.B1, n, E.kap, I1, dI1, K1, dK1);
-    const double P0 = M.ic_v, dP0 = -M.ic_s / E.kap;   // d/dz at rho0 (z = kap rho)
+    // d/dz at rho0 (z = kap rho); the scripts give dP/dr, and dr = r_sign d(rho)
+    const double P0 = M.ic_v, dP0 = M.r_sign * M.ic_s / E.kap;
     // Wronskian I K' - I' K = -1/z.  K0 = e^{z0} K(z0), I0 = e^{-z0} I(z0), hence the e^{+-(z0-z1)}.
     const double As = -E.z0 * (P0 * dK0 - dP0 * K0);
     const double Bs = -E.z0 * (dP0 * I0 - P0 * dI0);
     yb = As * I1 * E.ea + Bs * K1 * E.eb;
-    ypb = -E.kap * (As * dI1 * E.ea + Bs * dK1 * E.eb);
+    ypb = M.r_sign * E.kap * (As * dI1 * E.ea + Bs * dK1 * E.eb);
 }
 
 // ------------------------------------------------------------ full point ----
@@ -281,7 +310,10 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
                              const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM]) {
     const double nanv = nan("");
     const Point pt = make_point(M, k, w);
-    const double me = m_e2(M, pt.K, pt.A);
+    // exterior Doppler shift (flow script :207): (w - k U_e)
+    const double We = (KIND == KIND_SLAB_FLOW) ? fma(-k, M.U_e, w) : w;
+    const double Ae = (KIND == KIND_SLAB_FLOW) ? We * We : pt.A;
+    const double me = m_e2(M, pt.K, Ae);
     if (!(me >= 0.0)) {                       // "if m_e < 0: pass"  (Density_cylinder.py:760)
 #pragma unroll
         for (int s = 0; s < NM; ++s) { ext_q[s] = nanv; int_q[s] = nanv; }
@@ -317,14 +349,23 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
     } else {
         double yb, ypb;
         exterior_slab(M, k, me, yb, ypb);
-        // P_e = p_e_const vx'   (..._coronal.py:221,250)
-        const double p_e_const = M.rho_e * M.se2 * (pt.K * M.cTe2 - pt.A) / (w * (pt.K * M.ce2 - pt.A));
+        // P_e = p_e_const vx'   (..._coronal.py:221,250 / flow :209,291)
+        const double p_e_const = M.rho_e * M.se2 * (pt.K * M.cTe2 - Ae) / (We * (pt.K * M.ce2 - Ae));
         double y[2] = {1.0, 0.0}, yp[2] = {0.0, 1.0};
         const double m2[2] = {0.0, 0.0};
         integrate_layer<KIND, SCHEME, 2>(M, pt, tab, m2, y, yp);
-        // P_i(-1) = P_Ti(-1) vx'(-1)   (:234,267)
-        const double ub = M.rho_b * pt.A;
-        const double P_Ti = M.S * (pt.Ktau - ub) / (w * (pt.Kalpha - ub));
+        double P_Ti;
+        if (KIND == KIND_SLAB_FLOW) {
+            // displacement continuity: vx_i(-1) = vx_e(-1) (w - k U(-1))/(w - k U_e)   (flow :290)
+            const double Ob = fma(-k, M.U_b, w);
+            yb *= Ob / We;
+            // P_Ti = rho_i (vA^2+c^2)(k^2 cT^2 - Ob^2)/(Ob (k^2 c^2 - Ob^2))   (flow :223)
+            P_Ti = M.rho_i * M.si * (pt.K * M.cTi2 - Ob * Ob) / (Ob * (pt.K * M.ci2 - Ob * Ob));
+        } else {
+            // P_i(-1) = P_Ti(-1) vx'(-1)   (:234,267)
+            const double ub = M.rho_b * pt.A;
+            P_Ti = M.S * (pt.Ktau - ub) / (w * (pt.Kalpha - ub));
+        }
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
             // sausage: vx(1) = -vx(-1) (:259); kink: vx(1) = +vx(-1) (:696)

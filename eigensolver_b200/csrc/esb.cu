@@ -72,8 +72,11 @@ __global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
         const size_t o = (size_t)ik * g.nw + iw;
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
-            g.ext[s * plane + o] = e[s];
-            g.intq[s * plane + o] = i[s];
+            // one class of "no value": skipped (m_e < 0) or overflowed (exterior growth beyond
+            // the double range, where the reference's odeint fails too) -> NaN in both grids
+            const bool fin = isfinite(e[s]) && isfinite(i[s]);
+            g.ext[s * plane + o] = fin ? e[s] : nan("");
+            g.intq[s * plane + o] = fin ? i[s] : nan("");
         }
     }
 }
@@ -382,10 +385,11 @@ static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
 
 static int check_model(const esb_model* m) {
     if (!m) return ESB_ERR_ARG;
-    if (m->kind != ESB_SLAB_DENSITY && m->kind != ESB_CYLINDER_DENSITY) return ESB_ERR_ARG;
+    if (m->kind != ESB_SLAB_DENSITY && m->kind != ESB_CYLINDER_DENSITY && m->kind != ESB_SLAB_FLOW)
+        return ESB_ERR_ARG;
     if (m->scheme != ESB_RK4 && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->n_steps < 2 || m->n_steps > 8192) return ESB_ERR_ARG;
-    if (m->kind == ESB_SLAB_DENSITY && (m->n_steps % 2)) return ESB_ERR_ARG;
+    if (m->kind != ESB_CYLINDER_DENSITY && (m->n_steps % 2)) return ESB_ERR_ARG;
     return ESB_OK;
 }
 
@@ -403,6 +407,7 @@ extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
     out->ext_wavelengths = 3.0;
     out->ext_ic_value = 1e-8;
     out->s_start = -1.0;
+    out->r_sign = -1;
     if (kind == ESB_CYLINDER_DENSITY) {          // Density_cylinder.py:69-72,120,768
         out->vA_i0 = 2.0; out->vA_e = 5.0; out->c_e = 0.5;
         out->ext_ic_slope = 1e-15;
@@ -413,6 +418,12 @@ extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
         out->ext_ic_slope = 1e-8;
         out->s_end = 1.0;
         out->n_steps = 256;
+    } else if (kind == ESB_SLAB_FLOW) {          // flow_multiprocessor_coronal.py:47-52,72,229
+        out->vA_i0 = 1.0; out->c_i0 = 0.3; out->vA_e = 2.5; out->c_e = 0.2;
+        out->U_e = 0.0;
+        out->ext_ic_slope = 1e-15;
+        out->s_end = 1.0;
+        out->n_steps = 384;      // c_i = 0.3 vA_i: shorter interior wavelengths than the density slabs
     } else {
         return ESB_ERR_ARG;
     }
@@ -501,10 +512,17 @@ extern "C" double esb_last_kernel_ms(const esb_context* c) {
     return ms;
 }
 
-extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* rho, const double* drho,
-                             int32_t n_nodes, double rho_boundary) {
+// fields[f][node]: density kinds {rho, rho'}; slab flow {U, U', U''}.
+// boundary[]: density kinds {rho(s_start)}; slab flow {U(s_start)}.
+extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const double* const* fields,
+                                    int32_t n_fields, int32_t n_nodes, const double* boundary,
+                                    int32_t n_boundary) {
     if (!c) return ESB_ERR_ARG;
-    if (check_model(m) || !rho || !drho) return fail(c, ESB_ERR_ARG, "bad model");
+    if (check_model(m) || !fields || !boundary) return fail(c, ESB_ERR_ARG, "bad model");
+    const int need_fields = m->kind == ESB_SLAB_FLOW ? 3 : 2;
+    if (n_fields != need_fields || n_boundary < 1) return fail(c, ESB_ERR_ARG, "wrong number of profile fields");
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f]) return fail(c, ESB_ERR_ARG, "null profile field");
     int32_t need = 0;
     esb_mesh_size(m, &need);
     if (n_nodes != need) return fail(c, ESB_ERR_ARG, "n_nodes does not match esb_mesh_size()");
@@ -518,16 +536,16 @@ extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* r
             const double r = nodes[i];
             f[0] = 1.0 / r;
             f[1] = 1.0 / (r * r);
-            f[2] = rho[i];
-            f[3] = drho[i];
+            f[2] = fields[0][i];
+            f[3] = fields[1][i];
         } else {
-            f[0] = rho[i];
-            f[1] = drho[i];
+            for (int q = 0; q < n_fields; ++q) f[q] = fields[q][i];
         }
     }
     for (int i = 0; i < N; ++i) tab[(size_t)need * TAB_FIELDS + i] = nodes[(i + 1) * nps] - nodes[i * nps];
 
     DevModel& d = c->dm;
+    memset(&d, 0, sizeof(d));
     d.kind = m->kind;
     d.scheme = m->scheme;
     d.n_steps = N;
@@ -538,19 +556,30 @@ extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* r
     d.cTe2 = d.ce2 * d.vAe2 / d.se2;
     const double g = m->gamma;
     d.rho_e = m->rho_i0 * (m->c_i0 * m->c_i0 + g * 0.5 * m->vA_i0 * m->vA_i0) /
-              (d.ce2 + g * 0.5 * d.vAe2);                    // Density_cylinder.py:80
+              (d.ce2 + g * 0.5 * d.vAe2);                    // Density_cylinder.py:80 / flow :56
     d.ic_v = m->ext_ic_value;
     d.ic_s = m->ext_ic_slope;
     d.ext_len = m->ext_wavelengths * 2.0 * M_PI;
-    // c_i^2 = rho_e (c_e^2 + gamma/2 vA_e^2)/rho - gamma/2 vA_i^2   (Density_cylinder.py:210)
-    // cylinder: vA_i^2 = B_0^2/rho = vA_i0^2 rho_i0/rho                (Density_cylinder.py:188-200)
-    // slab:     vA_i^2 = vA_i0^2 rho_i0/profile = vA_i0^2 rho_i0 rho_A/rho   (..._coronal.py:117)
-    d.beta = m->vA_i0 * m->vA_i0 * m->rho_i0 * (m->kind == ESB_SLAB_DENSITY ? m->rho_A : 1.0);
-    d.alpha = d.rho_e * (d.ce2 + 0.5 * g * d.vAe2) - 0.5 * g * d.beta;
-    d.S = d.alpha + d.beta;
-    d.tau = d.alpha * d.beta / d.S;
-    d.rho_b = rho_boundary;
     d.s_start = m->s_start;
+    d.r_sign = m->r_sign >= 0 ? 1.0 : -1.0;
+    if (m->kind == ESB_SLAB_FLOW) {
+        d.ci2 = m->c_i0 * m->c_i0;
+        d.vAi2 = m->vA_i0 * m->vA_i0;
+        d.si = d.ci2 + d.vAi2;
+        d.cTi2 = d.ci2 * d.vAi2 / d.si;
+        d.rho_i = m->rho_i0;
+        d.U_e = m->U_e;
+        d.U_b = boundary[0];
+    } else {
+        // c_i^2 = rho_e (c_e^2 + gamma/2 vA_e^2)/rho - gamma/2 vA_i^2   (Density_cylinder.py:210)
+        // cylinder: vA_i^2 = B_0^2/rho = vA_i0^2 rho_i0/rho                (Density_cylinder.py:188-200)
+        // slab:     vA_i^2 = vA_i0^2 rho_i0/profile = vA_i0^2 rho_i0 rho_A/rho   (..._coronal.py:117)
+        d.beta = m->vA_i0 * m->vA_i0 * m->rho_i0 * (m->kind == ESB_SLAB_DENSITY ? m->rho_A : 1.0);
+        d.alpha = d.rho_e * (d.ce2 + 0.5 * g * d.vAe2) - 0.5 * g * d.beta;
+        d.S = d.alpha + d.beta;
+        d.tau = d.alpha * d.beta / d.S;
+        d.rho_b = boundary[0];
+    }
 
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (c->d_tab) cudaFree(c->d_tab);
@@ -565,6 +594,14 @@ extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* r
     c->model = *m;
     c->model_set = true;
     return ESB_OK;
+}
+
+extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* rho, const double* drho,
+                             int32_t n_nodes, double rho_boundary) {
+    if (!c) return ESB_ERR_ARG;
+    if (!m || m->kind == ESB_SLAB_FLOW) return fail(c, ESB_ERR_ARG, "esb_set_model is for the density kinds");
+    const double* fields[2] = {rho, drho};
+    return esb_set_model_fields(c, m, fields, 2, n_nodes, &rho_boundary, 1);
 }
 
 // ---- launches ---------------------------------------------------------------
@@ -604,7 +641,7 @@ static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
 }
 
 static int check_mode(const esb_context* c, int mode) {
-    if (c->model.kind == ESB_SLAB_DENSITY) return (mode == 0 || mode == 1) ? 0 : -1;
+    if (c->model.kind != ESB_CYLINDER_DENSITY) return (mode == 0 || mode == 1) ? 0 : -1;
     return (mode >= 0 && mode <= ESB_MAX_ORDER) ? 0 : -1;
 }
 
@@ -634,12 +671,17 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     cudaError_t e;
-    if (c->dm.kind == KIND_CYL_DENSITY)
-        e = c->dm.scheme == SCHEME_RK8 ? launch_grid<KIND_CYL_DENSITY, SCHEME_RK8>(g, s)
-                                       : launch_grid<KIND_CYL_DENSITY, SCHEME_RK4>(g, s);
-    else
-        e = c->dm.scheme == SCHEME_RK8 ? launch_grid<KIND_SLAB_DENSITY, SCHEME_RK8>(g, s)
-                                       : launch_grid<KIND_SLAB_DENSITY, SCHEME_RK4>(g, s);
+    const bool rk8 = c->dm.scheme == SCHEME_RK8;
+    switch (c->dm.kind) {
+        case KIND_CYL_DENSITY:
+            e = rk8 ? launch_grid<KIND_CYL_DENSITY, SCHEME_RK8>(g, s) : launch_grid<KIND_CYL_DENSITY, SCHEME_RK4>(g, s);
+            break;
+        case KIND_SLAB_FLOW:
+            e = rk8 ? launch_grid<KIND_SLAB_FLOW, SCHEME_RK8>(g, s) : launch_grid<KIND_SLAB_FLOW, SCHEME_RK4>(g, s);
+            break;
+        default:
+            e = rk8 ? launch_grid<KIND_SLAB_DENSITY, SCHEME_RK8>(g, s) : launch_grid<KIND_SLAB_DENSITY, SCHEME_RK4>(g, s);
+    }
     CUDA_TRY(c, e);
     CUDA_TRY(c, cudaEventRecord(c->ev1, s));
     c->timed = true;
@@ -826,12 +868,20 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         r.tol_percent = tol_percent;
         r.omega = sl.om; r.ext = sl.e; r.intq = sl.i; r.accepted = sl.acc; r.iters = sl.it;
         cudaError_t e;
-        if (c->dm.kind == KIND_CYL_DENSITY)
-            e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, s)
-                                           : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, s);
-        else
-            e = c->dm.scheme == SCHEME_RK8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)
-                                           : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, s);
+        const bool rk8 = c->dm.scheme == SCHEME_RK8;
+        switch (c->dm.kind) {
+            case KIND_CYL_DENSITY:
+                e = rk8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, s)
+                        : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, s);
+                break;
+            case KIND_SLAB_FLOW:
+                e = rk8 ? launch_refine<KIND_SLAB_FLOW, SCHEME_RK8>(r, s)
+                        : launch_refine<KIND_SLAB_FLOW, SCHEME_RK4>(r, s);
+                break;
+            default:
+                e = rk8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)
+                        : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, s);
+        }
         CUDA_TRY(c, e);
         c->launches += 1;
     }

@@ -71,6 +71,50 @@ class GaussianDensity:
         return rho, drho
 
 
+@dataclasses.dataclass(frozen=True)
+class FlowMedium:
+    """Speeds of the slab flow script (flow_multiprocessor_coronal.py:47-56): uniform density and
+    field inside the slab, exterior at rest or streaming with U_e."""
+    vA_i: float = 1.0
+    c_i: float = 0.3
+    vA_e: float = 2.5
+    c_e: float = 0.2
+    U_i0: float = 0.9
+    U_e: float = 0.0
+    gamma: float = 5.0 / 3.0
+    rho_i: float = 1.0
+
+    @property
+    def rho_e(self):
+        g = self.gamma
+        return self.rho_i * (self.c_i**2 + g * 0.5 * self.vA_i**2) / (self.c_e**2 + g * 0.5 * self.vA_e**2)
+
+    @property
+    def cT_i(self):
+        return math.sqrt(self.c_i**2 * self.vA_i**2 / (self.c_i**2 + self.vA_i**2))
+
+    @property
+    def cT_e(self):
+        return math.sqrt(self.c_e**2 * self.vA_e**2 / (self.c_e**2 + self.vA_e**2))
+
+
+SLAB_FLOW_CORONAL = FlowMedium()
+
+
+@dataclasses.dataclass(frozen=True)
+class GaussianFlow:
+    """U(x) = U_e + (U_i0 - U_e) exp(-(x-x0)^2/width^2)   (flow_multiprocessor_coronal.py:77)."""
+    width: float = 1e5
+    x0: float = 0.0
+
+    def __call__(self, medium, x):
+        x = np.asarray(x, dtype=np.float64)
+        g = np.exp(-((x - self.x0) ** 2) / self.width**2)
+        t = -2.0 * (x - self.x0) / self.width**2
+        dU0 = medium.U_i0 - medium.U_e
+        return medium.U_e + dU0 * g, dU0 * g * t, dU0 * g * (t * t - 2.0 / self.width**2)
+
+
 @dataclasses.dataclass
 class RootTable:
     """Result of a root search.  `k`, `omega` of accepted modes are what the
@@ -90,7 +134,7 @@ class RootTable:
         return self.k[m], self.omega[m]
 
 
-_KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY}
+_KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY, "slab_flow": L.SLAB_FLOW}
 _SCHEMES = {"rk4": L.RK4, "rk8": L.RK8}
 _LAYOUTS = {"shared": L.OMEGA_SHARED, "phase_speed": L.OMEGA_PHASE_SPEED, "per_k": L.OMEGA_PER_K}
 _MODES = {"sausage": 0, "kink": 1, "fluting": 2, "fluting2": 2, "fluting3": 3}
@@ -108,18 +152,30 @@ class DispersionSolver:
     """One GPU context evaluating D(omega,k) for one equilibrium model."""
 
     def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh="clustered",
-                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0):
+                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative"):
+        """kind: "cylinder_density" | "slab_density" | "slab_flow".
+        profile: callable (medium, x) -> (rho, rho') for the density kinds, (U, U', U'') for
+        "slab_flow"; any function may be given (this replaces the reference's sympy profile).
+        coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
+        layer 1 -> 0.001, exterior slope given as dP/dr)."""
         self.lib = L.load()
         self.kind = kind
         m = L.esb_model()
         L.check(self.lib, None, self.lib.esb_model_defaults(_KINDS[kind], C.byref(m)), "esb_model_defaults")
         if medium is None:
-            medium = CYLINDER_CORONAL if kind == "cylinder_density" else SLAB_CORONAL
+            medium = {"cylinder_density": CYLINDER_CORONAL, "slab_density": SLAB_CORONAL,
+                      "slab_flow": SLAB_FLOW_CORONAL}[kind]
         self.medium = medium
-        self.profile = profile if profile is not None else GaussianDensity(
-            0.95 if kind == "cylinder_density" else 0.9)
-        m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
-        m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, rho_A
+        if profile is None:
+            profile = {"cylinder_density": GaussianDensity(0.95), "slab_density": GaussianDensity(0.9),
+                       "slab_flow": GaussianFlow(1e5)}[kind]
+        self.profile = profile
+        if kind == "slab_flow":
+            m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
+            m.gamma, m.rho_i0, m.rho_A, m.U_e = medium.gamma, medium.rho_i, 1.0, medium.U_e
+        else:
+            m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
+            m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, rho_A
         m.scheme = _SCHEMES[scheme]
         m.mesh = L.MESH_UNIFORM if mesh == "uniform" else L.MESH_CLUSTERED
         m.ext_wavelengths = ext_wavelengths
@@ -127,6 +183,11 @@ class DispersionSolver:
             m.n_steps = int(n_steps)
         elif scheme == "rk4":
             m.n_steps = 2048
+        if coordinate == "positive":
+            if kind != "cylinder_density":
+                raise ValueError("coordinate='positive' applies to the cylinder")
+            m.r_sign, m.s_start, m.s_end = 1, 1.0, 0.001
+            m.ext_ic_slope = 1e-8            # Density_cylinder_photospheric.py: P0 = [1e-8, 1e-8]
         if ext_ic is not None:
             m.ext_ic_value, m.ext_ic_slope = ext_ic
         self.model = m
@@ -134,19 +195,20 @@ class DispersionSolver:
         L.check(self.lib, None, self.lib.esb_mesh_size(C.byref(m), C.byref(n)), "esb_mesh_size")
         self.nodes = np.empty(n.value, dtype=np.float64)
         L.check(self.lib, None, self.lib.esb_mesh_nodes(C.byref(m), _dptr(self.nodes)), "esb_mesh_nodes")
-        rho, drho = self.profile(medium, self.nodes)
-        rho = np.ascontiguousarray(rho * rho_A, dtype=np.float64)
-        drho = np.ascontiguousarray(drho * rho_A, dtype=np.float64)
-        rho_b = float(self.profile(medium, np.array([m.s_start]))[0][0] * rho_A)
+        scale = rho_A if kind != "slab_flow" else 1.0
+        fields = [np.ascontiguousarray(np.asarray(f, dtype=np.float64) * scale)
+                  for f in self.profile(medium, self.nodes)]
+        boundary = np.array([float(self.profile(medium, np.array([m.s_start]))[0][0]) * scale])
         self.ctx = L._ctx()
         rc = self.lib.esb_create(int(device), C.byref(self.ctx))
         if rc != L.ESB_OK:
             self.ctx = None
             raise L.EsbError("esb_create failed (status %d): no usable CUDA device %d; "
                              "eigensolver_b200 has no CPU fallback" % (rc, device))
+        fptr = (C.POINTER(C.c_double) * len(fields))(*[_dptr(f) for f in fields])
         L.check(self.lib, self.ctx,
-                self.lib.esb_set_model(self.ctx, C.byref(m), _dptr(rho), _dptr(drho), n.value, rho_b),
-                "esb_set_model")
+                self.lib.esb_set_model_fields(self.ctx, C.byref(m), fptr, len(fields), n.value, _dptr(boundary),
+                                              boundary.size), "esb_set_model_fields")
 
     # ------------------------------------------------------------------
     def close(self):

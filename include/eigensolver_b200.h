@@ -50,7 +50,8 @@ enum esb_status {
 /* Solver family = which reference script the model restates. */
 enum esb_model_kind {
     ESB_SLAB_DENSITY = 0,     /* slab, rho(x)   : ...Inhomogeneous_method_coronal.py        */
-    ESB_CYLINDER_DENSITY = 1  /* cylinder rho(r): Density_cylinder.py                       */
+    ESB_CYLINDER_DENSITY = 1, /* cylinder rho(r): Density_cylinder.py                       */
+    ESB_SLAB_FLOW = 2         /* slab, sheared flow U(x): flow_multiprocessor_coronal.py    */
 };
 
 /* Fixed-step integrator used across the layer. */
@@ -79,6 +80,11 @@ typedef struct esb_model {
     double ext_ic_slope;   /*   1e-8) slab :247, (1e-8, 1e-15) cylinder :768              */
     double ext_wavelengths;/* exterior domain = ext_wavelengths*2*pi/k  (reference: 3)     */
     double s_start, s_end; /* layer: boundary and far end: (-1, 1) slab, (-1, -0.001) cyl  */
+    double U_e;            /* ESB_SLAB_FLOW: exterior flow speed (flow script :52); there c_i0,
+                              vA_i0, rho_i0 are the uniform interior c_i, vA_i, rho_i          */
+    int32_t r_sign;        /* cylinder: -1 = script written in r<0 (coronal, default), +1 = r>0
+                              (photospheric: s_start=1, s_end=0.001, slope given as dP/dr)     */
+    int32_t reserved;
 } esb_model;
 
 /* Defaults of the reference scripts for `kind` (coronal parameter set). */
@@ -100,9 +106,17 @@ const char* esb_last_error(const esb_context* ctx);
 int esb_set_model(esb_context* ctx, const esb_model* m, const double* rho, const double* drho,
                   int32_t n_nodes, double rho_boundary);
 
+/* Generic form: fields[f][n_nodes] sampled at esb_mesh_nodes().
+ *   density kinds : fields = {rho, rho'},       boundary = {rho(s_start)}
+ *   ESB_SLAB_FLOW : fields = {U, U', U''},      boundary = {U(s_start)}                     */
+int esb_set_model_fields(esb_context* ctx, const esb_model* m, const double* const* fields,
+                         int32_t n_fields, int32_t n_nodes, const double* boundary,
+                         int32_t n_boundary);
+
 /* D over a grid.  mode: slab 0 = sausage, 1 = kink; cylinder = azimuthal order
  * 0 (sausage), 1 (kink), 2, 3 (fluting).  ext/intq: [nk*nw] row-major, NaN where the
- * reference skips the point (m_e < 0).  D = ext - intq. */
+ * reference skips the point (m_e < 0) or where the exterior solution overflows the double
+ * range (there the reference's odeint fails as well).  D = ext - intq. */
 int esb_dispersion_grid(esb_context* ctx, int32_t mode, const double* k, int32_t nk,
                         const double* w, int32_t nw, int32_t omega_layout, double* ext,
                         double* intq);

@@ -30,7 +30,7 @@
 #include <string.h>
 
 typedef struct {
-    int kind;            /* 0 slab density, 1 cylinder density */
+    int kind;            /* 0 slab density, 1 cylinder density, 2 slab sheared flow */
     int n_ext;           /* exterior steps */
     int n_int;           /* interior steps */
     int pad;
@@ -39,6 +39,9 @@ typedef struct {
     double ic_v, ic_s;   /* exterior initial values */
     double ext_wavelengths;
     double s_start, s_end;
+    double U_i0, U_e;    /* kind 2: flow profile U_e + (U_i0-U_e) exp(-(x-x0)^2/width^2); c_i0, vA_i0,
+                            rho_i0 are then the uniform interior values */
+    double r_sign;       /* cylinder: -1 scripts in r<0 (coronal), +1 scripts in r>0 (photospheric) */
 } ork_model;
 
 /* ---- Cooper-Verner 8th order tableau, table driven -------------------- */
@@ -166,6 +169,25 @@ static void coef_int_cyl(const void* c, double r, double* a, double* b) {
     *b = (double)(p->mode * p->mode) / (r * r) + p->K - p->A * p->A / (s * (p->A - p->K * cT2));
 }
 
+/* slab with sheared flow: flow_multiprocessor_coronal.py:211-219,297 */
+static void coef_int_flow(const void* c, double x, double* a, double* b) {
+    const pt_ctx* p = (const pt_ctx*)c;
+    const ork_model* m = p->m;
+    const double g = exp(-(x - m->x0) * (x - m->x0) / (m->width * m->width));
+    const double t1 = -2.0 * (x - m->x0) / (m->width * m->width);
+    const double U = m->U_e + (m->U_i0 - m->U_e) * g;
+    const double dU = (m->U_i0 - m->U_e) * g * t1;
+    const double ddU = (m->U_i0 - m->U_e) * g * (t1 * t1 - 2.0 / (m->width * m->width));
+    const double c2 = m->c_i0 * m->c_i0, vA2 = m->vA_i0 * m->vA_i0, s = c2 + vA2, cT2 = c2 * vA2 / s;
+    const double Om = p->w - p->k * U;
+    const double m0 = (p->K * c2 - Om * Om) * (p->K * vA2 - Om * Om) / (s * (p->K * cT2 - Om * Om));
+    const double t = Om * Om - p->K * cT2;
+    const double D = 2.0 * p->k * dU * (t + p->K * p->K * cT2 * c2 / (s * t)) / (Om * (Om * Om - p->K * c2));
+    const double coeff = p->k * ddU / Om + p->k * dU * D / Om - m0;
+    *a = -D;
+    *b = -coeff;
+}
+
 static double cluster(double t) {
     const double s = sin(0.5 * M_PI * t);
     return s * s;
@@ -179,7 +201,9 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
     p.rho_e = rho_e_of(m);
     const double vAe2 = m->vA_e * m->vA_e, ce2 = m->c_e * m->c_e;
     p.cT_e2 = ce2 * vAe2 / (ce2 + vAe2);
-    p.m_e = ((p.K * vAe2 - p.A) * (p.K * ce2 - p.A)) / ((vAe2 + ce2) * (p.K * p.cT_e2 - p.A));
+    const double We = (m->kind == 2) ? w - k * m->U_e : w;     /* exterior Doppler shift (flow :207) */
+    const double Ae = We * We;
+    p.m_e = ((p.K * vAe2 - Ae) * (p.K * ce2 - Ae)) / ((vAe2 + ce2) * (p.K * p.cT_e2 - Ae));
     if (!(p.m_e >= 0.0)) {
         *ext_q = NAN; *int_q = NAN;
         return 1;
@@ -187,46 +211,57 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
     /* exterior */
     double y[2], yp[2];
     y[0] = m->ic_v; yp[0] = m->ic_s;
-    const double x0 = -m->ext_wavelengths * 2.0 * M_PI / k;
-    if (m->kind == 0) {
+    const double rs = (m->kind == 1 && m->r_sign > 0) ? 1.0 : -1.0;
+    const double x0 = rs * m->ext_wavelengths * 2.0 * M_PI / k;
+    if (m->kind != 1) {
         const double h = (-1.0 - x0) / m->n_ext;
         for (int i = 0; i < m->n_ext; ++i) rk8_step(coef_ext_slab, &p, x0 + i * h, h, 1, y, yp);
     } else {
         /* geometric mesh in |r| resolves both the far field and the 1/r^2 term near r=-1 */
-        const double L = log(-x0);
+        const double L = log(fabs(x0));
         double r = x0;
         for (int i = 0; i < m->n_ext; ++i) {
-            const double rn = (i == m->n_ext - 1) ? -1.0 : -exp(L * (1.0 - (double)(i + 1) / m->n_ext));
+            const double rn = (i == m->n_ext - 1) ? rs : rs * exp(L * (1.0 - (double)(i + 1) / m->n_ext));
             rk8_step(coef_ext_cyl, &p, r, rn - r, 1, y, yp);
             r = rn;
         }
     }
     const double yb = y[0], ypb = yp[0];
-    double rho, drho, c2, dc2, vA2, dvA2;
-    profile(&p, m->s_start, &rho, &drho, &c2, &dc2, &vA2, &dvA2);
+    double rho = 0, drho = 0, c2 = 0, dc2 = 0, vA2 = 0, dvA2 = 0;
+    if (m->kind != 2) profile(&p, m->s_start, &rho, &drho, &c2, &dc2, &vA2, &dvA2);
     /* interior: two fundamental solutions forward from the boundary */
     double Y[2] = {1.0, 0.0}, Yp[2] = {0.0, 1.0};
     const int N = m->n_int;
-    if (m->kind == 0) {
+    if (m->kind != 1) {
+        const coef_fn cf = (m->kind == 2) ? coef_int_flow : coef_int_slab;
         const int H = N / 2;
         const double mid = 0.5 * (m->s_start + m->s_end);
         double x = m->s_start;
         for (int i = 1; i <= H; ++i) {
             const double xn = (i == H) ? mid : m->s_start + (mid - m->s_start) * cluster((double)i / H);
-            rk8_step(coef_int_slab, &p, x, xn - x, 2, Y, Yp);
+            rk8_step(cf, &p, x, xn - x, 2, Y, Yp);
             x = xn;
         }
         for (int i = 1; i <= H; ++i) {
             const double xn = (i == H) ? m->s_end : mid + (m->s_end - mid) * cluster((double)i / H);
-            rk8_step(coef_int_slab, &p, x, xn - x, 2, Y, Yp);
+            rk8_step(cf, &p, x, xn - x, 2, Y, Yp);
             x = xn;
         }
         /* sausage: vx(1) + vx(-1) = 0, kink: vx(1) - vx(-1) = 0 */
         const double target = (mode == 0) ? -1.0 : 1.0;
-        const double slope = yb * (target - Y[0]) / Y[1];
-        const double cT2 = c2 * vA2 / (c2 + vA2);
-        const double p_e_const = p.rho_e * (vAe2 + ce2) * (p.K * p.cT_e2 - p.A) / (w * (p.K * ce2 - p.A));
-        const double P_Ti = rho * (vA2 + c2) * (p.K * cT2 - p.A) / (w * (p.K * c2 - p.A));
+        const double p_e_const = p.rho_e * (vAe2 + ce2) * (p.K * p.cT_e2 - Ae) / (We * (p.K * ce2 - Ae));
+        double y0 = yb, P_Ti;
+        if (m->kind == 2) {
+            const double g = exp(-(m->s_start - m->x0) * (m->s_start - m->x0) / (m->width * m->width));
+            const double Ob = w - k * (m->U_e + (m->U_i0 - m->U_e) * g);
+            const double ci2 = m->c_i0 * m->c_i0, vi2 = m->vA_i0 * m->vA_i0, cTi2 = ci2 * vi2 / (ci2 + vi2);
+            y0 = yb * Ob / We;                               /* left_solution scaling (flow :290) */
+            P_Ti = m->rho_i0 * (vi2 + ci2) * (p.K * cTi2 - Ob * Ob) / (Ob * (p.K * ci2 - Ob * Ob));
+        } else {
+            const double cT2 = c2 * vA2 / (c2 + vA2);
+            P_Ti = rho * (vA2 + c2) * (p.K * cT2 - p.A) / (w * (p.K * c2 - p.A));
+        }
+        const double slope = y0 * (target - Y[0]) / Y[1];
         *ext_q = p_e_const * ypb;
         *int_q = P_Ti * slope;
     } else {

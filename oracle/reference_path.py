@@ -164,9 +164,13 @@ class _Base:
     n_ext_out = 500
     n_int_out = 500
 
+    boundary = -1.0
+    #: exterior domain = ext_wavelengths*2*pi/k (3 everywhere except the photospheric slab script: 7)
+    ext_wavelengths = 3.0
+
     def ext_start(self, k):
         # "Number of wavelengths/2*pi accomodated in the domain" (Density_cylinder.py:553)
-        return -3.0 * 2.0 * np.pi / k
+        return self.boundary * self.ext_wavelengths * 2.0 * np.pi / k
 
 
 class SlabDensity(_Base):
@@ -242,10 +246,19 @@ class CylinderDensity(_Base):
     s0, s1 = -1.0, -0.001          # :120  ix = linspace(-1., -0.001, 500)
     slope_guess = -0.001           # :790  fsolve(objective_dPi, -0.001)
 
-    def __init__(self, profile: GaussianDensity, m: int):
+    def __init__(self, profile: GaussianDensity, m: int, coordinate: str = "negative"):
         self.profile = profile
         self.medium = profile.medium
         self.m = int(m)
+        self.boundary = -1.0
+        if coordinate == "positive":
+            # Density_cylinder_photospheric.py: ix = linspace(1., 0.001, 1e3) (:120),
+            # lx = linspace(3.*2.*pi/k, 1., 500) (:696), P0 = [1e-8, 1e-8] (:771), fsolve(.., 0.001)
+            self.s0, self.s1 = 1.0, 0.001
+            self.ext_ic = (1e-8, 1e-8)
+            self.slope_guess = 0.001
+            self.n_int_out = 1000
+            self.boundary = 1.0
         self.mode = {0: "sausage", 1: "kink"}.get(self.m, "fluting%d" % self.m)
 
     def ext_rhs(self, k, w):
@@ -289,14 +302,114 @@ class CylinderDensity(_Base):
         return slope / (rho * (w * w - k * k * vA2))
 
 
+@dataclasses.dataclass
+class FlowMedium:
+    """Speeds of the slab flow script (flow_multiprocessor_coronal.py:47-56): uniform density
+    and field inside, Gaussian shear flow U(x) = U_e + (U_i0-U_e) exp(-(x-x0)^2/dx^2)."""
+    vA_i: float = 1.0
+    c_i: float = 0.3
+    vA_e: float = 2.5
+    c_e: float = 0.2
+    U_i0: float = 0.9
+    U_e: float = 0.0
+    gamma: float = GAMMA
+    rho_i: float = 1.0
+    width: float = 1e5
+    x0: float = 0.0
+
+    @property
+    def rho_e(self):
+        g = self.gamma
+        return self.rho_i * (self.c_i**2 + g * 0.5 * self.vA_i**2) / (self.c_e**2 + g * 0.5 * self.vA_e**2)
+
+    @property
+    def cT_i2(self):
+        return self.c_i**2 * self.vA_i**2 / (self.c_i**2 + self.vA_i**2)
+
+    @property
+    def cT_e2(self):
+        return self.c_e**2 * self.vA_e**2 / (self.c_e**2 + self.vA_e**2)
+
+    def U(self, x):
+        g = np.exp(-(x - self.x0) ** 2 / self.width**2)
+        t = -2.0 * (x - self.x0) / self.width**2
+        U = self.U_e + (self.U_i0 - self.U_e) * g
+        dU = (self.U_i0 - self.U_e) * g * t
+        ddU = (self.U_i0 - self.U_e) * g * (t * t - 2.0 / self.width**2)
+        return U, dU, ddU
+
+    def m_e(self, k, w):
+        W2 = (w - k * self.U_e) ** 2
+        K = k * k
+        return ((K * self.vA_e**2 - W2) * (K * self.c_e**2 - W2)) / (
+            (self.vA_e**2 + self.c_e**2) * (K * self.cT_e2 - W2))
+
+
+class SlabFlow(_Base):
+    """Slab with a non-uniform (sheared) flow, reference
+    Slab/Non uniform flow/Solver/flow_multiprocessor_coronal.py  (sausage :139-330, kink :347-)."""
+    geometry = "slab"
+    ext_ic = (1e-8, 1e-15)         # :229  V0 = [1e-8, 1e-15]
+    s0, s1 = -1.0, 1.0             # :72   ix = linspace(-1, 1, 500)
+    slope_guess = 0.0              # :304  fsolve(objective_dvxi, 0.)
+    n_int_out = 500
+
+    def __init__(self, medium: FlowMedium, mode: str):
+        assert mode in ("sausage", "kink")
+        self.medium = medium
+        self.mode = mode
+
+    def ext_rhs(self, k, w):
+        m_e = self.medium.m_e(k, w)
+        return lambda y, x: [y[1], m_e * y[0]]
+
+    def ext_match(self, k, w, y_b):
+        md = self.medium
+        K = k * k
+        We = w - k * md.U_e
+        p_e_const = md.rho_e * (md.vA_e**2 + md.c_e**2) * (K * md.cT_e2 - We**2) / (We * (K * md.c_e**2 - We**2))  # :209
+        Ub = md.U(self.s0)[0]
+        # left_solution = Ls[:,0]*(w - k U_i(-1))/(w - k U_e)  (:290): continuity of the displacement
+        return y_b[0] * (w - k * Ub) / We, p_e_const * y_b[1]
+
+    def coeffs(self, x, k, w):
+        """vx'' = -D vx' - coeff vx  (dVx_dx_i :297): a = -D, b = -coeff."""
+        md = self.medium
+        K = k * k
+        U, dU, ddU = md.U(x)
+        Om = w - k * U
+        c2, vA2, cT2 = md.c_i**2, md.vA_i**2, md.cT_i2
+        s = c2 + vA2
+        m0 = (K * c2 - Om**2) * (K * vA2 - Om**2) / (s * (K * cT2 - Om**2))                      # :211
+        t = Om**2 - K * cT2
+        Dx = 2.0 * k * dU * (t + K * K * cT2 * c2 / (s * t)) / (Om * (Om**2 - K * c2))           # :215
+        coeff = k * ddU / Om + k * dU * Dx / Om - m0                                               # :219
+        return -Dx, -coeff
+
+    def end_residual(self, y_end, y_start0):
+        return y_end[0] + y_start0 if self.mode == "sausage" else y_end[0] - y_start0
+
+    def int_match(self, k, w, y0, slope):
+        md = self.medium
+        K = k * k
+        Om = w - k * md.U(self.s0)[0]
+        c2, vA2, cT2 = md.c_i**2, md.vA_i**2, md.cT_i2
+        P_Ti = md.rho_i * (vA2 + c2) * (K * cT2 - Om**2) / (Om * (K * c2 - Om**2))                 # :223
+        return P_Ti * slope
+
+
 # --------------------------------------------------------------------------
 # the dispersion function
 # --------------------------------------------------------------------------
-def _ode_kw(rtol, atol):
+def _ode_kw(rtol, atol, scale=1.0):
+    """atol="scaled": absolute tolerance = rtol x the magnitude of the initial data, i.e. a
+    purely relative control that does not stall where an oscillating solution crosses zero."""
     kw = {}
     if rtol is not None:
         kw["rtol"] = rtol
-    if atol is not None:
+    if isinstance(atol, str):
+        kw["atol"] = (rtol or 1.49012e-8) * abs(scale)
+    elif atol is not None:
         kw["atol"] = atol
     if rtol is not None and rtol < 1e-9:
         kw["mxstep"] = 200000
@@ -307,8 +420,9 @@ def exterior(model, k, w, rtol=None, atol=None):
     """Step 2: boundary values (y, y') of the exterior solution at x=-1, or None if skipped."""
     if model.medium.m_e(k, w) < 0:           # "if m_e < 0: pass"  Density_cylinder.py:760
         return None
-    lx = np.linspace(model.ext_start(k), -1.0, model.n_ext_out)
-    Ls = odeint(model.ext_rhs(k, w), list(model.ext_ic), lx, **_ode_kw(rtol, atol))
+    lx = np.linspace(model.ext_start(k), model.boundary, model.n_ext_out)
+    Ls = odeint(model.ext_rhs(k, w), list(model.ext_ic), lx,
+                **_ode_kw(rtol, atol, 1e-3 * max(abs(model.ext_ic[0]), abs(model.ext_ic[1]))))
     return Ls[-1]
 
 
@@ -320,7 +434,7 @@ def dispersion(model, k, w, rtol=None, atol=None, xtol=None, shoot="fsolve"):
         return float("nan"), float("nan")
     y0, ext_q = model.ext_match(k, w, yb)
     ix = np.linspace(model.s0, model.s1, model.n_int_out)
-    okw = _ode_kw(rtol, atol)
+    okw = _ode_kw(rtol, atol, y0 if y0 != 0 else 1.0)
 
     def rhs(y, s):
         a, b = model.coeffs(s, k, w)
@@ -336,7 +450,7 @@ def dispersion(model, k, w, rtol=None, atol=None, xtol=None, shoot="fsolve"):
         # the interior ODE is linear, so the residual is affine in the slope:
         # two integrations give the same slope fsolve converges to.
         U0 = odeint(rhs, [y0, 0.0], ix, **okw)[-1]
-        U1 = odeint(rhs, [0.0, 1.0], ix, **okw)[-1]
+        U1 = odeint(rhs, [0.0, 1.0], ix, **_ode_kw(rtol, atol, 1.0))[-1]
         r0 = model.end_residual(U0, y0)
         r1 = model.end_residual(U1, 0.0)
         slope = -r0 / r1

@@ -19,7 +19,8 @@ class ork_model(C.Structure):
                 ("c_i0", C.c_double), ("vA_i0", C.c_double), ("vA_e", C.c_double), ("c_e", C.c_double),
                 ("gamma", C.c_double), ("rho_i0", C.c_double), ("rho_A", C.c_double),
                 ("width", C.c_double), ("x0", C.c_double), ("ic_v", C.c_double), ("ic_s", C.c_double),
-                ("ext_wavelengths", C.c_double), ("s_start", C.c_double), ("s_end", C.c_double)]
+                ("ext_wavelengths", C.c_double), ("s_start", C.c_double), ("s_end", C.c_double),
+                ("U_i0", C.c_double), ("U_e", C.c_double), ("r_sign", C.c_double)]
 
 
 def build():
@@ -46,12 +47,29 @@ def lib():
     return _lib
 
 
-def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rho_A=1.0):
-    """kind: 'slab_density' | 'cylinder_density'; medium: any object with c_i0, vA_i0, vA_e, c_e,
-    gamma, rho_i0 attributes (defaults: the reference's coronal sets)."""
+def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rho_A=1.0,
+               coordinate="negative", ext_wavelengths=3.0):
+    """kind: 'slab_density' | 'cylinder_density' | 'slab_flow'; medium: any object with c_i0, vA_i0,
+    vA_e, c_e, gamma, rho_i0 attributes (flow: vA_i, c_i, vA_e, c_e, U_i0, U_e, gamma, rho_i);
+    defaults: the reference's coronal sets.  coordinate='positive': cylinder scripts in r > 0."""
     m = ork_model()
     cyl = kind == "cylinder_density"
-    m.kind = 1 if cyl else 0
+    m.kind = {"slab_density": 0, "cylinder_density": 1, "slab_flow": 2}[kind]
+    m.r_sign = -1.0
+    if kind == "slab_flow":
+        vals = medium if medium is not None else type("M", (), dict(
+            vA_i=1.0, c_i=0.3, vA_e=2.5, c_e=0.2, U_i0=0.9, U_e=0.0, gamma=5.0 / 3.0, rho_i=1.0))
+        m.c_i0, m.vA_i0, m.vA_e, m.c_e = vals.c_i, vals.vA_i, vals.vA_e, vals.c_e
+        m.gamma, m.rho_i0, m.U_i0, m.U_e = vals.gamma, vals.rho_i, vals.U_i0, vals.U_e
+        m.rho_A = 1.0
+        m.width = width if width is not None else 1e5
+        m.x0 = x0
+        m.ic_v, m.ic_s = 1e-8, 1e-15
+        m.ext_wavelengths = ext_wavelengths
+        m.s_start, m.s_end = -1.0, 1.0
+        m.n_ext = n_ext or 3000
+        m.n_int = n_int or 384
+        return m
     if medium is None:
         vals = (1.0, 2.0, 5.0, 0.5) if cyl else (1.0, 1.2, 3.0, 0.4)
         m.c_i0, m.vA_i0, m.vA_e, m.c_e = vals
@@ -64,10 +82,13 @@ def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rh
     m.x0 = x0
     m.ic_v = 1e-8
     m.ic_s = 1e-15 if cyl else 1e-8
-    m.ext_wavelengths = 3.0
+    m.ext_wavelengths = ext_wavelengths
     m.s_start = -1.0
     m.s_end = -0.001 if cyl else 1.0
-    m.n_ext = n_ext or (6000 if cyl else 3000)
+    if coordinate == "positive":
+        assert cyl
+        m.r_sign, m.s_start, m.s_end, m.ic_s = 1.0, 1.0, 0.001, 1e-8
+    m.n_ext = n_ext or int((6000 if cyl else 3000) * max(1.0, ext_wavelengths / 3.0))
     m.n_int = n_int or (320 if cyl else 384)
     return m
 

@@ -40,6 +40,17 @@ POINTS = {
     ),
 }
 
+POINTS.update({
+    # (overrides applied to the script's own assignment lines)
+    "cylinder_density_photospheric": dict(
+        ks=[0.1, 0.6, 1.5, 3.0, 4.5], Ws=[0.55, 0.65, 0.95, 1.2, 1.45, 0.49, 1.6], overrides={}),
+    "slab_density_photospheric": dict(
+        ks=[0.1, 0.6, 1.5, 3.0], Ws=[0.3, 0.5, 0.65, 1.05, 1.2, 1.28, 0.75, 1.4], overrides={"dx": 0.9}),
+    "slab_flow_coronal": dict(
+        ks=[0.1, 0.6, 1.5, 3.0, 4.5], Ws=[1.3, 1.6, 2.0, 2.4, -0.3, -1.0, -2.0, -0.1, 2.6, 0.1995],
+        overrides={"dx": 1.0}),
+})
+
 SCANS = {
     # (mode, k, W_lo, W_hi, n)  - intervals that contain a mode
     "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),
@@ -52,13 +63,24 @@ PICKLES = {
                     {"09": 0.9, "1": 1.0, "125": 1.25, "15": 1.5, "175": 1.75, "3": 3.0, "1e5": 1e5}),
     "slab_coronal": ("Slab/Non uniform density/Coronal/Example data/width%s_coronal.pickle",
                      {"09": 0.9, "15": 1.5, "3": 3.0, "1e5": 1e5}),
+    "cyl_photospheric": ("Cylinder/Non-uniform density/Photospheric/Example data/"
+                         "Cylindrical_photospheric_width_%s.pickle", {"09": 0.9, "15": 1.5, "3": 3.0, "1e5": 1e5}),
+    "slab_photospheric": ("Slab/Non uniform density/Photospheric/Example data/width%s.pickle",
+                          {"09": 0.9, "15": 1.5, "3": 3.0, "1e5": 1e5}),
+    "flow_coronal": ("Slab/Non uniform flow/Example data/flow_width%s_coronal.pickle",
+                     # produced with U_i0 = 0.35 (tests/helpers.py ROOT_CASES); the file named
+                     # "width125" matches width 2.5 (median mismatch 0.6 %), not 1.25 (15 %)
+                     {"1": 1.0, "125": 2.5, "15": 1.5, "3": 3.0, "5": 5.0, "1e5": 1e5}),
 }
 
 
 def main():
+    only = sys.argv[1:]
     for name, spec in POINTS.items():
+        if only and name not in only:
+            continue
         t0 = time.time()
-        ref = ReferenceSolver(name)
+        ref = ReferenceSolver(name, overrides=spec.get("overrides"))
         rows = []
         for mode_id, mode in ((0, "sausage"), (1, "kink")):
             for k in spec["ks"]:
@@ -69,7 +91,7 @@ def main():
                  w=a[:, 2], D=a[:, 3])
         print(name, len(rows), "points in %.0f s" % (time.time() - t0), flush=True)
         out = {}
-        for n, (mode, k, lo, hi, num) in enumerate(SCANS[name]):
+        for n, (mode, k, lo, hi, num) in enumerate(SCANS.get(name, [])):
             freq = np.linspace(lo * k, hi * k, num)
             ks, ws = ref.roots(mode, k, freq)
             out["scan%d_mode" % n] = np.array([0 if mode == "sausage" else 1])
@@ -78,8 +100,11 @@ def main():
             out["scan%d_sol_ks" % n] = ks
             out["scan%d_sol_ws" % n] = ws
             print(name, mode, k, "->", ws, flush=True)
-        np.savez(os.path.join(HERE, "ref_scan_%s.npz" % name), **out)
+        if out:
+            np.savez(os.path.join(HERE, "ref_scan_%s.npz" % name), **out)
 
+    if only and "roots" not in only:
+        return
     roots = {}
     for fam, (pat, widths) in PICKLES.items():
         for tag, width in widths.items():

@@ -45,6 +45,16 @@ SOLVERS = {
         "wavenumber = np.linspace(0.001,0.75, 25.)",
         {"sausage": ("sausage", "P_diff_check"), "kink": ("kink", "P_diff_check_kink")},
     ),
+    "cylinder_density_photospheric": (
+        "Cylinder/Non-uniform density/Photospheric/Solvers/Density_cylinder_photospheric.py",
+        "wavenumber = np.linspace(0.01,4.5,130)",
+        {"sausage": ("sausage", "xi_diff_check"), "kink": ("kink", "xi_diff_check")},
+    ),
+    "slab_density_photospheric": (
+        "Slab/Non uniform density/Photospheric/Solvers/multiprocessor_Inhomogeneous_method.py",
+        "wavenumber = np.linspace(",
+        {"sausage": ("sausage", "P_diff_check"), "kink": ("kink", "P_diff_check_kink")},
+    ),
     "slab_flow_coronal": (
         "Slab/Non uniform flow/Solver/flow_multiprocessor_coronal.py",
         "wavenumber = np.linspace(",
@@ -130,8 +140,10 @@ class ReferenceSolver:
         self.max_interior = max_interior
         with open(os.path.join(REF_ROOT, path)) as fh:
             src = fh.read()
-        cut = src.rfind(marker) if name != "slab_flow_coronal" else src.find(
-            marker, src.find("kink_ws.put(sol_omegas_kink1)"))
+        if name in ("slab_flow_coronal", "slab_density_photospheric"):
+            cut = src.find(marker, src.find("kink_ws.put(sol_omegas_kink1)"))
+        else:
+            cut = src.rfind(marker)
         assert cut > 0, "driver marker not found"
         src = src[:cut]
         # parameter overrides (e.g. profile width) are applied by rewriting the

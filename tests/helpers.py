@@ -1,7 +1,8 @@
-"""Shared test helpers (tests only)."""
+"""Shared test helpers (tests only): the model variants under test and their 'noise floor'."""
 import numpy as np
 
 from oracle import reference_path as rp
+from oracle import rk_oracle as ork
 
 
 def continua(profile, s0, s1, slab):
@@ -14,7 +15,14 @@ def continua(profile, s0, s1, slab):
     iv = [(np.sqrt(vA2.min()), np.sqrt(vA2.max())), (np.sqrt(cT2.min()), np.sqrt(cT2.max()))]
     if slab:
         iv.append((np.sqrt(c2.min()), np.sqrt(c2.max())))
-    return iv
+    return iv + [(-hi, -lo) for lo, hi in iv]
+
+
+def flow_continua(md):
+    """Doppler-shifted resonances of the sheared-flow slab: W - U(x) in {0, +-cT_i, +-c_i}."""
+    U = md.U(np.linspace(-1, 1, 4001))[0]
+    cT = np.sqrt(md.cT_i2)
+    return [(U.min() + d, U.max() + d) for d in (0.0, cT, -cT, md.c_i, -md.c_i)]
 
 
 def regular_mask(W, intervals, margin=0.01):
@@ -31,3 +39,85 @@ def cyl_profile(width=0.95, medium=rp.CYL_CORONAL):
 
 def slab_profile(width=0.9, medium=rp.SLAB_CORONAL):
     return rp.GaussianDensity(medium, width=width)
+
+
+class Case:
+    """One solver variant: how to build the GPU solver, both oracles and the regular mask."""
+
+    def __init__(self, name, kind, modes, W, width, medium_name=None, coordinate="negative",
+                 roots_window=None, fixture=None, family=None, ext_wavelengths=3.0, U_i0=0.9):
+        self.ext_wavelengths = ext_wavelengths
+        self.U_i0 = U_i0
+        self.name, self.kind, self.modes, self.W, self.width = name, kind, modes, W, width
+        self.medium_name, self.coordinate = medium_name, coordinate
+        self.roots_window = roots_window
+        self.fixture = fixture          # ref_D_<fixture>.npz
+        self.family = family            # key prefix in ref_roots.npz
+
+    # ---- oracles
+    def rp_medium(self):
+        if self.kind == "slab_flow":
+            return rp.FlowMedium(width=self.width, U_i0=self.U_i0)
+        return getattr(rp, self.medium_name)
+
+    def scipy_model(self, mode, width=None, fast=True):
+        w = self.width if width is None else width
+        if self.kind == "cylinder_density":
+            return rp.CylinderDensity(cyl_profile(w, self.rp_medium()), mode, coordinate=self.coordinate)
+        if self.kind == "slab_density":
+            m = rp.SlabDensity(slab_profile(w, self.rp_medium()), "sausage" if mode == 0 else "kink",
+                               500 if fast else None)
+            m.ext_wavelengths = self.ext_wavelengths
+            return m
+        return rp.SlabFlow(rp.FlowMedium(width=w, U_i0=self.U_i0), "sausage" if mode == 0 else "kink")
+
+    def c_model(self, width=None, **kw):
+        w = self.width if width is None else width
+        if self.kind == "slab_flow":
+            return ork.make_model("slab_flow", medium=rp.FlowMedium(width=w, U_i0=self.U_i0), width=w, **kw)
+        return ork.make_model(self.kind, medium=self.rp_medium(), width=w, coordinate=self.coordinate,
+                              ext_wavelengths=self.ext_wavelengths, **kw)
+
+    def intervals(self, width=None):
+        w = self.width if width is None else width
+        if self.kind == "slab_flow":
+            return flow_continua(rp.FlowMedium(width=w, U_i0=self.U_i0))
+        if self.kind == "cylinder_density":
+            s0, s1 = (1.0, 0.001) if self.coordinate == "positive" else (-1.0, -0.001)
+            return continua(cyl_profile(w, self.rp_medium()), s0, s1, False)
+        return continua(slab_profile(w, self.rp_medium()), -1.0, 1.0, True)
+
+    # ---- GPU solver
+    def gpu_solver(self, esb, width=None, **kw):
+        w = self.width if width is None else width
+        if self.kind == "slab_flow":
+            return esb.DispersionSolver("slab_flow", medium=esb.FlowMedium(U_i0=self.U_i0),
+                                        profile=esb.GaussianFlow(w), **kw)
+        medium = {"CYL_CORONAL": esb.CYLINDER_CORONAL, "CYL_PHOTOSPHERIC": esb.CYLINDER_PHOTOSPHERIC,
+                  "SLAB_CORONAL": esb.SLAB_CORONAL, "SLAB_PHOTOSPHERIC": esb.SLAB_PHOTOSPHERIC}[self.medium_name]
+        return esb.DispersionSolver(self.kind, medium=medium, profile=esb.GaussianDensity(w),
+                                    coordinate=self.coordinate, ext_wavelengths=self.ext_wavelengths, **kw)
+
+
+CASES = {c.name: c for c in [
+    Case("cylinder_density", "cylinder_density", (0, 1, 2), (0.40, 5.2), 0.95, "CYL_CORONAL",
+         roots_window=(2.95, 4.95), fixture="cylinder_density_coronal", family="cyl_coronal"),
+    Case("slab_density", "slab_density", (0, 1), (0.30, 3.2), 0.9, "SLAB_CORONAL",
+         roots_window=(1.75, 2.95), fixture="slab_density_coronal", family="slab_coronal"),
+    Case("cylinder_photospheric", "cylinder_density", (0, 1, 2), (0.40, 1.6), 0.9, "CYL_PHOTOSPHERIC",
+         coordinate="positive", roots_window=(0.9, 1.49), fixture="cylinder_density_photospheric",
+         family="cyl_photospheric"),
+    Case("slab_photospheric", "slab_density", (0, 1), (0.20, 1.45), 0.9, "SLAB_PHOTOSPHERIC",
+         roots_window=(1.02, 1.29), fixture="slab_density_photospheric", family="slab_photospheric",
+         ext_wavelengths=7.0),
+    Case("slab_flow", "slab_flow", (0, 1), (-2.7, 2.7), 1.0, None,
+         roots_window=(1.25, 2.45), fixture="slab_flow_coronal"),
+]}
+
+# The shipped flow root tables (Example data/flow_width*_coronal.pickle) were produced with
+# U_i0 = 0.35 vA_i - the value in the script's own comment ("#0.35*vA_i  coronal", :51) - not with
+# the 0.9 the script currently assigns: with 0.35 their median mismatch is 0.65 %, with 0.9 it is
+# 110-180 %.
+ROOT_CASES = dict(CASES)
+ROOT_CASES["slab_flow"] = Case("slab_flow_u035", "slab_flow", (0, 1), (-2.7, 2.7), 1.0, None,
+                               family="flow_coronal", U_i0=0.35)
