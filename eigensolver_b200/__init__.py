@@ -7,7 +7,7 @@ ABI of include/eigensolver_b200.h; this package is the thin host side.
 from ._lib import EsbError, LIB_PATH, load  # noqa: F401
 from .solver import (CYLINDER_CORONAL, CYLINDER_PHOTOSPHERIC, SLAB_CORONAL, SLAB_FLOW_CORONAL,  # noqa: F401
                      SLAB_PHOTOSPHERIC, DispersionSolver, FlowMedium, GaussianDensity, GaussianFlow, Medium,
-                     RootTable, bessel_ik_scaled)
+                     PowerLawRotation, RootTable, bessel_ik_scaled)
 from .reference_api import ReferenceScript  # noqa: F401
 
 __version__ = "0.1.0"

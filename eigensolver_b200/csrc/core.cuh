@@ -21,7 +21,7 @@
 
 namespace esb {
 
-enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1, KIND_SLAB_FLOW = 2 };
+enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1, KIND_SLAB_FLOW = 2, KIND_CYL_ROTATION = 3 };
 enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1 };
 enum { OMEGA_SHARED = 0, OMEGA_PHASE_SPEED = 1, OMEGA_PER_K = 2 };
 
@@ -40,6 +40,9 @@ struct DevModel {
     double r_sign;            // cylinder: -1 scripts written in r<0 (coronal), +1 in r>0 (photospheric)
     // slab with a sheared flow U(x): uniform interior c_i, vA_i, rho_i
     double ci2, vAi2, cTi2, si, rho_i, U_e, U_b;
+    // cylinder with rotational flow v_phi(r): uniform rho_i, vA_i (vAi2, rho_i above);
+    // rho v_phi^2 at the boundary enters the kink end condition
+    double rho_vb2;
 };
 
 // ---------------------------------------------------------------- tableau ----
@@ -153,52 +156,81 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
 }
 
 // ------------------------------------------------------------- integrator ----
-// State of NS independent solutions: y[s] = value, yp[s] = derivative.
-// ca/cb hold the coefficients at the step's nodes; node 0 is carried over from the
-// previous step (it is that step's end node).
-template <int NS>
-ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[5],
-                     const double (&cbs)[NS][5]) {
-    // stage -> node: 1:0  2:2 3:2  4:3 5:3  6:2  7:1 8:1  9:2  10:3  11:4
+// One Cooper-Verner step of the linear system (u, v)' = f(node; u, v) for NS independent
+// solutions.  RHS(s, n, U, V, FU, FV) evaluates the right-hand side of solution s at stage node n.
+// stage -> node: 1:0  2:2 3:2  4:3 5:3  6:2  7:1 8:1  9:2  10:3  11:4
+template <int NS, class RHS>
+ESB_HD void rk8_generic(double (&y)[NS], double (&yp)[NS], double h, const RHS& rhs) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const double p = y[s], q = yp[s];
-        const double(&cb)[5] = cbs[s];
-#define ESB_G(P, Q, n) fma(ca[n], (Q), cb[n] * (P))
-        const double Q1 = q, G1 = ESB_G(p, q, 0);
-        const double P2 = fma(h, a21 * Q1, p), Q2 = fma(h, a21 * G1, q), G2 = ESB_G(P2, Q2, 2);
-        const double P3 = fma(h, fma(a32, Q2, a31 * Q1), p), Q3 = fma(h, fma(a32, G2, a31 * G1), q),
-                     G3 = ESB_G(P3, Q3, 2);
-        const double P4 = fma(h, fma(a43, Q3, fma(a42, Q2, a41 * Q1)), p),
-                     Q4 = fma(h, fma(a43, G3, fma(a42, G2, a41 * G1)), q), G4 = ESB_G(P4, Q4, 3);
-        const double P5 = fma(h, fma(a54, Q4, fma(a53, Q3, a51 * Q1)), p),
-                     Q5 = fma(h, fma(a54, G4, fma(a53, G3, a51 * G1)), q), G5 = ESB_G(P5, Q5, 3);
-        const double P6 = fma(h, fma(a65, Q5, fma(a64, Q4, fma(a63, Q3, a61 * Q1))), p),
-                     Q6 = fma(h, fma(a65, G5, fma(a64, G4, fma(a63, G3, a61 * G1))), q),
-                     G6 = ESB_G(P6, Q6, 2);
-        const double P7 = fma(h, fma(a76, Q6, fma(a75, Q5, fma(a74, Q4, fma(a73, Q3, a71 * Q1)))), p),
-                     Q7 = fma(h, fma(a76, G6, fma(a75, G5, fma(a74, G4, fma(a73, G3, a71 * G1)))), q),
-                     G7 = ESB_G(P7, Q7, 1);
-        const double P8 = fma(h, fma(a87, Q7, fma(a86, Q6, fma(a85, Q5, a81 * Q1))), p),
-                     Q8 = fma(h, fma(a87, G7, fma(a86, G6, fma(a85, G5, a81 * G1))), q),
-                     G8 = ESB_G(P8, Q8, 1);
-        const double P9 = fma(h, fma(a98, Q8, fma(a97, Q7, fma(a96, Q6, fma(a95, Q5, a91 * Q1)))), p),
-                     Q9 = fma(h, fma(a98, G8, fma(a97, G7, fma(a96, G6, fma(a95, G5, a91 * G1)))), q),
-                     G9 = ESB_G(P9, Q9, 2);
-        const double P10 = fma(h, fma(a109, Q9, fma(a108, Q8, fma(a107, Q7, fma(a106, Q6,
-                                  fma(a105, Q5, a101 * Q1))))), p),
+        double F1, G1, F2, G2, F3, G3, F4, G4, F5, G5, F6, G6, F7, G7, F8, G8, F9, G9, F10, G10, F11, G11;
+        rhs(s, 0, p, q, F1, G1);
+        const double P2 = fma(h, a21 * F1, p), Q2 = fma(h, a21 * G1, q);
+        rhs(s, 2, P2, Q2, F2, G2);
+        const double P3 = fma(h, fma(a32, F2, a31 * F1), p), Q3 = fma(h, fma(a32, G2, a31 * G1), q);
+        rhs(s, 2, P3, Q3, F3, G3);
+        const double P4 = fma(h, fma(a43, F3, fma(a42, F2, a41 * F1)), p),
+                     Q4 = fma(h, fma(a43, G3, fma(a42, G2, a41 * G1)), q);
+        rhs(s, 3, P4, Q4, F4, G4);
+        const double P5 = fma(h, fma(a54, F4, fma(a53, F3, a51 * F1)), p),
+                     Q5 = fma(h, fma(a54, G4, fma(a53, G3, a51 * G1)), q);
+        rhs(s, 3, P5, Q5, F5, G5);
+        const double P6 = fma(h, fma(a65, F5, fma(a64, F4, fma(a63, F3, a61 * F1))), p),
+                     Q6 = fma(h, fma(a65, G5, fma(a64, G4, fma(a63, G3, a61 * G1))), q);
+        rhs(s, 2, P6, Q6, F6, G6);
+        const double P7 = fma(h, fma(a76, F6, fma(a75, F5, fma(a74, F4, fma(a73, F3, a71 * F1)))), p),
+                     Q7 = fma(h, fma(a76, G6, fma(a75, G5, fma(a74, G4, fma(a73, G3, a71 * G1)))), q);
+        rhs(s, 1, P7, Q7, F7, G7);
+        const double P8 = fma(h, fma(a87, F7, fma(a86, F6, fma(a85, F5, a81 * F1))), p),
+                     Q8 = fma(h, fma(a87, G7, fma(a86, G6, fma(a85, G5, a81 * G1))), q);
+        rhs(s, 1, P8, Q8, F8, G8);
+        const double P9 = fma(h, fma(a98, F8, fma(a97, F7, fma(a96, F6, fma(a95, F5, a91 * F1)))), p),
+                     Q9 = fma(h, fma(a98, G8, fma(a97, G7, fma(a96, G6, fma(a95, G5, a91 * G1)))), q);
+        rhs(s, 2, P9, Q9, F9, G9);
+        const double P10 = fma(h, fma(a109, F9, fma(a108, F8, fma(a107, F7, fma(a106, F6,
+                                  fma(a105, F5, a101 * F1))))), p),
                      Q10 = fma(h, fma(a109, G9, fma(a108, G8, fma(a107, G7, fma(a106, G6,
-                                  fma(a105, G5, a101 * G1))))), q),
-                     G10 = ESB_G(P10, Q10, 3);
-        const double P11 = fma(h, fma(a1110, Q10, fma(a119, Q9, fma(a118, Q8, fma(a117, Q7,
-                                  fma(a116, Q6, a115 * Q5))))), p),
+                                  fma(a105, G5, a101 * G1))))), q);
+        rhs(s, 3, P10, Q10, F10, G10);
+        const double P11 = fma(h, fma(a1110, F10, fma(a119, F9, fma(a118, F8, fma(a117, F7,
+                                  fma(a116, F6, a115 * F5))))), p),
                      Q11 = fma(h, fma(a1110, G10, fma(a119, G9, fma(a118, G8, fma(a117, G7,
-                                  fma(a116, G6, a115 * G5))))), q),
-                     G11 = ESB_G(P11, Q11, 4);
-        y[s] = fma(h, fma(b8_11, Q11, fma(b8_10, Q10, fma(b8_9, Q9, fma(b8_8, Q8, b8_1 * Q1)))), p);
+                                  fma(a116, G6, a115 * G5))))), q);
+        rhs(s, 4, P11, Q11, F11, G11);
+        y[s] = fma(h, fma(b8_11, F11, fma(b8_10, F10, fma(b8_9, F9, fma(b8_8, F8, b8_1 * F1)))), p);
         yp[s] = fma(h, fma(b8_11, G11, fma(b8_10, G10, fma(b8_9, G9, fma(b8_8, G8, b8_1 * G1)))), q);
-#undef ESB_G
     }
+}
+
+// y'' = a y' + b_s y : (u, v) = (y, y'), u' = v, v' = a v + b_s u
+template <int NS>
+struct RhsSecondOrder {
+    const double (&ca)[5];
+    const double (&cbs)[NS][5];
+    ESB_HD void operator()(int s, int n, double U, double V, double& FU, double& FV) const {
+        FU = V;
+        FV = fma(ca[n], V, cbs[s][n] * U);
+    }
+};
+
+// general 2x2 system (rotational-flow cylinder): (u, v)' = [[m11, m12], [m21, m22]] (u, v)
+struct RhsSystem {
+    const double (&m11)[5];
+    const double (&m12)[5];
+    const double (&m21)[5];
+    const double (&m22)[5];
+    ESB_HD void operator()(int, int n, double U, double V, double& FU, double& FV) const {
+        FU = fma(m11[n], U, m12[n] * V);
+        FV = fma(m21[n], U, m22[n] * V);
+    }
+};
+
+template <int NS>
+ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[5],
+                     const double (&cbs)[NS][5]) {
+    const RhsSecondOrder<NS> rhs{ca, cbs};
+    rk8_generic<NS>(y, yp, h, rhs);
 }
 
 template <int NS>
@@ -245,6 +277,64 @@ ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __
         else rk4_step<NS>(y, yp, h, ca, cbs);
         a0 = ca[NN - 1]; b0 = cb[NN - 1]; bm0 = bm[NN - 1];
     }
+}
+
+// ------------------------------------------------- rotational-flow cylinder ----
+// Reference: Twisted_photospheric_nonlinear_flow_kink_fast.py:264-297.  With B_phi = 0, v_z = 0,
+// uniform rho and B:  Om = w - m v_phi/r,  a1 = Om^2 - k^2 vA^2,  A2 = (c^2+vA^2)(Om^2 - w_c^2)
+//   D  = rho a1 A2                      Q = -a1 rho v_phi^2/r          T = rho v_phi Om
+//   C1 = Q Om^2 - 2 m A2 T/r^2          C2 = Om^4 - A2 (m^2/r^2 + k^2)
+//   C3 = D (rho a1 + r d/dr(-rho v_phi^2/r^2)) + Q^2 - 4 A2 T^2/r^2
+// The reference eliminates xi from  D P' = C3 xi - C1 P,  D (r xi)' = C1 r xi - C2 r P  to get
+// P'' = -(F'/F) P' + (g/F) P with F = r D/C3 (sympy-differentiated).  The kernel integrates the
+// first-order pair in (P, xi) directly - the same solutions, no coefficient derivatives:
+//   P'  = -(C1/D) P + (C3/D) xi          xi' = -(C2/D) P + (C1/D - 1/r) xi
+// staged node f = {1/r, v_phi, r d/dr(-rho v_phi^2/r^2), c^2}.
+struct RotCoef { double m11, m12, m21, m22, C1, C3; };
+
+ESB_HD RotCoef node_rot(const DevModel& M, const Point& p, double m, const double* f) {
+    const double invr = f[0], vphi = f[1], f2 = f[2], c2 = f[3];
+    const double Om = fma(-m * vphi, invr, p.w);
+    const double O2 = Om * Om;
+    const double s = c2 + M.vAi2;
+    const double wA2 = p.K * M.vAi2;
+    const double a1 = O2 - wA2;
+    const double A2 = fma(O2, s, -wA2 * c2);             // s (Om^2 - w_c^2), w_c^2 = w_A^2 c^2/s
+    const double Dd = M.rho_i * a1 * A2;
+    const double Q = -a1 * M.rho_i * vphi * vphi * invr;
+    const double T = M.rho_i * vphi * Om;
+    const double invr2 = invr * invr;
+    RotCoef c;
+    c.C1 = fma(Q, O2, -2.0 * m * A2 * T * invr2);
+    const double C2 = fma(O2, O2, -A2 * fma(m * m, invr2, p.K));
+    c.C3 = fma(Dd, fma(M.rho_i, a1, f2), fma(Q, Q, -4.0 * A2 * T * T * invr2));
+    const double invD = 1.0 / Dd;
+    c.m11 = -c.C1 * invD;
+    c.m12 = c.C3 * invD;
+    c.m21 = -C2 * invD;
+    c.m22 = fma(c.C1, invD, -invr);
+    return c;
+}
+
+// two fundamental solutions of the (P, xi) system along the staged mesh; `end` = coefficients
+// at the last node (needed by the sausage end condition)
+ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, const double* __restrict__ tab,
+                               double (&P)[2], double (&X)[2], RotCoef& end) {
+    const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
+    RotCoef c0 = node_rot(M, pt, m, tab);
+    for (int i = 0; i < M.n_steps; ++i) {
+        const double* f = tab + (size_t)(i * 4) * TAB_FIELDS;
+        double m11[5], m12[5], m21[5], m22[5];
+        m11[0] = c0.m11; m12[0] = c0.m12; m21[0] = c0.m21; m22[0] = c0.m22;
+#pragma unroll
+        for (int n = 1; n < 5; ++n) {
+            c0 = node_rot(M, pt, m, f + n * TAB_FIELDS);
+            m11[n] = c0.m11; m12[n] = c0.m12; m21[n] = c0.m21; m22[n] = c0.m22;
+        }
+        const RhsSystem rhs{m11, m12, m21, m22};
+        rk8_generic<2>(P, X, hs[i], rhs);
+    }
+    end = c0;
 }
 
 // --------------------------------------------------------------- exterior ----
@@ -319,7 +409,34 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
         for (int s = 0; s < NM; ++s) { ext_q[s] = nanv; int_q[s] = nanv; }
         return;
     }
-    if (KIND == KIND_CYL_DENSITY) {
+    if constexpr (KIND == KIND_CYL_ROTATION) {
+        int nmax = 0;
+#pragma unroll
+        for (int s = 0; s < NM; ++s) nmax = modes[s] > nmax ? modes[s] : nmax;
+        ExtCyl E;
+        exterior_cyl_prepare(M, k, me, nmax, E);
+        const double xi_e_const = -1.0 / (M.rho_e * (pt.K * M.vAe2 - pt.A));        // :263
+#pragma unroll
+        for (int s = 0; s < NM; ++s) {
+            double Pb, ypb;
+            exterior_cyl_order(M, E, modes[s], Pb, ypb);
+            const double xi_e = xi_e_const * ypb;
+            // fundamental solutions (P, xi) = (1, 0), (0, 1) at the boundary r = s_start
+            double P[2] = {1.0, 0.0}, X[2] = {0.0, 1.0};
+            RotCoef ce;
+            integrate_rotation(M, pt, double(modes[s]), tab, P, X, ce);
+            double xi_b;
+            if (modes[s] == 0) {
+                // sausage: P'(end) = 0  <=>  C3 xi - C1 P = 0 at the end node   (sausage script :306)
+                xi_b = -Pb * fma(ce.C3, X[0], -ce.C1 * P[0]) / fma(ce.C3, X[1], -ce.C1 * P[1]);
+            } else {
+                // kink (:308): P(end) + (B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1) = 0
+                xi_b = (M.rho_vb2 * xi_e - Pb * P[0]) / P[1];
+            }
+            ext_q[s] = xi_e;
+            int_q[s] = xi_b;      // xi_i(1) = (C1 P + D P')/C3 at r = 1   (:314)
+        }
+    } else if constexpr (KIND == KIND_CYL_DENSITY) {
         int nmax = 0;
 #pragma unroll
         for (int s = 0; s < NM; ++s) nmax = modes[s] > nmax ? modes[s] : nmax;

@@ -356,7 +356,16 @@ static double cluster(double t) {   // sin^2(pi t/2): clusters nodes at both end
 static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
     const int N = m->n_steps;
     bp.resize(N + 1);
-    if (m->kind == ESB_CYLINDER_DENSITY) {
+    if (m->kind == ESB_CYLINDER_ROTATION) {
+        // forward, boundary (s_start) -> axis end (s_end): the kink end condition is inhomogeneous
+        for (int i = 0; i <= N; ++i) {
+            const double t = double(i) / N;
+            const double f = m->mesh == 1 ? t : cluster(t);
+            bp[i] = m->s_start + (m->s_end - m->s_start) * f;
+        }
+        bp[0] = m->s_start;
+        bp[N] = m->s_end;
+    } else if (m->kind == ESB_CYLINDER_DENSITY) {
         // from the axis end (s_end) out to the boundary (s_start)
         for (int i = 0; i <= N; ++i) {
             const double t = double(i) / N;
@@ -385,11 +394,11 @@ static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
 
 static int check_model(const esb_model* m) {
     if (!m) return ESB_ERR_ARG;
-    if (m->kind != ESB_SLAB_DENSITY && m->kind != ESB_CYLINDER_DENSITY && m->kind != ESB_SLAB_FLOW)
-        return ESB_ERR_ARG;
+    if (m->kind < ESB_SLAB_DENSITY || m->kind > ESB_CYLINDER_ROTATION) return ESB_ERR_ARG;
+    if (m->kind == ESB_CYLINDER_ROTATION && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->scheme != ESB_RK4 && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->n_steps < 2 || m->n_steps > 8192) return ESB_ERR_ARG;
-    if (m->kind != ESB_CYLINDER_DENSITY && (m->n_steps % 2)) return ESB_ERR_ARG;
+    if ((m->kind == ESB_SLAB_DENSITY || m->kind == ESB_SLAB_FLOW) && (m->n_steps % 2)) return ESB_ERR_ARG;
     return ESB_OK;
 }
 
@@ -424,6 +433,13 @@ extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
         out->ext_ic_slope = 1e-15;
         out->s_end = 1.0;
         out->n_steps = 384;      // c_i = 0.3 vA_i: shorter interior wavelengths than the density slabs
+    } else if (kind == ESB_CYLINDER_ROTATION) {  // Twisted_photospheric_nonlinear_flow_kink_fast.py:73-76,96,302
+        out->vA_i0 = 2.0; out->vA_e = 0.5; out->c_e = 1.5;
+        out->ext_ic_slope = 1e-8;
+        out->r_sign = 1;
+        out->s_start = 1.0;
+        out->s_end = 0.001;
+        out->n_steps = 256;
     } else {
         return ESB_ERR_ARG;
     }
@@ -519,7 +535,7 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
                                     int32_t n_boundary) {
     if (!c) return ESB_ERR_ARG;
     if (check_model(m) || !fields || !boundary) return fail(c, ESB_ERR_ARG, "bad model");
-    const int need_fields = m->kind == ESB_SLAB_FLOW ? 3 : 2;
+    const int need_fields = (m->kind == ESB_SLAB_FLOW || m->kind == ESB_CYLINDER_ROTATION) ? 3 : 2;
     if (n_fields != need_fields || n_boundary < 1) return fail(c, ESB_ERR_ARG, "wrong number of profile fields");
     for (int f = 0; f < n_fields; ++f)
         if (!fields[f]) return fail(c, ESB_ERR_ARG, "null profile field");
@@ -538,6 +554,13 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
             f[1] = 1.0 / (r * r);
             f[2] = fields[0][i];
             f[3] = fields[1][i];
+        } else if (m->kind == ESB_CYLINDER_ROTATION) {
+            // fields = {v_phi, v_phi', c^2};  r d/dr(-rho v_phi^2/r^2) = -2 rho v_phi (r v_phi' - v_phi)/r^2
+            const double r = nodes[i], v = fields[0][i], dv = fields[1][i];
+            f[0] = 1.0 / r;
+            f[1] = v;
+            f[2] = -2.0 * m->rho_i0 * v * (r * dv - v) / (r * r);
+            f[3] = fields[2][i];
         } else {
             for (int q = 0; q < n_fields; ++q) f[q] = fields[q][i];
         }
@@ -570,6 +593,10 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
         d.rho_i = m->rho_i0;
         d.U_e = m->U_e;
         d.U_b = boundary[0];
+    } else if (m->kind == ESB_CYLINDER_ROTATION) {
+        d.vAi2 = m->vA_i0 * m->vA_i0;
+        d.rho_i = m->rho_i0;
+        d.rho_vb2 = m->rho_i0 * boundary[0] * boundary[0];
     } else {
         // c_i^2 = rho_e (c_e^2 + gamma/2 vA_e^2)/rho - gamma/2 vA_i^2   (Density_cylinder.py:210)
         // cylinder: vA_i^2 = B_0^2/rho = vA_i0^2 rho_i0/rho                (Density_cylinder.py:188-200)
@@ -641,7 +668,8 @@ static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
 }
 
 static int check_mode(const esb_context* c, int mode) {
-    if (c->model.kind != ESB_CYLINDER_DENSITY) return (mode == 0 || mode == 1) ? 0 : -1;
+    if (c->model.kind == ESB_SLAB_DENSITY || c->model.kind == ESB_SLAB_FLOW)
+        return (mode == 0 || mode == 1) ? 0 : -1;
     return (mode >= 0 && mode <= ESB_MAX_ORDER) ? 0 : -1;
 }
 
@@ -678,6 +706,9 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
             break;
         case KIND_SLAB_FLOW:
             e = rk8 ? launch_grid<KIND_SLAB_FLOW, SCHEME_RK8>(g, s) : launch_grid<KIND_SLAB_FLOW, SCHEME_RK4>(g, s);
+            break;
+        case KIND_CYL_ROTATION:
+            e = launch_grid<KIND_CYL_ROTATION, SCHEME_RK8>(g, s);
             break;
         default:
             e = rk8 ? launch_grid<KIND_SLAB_DENSITY, SCHEME_RK8>(g, s) : launch_grid<KIND_SLAB_DENSITY, SCHEME_RK4>(g, s);
@@ -877,6 +908,9 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
             case KIND_SLAB_FLOW:
                 e = rk8 ? launch_refine<KIND_SLAB_FLOW, SCHEME_RK8>(r, s)
                         : launch_refine<KIND_SLAB_FLOW, SCHEME_RK4>(r, s);
+                break;
+            case KIND_CYL_ROTATION:
+                e = launch_refine<KIND_CYL_ROTATION, SCHEME_RK8>(r, s);
                 break;
             default:
                 e = rk8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)

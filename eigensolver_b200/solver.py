@@ -115,6 +115,23 @@ class GaussianFlow:
         return medium.U_e + dU0 * g, dU0 * g * t, dU0 * g * (t * t - 2.0 / self.width**2)
 
 
+@dataclasses.dataclass(frozen=True)
+class PowerLawRotation:
+    """v_phi = v_twist r^power with the pressure that balances it,
+    P_i = rho v_twist^2 r^(2 power)/(2 power) + P_0, c_i^2 = gamma P_i/rho
+    (Twisted_photospheric_nonlinear_flow_kink_fast.py:105-111)."""
+    v_twist: float = 0.25
+    power: float = 0.8
+
+    def __call__(self, medium, r):
+        r = np.asarray(r, dtype=np.float64)
+        v = self.v_twist * r**self.power
+        dv = self.v_twist * self.power * r ** (self.power - 1.0)
+        P0 = medium.c_i0**2 * medium.rho_i0 / medium.gamma
+        Pi = medium.rho_i0 * self.v_twist**2 * r ** (2.0 * self.power) / (2.0 * self.power) + P0
+        return v, dv, medium.gamma * Pi / medium.rho_i0
+
+
 @dataclasses.dataclass
 class RootTable:
     """Result of a root search.  `k`, `omega` of accepted modes are what the
@@ -134,7 +151,8 @@ class RootTable:
         return self.k[m], self.omega[m]
 
 
-_KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY, "slab_flow": L.SLAB_FLOW}
+_KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY, "slab_flow": L.SLAB_FLOW,
+          "cylinder_rotation": L.CYLINDER_ROTATION}
 _SCHEMES = {"rk4": L.RK4, "rk8": L.RK8}
 _LAYOUTS = {"shared": L.OMEGA_SHARED, "phase_speed": L.OMEGA_PHASE_SPEED, "per_k": L.OMEGA_PER_K}
 _MODES = {"sausage": 0, "kink": 1, "fluting": 2, "fluting2": 2, "fluting3": 3}
@@ -152,10 +170,12 @@ class DispersionSolver:
     """One GPU context evaluating D(omega,k) for one equilibrium model."""
 
     def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh="clustered",
-                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative"):
-        """kind: "cylinder_density" | "slab_density" | "slab_flow".
+                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None):
+        """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation".
         profile: callable (medium, x) -> (rho, rho') for the density kinds, (U, U', U'') for
-        "slab_flow"; any function may be given (this replaces the reference's sympy profile).
+        "slab_flow", (v_phi, v_phi', c_i^2) for "cylinder_rotation"; any function may be given (this
+        replaces the reference's sympy profile).  s_end: far end of the layer (the rotational sausage
+        script stops at r = 0.01, the kink one at 0.001).
         coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
         layer 1 -> 0.001, exterior slope given as dP/dr)."""
         self.lib = L.load()
@@ -164,11 +184,11 @@ class DispersionSolver:
         L.check(self.lib, None, self.lib.esb_model_defaults(_KINDS[kind], C.byref(m)), "esb_model_defaults")
         if medium is None:
             medium = {"cylinder_density": CYLINDER_CORONAL, "slab_density": SLAB_CORONAL,
-                      "slab_flow": SLAB_FLOW_CORONAL}[kind]
+                      "slab_flow": SLAB_FLOW_CORONAL, "cylinder_rotation": CYLINDER_PHOTOSPHERIC}[kind]
         self.medium = medium
         if profile is None:
             profile = {"cylinder_density": GaussianDensity(0.95), "slab_density": GaussianDensity(0.9),
-                       "slab_flow": GaussianFlow(1e5)}[kind]
+                       "slab_flow": GaussianFlow(1e5), "cylinder_rotation": PowerLawRotation()}[kind]
         self.profile = profile
         if kind == "slab_flow":
             m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
@@ -190,12 +210,14 @@ class DispersionSolver:
             m.ext_ic_slope = 1e-8            # Density_cylinder_photospheric.py: P0 = [1e-8, 1e-8]
         if ext_ic is not None:
             m.ext_ic_value, m.ext_ic_slope = ext_ic
+        if s_end is not None:
+            m.s_end = float(s_end)
         self.model = m
         n = C.c_int32()
         L.check(self.lib, None, self.lib.esb_mesh_size(C.byref(m), C.byref(n)), "esb_mesh_size")
         self.nodes = np.empty(n.value, dtype=np.float64)
         L.check(self.lib, None, self.lib.esb_mesh_nodes(C.byref(m), _dptr(self.nodes)), "esb_mesh_nodes")
-        scale = rho_A if kind != "slab_flow" else 1.0
+        scale = rho_A if kind in ("cylinder_density", "slab_density") else 1.0
         fields = [np.ascontiguousarray(np.asarray(f, dtype=np.float64) * scale)
                   for f in self.profile(medium, self.nodes)]
         boundary = np.array([float(self.profile(medium, np.array([m.s_start]))[0][0]) * scale])

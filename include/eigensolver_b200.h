@@ -51,7 +51,9 @@ enum esb_status {
 enum esb_model_kind {
     ESB_SLAB_DENSITY = 0,     /* slab, rho(x)   : ...Inhomogeneous_method_coronal.py        */
     ESB_CYLINDER_DENSITY = 1, /* cylinder rho(r): Density_cylinder.py                       */
-    ESB_SLAB_FLOW = 2         /* slab, sheared flow U(x): flow_multiprocessor_coronal.py    */
+    ESB_SLAB_FLOW = 2,        /* slab, sheared flow U(x): flow_multiprocessor_coronal.py    */
+    ESB_CYLINDER_ROTATION = 3 /* cylinder, rotational flow v_phi(r): Twisted_photospheric_*.py
+                                 (uniform rho_i0, vA_i0; written in r > 0; RK8 only)         */
 };
 
 /* Fixed-step integrator used across the layer. */
@@ -108,7 +110,8 @@ int esb_set_model(esb_context* ctx, const esb_model* m, const double* rho, const
 
 /* Generic form: fields[f][n_nodes] sampled at esb_mesh_nodes().
  *   density kinds : fields = {rho, rho'},       boundary = {rho(s_start)}
- *   ESB_SLAB_FLOW : fields = {U, U', U''},      boundary = {U(s_start)}                     */
+ *   ESB_SLAB_FLOW : fields = {U, U', U''},      boundary = {U(s_start)}
+ *   ESB_CYLINDER_ROTATION : fields = {v_phi, v_phi', c_i^2}, boundary = {v_phi(s_start)}    */
 int esb_set_model_fields(esb_context* ctx, const esb_model* m, const double* const* fields,
                          int32_t n_fields, int32_t n_nodes, const double* boundary,
                          int32_t n_boundary);

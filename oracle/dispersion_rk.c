@@ -30,7 +30,7 @@
 #include <string.h>
 
 typedef struct {
-    int kind;            /* 0 slab density, 1 cylinder density, 2 slab sheared flow */
+    int kind;            /* 0 slab density, 1 cylinder density, 2 slab sheared flow, 3 cylinder rotation */
     int n_ext;           /* exterior steps */
     int n_int;           /* interior steps */
     int pad;
@@ -42,6 +42,7 @@ typedef struct {
     double U_i0, U_e;    /* kind 2: flow profile U_e + (U_i0-U_e) exp(-(x-x0)^2/width^2); c_i0, vA_i0,
                             rho_i0 are then the uniform interior values */
     double r_sign;       /* cylinder: -1 scripts in r<0 (coronal), +1 scripts in r>0 (photospheric) */
+    double v_twist, power; /* kind 3: v_phi = v_twist r^power (uniform rho_i0, vA_i0; r > 0) */
 } ork_model;
 
 /* ---- Cooper-Verner 8th order tableau, table driven -------------------- */
@@ -188,6 +189,51 @@ static void coef_int_flow(const void* c, double x, double* a, double* b) {
     *b = -coeff;
 }
 
+/* cylinder with rotational flow: Twisted_photospheric_nonlinear_flow_kink_fast.py:264-297.
+ * D, C1, C2, C3 are written as the reference writes them; F = r D/C3 and r C1/C3 are
+ * differentiated numerically (8th-order central differences) where the reference uses sympy. */
+typedef struct { double D, C1, C2, C3; } rot_c;
+static rot_c rot_coeffs(const pt_ctx* p, double r) {
+    const ork_model* m = p->m;
+    const double rho = m->rho_i0, mm = (double)p->mode;
+    const double vphi = m->v_twist * pow(r, m->power);
+    const double P0 = m->c_i0 * m->c_i0 * rho / m->gamma;
+    const double Pi = rho * m->v_twist * m->v_twist * pow(r, 2.0 * m->power) / (2.0 * m->power) + P0;
+    const double c2 = m->gamma * Pi / rho, vA2 = m->vA_i0 * m->vA_i0;
+    const double shift = p->w - mm * vphi / r;
+    const double alf = p->k * sqrt(vA2);
+    const double cusp2 = alf * alf * c2 / (c2 + vA2);
+    const double s2 = shift * shift;
+    rot_c c;
+    c.D = rho * (c2 + vA2) * (s2 - alf * alf) * (s2 - cusp2);
+    const double Q = -(s2 - alf * alf) * rho * vphi * vphi / r;
+    const double T = rho * vphi * shift;
+    c.C1 = Q * s2 - 2.0 * mm * (c2 + vA2) * (s2 - cusp2) * T / (r * r);
+    c.C2 = s2 * s2 - (c2 + vA2) * (mm * mm / (r * r) + p->k * p->k) * (s2 - cusp2);
+    /* C3_diff = -rho (v_phi/r)^2 ; r d/dr C3_diff = -rho v_twist^2 (2 power - 2) r^(2 power - 2) */
+    const double rdC3 = -rho * m->v_twist * m->v_twist * (2.0 * m->power - 2.0) * pow(r, 2.0 * m->power - 2.0);
+    c.C3 = c.D * (rho * (s2 - alf * alf) + rdC3) + (Q * Q - 4.0 * (c2 + vA2) * (s2 - cusp2) * T * T / (r * r));
+    return c;
+}
+static void coef_int_rot(const void* cv, double r, double* a, double* b) {
+    const pt_ctx* p = (const pt_ctx*)cv;
+    static const double w8[4] = {4.0 / 5.0, -1.0 / 5.0, 4.0 / 105.0, -1.0 / 280.0};
+    const double h = 2e-3 * r;
+    double dF = 0.0, dG = 0.0;
+    for (int j = 1; j <= 4; ++j) {
+        const rot_c cp = rot_coeffs(p, r + j * h), cm = rot_coeffs(p, r - j * h);
+        dF += w8[j - 1] * ((r + j * h) * cp.D / cp.C3 - (r - j * h) * cm.D / cm.C3);
+        dG += w8[j - 1] * ((r + j * h) * cp.C1 / cp.C3 - (r - j * h) * cm.C1 / cm.C3);
+    }
+    dF /= h;
+    dG /= h;
+    const rot_c c = rot_coeffs(p, r);
+    const double F = r * c.D / c.C3;
+    const double g = -dG - r * (c.C2 - c.C1 * c.C1 / c.C3) / c.D;
+    *a = -dF / F;                                       /* dP_dr_i  (:304) */
+    *b = g / F;
+}
+
 static double cluster(double t) {
     const double s = sin(0.5 * M_PI * t);
     return s * s;
@@ -211,9 +257,9 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
     /* exterior */
     double y[2], yp[2];
     y[0] = m->ic_v; yp[0] = m->ic_s;
-    const double rs = (m->kind == 1 && m->r_sign > 0) ? 1.0 : -1.0;
+    const double rs = (m->kind == 3 || (m->kind == 1 && m->r_sign > 0)) ? 1.0 : -1.0;
     const double x0 = rs * m->ext_wavelengths * 2.0 * M_PI / k;
-    if (m->kind != 1) {
+    if (m->kind == 0 || m->kind == 2) {
         const double h = (-1.0 - x0) / m->n_ext;
         for (int i = 0; i < m->n_ext; ++i) rk8_step(coef_ext_slab, &p, x0 + i * h, h, 1, y, yp);
     } else {
@@ -228,11 +274,25 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
     }
     const double yb = y[0], ypb = yp[0];
     double rho = 0, drho = 0, c2 = 0, dc2 = 0, vA2 = 0, dvA2 = 0;
-    if (m->kind != 2) profile(&p, m->s_start, &rho, &drho, &c2, &dc2, &vA2, &dvA2);
+    if (m->kind < 2) profile(&p, m->s_start, &rho, &drho, &c2, &dc2, &vA2, &dvA2);
     /* interior: two fundamental solutions forward from the boundary */
     double Y[2] = {1.0, 0.0}, Yp[2] = {0.0, 1.0};
     const int N = m->n_int;
-    if (m->kind != 1) {
+    if (m->kind == 3) {
+        double x = m->s_start;
+        for (int i = 1; i <= N; ++i) {
+            const double xn = (i == N) ? m->s_end : m->s_start + (m->s_end - m->s_start) * cluster((double)i / N);
+            rk8_step(coef_int_rot, &p, x, xn - x, 2, Y, Yp);
+            x = xn;
+        }
+        const double xi_e = -ypb / (p.rho_e * (p.K * vAe2 - p.A));
+        /* sausage: P'(end) = 0 ; kink: P(end) + (0 - rho v_phi(1)^2) xi_e = 0   (:308) */
+        const double rv2 = m->rho_i0 * m->v_twist * m->v_twist;
+        const double slope = (mode == 0) ? -yb * Yp[0] / Yp[1] : (rv2 * xi_e - yb * Y[0]) / Y[1];
+        const rot_c cb = rot_coeffs(&p, m->s_start);
+        *ext_q = xi_e;
+        *int_q = (cb.C1 * yb + cb.D * slope) / cb.C3;       /* inside_xi_solution[0]  (:314) */
+    } else if (m->kind != 1) {
         const coef_fn cf = (m->kind == 2) ? coef_int_flow : coef_int_slab;
         const int H = N / 2;
         const double mid = 0.5 * (m->s_start + m->s_end);

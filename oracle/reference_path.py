@@ -398,6 +398,87 @@ class SlabFlow(_Base):
         return P_Ti * slope
 
 
+class CylinderRotation(_Base):
+    """Cylinder with a rotational (twisted) flow v_phi = v_twist r^power, reference
+    Cylinder/Rotational flow/Photospheric/Solvers/Twisted_photospheric_nonlinear_flow_kink_fast.py
+    (kink: scan loop :259-336) and Twisted_photospheric_flow_sausage.py (sausage).
+
+    Like the reference, the coefficients F, dF/dr and g of the interior ODE are built with sympy
+    from D, Q, T, C1, C2, C3 (:264-297) and differentiated symbolically; unlike the reference they
+    are lambdified ONCE with (r, omega, k) as arguments instead of once per (k, omega)."""
+    geometry = "cylinder"
+    ext_ic = (1e-8, 1e-8)          # :302  P0 = [1e-8, 1e-8]
+    s0 = 1.0                       # :96   ix = linspace(1., 0.001, 2e3)   (sausage script: 0.01)
+    slope_guess = 0.001            # :311  fsolve(objective_dPi, 0.001)
+    boundary = 1.0
+    n_int_out = 2000
+
+    def __init__(self, medium: Medium, m: int, v_twist=0.25, power=0.8, s_end=None):
+        import sympy as sym
+        self.medium = medium
+        self.m = int(m)
+        self.v_twist, self.power = float(v_twist), float(power)
+        self.s1 = s_end if s_end is not None else (0.01 if self.m == 0 else 0.001)
+        self.mode = {0: "sausage", 1: "kink"}.get(self.m, "fluting%d" % self.m)
+        md = medium
+        r, w, k = sym.symbols("r w k", positive=True)
+        mm = sym.Integer(self.m)
+        rho = sym.Float(md.rho_i0)
+        B0 = sym.Float(md.B_0)
+        P0 = sym.Float(md.c_i0**2 * md.rho_i0 / md.gamma)
+        vphi = sym.Float(self.v_twist) * r ** sym.Float(self.power)                     # :107
+        P_i = rho * sym.Float(self.v_twist) ** 2 * (r ** (2 * sym.Float(self.power)) /
+                                                    (2 * sym.Float(self.power))) + P0    # :109
+        c2 = P_i * sym.Float(md.gamma) / rho                                              # :111
+        vA2 = B0**2 / rho
+        shift = w - mm * vphi / r                                                         # :264 (v_z = 0)
+        alf = k * B0 / sym.sqrt(rho)                                                      # :266 (B_phi = 0)
+        cusp2 = alf**2 * c2 / (c2 + vA2)
+        D = rho * (c2 + vA2) * (shift**2 - alf**2) * (shift**2 - cusp2)                   # :270
+        Q = -(shift**2 - alf**2) * rho * vphi**2 / r                                      # :273
+        T = rho * vphi * shift                                                            # :275
+        C1 = Q * shift**2 - 2 * mm * (c2 + vA2) * (shift**2 - cusp2) * T / r**2           # :277
+        C2 = shift**4 - (c2 + vA2) * (mm**2 / r**2 + k**2) * (shift**2 - cusp2)           # :280
+        C3_diff = -rho * (vphi / r) ** 2                                                  # :283
+        C3 = D * (rho * (shift**2 - alf**2) + r * sym.diff(C3_diff, r)) + (
+            Q**2 - 4 * (c2 + vA2) * (shift**2 - cusp2) * T**2 / r**2)                     # :285
+        F = r * D / C3                                                                    # :288
+        dF = sym.diff(F, r)                                                               # :291
+        g = -sym.diff(r * C1 / C3, r) - r * (C2 - C1**2 / C3) / D                         # :294
+        self._a = sym.lambdify((r, w, k), -dF / F, "numpy", cse=True)
+        self._b = sym.lambdify((r, w, k), g / F, "numpy", cse=True)
+        self._xi = sym.lambdify((r, w, k), (C1 / C3, D / C3), "numpy", cse=True)
+        self._rho_v2_b = md.rho_i0 * self.v_twist**2          # rho(1) v_phi(1)^2
+
+    def ext_rhs(self, k, w):
+        m_e = self.medium.m_e(k, w)
+        mm = float(self.m * self.m)
+        return lambda y, r: [y[1], -y[1] / r + (m_e + mm / (r * r)) * y[0]]               # :300
+
+    def ext_match(self, k, w, y_b):
+        md = self.medium
+        xi_e_const = -1.0 / (md.rho_e * (k * k * md.vA_e**2 - w * w))                     # :263
+        self._xi_e = xi_e_const * y_b[1]
+        return y_b[0], self._xi_e
+
+    def coeffs(self, r, k, w):
+        # LSODA may step past the last output point, i.e. to r <= 0; numpy semantics (nan) there,
+        # not Python's complex power
+        r = np.float64(r)
+        return self._a(r, w, k), self._b(r, w, k)
+
+    def end_residual(self, y_end, y_start0):
+        if self.m == 0:
+            return y_end[1]                                   # sausage: P'(axis) = 0
+        # kink (:308): U[:,0][-1] + (B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1);  the xi_e term belongs
+        # to the inhomogeneous part (it is passed with the start value, see dispersion())
+        return y_end[0] - (self._rho_v2_b * self._xi_e if y_start0 != 0.0 else 0.0)
+
+    def int_match(self, k, w, y0, slope):
+        c1, d = self._xi(self.s0, w, k)
+        return c1 * y0 + d * slope                            # (C1 P + D P')/C3 at r = 1  (:314)
+
+
 # --------------------------------------------------------------------------
 # the dispersion function
 # --------------------------------------------------------------------------

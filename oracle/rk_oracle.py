@@ -20,7 +20,8 @@ class ork_model(C.Structure):
                 ("gamma", C.c_double), ("rho_i0", C.c_double), ("rho_A", C.c_double),
                 ("width", C.c_double), ("x0", C.c_double), ("ic_v", C.c_double), ("ic_s", C.c_double),
                 ("ext_wavelengths", C.c_double), ("s_start", C.c_double), ("s_end", C.c_double),
-                ("U_i0", C.c_double), ("U_e", C.c_double), ("r_sign", C.c_double)]
+                ("U_i0", C.c_double), ("U_e", C.c_double), ("r_sign", C.c_double),
+                ("v_twist", C.c_double), ("power", C.c_double)]
 
 
 def build():
@@ -48,14 +49,29 @@ def lib():
 
 
 def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rho_A=1.0,
-               coordinate="negative", ext_wavelengths=3.0):
+               coordinate="negative", ext_wavelengths=3.0, v_twist=0.25, power=0.8, s_end=None):
     """kind: 'slab_density' | 'cylinder_density' | 'slab_flow'; medium: any object with c_i0, vA_i0,
     vA_e, c_e, gamma, rho_i0 attributes (flow: vA_i, c_i, vA_e, c_e, U_i0, U_e, gamma, rho_i);
     defaults: the reference's coronal sets.  coordinate='positive': cylinder scripts in r > 0."""
     m = ork_model()
     cyl = kind == "cylinder_density"
-    m.kind = {"slab_density": 0, "cylinder_density": 1, "slab_flow": 2}[kind]
+    m.kind = {"slab_density": 0, "cylinder_density": 1, "slab_flow": 2, "cylinder_rotation": 3}[kind]
     m.r_sign = -1.0
+    if kind == "cylinder_rotation":
+        # Twisted_photospheric_nonlinear_flow_kink_fast.py:73-76 (photospheric speeds), r > 0
+        md = medium
+        vals = (md.c_i0, md.vA_i0, md.vA_e, md.c_e, md.gamma, md.rho_i0) if md is not None else (
+            1.0, 2.0, 0.5, 1.5, 5.0 / 3.0, 1.0)
+        m.c_i0, m.vA_i0, m.vA_e, m.c_e, m.gamma, m.rho_i0 = vals
+        m.rho_A, m.width, m.x0 = 1.0, 1.0, 0.0
+        m.ic_v, m.ic_s = 1e-8, 1e-8
+        m.ext_wavelengths = ext_wavelengths
+        m.r_sign, m.s_start = 1.0, 1.0
+        m.s_end = s_end if s_end is not None else 0.001
+        m.v_twist, m.power = v_twist, power
+        m.n_ext = n_ext or 6000
+        m.n_int = n_int or 320
+        return m
     if kind == "slab_flow":
         vals = medium if medium is not None else type("M", (), dict(
             vA_i=1.0, c_i=0.3, vA_e=2.5, c_e=0.2, U_i0=0.9, U_e=0.0, gamma=5.0 / 3.0, rho_i=1.0))

@@ -12,11 +12,10 @@ names = sys.argv[1:] or list(CASES)
 for name in names:
     case = CASES[name]
     k = np.linspace(0.05, 4.5, 20); W = np.linspace(case.W[0], case.W[1], 240)
-    reg = regular_mask(W, case.intervals(), 0.02)
     model = case.c_model()
     for mode in case.modes:
         e0, i0 = ork.grid(model, mode, k, W)
-        ok = reg[None, :] & ~np.isnan(e0)
+        ok = case.regular(k, W, mode) & ~np.isnan(e0)
         for n in (128, 192, 256, 384, 512):
             with case.gpu_solver(esb, n_steps=n) as s:
                 e, i = s.dispersion_grid(mode, k, W)

@@ -49,6 +49,13 @@ POINTS.update({
     "slab_flow_coronal": dict(
         ks=[0.1, 0.6, 1.5, 3.0, 4.5], Ws=[1.3, 1.6, 2.0, 2.4, -0.3, -1.0, -2.0, -0.1, 2.6, 0.1995],
         overrides={"dx": 1.0}),
+    # rotational flow in its regular regime (power >= 1); the kink script is run with the sausage
+    # script's v_twist/power instead of its own (0.25, 0.8), see tests/helpers.py
+    "cylinder_rotation_sausage": dict(
+        ks=[0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.55, 0.8, 0.97, 1.1, 1.2, 1.3, 1.45, 0.49, 1.6], overrides={}),
+    "cylinder_rotation_kink": dict(
+        ks=[0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.55, 0.8, 0.97, 1.1, 1.2, 1.3, 1.45, 0.49, 1.6],
+        overrides={"v_twist": 0.15, "power": 1.25}),
 })
 
 SCANS = {
@@ -83,6 +90,8 @@ def main():
         ref = ReferenceSolver(name, overrides=spec.get("overrides"))
         rows = []
         for mode_id, mode in ((0, "sausage"), (1, "kink")):
+            if mode not in ref.modes:
+                continue
             for k in spec["ks"]:
                 for W in spec["Ws"]:
                     rows.append((mode_id, k, W * k, ref.D(mode, k, W * k)))
@@ -116,6 +125,15 @@ def main():
             roots[key + "_sausage_k"] = np.asarray(sk, dtype=np.float64)
             roots[key + "_kink_w"] = np.asarray(kw, dtype=np.float64)
             roots[key + "_kink_k"] = np.asarray(kk, dtype=np.float64)
+    # rotational flow: [omega, k] per file; regular regime (power >= 1) only
+    rot = "Cylinder/Rotational flow/Photospheric/Example data/Cylindrical_photospheric_vtwist%s_power%s_%s.pickle"
+    for vt, pw, kind in (("01", "1", "sausage_fast"), ("01", "125", "sausage_fast"), ("015", "1", "sausage_fast"),
+                         ("01", "1", "fund_kink"), ("01", "125", "fund_kink"), ("015", "1", "fund_kink")):
+        with open(os.path.join(REF_ROOT, rot % (vt, pw, kind)), "rb") as fh:
+            w, k = pickle.load(fh, encoding="latin1")
+        key = "rot_v%s_p%s_%s" % (vt, pw, "sausage" if "sausage" in kind else "kink")
+        roots[key + "_w"] = np.real(np.asarray(w)).astype(np.float64)
+        roots[key + "_k"] = np.real(np.asarray(k)).astype(np.float64)
     np.savez(os.path.join(HERE, "ref_roots.npz"), **roots)
     print("ref_roots.npz:", len(roots) // 5, "tables")
 

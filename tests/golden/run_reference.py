@@ -55,6 +55,16 @@ SOLVERS = {
         "wavenumber = np.linspace(",
         {"sausage": ("sausage", "P_diff_check"), "kink": ("kink", "P_diff_check_kink")},
     ),
+    "cylinder_rotation_kink": (
+        "Cylinder/Rotational flow/Photospheric/Solvers/Twisted_photospheric_nonlinear_flow_kink_fast.py",
+        "wavenumber = np.linspace(0.25,0.37,20)",
+        {"kink": ("kink", "xi_diff_check")},
+    ),
+    "cylinder_rotation_sausage": (
+        "Cylinder/Rotational flow/Photospheric/Solvers/Twisted_photospheric_flow_sausage.py",
+        "wavenumber = np.linspace(0.75,4.,110.)",
+        {"sausage": ("sausage", "xi_diff_check")},
+    ),
     "slab_flow_coronal": (
         "Slab/Non uniform flow/Solver/flow_multiprocessor_coronal.py",
         "wavenumber = np.linspace(",
@@ -158,6 +168,16 @@ class ReferenceSolver:
         with _legacy_linspace(max_interior), _legacy_odeint(), open(os.devnull, "w") as dn, \
                 contextlib.redirect_stdout(dn):
             exec(compile(src, path, "exec"), self.ns)
+        if "odeintz" in self.ns:
+            # the rotational-flow scripts wrap odeint for complex values (odeintz, :51-72) and
+            # build np.array([P_b, dPi]) themselves: same ragged-y0 coercion as _legacy_odeint
+            orig_z = self.ns["odeintz"]
+
+            def odeintz(func, z0, t, **kw):
+                z0 = [complex(np.asarray(v).reshape(-1)[0]) for v in z0]
+                return orig_z(func, z0, t, **kw)
+
+            self.ns["odeintz"] = odeintz
 
     def D(self, mode, k, w):
         """One evaluation of the reference dispersion function at (k, w).
@@ -171,6 +191,7 @@ class ReferenceSolver:
         if len(store) == n0:
             return float("nan")
         val = store[n0]
+        val = complex(val).real if abs(complex(val).imag) == 0.0 else complex(val)
         # keep the running lists short so memory stays flat
         del store[1:]
         for g in ("sign_check", "sign_check_kink", "sign_check_sausage", "all_ws", "all_ks",

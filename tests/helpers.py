@@ -41,13 +41,53 @@ def slab_profile(width=0.9, medium=rp.SLAB_CORONAL):
     return rp.GaussianDensity(medium, width=width)
 
 
+def rotation_continua(md, v_twist, power, s_end, m, k):
+    """Rotational-flow cylinder: Om(r) = w - m v_phi/r resonates where Om^2 = k^2 vA^2, k^2 cT(r)^2
+    or Om = 0.  In phase speed W = w/k the bands depend on k (the Doppler shift does not scale)."""
+    r = np.geomspace(s_end, 1.0, 4001)
+    shift = m * v_twist * r ** (power - 1.0) / k
+    P0 = md.c_i0**2 * md.rho_i0 / md.gamma
+    c2 = md.gamma * (md.rho_i0 * v_twist**2 * r ** (2 * power) / (2 * power) + P0) / md.rho_i0
+    vA2 = md.vA_i0**2
+    cT = np.sqrt(c2 * vA2 / (c2 + vA2))
+    iv = []
+    for d in (0.0 * cT, cT, -cT, 0 * cT + np.sqrt(vA2), 0 * cT - np.sqrt(vA2)):
+        iv.append(((shift + d).min(), (shift + d).max()))
+    return iv
+
+
+def rotation_regular(md, v_twist, power, s_end, m, k, W):
+    """True where neither D nor C3 changes sign inside the layer.  D = 0 is a genuine resonance.
+    C3 = 0 is a singular point of the reference's SECOND-order form only (F = r D/C3 -> infinity:
+    an apparent singularity, the (P, xi) system the GPU integrates is regular there); odeint and
+    the C oracle both integrate the second-order form and return noise at such points."""
+    r = np.geomspace(s_end, 1.0, 600)[None, :]
+    w = (np.asarray(W) * k)[:, None]
+    rho, vA2 = md.rho_i0, md.vA_i0**2
+    vphi = v_twist * r**power
+    P0 = md.c_i0**2 * rho / md.gamma
+    c2 = md.gamma * (rho * v_twist**2 * r ** (2 * power) / (2 * power) + P0) / rho
+    Om = w - m * vphi / r
+    a1 = Om**2 - k * k * vA2
+    A2 = Om**2 * (c2 + vA2) - k * k * vA2 * c2
+    D = rho * a1 * A2
+    Q = -a1 * rho * vphi**2 / r
+    T = rho * vphi * Om
+    f2 = -rho * v_twist**2 * (2 * power - 2) * r ** (2 * power - 2)
+    C3 = D * (rho * a1 + f2) + Q**2 - 4 * A2 * T**2 / r**2
+    same = lambda x: (np.sign(x).min(axis=1) == np.sign(x).max(axis=1)) & (np.abs(x).min(axis=1) > 0)
+    return same(D) & same(C3)
+
+
 class Case:
     """One solver variant: how to build the GPU solver, both oracles and the regular mask."""
 
     def __init__(self, name, kind, modes, W, width, medium_name=None, coordinate="negative",
-                 roots_window=None, fixture=None, family=None, ext_wavelengths=3.0, U_i0=0.9):
+                 roots_window=None, fixture=None, family=None, ext_wavelengths=3.0, U_i0=0.9,
+                 v_twist=0.15, power=1.25, s_end=None):
         self.ext_wavelengths = ext_wavelengths
         self.U_i0 = U_i0
+        self.v_twist, self.power, self.s_end = v_twist, power, s_end
         self.name, self.kind, self.modes, self.W, self.width = name, kind, modes, W, width
         self.medium_name, self.coordinate = medium_name, coordinate
         self.roots_window = roots_window
@@ -62,6 +102,12 @@ class Case:
 
     def scipy_model(self, mode, width=None, fast=True):
         w = self.width if width is None else width
+        if self.kind == "cylinder_rotation":
+            key = (mode,)
+            cache = self.__dict__.setdefault("_rot_cache", {})
+            if key not in cache:       # sympy set-up once per mode
+                cache[key] = rp.CylinderRotation(self.rp_medium(), mode, self.v_twist, self.power, self.s_end)
+            return cache[key]
         if self.kind == "cylinder_density":
             return rp.CylinderDensity(cyl_profile(w, self.rp_medium()), mode, coordinate=self.coordinate)
         if self.kind == "slab_density":
@@ -73,6 +119,9 @@ class Case:
 
     def c_model(self, width=None, **kw):
         w = self.width if width is None else width
+        if self.kind == "cylinder_rotation":
+            return ork.make_model("cylinder_rotation", medium=self.rp_medium(), v_twist=self.v_twist,
+                                  power=self.power, s_end=self.s_end, **kw)
         if self.kind == "slab_flow":
             return ork.make_model("slab_flow", medium=rp.FlowMedium(width=w, U_i0=self.U_i0), width=w, **kw)
         return ork.make_model(self.kind, medium=self.rp_medium(), width=w, coordinate=self.coordinate,
@@ -87,9 +136,30 @@ class Case:
             return continua(cyl_profile(w, self.rp_medium()), s0, s1, False)
         return continua(slab_profile(w, self.rp_medium()), -1.0, 1.0, True)
 
+    def regular(self, k, W, mode, margin=0.02, width=None):
+        """2-D mask [nk, nw]: True where no resonance sits inside the layer (above the noise floor)."""
+        k = np.atleast_1d(k)
+        if self.kind == "cylinder_rotation":
+            W = np.atleast_1d(W)
+            out = []
+            for kk in k:
+                a = regular_mask(W, rotation_continua(self.rp_medium(), self.v_twist, self.power,
+                                                      self.s_end or 0.001, mode, kk), margin)
+                # also at W +- margin, so that points next to a sign change are excluded too
+                for dW in (-margin, 0.0, margin):
+                    a &= rotation_regular(self.rp_medium(), self.v_twist, self.power, self.s_end or 0.001,
+                                          mode, kk, W + dW)
+                out.append(a)
+            return np.array(out)
+        return np.broadcast_to(regular_mask(W, self.intervals(width), margin), (k.size, np.size(W))).copy()
+
     # ---- GPU solver
     def gpu_solver(self, esb, width=None, **kw):
         w = self.width if width is None else width
+        if self.kind == "cylinder_rotation":
+            return esb.DispersionSolver("cylinder_rotation", medium=esb.CYLINDER_PHOTOSPHERIC,
+                                        profile=esb.PowerLawRotation(self.v_twist, self.power),
+                                        s_end=self.s_end, **kw)
         if self.kind == "slab_flow":
             return esb.DispersionSolver("slab_flow", medium=esb.FlowMedium(U_i0=self.U_i0),
                                         profile=esb.GaussianFlow(w), **kw)
@@ -112,12 +182,17 @@ CASES = {c.name: c for c in [
          ext_wavelengths=7.0),
     Case("slab_flow", "slab_flow", (0, 1), (-2.7, 2.7), 1.0, None,
          roots_window=(1.25, 2.45), fixture="slab_flow_coronal"),
+    # rotational flow: the regular regime (power >= 1: the Doppler shift m v_phi/r stays bounded at
+    # the axis).  The kink script's own default (v_twist 0.25, power 0.8) puts a cusp resonance at
+    # r ~ 0.007 for every (k, omega) it scans: there the reference's output is solver noise.
+    Case("cylinder_rotation", "cylinder_rotation", (0, 1, 2), (0.40, 1.6), None, "CYL_PHOTOSPHERIC",
+         roots_window=(0.9, 1.49), v_twist=0.15, power=1.25, s_end=0.01),
 ]}
 
 # The shipped flow root tables (Example data/flow_width*_coronal.pickle) were produced with
 # U_i0 = 0.35 vA_i - the value in the script's own comment ("#0.35*vA_i  coronal", :51) - not with
 # the 0.9 the script currently assigns: with 0.35 their median mismatch is 0.65 %, with 0.9 it is
 # 110-180 %.
-ROOT_CASES = dict(CASES)
+ROOT_CASES = {n: c for n, c in CASES.items() if c.family}
 ROOT_CASES["slab_flow"] = Case("slab_flow_u035", "slab_flow", (0, 1), (-2.7, 2.7), 1.0, None,
                                family="flow_coronal", U_i0=0.35)
