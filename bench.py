@@ -149,7 +149,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     import eigensolver_b200 as esb
-    from eigensolver_b200.distributed import gather_root_tables
+    from eigensolver_b200.distributed import gather_root_tables, gather_root_tables_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,11 +193,10 @@ def run_gpu_arm(args):
         """axes resident in HBM; root tables stay on the device until the gather."""
         ns = solver.sweep_resident_multi(MODES)
         kms = [solver.last_kernel_ms()]
-        tables = ns
-        if world > 1:
-            tables = [solver.download_roots(n, slot) for slot, n in enumerate(ns)]
-            gather(tables)
-        return kms, tables
+        if world > 1:       # NCCL gather of the root tables straight from the device buffers
+            for slot in range(len(MODES)):
+                gather_root_tables_device(solver, slot, rank * NK, dev)
+        return kms, ns
 
     def step_e2e():
         """public host API: pinned k/omega in, root tables (host) out, every mode."""

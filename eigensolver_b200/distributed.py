@@ -52,3 +52,40 @@ def gather_root_tables(k_index, omega, accepted, k_offset, device=None, group=No
     parts = [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
     allp = np.concatenate(parts, axis=0) if parts else np.zeros((0, 3))
     return allp[:, 0].astype(np.int64), allp[:, 1].copy(), allp[:, 2].astype(np.int32)
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def gather_root_tables_device(solver, slot, k_offset, device, group=None):
+    """All-gather the root table of mode slot `slot` straight from the solver's device buffers
+    (no host round trip): NCCL over NVLink moves (global k index, omega, accepted) of every rank.
+    Returns a float64 tensor [total, 3] on `device`, ordered by rank = sorted by global k index."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    info = solver.roots_device(slot)
+    n = info["n"]
+    cnt = torch.tensor([n], dtype=torch.int64, device=device)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts = counts.tolist()
+    cap = max(max(counts), 1)
+    pay = torch.zeros((cap, 3), dtype=torch.float64, device=device)
+    if n:
+        ki = torch.as_tensor(_DevArray(info["k_index"][0], n, "<i4"), device=device)
+        om = torch.as_tensor(_DevArray(info["omega"][0], n, "<f8"), device=device)
+        ac = torch.as_tensor(_DevArray(info["accepted"][0], n, "<i4"), device=device)
+        pay[:n, 0] = ki.to(torch.float64) + float(k_offset)
+        pay[:n, 1] = om
+        pay[:n, 2] = ac.to(torch.float64)
+    out = torch.empty((world * cap, 3), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, pay, group=group)
+    parts = [out[r * cap: r * cap + c] for r, c in enumerate(counts)]
+    return torch.cat(parts, dim=0)

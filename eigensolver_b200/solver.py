@@ -357,6 +357,18 @@ class DispersionSolver:
                 "esb_download_roots_slot")
         return RootTable(ki, wi, self._k_host[ki], om, ex, iq, ac, it, n)
 
+    def roots_device(self, slot=0):
+        """Device pointers of the root table of mode slot `slot` (valid until the next sweep):
+        dict name -> (pointer, numpy dtype string), plus 'n'.  Used for device-side gathers."""
+        out = L.esb_roots()
+        n = C.c_int32(0)
+        L.check(self.lib, self.ctx, self.lib.esb_roots_device(self.ctx, int(slot), C.byref(out), C.byref(n)),
+                "esb_roots_device")
+        addr = lambda p: C.cast(p, C.c_void_p).value or 0
+        return {"n": n.value, "k_index": (addr(out.k_index), "<i4"), "w_index": (addr(out.w_index), "<i4"),
+                "omega": (addr(out.omega), "<f8"), "ext": (addr(out.ext), "<f8"), "intq": (addr(out.intq), "<f8"),
+                "accepted": (addr(out.accepted), "<i4"), "iterations": (addr(out.iterations), "<i4")}
+
     def set_stream(self, stream_ptr):
         """Run this context on an external cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
         L.check(self.lib, self.ctx, self.lib.esb_set_stream(self.ctx, C.c_void_p(int(stream_ptr))),

@@ -318,3 +318,33 @@ def test_full_size_properties(solvers):
     hi_half = s.find_roots(1, k[500:], W)
     assert np.array_equal(np.concatenate([lo_half.omega, hi_half.omega]), tab.omega)
     assert np.array_equal(np.concatenate([lo_half.k_index, hi_half.k_index + 500]), tab.k_index)
+
+
+def test_device_side_gather_equals_host_table(solvers):
+    """The NCCL gather used by the multi-GPU bench reads the root table straight from the
+    library's device buffers; with one rank it must reproduce the host-side table."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from eigensolver_b200.distributed import gather_root_tables_device
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", 0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        s = solvers["cylinder_density"]
+        k = np.linspace(0.5, 4.0, 33); W = np.linspace(2.95, 4.95, 257)
+        s.upload_axes(k, W)
+        ns = s.sweep_resident_multi([0, 1])
+        for slot, n in enumerate(ns):
+            host = s.download_roots(n, slot)
+            g = gather_root_tables_device(s, slot, 1000, dev).cpu().numpy()
+            assert g.shape == (n, 3)
+            assert np.array_equal(g[:, 0], host.k_index + 1000.0)
+            assert np.array_equal(g[:, 1], host.omega)
+            assert np.array_equal(g[:, 2], host.accepted.astype(np.float64))
+    finally:
+        dist.destroy_process_group()
