@@ -213,24 +213,45 @@ class DispersionSolver:
         if s_end is not None:
             m.s_end = float(s_end)
         self.model = m
+        self._rho_A = rho_A
         n = C.c_int32()
         L.check(self.lib, None, self.lib.esb_mesh_size(C.byref(m), C.byref(n)), "esb_mesh_size")
         self.nodes = np.empty(n.value, dtype=np.float64)
         L.check(self.lib, None, self.lib.esb_mesh_nodes(C.byref(m), _dptr(self.nodes)), "esb_mesh_nodes")
-        scale = rho_A if kind in ("cylinder_density", "slab_density") else 1.0
-        fields = [np.ascontiguousarray(np.asarray(f, dtype=np.float64) * scale)
-                  for f in self.profile(medium, self.nodes)]
-        boundary = np.array([float(self.profile(medium, np.array([m.s_start]))[0][0]) * scale])
         self.ctx = L._ctx()
         rc = self.lib.esb_create(int(device), C.byref(self.ctx))
         if rc != L.ESB_OK:
             self.ctx = None
             raise L.EsbError("esb_create failed (status %d): no usable CUDA device %d; "
                              "eigensolver_b200 has no CPU fallback" % (rc, device))
+        self._upload_model()
+
+    def _upload_model(self):
+        m, medium, kind = self.model, self.medium, self.kind
+        scale = self._rho_A if kind in ("cylinder_density", "slab_density") else 1.0
+        fields = [np.ascontiguousarray(np.asarray(f, dtype=np.float64) * scale)
+                  for f in self.profile(medium, self.nodes)]
+        boundary = np.array([float(self.profile(medium, np.array([m.s_start]))[0][0]) * scale])
         fptr = (C.POINTER(C.c_double) * len(fields))(*[_dptr(f) for f in fields])
         L.check(self.lib, self.ctx,
-                self.lib.esb_set_model_fields(self.ctx, C.byref(m), fptr, len(fields), n.value, _dptr(boundary),
-                                              boundary.size), "esb_set_model_fields")
+                self.lib.esb_set_model_fields(self.ctx, C.byref(m), fptr, len(fields), self.nodes.size,
+                                              _dptr(boundary), boundary.size), "esb_set_model_fields")
+
+    def reconfigure(self, medium=None, profile=None):
+        """Swap the equilibrium (speeds and/or profile) on the same context and mesh: one small
+        table upload, no reallocation.  This is what a parameter scan does between sweeps."""
+        m = self.model
+        if medium is not None:
+            self.medium = medium
+            if self.kind == "slab_flow":
+                m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
+                m.gamma, m.rho_i0, m.U_e = medium.gamma, medium.rho_i, medium.U_e
+            else:
+                m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
+                m.gamma, m.rho_i0 = medium.gamma, medium.rho_i0
+        if profile is not None:
+            self.profile = profile
+        self._upload_model()
 
     # ------------------------------------------------------------------
     def close(self):
