@@ -55,7 +55,7 @@ __device__ __forceinline__ void stage_table(const double* __restrict__ g, double
 // NM modes are evaluated per thread, sharing the staged coefficients (cylinder) or the whole
 // integration (slab); outputs are mode-slot major.
 template <int KIND, int SCHEME, int NM>
-__global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
+__global__ void __launch_bounds__(128, 5) grid_kernel(GridArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,25 +158,32 @@ __global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ of
 }
 
 // ---- refinement ----
+struct RefineSlot {
+    const double* gext;     // D grid of the scan (end-point values of every bracket)
+    const double* gint;
+    const int* bk;
+    const int* bw;
+    double* omega;
+    double* ext;
+    double* intq;
+    int* accepted;
+    int* iters;
+    int mode;
+    int begin;              // first global work index of this slot
+};
+
 struct RefineArgs {
     DevModel M;
     const double* tab;
     int tab_doubles;
     const double* k;
     const double* w;
-    int nk, nw, layout, mode;
-    const double* gext;     // D grid of the scan (end-point values of every bracket)
-    const double* gint;
-    const int* bk;
-    const int* bw;
-    int n_brackets;
+    int nk, nw, layout;
+    int n_slots;
+    int n_total;            // brackets of all slots together
+    RefineSlot slot[3];
     int* counter;           // work queue head (zeroed before launch)
     double tol_percent;
-    double* omega;
-    double* ext;
-    double* intq;
-    int* accepted;
-    int* iters;
 };
 
 __device__ __forceinline__ double mismatch_pct(double e, double i) {
@@ -193,29 +200,33 @@ __device__ __forceinline__ double mismatch_pct(double e, double i) {
 // to 1e-7 relative is a pole of D (sign change through infinity): it is reported,
 // unaccepted, without being bisected to machine precision.
 template <int KIND, int SCHEME>
-__global__ void __launch_bounds__(64) refine_kernel(RefineArgs r) {
+__global__ void __launch_bounds__(128) refine_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
     stage_table(r.tab, stab, r.tab_doubles);
     const double eps = 2.220446049250313e-16;
     bool have = false, pending = false, exhausted = false;
-    int t = 0, it = 0;
+    int t = 0, it = 0, sl = 0, mode = 0;
     double k = 1.0, a = 0, b = 1.0, c = 0, ea = 0, ia = 0, eb = 0, ib = 0, ec = 0, ic = 0, d = 0, e = 0,
            f0min = 0;
     for (;;) {
         while (!pending && !exhausted) {
             if (!have) {
                 t = atomicAdd(r.counter, 1);
-                if (t >= r.n_brackets) {
+                if (t >= r.n_total) {
                     exhausted = true;
                     break;
                 }
-                const int ik = r.bk[t], jw = r.bw[t];
+                // one queue over the brackets of all mode slots
+                sl = (r.n_slots > 2 && t >= r.slot[2].begin) ? 2 : (r.n_slots > 1 && t >= r.slot[1].begin) ? 1 : 0;
+                t -= r.slot[sl].begin;
+                mode = r.slot[sl].mode;
+                const int ik = r.slot[sl].bk[t], jw = r.slot[sl].bw[t];
                 k = r.k[ik];
                 a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
                 b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
                 const size_t o = (size_t)ik * r.nw + jw;
-                ea = r.gext[o]; ia = r.gint[o];
-                eb = r.gext[o + 1]; ib = r.gint[o + 1];
+                ea = r.slot[sl].gext[o]; ia = r.slot[sl].gint[o];
+                eb = r.slot[sl].gext[o + 1]; ib = r.slot[sl].gint[o + 1];
                 c = a; ec = ea; ic = ia;
                 d = b - a; e = d;
                 f0min = fmin(fabs(ea - ia), fabs(eb - ib));
@@ -239,11 +250,11 @@ __global__ void __launch_bounds__(64) refine_kernel(RefineArgs r) {
             const bool pole = it >= 2 && mismatch_pct(eb, ib) > 50.0 &&
                               (fabs(fb) > 4.0 * f0min || fabs(xm) < 1e-7 * fabs(b));
             if (converged || pole) {
-                r.omega[t] = b;
-                r.ext[t] = eb;
-                r.intq[t] = ib;
-                r.iters[t] = it;
-                r.accepted[t] = (mismatch_pct(eb, ib) < r.tol_percent) ? 1 : 0;
+                r.slot[sl].omega[t] = b;
+                r.slot[sl].ext[t] = eb;
+                r.slot[sl].intq[t] = ib;
+                r.slot[sl].iters[t] = it;
+                r.slot[sl].accepted[t] = (mismatch_pct(eb, ib) < r.tol_percent) ? 1 : 0;
                 have = false;
                 continue;
             }
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(64) refine_kernel(RefineArgs r) {
         }
         if (!__any_sync(0xffffffffu, pending)) break;
         double en, in_;
-        eval_point<KIND, SCHEME>(r.M, stab, k, b, r.mode, en, in_);
+        eval_point<KIND, SCHEME>(r.M, stab, k, b, mode, en, in_);
         if (pending) {
             eb = en;
             ib = in_;
@@ -638,6 +649,11 @@ static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME, NM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // the table is read-only broadcast data: give shared memory the whole carve-out so that the
+    // resident-CTA count is limited by registers, not by the default L1/shared split
+    e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME, NM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     dim3 block(128);
     dim3 grid((g.nw + 127) / 128, g.nk < 65535 ? g.nk : 65535);
     grid_kernel<KIND, SCHEME, NM><<<grid, block, smem, s>>>(g);
@@ -660,10 +676,13 @@ static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int blocks = (r.n_brackets + 63) / 64;
-    const int cap = 148 * 8;           // persistent: at most 8 CTAs of 64 threads per SM
+    e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int blocks = (r.n_total + 127) / 128;
+    const int cap = 148 * 4;           // persistent: 4 CTAs of 128 threads per SM (register limit)
     if (blocks > cap) blocks = cap;
-    refine_kernel<KIND, SCHEME><<<blocks, 64, smem, s>>>(r);
+    refine_kernel<KIND, SCHEME><<<blocks, 128, smem, s>>>(r);
     return cudaGetLastError();
 }
 
@@ -865,11 +884,20 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, (size_t)nk + 1))) return rc;
     if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)ESB_MAX_MODES))) return rc;
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, ESB_MAX_MODES * sizeof(int), s));
+    RefineArgs r;
+    r.M = c->dm;
+    r.tab = c->d_tab;
+    r.tab_doubles = c->tab_doubles;
+    r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout;
+    r.n_slots = 0;
+    r.n_total = 0;
+    r.counter = c->d_counter;
+    r.tol_percent = tol_percent;
     for (int m = 0; m < n_modes; ++m) {
         esb_context::RootBuf& sl = c->slots[m];
         const double* gext = c->d_ext + m * plane;
         const double* gint = c->d_int + m * plane;
-        // pass 1: count (one 4-byte D2H + sync: the refine launch needs the bracket count)
+        // pass 1: count (one 4-byte D2H + sync: buffer sizes and the refine launch need the count)
         int total = 0;
         rc = esb_brackets_dev(c, gext, gint, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, s);
         if (rc) return rc;
@@ -888,16 +916,15 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
             CUDA_TRY(c, cudaGetLastError());
             c->launches += 1;
         }
-        RefineArgs r;
-        r.M = c->dm;
-        r.tab = c->d_tab;
-        r.tab_doubles = c->tab_doubles;
-        r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout; r.mode = modes[m];
-        r.gext = gext; r.gint = gint;
-        r.bk = sl.bk; r.bw = sl.bw; r.n_brackets = total;
-        r.counter = c->d_counter + m;
-        r.tol_percent = tol_percent;
-        r.omega = sl.om; r.ext = sl.e; r.intq = sl.i; r.accepted = sl.acc; r.iters = sl.it;
+        RefineSlot& q = r.slot[r.n_slots++];
+        q.gext = gext; q.gint = gint; q.bk = sl.bk; q.bw = sl.bw;
+        q.omega = sl.om; q.ext = sl.e; q.intq = sl.i; q.accepted = sl.acc; q.iters = sl.it;
+        q.mode = modes[m];
+        q.begin = r.n_total;
+        r.n_total += total;
+    }
+    if (r.n_total > 0) {
+        // ONE persistent launch refines the brackets of every mode (single work queue)
         cudaError_t e;
         const bool rk8 = c->dm.scheme == SCHEME_RK8;
         switch (c->dm.kind) {
@@ -975,6 +1002,7 @@ extern "C" int esb_find_roots(esb_context* c, int32_t mode, const double* k, int
 __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
            x7 = x0 + 7;
+#pragma unroll 8
     for (int i = 0; i < iters; ++i) {
         x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
         x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
