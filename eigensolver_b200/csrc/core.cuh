@@ -157,64 +157,68 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
 
 // ------------------------------------------------------------- integrator ----
 // One Cooper-Verner step of the linear system (u, v)' = f(node; u, v) for NS independent
-// solutions.  RHS(s, n, U, V, FU, FV) evaluates the right-hand side of solution s at stage node n.
+// solutions.  RHS(s, n, U, V, hFU, hFV) returns the right-hand side of solution s at stage node n
+// ALREADY MULTIPLIED BY THE STEP h (the step is folded into the node coefficients once per step),
+// so every stage value is a pure FMA chain  y + sum_j a_ij (h f_j).
 // stage -> node: 1:0  2:2 3:2  4:3 5:3  6:2  7:1 8:1  9:2  10:3  11:4
 template <int NS, class RHS>
-ESB_HD void rk8_generic(double (&y)[NS], double (&yp)[NS], double h, const RHS& rhs) {
+ESB_HD void rk8_generic(double (&y)[NS], double (&yp)[NS], const RHS& rhs) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const double p = y[s], q = yp[s];
         double F1, G1, F2, G2, F3, G3, F4, G4, F5, G5, F6, G6, F7, G7, F8, G8, F9, G9, F10, G10, F11, G11;
         rhs(s, 0, p, q, F1, G1);
-        const double P2 = fma(h, a21 * F1, p), Q2 = fma(h, a21 * G1, q);
+        const double P2 = fma(a21, F1, p), Q2 = fma(a21, G1, q);
         rhs(s, 2, P2, Q2, F2, G2);
-        const double P3 = fma(h, fma(a32, F2, a31 * F1), p), Q3 = fma(h, fma(a32, G2, a31 * G1), q);
+        const double P3 = fma(a32, F2, fma(a31, F1, p)), Q3 = fma(a32, G2, fma(a31, G1, q));
         rhs(s, 2, P3, Q3, F3, G3);
-        const double P4 = fma(h, fma(a43, F3, fma(a42, F2, a41 * F1)), p),
-                     Q4 = fma(h, fma(a43, G3, fma(a42, G2, a41 * G1)), q);
+        const double P4 = fma(a43, F3, fma(a42, F2, fma(a41, F1, p))),
+                     Q4 = fma(a43, G3, fma(a42, G2, fma(a41, G1, q)));
         rhs(s, 3, P4, Q4, F4, G4);
-        const double P5 = fma(h, fma(a54, F4, fma(a53, F3, a51 * F1)), p),
-                     Q5 = fma(h, fma(a54, G4, fma(a53, G3, a51 * G1)), q);
+        const double P5 = fma(a54, F4, fma(a53, F3, fma(a51, F1, p))),
+                     Q5 = fma(a54, G4, fma(a53, G3, fma(a51, G1, q)));
         rhs(s, 3, P5, Q5, F5, G5);
-        const double P6 = fma(h, fma(a65, F5, fma(a64, F4, fma(a63, F3, a61 * F1))), p),
-                     Q6 = fma(h, fma(a65, G5, fma(a64, G4, fma(a63, G3, a61 * G1))), q);
+        const double P6 = fma(a65, F5, fma(a64, F4, fma(a63, F3, fma(a61, F1, p)))),
+                     Q6 = fma(a65, G5, fma(a64, G4, fma(a63, G3, fma(a61, G1, q))));
         rhs(s, 2, P6, Q6, F6, G6);
-        const double P7 = fma(h, fma(a76, F6, fma(a75, F5, fma(a74, F4, fma(a73, F3, a71 * F1)))), p),
-                     Q7 = fma(h, fma(a76, G6, fma(a75, G5, fma(a74, G4, fma(a73, G3, a71 * G1)))), q);
+        const double P7 = fma(a76, F6, fma(a75, F5, fma(a74, F4, fma(a73, F3, fma(a71, F1, p))))),
+                     Q7 = fma(a76, G6, fma(a75, G5, fma(a74, G4, fma(a73, G3, fma(a71, G1, q)))));
         rhs(s, 1, P7, Q7, F7, G7);
-        const double P8 = fma(h, fma(a87, F7, fma(a86, F6, fma(a85, F5, a81 * F1))), p),
-                     Q8 = fma(h, fma(a87, G7, fma(a86, G6, fma(a85, G5, a81 * G1))), q);
+        const double P8 = fma(a87, F7, fma(a86, F6, fma(a85, F5, fma(a81, F1, p)))),
+                     Q8 = fma(a87, G7, fma(a86, G6, fma(a85, G5, fma(a81, G1, q))));
         rhs(s, 1, P8, Q8, F8, G8);
-        const double P9 = fma(h, fma(a98, F8, fma(a97, F7, fma(a96, F6, fma(a95, F5, a91 * F1)))), p),
-                     Q9 = fma(h, fma(a98, G8, fma(a97, G7, fma(a96, G6, fma(a95, G5, a91 * G1)))), q);
+        const double P9 = fma(a98, F8, fma(a97, F7, fma(a96, F6, fma(a95, F5, fma(a91, F1, p))))),
+                     Q9 = fma(a98, G8, fma(a97, G7, fma(a96, G6, fma(a95, G5, fma(a91, G1, q)))));
         rhs(s, 2, P9, Q9, F9, G9);
-        const double P10 = fma(h, fma(a109, F9, fma(a108, F8, fma(a107, F7, fma(a106, F6,
-                                  fma(a105, F5, a101 * F1))))), p),
-                     Q10 = fma(h, fma(a109, G9, fma(a108, G8, fma(a107, G7, fma(a106, G6,
-                                  fma(a105, G5, a101 * G1))))), q);
+        const double P10 = fma(a109, F9, fma(a108, F8, fma(a107, F7, fma(a106, F6, fma(a105, F5,
+                                  fma(a101, F1, p)))))),
+                     Q10 = fma(a109, G9, fma(a108, G8, fma(a107, G7, fma(a106, G6, fma(a105, G5,
+                                  fma(a101, G1, q))))));
         rhs(s, 3, P10, Q10, F10, G10);
-        const double P11 = fma(h, fma(a1110, F10, fma(a119, F9, fma(a118, F8, fma(a117, F7,
-                                  fma(a116, F6, a115 * F5))))), p),
-                     Q11 = fma(h, fma(a1110, G10, fma(a119, G9, fma(a118, G8, fma(a117, G7,
-                                  fma(a116, G6, a115 * G5))))), q);
+        const double P11 = fma(a1110, F10, fma(a119, F9, fma(a118, F8, fma(a117, F7, fma(a116, F6,
+                                  fma(a115, F5, p)))))),
+                     Q11 = fma(a1110, G10, fma(a119, G9, fma(a118, G8, fma(a117, G7, fma(a116, G6,
+                                  fma(a115, G5, q))))));
         rhs(s, 4, P11, Q11, F11, G11);
-        y[s] = fma(h, fma(b8_11, F11, fma(b8_10, F10, fma(b8_9, F9, fma(b8_8, F8, b8_1 * F1)))), p);
-        yp[s] = fma(h, fma(b8_11, G11, fma(b8_10, G10, fma(b8_9, G9, fma(b8_8, G8, b8_1 * G1)))), q);
+        y[s] = fma(b8_11, F11, fma(b8_10, F10, fma(b8_9, F9, fma(b8_8, F8, fma(b8_1, F1, p)))));
+        yp[s] = fma(b8_11, G11, fma(b8_10, G10, fma(b8_9, G9, fma(b8_8, G8, fma(b8_1, G1, q)))));
     }
 }
 
-// y'' = a y' + b_s y : (u, v) = (y, y'), u' = v, v' = a v + b_s u
+// y'' = a y' + b_s y : (u, v) = (y, y'), u' = v, v' = a v + b_s u.   ha = h a, hbs = h b_s.
 template <int NS>
 struct RhsSecondOrder {
-    const double (&ca)[5];
-    const double (&cbs)[NS][5];
+    double h;
+    const double (&ha)[5];
+    const double (&hbs)[NS][5];
     ESB_HD void operator()(int s, int n, double U, double V, double& FU, double& FV) const {
-        FU = V;
-        FV = fma(ca[n], V, cbs[s][n] * U);
+        FU = h * V;
+        FV = fma(ha[n], V, hbs[s][n] * U);
     }
 };
 
-// general 2x2 system (rotational-flow cylinder): (u, v)' = [[m11, m12], [m21, m22]] (u, v)
+// general 2x2 system (rotational-flow cylinder): (u, v)' = [[m11, m12], [m21, m22]] (u, v),
+// the four entries pre-multiplied by h
 struct RhsSystem {
     const double (&m11)[5];
     const double (&m12)[5];
@@ -226,11 +230,12 @@ struct RhsSystem {
     }
 };
 
+// ca, cbs: coefficients already multiplied by h
 template <int NS>
-ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ca)[5],
-                     const double (&cbs)[NS][5]) {
-    const RhsSecondOrder<NS> rhs{ca, cbs};
-    rk8_generic<NS>(y, yp, h, rhs);
+ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ha)[5],
+                     const double (&hbs)[NS][5]) {
+    const RhsSecondOrder<NS> rhs{h, ha, hbs};
+    rk8_generic<NS>(y, yp, rhs);
 }
 
 template <int NS>
@@ -269,13 +274,18 @@ ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __
         ca[0] = a0; cb[0] = b0; bm[0] = bm0;
 #pragma unroll
         for (int n = 1; n < NN; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n], bm[n]);
+        a0 = ca[NN - 1]; b0 = cb[NN - 1]; bm0 = bm[NN - 1];       // unscaled, carried to the next step
+        if constexpr (SCHEME == SCHEME_RK8) {
+            // fold the step into the node coefficients (shared by all solutions)
+#pragma unroll
+            for (int n = 0; n < NN; ++n) { ca[n] *= h; cb[n] *= h; bm[n] *= h; }
+        }
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int n = 0; n < NN; ++n) cbs[s][n] = (KIND == KIND_CYL_DENSITY) ? fma(m2[s], bm[n], cb[n]) : cb[n];
         if constexpr (SCHEME == SCHEME_RK8) rk8_step<NS>(y, yp, h, ca, cbs);
         else rk4_step<NS>(y, yp, h, ca, cbs);
-        a0 = ca[NN - 1]; b0 = cb[NN - 1]; bm0 = bm[NN - 1];
     }
 }
 
@@ -324,15 +334,16 @@ ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, con
     RotCoef c0 = node_rot(M, pt, m, tab);
     for (int i = 0; i < M.n_steps; ++i) {
         const double* f = tab + (size_t)(i * 4) * TAB_FIELDS;
+        const double h = hs[i];
         double m11[5], m12[5], m21[5], m22[5];
-        m11[0] = c0.m11; m12[0] = c0.m12; m21[0] = c0.m21; m22[0] = c0.m22;
+        m11[0] = h * c0.m11; m12[0] = h * c0.m12; m21[0] = h * c0.m21; m22[0] = h * c0.m22;
 #pragma unroll
         for (int n = 1; n < 5; ++n) {
             c0 = node_rot(M, pt, m, f + n * TAB_FIELDS);
-            m11[n] = c0.m11; m12[n] = c0.m12; m21[n] = c0.m21; m22[n] = c0.m22;
+            m11[n] = h * c0.m11; m12[n] = h * c0.m12; m21[n] = h * c0.m21; m22[n] = h * c0.m22;
         }
         const RhsSystem rhs{m11, m12, m21, m22};
-        rk8_generic<2>(P, X, hs[i], rhs);
+        rk8_generic<2>(P, X, rhs);
     }
     end = c0;
 }

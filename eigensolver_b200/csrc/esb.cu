@@ -55,7 +55,7 @@ __device__ __forceinline__ void stage_table(const double* __restrict__ g, double
 // NM modes are evaluated per thread, sharing the staged coefficients (cylinder) or the whole
 // integration (slab); outputs are mode-slot major.
 template <int KIND, int SCHEME, int NM>
-__global__ void __launch_bounds__(128, 5) grid_kernel(GridArgs g) {
+__global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1034,6 +1034,39 @@ extern "C" int esb_fp64_peak(esb_context* c, double* tflops) {
     c->timed = false;
     c->launches += 4;
     *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) * 1e-12;
+    return ESB_OK;
+}
+
+// Host-side self test of the integrator the kernels use (same rk8_step / rk4_step code, compiled
+// for the host): y'' = sin(t) y' - (1 + t^2) y, y(0) = 1, y'(0) = 0.3, uniform steps over [0, T].
+extern "C" int esb_rk_selftest(int32_t scheme, int32_t n_steps, double T, double out[2]) {
+    if ((scheme != ESB_RK4 && scheme != ESB_RK8) || n_steps < 1 || !out) return ESB_ERR_ARG;
+    double y[1] = {1.0}, yp[1] = {0.3};
+    const double h = T / n_steps;
+    for (int i = 0; i < n_steps; ++i) {
+        const double t0 = i * h;
+        if (scheme == ESB_RK8) {
+            const double c[5] = {0.0, C8_M, 0.5, C8_P, 1.0};
+            double ha[5], hb[1][5];
+            for (int n = 0; n < 5; ++n) {
+                const double t = t0 + c[n] * h;
+                ha[n] = h * sin(t);
+                hb[0][n] = -h * (1.0 + t * t);
+            }
+            rk8_step<1>(y, yp, h, ha, hb);
+        } else {
+            const double c[3] = {0.0, 0.5, 1.0};
+            double a[3], b[1][3];
+            for (int n = 0; n < 3; ++n) {
+                const double t = t0 + c[n] * h;
+                a[n] = sin(t);
+                b[0][n] = -(1.0 + t * t);
+            }
+            rk4_step<1>(y, yp, h, a, b);
+        }
+    }
+    out[0] = y[0];
+    out[1] = yp[0];
     return ESB_OK;
 }
 

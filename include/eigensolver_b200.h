@@ -192,6 +192,11 @@ int esb_brackets_dev(esb_context* ctx, const double* d_ext, const double* d_intq
  * exterior solution, out = {e^-z I_n, d/dz, e^z K_n, d/dz}.  For unit tests. */
 int esb_bessel_ik_scaled(int32_t n, double z, double out[4]);
 
+/* Host-side helper (no GPU needed): integrates y'' = sin(t) y' - (1+t^2) y, y(0)=1, y'(0)=0.3
+ * over [0,T] in n_steps uniform steps with the SAME step functions the kernels use; out =
+ * {y(T), y'(T)}.  tests/test_tableau.py checks the 8th / 4th order of convergence with it. */
+int esb_rk_selftest(int32_t scheme, int32_t n_steps, double T, double out[2]);
+
 /* Timing hook for bench.py: device time (ms) of the last grid kernel launch
  * measured with CUDA events on the launching stream; <0 if none. */
 double esb_last_kernel_ms(const esb_context* ctx);
