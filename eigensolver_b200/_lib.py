@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeigensolver_b200.so")
 
 ESB_OK, ESB_ERR_ARG, ESB_ERR_CUDA, ESB_ERR_CAPACITY, ESB_ERR_ALLOC = 0, -1, -2, -3, -4
-SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW, CYLINDER_ROTATION = 0, 1, 2, 3
+SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW, CYLINDER_ROTATION, CYLINDER_FLOW = 0, 1, 2, 3, 4
 RK4, RK8 = 0, 1
 OMEGA_SHARED, OMEGA_PHASE_SPEED, OMEGA_PER_K = 0, 1, 2
 MESH_CLUSTERED, MESH_UNIFORM = 0, 1

@@ -21,7 +21,10 @@
 
 namespace esb {
 
-enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1, KIND_SLAB_FLOW = 2, KIND_CYL_ROTATION = 3 };
+enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1, KIND_SLAB_FLOW = 2, KIND_CYL_ROTATION = 3, KIND_CYL_FLOW = 4 };
+
+template <int KIND>
+constexpr bool is_cyl_second_order = (KIND == KIND_CYL_DENSITY || KIND == KIND_CYL_FLOW);
 enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1 };
 enum { OMEGA_SHARED = 0, OMEGA_PHASE_SPEED = 1, OMEGA_PER_K = 2 };
 
@@ -38,7 +41,8 @@ struct DevModel {
     double rho_b;             // density at the boundary s_start
     double s_start;           // boundary position (-1)
     double r_sign;            // cylinder: -1 scripts written in r<0 (coronal), +1 in r>0 (photospheric)
-    // slab with a sheared flow U(x): uniform interior c_i, vA_i, rho_i
+    // slab with a sheared flow U(x) / cylinder with an axial flow v_z(r): uniform interior c_i,
+    // vA_i, rho_i; U_b = flow speed at the boundary s_start
     double ci2, vAi2, cTi2, si, rho_i, U_e, U_b;
     // cylinder with rotational flow v_phi(r): uniform rho_i, vA_i (vAi2, rho_i above);
     // rho v_phi^2 at the boundary enters the kink end condition
@@ -119,6 +123,21 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
         const double inv = 1.0 / (X * Y);
         a = fma(drho * p.A * Y, inv, -invr);
         b = fma(-(u * u) * X, inv, p.K);
+        bm = invr2;
+    } else if (KIND == KIND_CYL_FLOW) {
+        // f = {1/r, 1/r^2, v_z, v_z'}.  Cylinder_method_flow_testing.py:711-762 with v_phi = B_phi = 0
+        // and uniform rho, c, vA:  Om = w - k v_z,  Q = T = C1 = 0,  C3 = D rho (Om^2 - wA^2),
+        //   F = r D/C3 = r/(rho (Om^2 - k^2 vA^2)),   g = -r C2/D
+        //   a = -F'/F = -1/r - 2 k v_z' Om/(Om^2 - k^2 vA^2)
+        //   b = g/F   = m^2/r^2 + k^2 - Om^4/(s (Om^2 - k^2 cT^2))
+        const double invr = f[0], invr2 = f[1], vz = f[2], dvz = f[3];
+        const double Om = fma(-p.k, vz, p.w);
+        const double O2 = Om * Om;
+        const double X = fma(-p.K, M.vAi2, O2);
+        const double Y = M.si * fma(-p.K, M.cTi2, O2);
+        const double inv = 1.0 / (X * Y);
+        a = fma(-2.0 * p.k * dvz * Om * Y, inv, -invr);
+        b = fma(-(O2 * O2) * X, inv, p.K);
         bm = invr2;
     } else if (KIND == KIND_SLAB_FLOW) {
         // f = {U, U', U''}.  vx'' = -D vx' - coeff vx  (flow_multiprocessor_coronal.py:211-219,297):
@@ -283,7 +302,7 @@ ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
-            for (int n = 0; n < NN; ++n) cbs[s][n] = (KIND == KIND_CYL_DENSITY) ? fma(m2[s], bm[n], cb[n]) : cb[n];
+            for (int n = 0; n < NN; ++n) cbs[s][n] = is_cyl_second_order<KIND> ? fma(m2[s], bm[n], cb[n]) : cb[n];
         if constexpr (SCHEME == SCHEME_RK8) rk8_step<NS>(y, yp, h, ca, cbs);
         else rk4_step<NS>(y, yp, h, ca, cbs);
     }
@@ -447,7 +466,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             ext_q[s] = xi_e;
             int_q[s] = xi_b;      // xi_i(1) = (C1 P + D P')/C3 at r = 1   (:314)
         }
-    } else if constexpr (KIND == KIND_CYL_DENSITY) {
+    } else if constexpr (is_cyl_second_order<KIND>) {
         int nmax = 0;
 #pragma unroll
         for (int s = 0; s < NM; ++s) nmax = modes[s] > nmax ? modes[s] : nmax;
@@ -467,7 +486,14 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             m2[s] = double(modes[s]) * double(modes[s]);
         }
         integrate_layer<KIND, SCHEME, NM>(M, pt, tab, m2, y, yp);
-        const double den = 1.0 / (M.rho_b * pt.A - pt.Kbeta);
+        double den;
+        if constexpr (KIND == KIND_CYL_FLOW) {
+            // (C1 P + D P')/C3 at r = -1 with C1 = 0: P'/(rho (Om_b^2 - k^2 vA^2)), Om_b = w - k v_z(-1)
+            const double Ob = fma(-k, M.U_b, w);
+            den = 1.0 / (M.rho_i * fma(-pt.K, M.vAi2, Ob * Ob));
+        } else {
+            den = 1.0 / (M.rho_b * pt.A - pt.Kbeta);
+        }
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
             const double slope = yb[s] * yp[s] / y[s];       // dPi that fsolve finds (:790)

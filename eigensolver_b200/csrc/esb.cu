@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/eigensolver_b200.h"
@@ -376,7 +377,7 @@ static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
         }
         bp[0] = m->s_start;
         bp[N] = m->s_end;
-    } else if (m->kind == ESB_CYLINDER_DENSITY) {
+    } else if (m->kind == ESB_CYLINDER_DENSITY || m->kind == ESB_CYLINDER_FLOW) {
         // from the axis end (s_end) out to the boundary (s_start)
         for (int i = 0; i <= N; ++i) {
             const double t = double(i) / N;
@@ -405,7 +406,7 @@ static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
 
 static int check_model(const esb_model* m) {
     if (!m) return ESB_ERR_ARG;
-    if (m->kind < ESB_SLAB_DENSITY || m->kind > ESB_CYLINDER_ROTATION) return ESB_ERR_ARG;
+    if (m->kind < ESB_SLAB_DENSITY || m->kind > ESB_CYLINDER_FLOW) return ESB_ERR_ARG;
     if (m->kind == ESB_CYLINDER_ROTATION && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->scheme != ESB_RK4 && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->n_steps < 2 || m->n_steps > 8192) return ESB_ERR_ARG;
@@ -450,6 +451,11 @@ extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
         out->r_sign = 1;
         out->s_start = 1.0;
         out->s_end = 0.001;
+        out->n_steps = 256;
+    } else if (kind == ESB_CYLINDER_FLOW) {      // Cylinder_method_flow_testing.py:66-69,120,774
+        out->vA_i0 = 2.0; out->vA_e = 5.0; out->c_e = 0.5;
+        out->ext_ic_slope = 1e-8;
+        out->s_end = -0.001;
         out->n_steps = 256;
     } else {
         return ESB_ERR_ARG;
@@ -546,6 +552,7 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
                                     int32_t n_boundary) {
     if (!c) return ESB_ERR_ARG;
     if (check_model(m) || !fields || !boundary) return fail(c, ESB_ERR_ARG, "bad model");
+    // density kinds {rho, rho'}; cylinder axial flow {v_z, v_z'}; slab flow / rotation: three fields
     const int need_fields = (m->kind == ESB_SLAB_FLOW || m->kind == ESB_CYLINDER_ROTATION) ? 3 : 2;
     if (n_fields != need_fields || n_boundary < 1) return fail(c, ESB_ERR_ARG, "wrong number of profile fields");
     for (int f = 0; f < n_fields; ++f)
@@ -559,7 +566,7 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     std::vector<double> tab((size_t)need * TAB_FIELDS + N, 0.0);
     for (int i = 0; i < need; ++i) {
         double* f = &tab[(size_t)i * TAB_FIELDS];
-        if (m->kind == ESB_CYLINDER_DENSITY) {
+        if (m->kind == ESB_CYLINDER_DENSITY || m->kind == ESB_CYLINDER_FLOW) {
             const double r = nodes[i];
             f[0] = 1.0 / r;
             f[1] = 1.0 / (r * r);
@@ -596,7 +603,7 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     d.ext_len = m->ext_wavelengths * 2.0 * M_PI;
     d.s_start = m->s_start;
     d.r_sign = m->r_sign >= 0 ? 1.0 : -1.0;
-    if (m->kind == ESB_SLAB_FLOW) {
+    if (m->kind == ESB_SLAB_FLOW || m->kind == ESB_CYLINDER_FLOW) {
         d.ci2 = m->c_i0 * m->c_i0;
         d.vAi2 = m->vA_i0 * m->vA_i0;
         d.si = d.ci2 + d.vAi2;
@@ -686,6 +693,29 @@ static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// (kind, scheme) of the uploaded model -> template instantiation.  The rotational kind exists for
+// RK8 only (check_model enforces it).
+template <class F>
+static cudaError_t dispatch_kind(int kind, int scheme, F&& f) {
+    using std::integral_constant;
+    const bool rk8 = scheme == SCHEME_RK8;
+#define ESB_KIND_CASE(K)                                                               \
+    case K:                                                                            \
+        return rk8 ? f(integral_constant<int, K>{}, integral_constant<int, SCHEME_RK8>{}) \
+                   : f(integral_constant<int, K>{}, integral_constant<int, SCHEME_RK4>{});
+    switch (kind) {
+        ESB_KIND_CASE(KIND_SLAB_DENSITY)
+        ESB_KIND_CASE(KIND_CYL_DENSITY)
+        ESB_KIND_CASE(KIND_SLAB_FLOW)
+        ESB_KIND_CASE(KIND_CYL_FLOW)
+        case KIND_CYL_ROTATION:
+            return f(integral_constant<int, KIND_CYL_ROTATION>{}, integral_constant<int, SCHEME_RK8>{});
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef ESB_KIND_CASE
+}
+
 static int check_mode(const esb_context* c, int mode) {
     if (c->model.kind == ESB_SLAB_DENSITY || c->model.kind == ESB_SLAB_FLOW)
         return (mode == 0 || mode == 1) ? 0 : -1;
@@ -717,21 +747,9 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
     g.ext = d_ext; g.intq = d_int;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
-    cudaError_t e;
-    const bool rk8 = c->dm.scheme == SCHEME_RK8;
-    switch (c->dm.kind) {
-        case KIND_CYL_DENSITY:
-            e = rk8 ? launch_grid<KIND_CYL_DENSITY, SCHEME_RK8>(g, s) : launch_grid<KIND_CYL_DENSITY, SCHEME_RK4>(g, s);
-            break;
-        case KIND_SLAB_FLOW:
-            e = rk8 ? launch_grid<KIND_SLAB_FLOW, SCHEME_RK8>(g, s) : launch_grid<KIND_SLAB_FLOW, SCHEME_RK4>(g, s);
-            break;
-        case KIND_CYL_ROTATION:
-            e = launch_grid<KIND_CYL_ROTATION, SCHEME_RK8>(g, s);
-            break;
-        default:
-            e = rk8 ? launch_grid<KIND_SLAB_DENSITY, SCHEME_RK8>(g, s) : launch_grid<KIND_SLAB_DENSITY, SCHEME_RK4>(g, s);
-    }
+    const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
+        return launch_grid<decltype(kind)::value, decltype(scheme)::value>(g, s);
+    });
     CUDA_TRY(c, e);
     CUDA_TRY(c, cudaEventRecord(c->ev1, s));
     c->timed = true;
@@ -925,24 +943,9 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     }
     if (r.n_total > 0) {
         // ONE persistent launch refines the brackets of every mode (single work queue)
-        cudaError_t e;
-        const bool rk8 = c->dm.scheme == SCHEME_RK8;
-        switch (c->dm.kind) {
-            case KIND_CYL_DENSITY:
-                e = rk8 ? launch_refine<KIND_CYL_DENSITY, SCHEME_RK8>(r, s)
-                        : launch_refine<KIND_CYL_DENSITY, SCHEME_RK4>(r, s);
-                break;
-            case KIND_SLAB_FLOW:
-                e = rk8 ? launch_refine<KIND_SLAB_FLOW, SCHEME_RK8>(r, s)
-                        : launch_refine<KIND_SLAB_FLOW, SCHEME_RK4>(r, s);
-                break;
-            case KIND_CYL_ROTATION:
-                e = launch_refine<KIND_CYL_ROTATION, SCHEME_RK8>(r, s);
-                break;
-            default:
-                e = rk8 ? launch_refine<KIND_SLAB_DENSITY, SCHEME_RK8>(r, s)
-                        : launch_refine<KIND_SLAB_DENSITY, SCHEME_RK4>(r, s);
-        }
+        const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
+            return launch_refine<decltype(kind)::value, decltype(scheme)::value>(r, s);
+        });
         CUDA_TRY(c, e);
         c->launches += 1;
     }

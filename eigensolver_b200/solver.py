@@ -116,6 +116,31 @@ class GaussianFlow:
 
 
 @dataclasses.dataclass(frozen=True)
+class AxialFlowMedium(Medium):
+    """Speeds of the cylinder axial-flow script (Cylinder_method_flow_testing.py:66-69,130-131):
+    uniform density, field and sound speed inside the tube, flow amplitude U_i0 on the axis, U_e
+    far from it (the script's exterior itself is at rest: m_e and xi_e use omega unshifted)."""
+    U_i0: float = 0.35
+    U_e: float = 0.0
+
+
+CYLINDER_FLOW_CORONAL = AxialFlowMedium(1.0, 2.0, 5.0, 0.5)
+
+
+@dataclasses.dataclass(frozen=True)
+class GaussianAxialFlow:
+    """v_z(r) = U_e + (U_i0 - U_e) exp(-(r-r0)^2/width^2)   (Cylinder_method_flow_testing.py:134)."""
+    width: float = 1e5
+    r0: float = 0.0
+
+    def __call__(self, medium, r):
+        r = np.asarray(r, dtype=np.float64)
+        g = np.exp(-((r - self.r0) ** 2) / self.width**2)
+        dU0 = medium.U_i0 - medium.U_e
+        return medium.U_e + dU0 * g, dU0 * g * (-2.0 * (r - self.r0) / self.width**2)
+
+
+@dataclasses.dataclass(frozen=True)
 class PowerLawRotation:
     """v_phi = v_twist r^power with the pressure that balances it,
     P_i = rho v_twist^2 r^(2 power)/(2 power) + P_0, c_i^2 = gamma P_i/rho
@@ -152,7 +177,7 @@ class RootTable:
 
 
 _KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY, "slab_flow": L.SLAB_FLOW,
-          "cylinder_rotation": L.CYLINDER_ROTATION}
+          "cylinder_rotation": L.CYLINDER_ROTATION, "cylinder_flow": L.CYLINDER_FLOW}
 _SCHEMES = {"rk4": L.RK4, "rk8": L.RK8}
 _LAYOUTS = {"shared": L.OMEGA_SHARED, "phase_speed": L.OMEGA_PHASE_SPEED, "per_k": L.OMEGA_PER_K}
 _MODES = {"sausage": 0, "kink": 1, "fluting": 2, "fluting2": 2, "fluting3": 3}
@@ -171,9 +196,11 @@ class DispersionSolver:
 
     def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh="clustered",
                  device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None):
-        """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation".
+        """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation" |
+        "cylinder_flow".
         profile: callable (medium, x) -> (rho, rho') for the density kinds, (U, U', U'') for
-        "slab_flow", (v_phi, v_phi', c_i^2) for "cylinder_rotation"; any function may be given (this
+        "slab_flow", (v_phi, v_phi', c_i^2) for "cylinder_rotation", (v_z, v_z') for
+        "cylinder_flow"; any function may be given (this
         replaces the reference's sympy profile).  s_end: far end of the layer (the rotational sausage
         script stops at r = 0.01, the kink one at 0.001).
         coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
@@ -184,11 +211,13 @@ class DispersionSolver:
         L.check(self.lib, None, self.lib.esb_model_defaults(_KINDS[kind], C.byref(m)), "esb_model_defaults")
         if medium is None:
             medium = {"cylinder_density": CYLINDER_CORONAL, "slab_density": SLAB_CORONAL,
-                      "slab_flow": SLAB_FLOW_CORONAL, "cylinder_rotation": CYLINDER_PHOTOSPHERIC}[kind]
+                      "slab_flow": SLAB_FLOW_CORONAL, "cylinder_rotation": CYLINDER_PHOTOSPHERIC,
+                      "cylinder_flow": CYLINDER_FLOW_CORONAL}[kind]
         self.medium = medium
         if profile is None:
             profile = {"cylinder_density": GaussianDensity(0.95), "slab_density": GaussianDensity(0.9),
-                       "slab_flow": GaussianFlow(1e5), "cylinder_rotation": PowerLawRotation()}[kind]
+                       "slab_flow": GaussianFlow(1e5), "cylinder_rotation": PowerLawRotation(),
+                       "cylinder_flow": GaussianAxialFlow(1.0)}[kind]
         self.profile = profile
         if kind == "slab_flow":
             m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
@@ -196,6 +225,7 @@ class DispersionSolver:
         else:
             m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
             m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, rho_A
+            m.U_e = getattr(medium, "U_e", 0.0)
         m.scheme = _SCHEMES[scheme]
         m.mesh = L.MESH_UNIFORM if mesh == "uniform" else L.MESH_CLUSTERED
         m.ext_wavelengths = ext_wavelengths
@@ -249,6 +279,7 @@ class DispersionSolver:
             else:
                 m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
                 m.gamma, m.rho_i0 = medium.gamma, medium.rho_i0
+                m.U_e = getattr(medium, "U_e", 0.0)
         if profile is not None:
             self.profile = profile
         self._upload_model()

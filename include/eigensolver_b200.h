@@ -52,8 +52,10 @@ enum esb_model_kind {
     ESB_SLAB_DENSITY = 0,     /* slab, rho(x)   : ...Inhomogeneous_method_coronal.py        */
     ESB_CYLINDER_DENSITY = 1, /* cylinder rho(r): Density_cylinder.py                       */
     ESB_SLAB_FLOW = 2,        /* slab, sheared flow U(x): flow_multiprocessor_coronal.py    */
-    ESB_CYLINDER_ROTATION = 3 /* cylinder, rotational flow v_phi(r): Twisted_photospheric_*.py
+    ESB_CYLINDER_ROTATION = 3,/* cylinder, rotational flow v_phi(r): Twisted_photospheric_*.py
                                  (uniform rho_i0, vA_i0; written in r > 0; RK8 only)         */
+    ESB_CYLINDER_FLOW = 4     /* cylinder, axial flow v_z(r): Cylinder_method_flow_testing.py
+                                 (uniform rho_i0, c_i0, vA_i0 inside; written in r < 0)      */
 };
 
 /* Fixed-step integrator used across the layer. */
@@ -83,7 +85,10 @@ typedef struct esb_model {
     double ext_wavelengths;/* exterior domain = ext_wavelengths*2*pi/k  (reference: 3)     */
     double s_start, s_end; /* layer: boundary and far end: (-1, 1) slab, (-1, -0.001) cyl  */
     double U_e;            /* ESB_SLAB_FLOW: exterior flow speed (flow script :52); there c_i0,
-                              vA_i0, rho_i0 are the uniform interior c_i, vA_i, rho_i          */
+                              vA_i0, rho_i0 are the uniform interior c_i, vA_i, rho_i.
+                              ESB_CYLINDER_FLOW: unused by the kernels (that script's exterior
+                              is at rest in its own frame: m_e and xi_e use omega unshifted,
+                              Cylinder_method_flow_testing.py:706-709)                         */
     int32_t r_sign;        /* cylinder: -1 = script written in r<0 (coronal, default), +1 = r>0
                               (photospheric: s_start=1, s_end=0.001, slope given as dP/dr)     */
     int32_t reserved;
@@ -111,7 +116,8 @@ int esb_set_model(esb_context* ctx, const esb_model* m, const double* rho, const
 /* Generic form: fields[f][n_nodes] sampled at esb_mesh_nodes().
  *   density kinds : fields = {rho, rho'},       boundary = {rho(s_start)}
  *   ESB_SLAB_FLOW : fields = {U, U', U''},      boundary = {U(s_start)}
- *   ESB_CYLINDER_ROTATION : fields = {v_phi, v_phi', c_i^2}, boundary = {v_phi(s_start)}    */
+ *   ESB_CYLINDER_ROTATION : fields = {v_phi, v_phi', c_i^2}, boundary = {v_phi(s_start)}
+ *   ESB_CYLINDER_FLOW : fields = {v_z, v_z'},   boundary = {v_z(s_start)}                    */
 int esb_set_model_fields(esb_context* ctx, const esb_model* m, const double* const* fields,
                          int32_t n_fields, int32_t n_nodes, const double* boundary,
                          int32_t n_boundary);

@@ -30,7 +30,8 @@
 #include <string.h>
 
 typedef struct {
-    int kind;            /* 0 slab density, 1 cylinder density, 2 slab sheared flow, 3 cylinder rotation */
+    int kind;            /* 0 slab density, 1 cylinder density, 2 slab sheared flow, 3 cylinder rotation,
+                            4 cylinder axial flow v_z(r) = U_e + (U_i0-U_e) exp(-(r-x0)^2/width^2) */
     int n_ext;           /* exterior steps */
     int n_int;           /* interior steps */
     int pad;
@@ -196,6 +197,20 @@ typedef struct { double D, C1, C2, C3; } rot_c;
 static rot_c rot_coeffs(const pt_ctx* p, double r) {
     const ork_model* m = p->m;
     const double rho = m->rho_i0, mm = (double)p->mode;
+    rot_c c;
+    if (m->kind == 4) {
+        /* Cylinder_method_flow_testing.py:711-746 with v_phi = B_phi = 0 (:190-196): Q = T = 0 */
+        const double vz = m->U_e + (m->U_i0 - m->U_e) * exp(-(r - m->x0) * (r - m->x0) / (m->width * m->width));
+        const double c2f = m->c_i0 * m->c_i0, vA2f = m->vA_i0 * m->vA_i0;
+        const double sh = p->w - p->k * vz;                       /* shift_freq  :713 */
+        const double al = p->k * sqrt(vA2f);                      /* alfven_freq :716 */
+        const double cu2 = al * al * c2f / (c2f + vA2f);          /* cusp_freq^2 :719 */
+        c.D = rho * (c2f + vA2f) * (sh * sh - al * al) * (sh * sh - cu2);
+        c.C1 = 0.0;
+        c.C2 = sh * sh * sh * sh - (c2f + vA2f) * (mm * mm / (r * r) + p->k * p->k) * (sh * sh - cu2);
+        c.C3 = c.D * rho * (sh * sh - al * al);
+        return c;
+    }
     const double vphi = m->v_twist * pow(r, m->power);
     const double P0 = m->c_i0 * m->c_i0 * rho / m->gamma;
     const double Pi = rho * m->v_twist * m->v_twist * pow(r, 2.0 * m->power) / (2.0 * m->power) + P0;
@@ -204,7 +219,6 @@ static rot_c rot_coeffs(const pt_ctx* p, double r) {
     const double alf = p->k * sqrt(vA2);
     const double cusp2 = alf * alf * c2 / (c2 + vA2);
     const double s2 = shift * shift;
-    rot_c c;
     c.D = rho * (c2 + vA2) * (s2 - alf * alf) * (s2 - cusp2);
     const double Q = -(s2 - alf * alf) * rho * vphi * vphi / r;
     const double T = rho * vphi * shift;
@@ -278,7 +292,7 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
     /* interior: two fundamental solutions forward from the boundary */
     double Y[2] = {1.0, 0.0}, Yp[2] = {0.0, 1.0};
     const int N = m->n_int;
-    if (m->kind == 3) {
+    if (m->kind == 3 || m->kind == 4) {
         double x = m->s_start;
         for (int i = 1; i <= N; ++i) {
             const double xn = (i == N) ? m->s_end : m->s_start + (m->s_end - m->s_start) * cluster((double)i / N);
@@ -287,7 +301,7 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
         }
         const double xi_e = -ypb / (p.rho_e * (p.K * vAe2 - p.A));
         /* sausage: P'(end) = 0 ; kink: P(end) + (0 - rho v_phi(1)^2) xi_e = 0   (:308) */
-        const double rv2 = m->rho_i0 * m->v_twist * m->v_twist;
+        const double rv2 = (m->kind == 4) ? 0.0 : m->rho_i0 * m->v_twist * m->v_twist;
         const double slope = (mode == 0) ? -yb * Yp[0] / Yp[1] : (rv2 * xi_e - yb * Y[0]) / Y[1];
         const rot_c cb = rot_coeffs(&p, m->s_start);
         *ext_q = xi_e;

@@ -28,6 +28,9 @@ Reference sources restated here (file:line refer to /root/reference):
       Cylinder/Non-uniform density/Coronal/solvers/Density_cylinder.py
         physics set-up 69-221, kink 546-824 (scan loop 694-821), sausage 847-1122
       Cylinder/Non-uniform density/Photospheric/Solvers/Density_cylinder_photospheric.py
+  cylinder, non-uniform axial flow:
+      Cylinder/Non-uniform flow/Coronal/solvers/Cylinder_method_flow_testing.py
+        physics set-up 66-218, kink 554-850 (scan loop 701-846), sausage 855-1131
   slab, non-uniform density:
       Slab/Non uniform density/Coronal/Solvers/multiprocessor_Inhomogeneous_method_coronal.py
         physics set-up 69-185, sausage 461-600 (scan loop), kink 640-790
@@ -477,6 +480,80 @@ class CylinderRotation(_Base):
     def int_match(self, k, w, y0, slope):
         c1, d = self._xi(self.s0, w, k)
         return c1 * y0 + d * slope                            # (C1 P + D P')/C3 at r = 1  (:314)
+
+
+@dataclasses.dataclass
+class AxialFlowMedium(Medium):
+    """Cylinder_method_flow_testing.py:66-69 (coronal speeds), :130-131 (U_i0, U_e), :123-124 (r0, dr)."""
+    U_i0: float = 0.35
+    U_e: float = 0.0
+    width: float = 1.0
+    r0: float = 0.0
+
+
+class CylinderFlow(_Base):
+    """Cylinder with a non-uniform axial flow v_z(r) = U_e + (U_i0-U_e) exp(-(r-r0)^2/dr^2), reference
+    Cylinder/Non-uniform flow/Coronal/solvers/Cylinder_method_flow_testing.py (kink :554-850, scan
+    loop :701-846; sausage :855-1131).  Uniform rho_i, B_i = B_0, c_i inside (B_phi = v_phi = 0 as
+    shipped, :190-196).
+
+    As in the reference, F, dF/dr and g are built with sympy from D, Q, T, C1, C2, C3 (:711-762) and
+    differentiated symbolically; they are lambdified once with (r, omega, k) as arguments."""
+    geometry = "cylinder"
+    ext_ic = (1e-8, 1e-8)          # :774  P0 = [1e-8, 1e-8]
+    s0, s1 = -1.0, -0.001          # :120  ix = linspace(-1., -0.001, 1e3)
+    slope_guess = -0.001           # :798  fsolve(objective_dPi, -0.001)
+    n_int_out = 1000
+
+    def __init__(self, medium: AxialFlowMedium, m: int):
+        import sympy as sym
+        self.medium = medium
+        self.m = int(m)
+        self.mode = {0: "sausage", 1: "kink"}.get(self.m, "fluting%d" % self.m)
+        md = medium
+        r = sym.symbols("r", negative=True)
+        w, k = sym.symbols("w k", positive=True)
+        mm = sym.Integer(self.m)
+        rho = sym.Float(md.rho_i0)                                                        # :145
+        B0 = sym.Float(md.B_0)                                                            # :184 (B_phi = 0)
+        vA2 = B0**2 / rho                                                                 # :174
+        c2 = sym.Float(md.rho_e * (md.c_e**2 + 0.5 * md.gamma * md.vA_e**2)) / rho - sym.Float(
+            0.5 * md.gamma) * vA2                                                         # :208
+        vz = sym.Float(md.U_e) + sym.Float(md.U_i0 - md.U_e) * sym.exp(
+            -(r - sym.Float(md.r0)) ** 2 / sym.Float(md.width) ** 2)                      # :134
+        shift = w - k * vz                                                                # :713 (v_phi = 0)
+        alf = k * B0 / sym.sqrt(rho)                                                      # :716
+        cusp2 = alf**2 * c2 / (c2 + vA2)                                                  # :719
+        D = rho * (c2 + vA2) * (shift**2 - alf**2) * (shift**2 - cusp2)                   # :722
+        C2 = shift**4 - (c2 + vA2) * (mm**2 / r**2 + k**2) * (shift**2 - cusp2)           # :738
+        C3 = D * rho * (shift**2 - alf**2)                                                # :744 (Q = T = 0)
+        F = r * D / C3                                                                    # :749
+        dF = sym.diff(F, r)                                                               # :754
+        g = -r * C2 / D                                                                   # :760 (C1 = 0)
+        self._a = sym.lambdify((r, w, k), sym.simplify(-dF / F), "numpy", cse=True)
+        self._b = sym.lambdify((r, w, k), g / F, "numpy", cse=True)
+        self._xi = sym.lambdify((r, w, k), D / C3, "numpy", cse=True)
+
+    def ext_rhs(self, k, w):
+        m_e = self.medium.m_e(k, w)                                                       # :706 (omega unshifted)
+        mm = float(self.m * self.m)
+        return lambda y, r: [y[1], -y[1] / r + (m_e + mm / (r * r)) * y[0]]               # :771 / :1070
+
+    def ext_match(self, k, w, y_b):
+        md = self.medium
+        xi_e_const = -1.0 / (md.rho_e * (k * k * md.vA_e**2 - w * w))                     # :709
+        return y_b[0], xi_e_const * y_b[1]
+
+    def coeffs(self, r, k, w):
+        r = np.float64(r)
+        return self._a(r, w, k), self._b(r, w, k)
+
+    def end_residual(self, y_end, y_start0):
+        # kink: P(axis) - B_phi(-1)^2 xi_e = P(axis) (:795); sausage: P'(axis) = 0 (:1092)
+        return y_end[1] if self.m == 0 else y_end[0]
+
+    def int_match(self, k, w, y0, slope):
+        return self._xi(self.s0, w, k) * slope            # (C1 P + D P')/C3 at r = -1, C1 = 0  (:806)
 
 
 # --------------------------------------------------------------------------

@@ -55,8 +55,24 @@ def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rh
     defaults: the reference's coronal sets.  coordinate='positive': cylinder scripts in r > 0."""
     m = ork_model()
     cyl = kind == "cylinder_density"
-    m.kind = {"slab_density": 0, "cylinder_density": 1, "slab_flow": 2, "cylinder_rotation": 3}[kind]
+    m.kind = {"slab_density": 0, "cylinder_density": 1, "slab_flow": 2, "cylinder_rotation": 3,
+              "cylinder_flow": 4}[kind]
     m.r_sign = -1.0
+    if kind == "cylinder_flow":
+        # Cylinder_method_flow_testing.py:66-69 (coronal speeds), r < 0, P0 = [1e-8, 1e-8] (:774)
+        md = medium
+        vals = (md.c_i0, md.vA_i0, md.vA_e, md.c_e, md.gamma, md.rho_i0, md.U_i0, md.U_e) if md is not None else (
+            1.0, 2.0, 5.0, 0.5, 5.0 / 3.0, 1.0, 0.35, 0.0)
+        m.c_i0, m.vA_i0, m.vA_e, m.c_e, m.gamma, m.rho_i0, m.U_i0, m.U_e = vals
+        m.rho_A = 1.0
+        m.width = width if width is not None else getattr(md, "width", 1.0)
+        m.x0 = x0
+        m.ic_v, m.ic_s = 1e-8, 1e-8
+        m.ext_wavelengths = ext_wavelengths
+        m.s_start, m.s_end = -1.0, (s_end if s_end is not None else -0.001)
+        m.n_ext = n_ext or 6000
+        m.n_int = n_int or 320
+        return m
     if kind == "cylinder_rotation":
         # Twisted_photospheric_nonlinear_flow_kink_fast.py:73-76 (photospheric speeds), r > 0
         md = medium

@@ -49,6 +49,11 @@ POINTS.update({
     "slab_flow_coronal": dict(
         ks=[0.1, 0.6, 1.5, 3.0, 4.5], Ws=[1.3, 1.6, 2.0, 2.4, -0.3, -1.0, -2.0, -0.1, 2.6, 0.1995],
         overrides={"dx": 1.0}),
+    # cylinder with an axial flow: the script ships with U_i0 = 0, dr = 1e5 (no flow at all)
+    "cylinder_flow_coronal": dict(
+        ks=[0.1, 0.6, 1.5, 3.0, 4.0],
+        Ws=[0.52, 0.75, 1.5, 2.7, 3.3, 4.0, 4.9, -0.6, -1.6, -3.0, -4.5, 0.45, 5.2],
+        overrides={"U_i0": 0.35, "dr": 1.0}),
     # rotational flow in its regular regime (power >= 1); the kink script is run with the sausage
     # script's v_twist/power instead of its own (0.25, 0.8), see tests/helpers.py
     "cylinder_rotation_sausage": dict(
@@ -74,6 +79,9 @@ PICKLES = {
                          "Cylindrical_photospheric_width_%s.pickle", {"09": 0.9, "15": 1.5, "3": 3.0, "1e5": 1e5}),
     "slab_photospheric": ("Slab/Non uniform density/Photospheric/Example data/width%s.pickle",
                           {"09": 0.9, "15": 1.5, "3": 3.0, "1e5": 1e5}),
+    "cylflow_coronal": ("Cylinder/Non-uniform flow/Coronal/Example data/Cylindrical_coronal_flow_%s.pickle",
+                        # produced with U_i0 = 0.05 and xi_tol = 6 % (tests/helpers.py ROOT_CASES)
+                        {"1e5": 1e5, "1": 1.0, "06": 0.6}),
     "flow_coronal": ("Slab/Non uniform flow/Example data/flow_width%s_coronal.pickle",
                      # produced with U_i0 = 0.35 (tests/helpers.py ROOT_CASES); the file named
                      # "width125" matches width 2.5 (median mismatch 0.6 %), not 1.25 (15 %)
@@ -121,10 +129,10 @@ def main():
                 sw, sk, kw, kk = pickle.load(fh, encoding="latin1")
             key = "%s_%s" % (fam, tag)
             roots[key + "_width"] = np.array([width])
-            roots[key + "_sausage_w"] = np.asarray(sw, dtype=np.float64)
-            roots[key + "_sausage_k"] = np.asarray(sk, dtype=np.float64)
-            roots[key + "_kink_w"] = np.asarray(kw, dtype=np.float64)
-            roots[key + "_kink_k"] = np.asarray(kk, dtype=np.float64)
+            roots[key + "_sausage_w"] = np.real(np.asarray(sw)).astype(np.float64)
+            roots[key + "_sausage_k"] = np.real(np.asarray(sk)).astype(np.float64)
+            roots[key + "_kink_w"] = np.real(np.asarray(kw)).astype(np.float64)
+            roots[key + "_kink_k"] = np.real(np.asarray(kk)).astype(np.float64)
     # rotational flow: [omega, k] per file; regular regime (power >= 1) only
     rot = "Cylinder/Rotational flow/Photospheric/Example data/Cylindrical_photospheric_vtwist%s_power%s_%s.pickle"
     for vt, pw, kind in (("01", "1", "sausage_fast"), ("01", "125", "sausage_fast"), ("015", "1", "sausage_fast"),

@@ -65,6 +65,11 @@ SOLVERS = {
         "wavenumber = np.linspace(0.75,4.,110.)",
         {"sausage": ("sausage", "xi_diff_check")},
     ),
+    "cylinder_flow_coronal": (
+        "Cylinder/Non-uniform flow/Coronal/solvers/Cylinder_method_flow_testing.py",
+        "wavenumber = np.linspace(0.01,4.,150.)",
+        {"sausage": ("sausage", "xi_diff_check"), "kink": ("kink", "xi_diff_check")},
+    ),
     "slab_flow_coronal": (
         "Slab/Non uniform flow/Solver/flow_multiprocessor_coronal.py",
         "wavenumber = np.linspace(",

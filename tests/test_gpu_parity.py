@@ -167,7 +167,7 @@ def test_shipped_root_tables(golden_dir):
                     pct = np.abs(e - i)[:, 0] * 100 / np.maximum(np.abs(e), np.abs(i))[:, 0]
                     pct = pct[np.isfinite(pct)]
                     total += len(pct)
-                    inside += int((pct < 1.5).sum())
+                    inside += int((pct < 1.5 * case.tol_percent).sum())
         assert total > 300 and inside / total > 0.85, (name, inside, total)
 
 

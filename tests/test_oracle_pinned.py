@@ -8,7 +8,7 @@
   formulation)  == oracle/dispersion_rk.c (the fast C restatement used on whole grids)
 
 for every solver variant in helpers.CASES (cylinder/slab density, coronal and
-photospheric parameter sets, and the sheared-flow slab).
+photospheric parameter sets, the sheared-flow slab, the axial-flow and the rotational-flow cylinder).
 """
 import os
 import warnings
@@ -26,7 +26,8 @@ TIGHT = dict(rtol=1e-12, atol="scaled", shoot="linear")
 
 @pytest.mark.parametrize("name,tol,stride", [("cylinder_density", 1e-7, 3), ("slab_density", 1e-8, 4),
                                              ("cylinder_photospheric", 1e-7, 1),
-                                             ("slab_photospheric", 1e-7, 3), ("slab_flow", 1e-7, 2)])
+                                             ("slab_photospheric", 1e-7, 3), ("slab_flow", 1e-7, 2),
+                                             ("cylinder_flow", 1e-7, 3)])
 def test_oracle_equals_executed_reference(golden_dir, name, tol, stride):
     """D from the reference's own sausage()/kink() vs the restatement at the SAME solver
     settings (scipy defaults, fsolve, the reference's output grids): agreement is at the
@@ -106,14 +107,14 @@ def test_shipped_root_tables_pass_acceptance_under_oracle(golden_dir):
                 pct = np.array(pct)
                 pct = pct[np.isfinite(pct)]
                 total += len(pct)
-                inside += int((pct < 1.5).sum())
+                inside += int((pct < 1.5 * case.tol_percent).sum())
                 if len(pct) > 5:
-                    medians.append(np.median(pct))
+                    medians.append(np.median(pct) / case.tol_percent)
         stats[name] = (inside, total, max(medians) if medians else None)
     for name, (inside, total, med) in stats.items():
         assert total > 50, (name, total)
         assert inside / total > 0.85, (name, inside, total)
-        assert med < 0.9, (name, med)      # accepted anywhere below 1 % -> median near 0.5 %
+        assert med < 0.9, (name, med)      # accepted anywhere below tol (1 %; 6 % cylinder flow) -> median near tol/2
 
 
 @pytest.mark.parametrize("name", list(CASES))
