@@ -38,13 +38,15 @@ NK, NW = 1000, 10000
 MODES = (0, 1, 2)
 K_RANGE = (0.01, 4.5)          # Density_cylinder.py:1126  wavenumber = linspace(0.01, 4.5, ...)
 W_RANGE = (0.5, 5.0)           # c_e .. vA_e : the phase-speed window in which m_e >= 0
-N_STEPS = 256
-# algorithmic FP64 flops (fma = 2, mul/add/div = 1), see DESIGN.md.  Per RK8 step:
-#   4 node-coefficient evaluations x 15 flop, shared by the modes evaluated together
-#   + per mode: 4 x 2 (b + m^2/r^2) + 231 stage arithmetic
-# one D evaluation alone: 60 + 239 = 299 flop/step; three fused: (60 + 3*239)/3 = 259 flop/step/eval
-FLOPS_PER_EVAL = 299 * N_STEPS + 700
-FLOPS_FUSED_LAUNCH = ((60 + 3 * 239) * N_STEPS + 3 * 500) * NK * NW
+N_STEPS = 144                  # the cylinder kind's default: graded mesh, see DESIGN.md
+# algorithmic FP64 flops (fma = 2, mul/add/div = 1), see DESIGN.md.  Per RK8 step in the step-scaled
+# variables (y, h y'):
+#   shared by the modes evaluated together: 4 node-coefficient evaluations x 14 flop + 16 (h a, h^2 b)
+#   per mode: 176 (88 FMAs of the 11 stage sums) + 33 (11 x mul + fma right-hand sides)
+#             + 10 (b + m^2/r^2 at 5 nodes) + 1 (rescaling h y' to the next step) = 220
+# one D evaluation alone: 72 + 220 = 292 flop/step; three fused: (72 + 3*220)/3 = 244 flop/step/eval
+FLOPS_PER_EVAL = 292 * N_STEPS + 700
+FLOPS_FUSED_LAUNCH = ((72 + 3 * 220) * N_STEPS + 3 * 500) * NK * NW
 WORKLOAD = "cylinder non-uniform density, n=0,1,2, 1000 k x 10000 omega per GPU"
 
 
@@ -113,6 +115,21 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------- GPU arm ----
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused grid kernel on this
+    workload, from the committed `ncu --set full` capture (profiles/ncu_traffic.json names the
+    report it was read from); None if no capture of this configuration is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            rec = json.load(fh)
+        if rec.get("nk") == NK and rec.get("nw") == NW and rec.get("modes") == list(MODES) and \
+                rec.get("n_steps") == N_STEPS:
+            return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -269,7 +286,7 @@ def run_gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "modes": list(MODES), "nk_per_gpu": NK, "nw": NW,
-                       "n_steps": N_STEPS, "scheme": "rk8", "profile": "inverted Gaussian, width 0.95",
+                       "n_steps": N_STEPS, "mesh": "graded", "scheme": "rk8", "profile": "inverted Gaussian, width 0.95",
                        "l2": "working set 480 MB of D written per step > 126 MB L2; inputs are 88 KB"},
             "roots_per_sec": n_brackets * world * args.steps / (ms * 1e-3),
             "modes_found_rank0": n_modes, "brackets_rank0": n_brackets,
@@ -277,7 +294,7 @@ def run_gpu_arm(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak, "traffic": ncu_traffic(),
                          "kernel": "grid_kernel<cylinder,rk8,3 modes fused>", "kernel_ms": kms,
                          "flops_per_launch": FLOPS_FUSED_LAUNCH,
                          "peak_source": "esb_fp64_peak: DFMA-chain kernel measured in this process "

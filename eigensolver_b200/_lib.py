@@ -16,7 +16,7 @@ ESB_OK, ESB_ERR_ARG, ESB_ERR_CUDA, ESB_ERR_CAPACITY, ESB_ERR_ALLOC = 0, -1, -2, 
 SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW, CYLINDER_ROTATION, CYLINDER_FLOW = 0, 1, 2, 3, 4
 RK4, RK8 = 0, 1
 OMEGA_SHARED, OMEGA_PHASE_SPEED, OMEGA_PER_K = 0, 1, 2
-MESH_CLUSTERED, MESH_UNIFORM = 0, 1
+MESH_CLUSTERED, MESH_UNIFORM, MESH_GRADED = 0, 1, 2
 
 
 class EsbError(RuntimeError):
@@ -31,6 +31,7 @@ class esb_model(C.Structure):
         ("ext_ic_value", C.c_double), ("ext_ic_slope", C.c_double), ("ext_wavelengths", C.c_double),
         ("s_start", C.c_double), ("s_end", C.c_double), ("U_e", C.c_double),
         ("r_sign", C.c_int32), ("reserved", C.c_int32),
+        ("mesh_axis", C.c_double), ("mesh_edge", C.c_double), ("mesh_edge_width", C.c_double),
     ]
 
 

@@ -224,15 +224,16 @@ ESB_HD void rk8_generic(double (&y)[NS], double (&yp)[NS], const RHS& rhs) {
     }
 }
 
-// y'' = a y' + b_s y : (u, v) = (y, y'), u' = v, v' = a v + b_s u.   ha = h a, hbs = h b_s.
+// y'' = a y' + b_s y in the step-scaled variables (u, z) = (y, h y'):  h u' = z,
+// h z' = (h a) z + (h^2 b_s) u.  ha = h a, h2bs = h^2 b_s: the first component's stage slope is the
+// stage value of z itself (no multiplication), the second is one multiply + one FMA.
 template <int NS>
 struct RhsSecondOrder {
-    double h;
     const double (&ha)[5];
-    const double (&hbs)[NS][5];
-    ESB_HD void operator()(int s, int n, double U, double V, double& FU, double& FV) const {
-        FU = h * V;
-        FV = fma(ha[n], V, hbs[s][n] * U);
+    const double (&h2bs)[NS][5];
+    ESB_HD void operator()(int s, int n, double U, double Z, double& FU, double& FZ) const {
+        FU = Z;
+        FZ = fma(ha[n], Z, h2bs[s][n] * U);
     }
 };
 
@@ -249,12 +250,11 @@ struct RhsSystem {
     }
 };
 
-// ca, cbs: coefficients already multiplied by h
+// one step for (y, z = h y'); ha = h a, h2bs = h^2 b_s
 template <int NS>
-ESB_HD void rk8_step(double (&y)[NS], double (&yp)[NS], double h, const double (&ha)[5],
-                     const double (&hbs)[NS][5]) {
-    const RhsSecondOrder<NS> rhs{h, ha, hbs};
-    rk8_generic<NS>(y, yp, rhs);
+ESB_HD void rk8_step(double (&y)[NS], double (&z)[NS], const double (&ha)[5], const double (&h2bs)[NS][5]) {
+    const RhsSecondOrder<NS> rhs{ha, h2bs};
+    rk8_generic<NS>(y, z, rhs);
 }
 
 template <int NS>
@@ -275,17 +275,25 @@ ESB_HD void rk4_step(double (&y)[NS], double (&yp)[NS], double h, const double (
     }
 }
 
-// Integrate NS solutions along the staged mesh.  tab: [n_nodes][TAB_FIELDS] then h[n_steps].
+// Integrate NS solutions along the staged mesh.  tab: [n_nodes][TAB_FIELDS], then h[n_steps], then
+// g[n_steps] = h[i+1]/h[i] (g[n_steps-1] = 1/h[n_steps-1]).
 // m2[s] = (azimuthal order)^2 of solution s (cylinder); the node coefficients are evaluated
-// once per node and shared by all solutions.
+// once per node and shared by all solutions.  RK8 runs in the step-scaled variables (y, z = h y'):
+// g[i] rescales z from one step to the next and back to y' after the last one.
 template <int KIND, int SCHEME, int NS>
 ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __restrict__ tab,
                             const double (&m2)[NS], double (&y)[NS], double (&yp)[NS]) {
     const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
+    const double* gs = hs + M.n_steps;
     constexpr int NPS = (SCHEME == SCHEME_RK8) ? 4 : 2;
     constexpr int NN = NPS + 1;
     double a0, b0, bm0;
     node_coeffs<KIND>(M, pt, tab, a0, b0, bm0);
+    if constexpr (SCHEME == SCHEME_RK8) {
+        const double h0 = hs[0];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) yp[s] *= h0;
+    }
     for (int i = 0; i < M.n_steps; ++i) {
         const double* f = tab + (size_t)(i * NPS) * TAB_FIELDS;
         const double h = hs[i];
@@ -295,16 +303,23 @@ ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __
         for (int n = 1; n < NN; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n], bm[n]);
         a0 = ca[NN - 1]; b0 = cb[NN - 1]; bm0 = bm[NN - 1];       // unscaled, carried to the next step
         if constexpr (SCHEME == SCHEME_RK8) {
-            // fold the step into the node coefficients (shared by all solutions)
+            // fold the step into the node coefficients (shared by all solutions): h a, h^2 b
+            const double h2 = h * h;
 #pragma unroll
-            for (int n = 0; n < NN; ++n) { ca[n] *= h; cb[n] *= h; bm[n] *= h; }
+            for (int n = 0; n < NN; ++n) { ca[n] *= h; cb[n] *= h2; bm[n] *= h2; }
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int n = 0; n < NN; ++n) cbs[s][n] = is_cyl_second_order<KIND> ? fma(m2[s], bm[n], cb[n]) : cb[n];
-        if constexpr (SCHEME == SCHEME_RK8) rk8_step<NS>(y, yp, h, ca, cbs);
-        else rk4_step<NS>(y, yp, h, ca, cbs);
+        if constexpr (SCHEME == SCHEME_RK8) {
+            rk8_step<NS>(y, yp, ca, cbs);
+            const double g = gs[i];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) yp[s] *= g;
+        } else {
+            rk4_step<NS>(y, yp, h, ca, cbs);
+        }
     }
 }
 

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -365,9 +366,47 @@ static double cluster(double t) {   // sin^2(pi t/2): clusters nodes at both end
     return s * s;
 }
 
+// mesh = 2 (cylinder kinds): breakpoints from the axis end to the boundary with the local step
+// H * min(1, |r|/axis, (edge + |r - boundary|)/edge_width); N steps fix H.  The node count up to r,
+// t(r) = int dr/h, is accumulated on a fine midpoint rule and inverted by linear interpolation.
+static void graded_breakpoints(const esb_model* m, std::vector<double>& out) {
+    const int N = m->n_steps, M = 400000;
+    const double a = m->s_end, b = m->s_start;                    // axis end, boundary
+    const double ax = m->mesh_axis > 0 ? m->mesh_axis : 1e300;
+    const double ew = m->mesh_edge_width > 0 ? m->mesh_edge_width : 0.0;
+    std::vector<double> t(M + 1);
+    t[0] = 0.0;
+    const double dr = (b - a) / M;
+    for (int j = 0; j < M; ++j) {
+        const double r = a + (j + 0.5) * dr;
+        double h = 1.0;
+        h = fmin(h, fabs(r) / ax);
+        if (ew > 0) h = fmin(h, (m->mesh_edge + fabs(r - b)) / ew);
+        t[j + 1] = t[j] + fabs(dr) / h;
+    }
+    out.resize(N + 1);
+    int j = 0;
+    for (int i = 0; i <= N; ++i) {
+        const double target = t[M] * double(i) / N;
+        while (j < M - 1 && t[j + 1] < target) ++j;
+        const double f = (target - t[j]) / (t[j + 1] - t[j]);
+        out[i] = a + (j + f) * dr;
+    }
+    out[0] = a;
+    out[N] = b;
+}
+
 static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
     const int N = m->n_steps;
     bp.resize(N + 1);
+    const bool cyl = m->kind == ESB_CYLINDER_ROTATION || m->kind == ESB_CYLINDER_DENSITY ||
+                     m->kind == ESB_CYLINDER_FLOW;
+    if (m->mesh == 2 && cyl) {
+        graded_breakpoints(m, bp);                                // axis -> boundary
+        if (m->kind == ESB_CYLINDER_ROTATION)                     // integrates boundary -> axis
+            for (int i = 0; i < (N + 1) / 2; ++i) std::swap(bp[i], bp[N - i]);
+        return ESB_OK;
+    }
     if (m->kind == ESB_CYLINDER_ROTATION) {
         // forward, boundary (s_start) -> axis end (s_end): the kink end condition is inhomogeneous
         for (int i = 0; i <= N; ++i) {
@@ -410,6 +449,8 @@ static int check_model(const esb_model* m) {
     if (m->kind == ESB_CYLINDER_ROTATION && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->scheme != ESB_RK4 && m->scheme != ESB_RK8) return ESB_ERR_ARG;
     if (m->n_steps < 2 || m->n_steps > 8192) return ESB_ERR_ARG;
+    if (m->mesh < 0 || m->mesh > 2) return ESB_ERR_ARG;
+    if (m->mesh == 2 && (m->kind == ESB_SLAB_DENSITY || m->kind == ESB_SLAB_FLOW)) return ESB_ERR_ARG;
     if ((m->kind == ESB_SLAB_DENSITY || m->kind == ESB_SLAB_FLOW) && (m->n_steps % 2)) return ESB_ERR_ARG;
     return ESB_OK;
 }
@@ -429,11 +470,15 @@ extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
     out->ext_ic_value = 1e-8;
     out->s_start = -1.0;
     out->r_sign = -1;
+    // graded mesh (mesh = 2): measured on the B200 (scripts/gpu_mesh.py) - with these
+    // parameters 128 steps reach the accuracy of 256 sin^2-clustered steps; 144 is the default
+    out->mesh_axis = 0.16; out->mesh_edge = 0.02; out->mesh_edge_width = 0.10;
     if (kind == ESB_CYLINDER_DENSITY) {          // Density_cylinder.py:69-72,120,768
         out->vA_i0 = 2.0; out->vA_e = 5.0; out->c_e = 0.5;
         out->ext_ic_slope = 1e-15;
         out->s_end = -0.001;
-        out->n_steps = 256;
+        out->mesh = 2;
+        out->n_steps = 144;
     } else if (kind == ESB_SLAB_DENSITY) {       // ..._coronal.py:69-72,91,247
         out->vA_i0 = 1.2; out->vA_e = 3.0; out->c_e = 0.4;
         out->ext_ic_slope = 1e-8;
@@ -456,7 +501,8 @@ extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
         out->vA_i0 = 2.0; out->vA_e = 5.0; out->c_e = 0.5;
         out->ext_ic_slope = 1e-8;
         out->s_end = -0.001;
-        out->n_steps = 256;
+        out->mesh = 2;
+        out->n_steps = 144;
     } else {
         return ESB_ERR_ARG;
     }
@@ -563,7 +609,8 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     std::vector<double> nodes(need);
     if (esb_mesh_nodes(m, nodes.data())) return fail(c, ESB_ERR_ARG, "mesh");
     const int N = m->n_steps, nps = nodes_per_step(m->scheme);
-    std::vector<double> tab((size_t)need * TAB_FIELDS + N, 0.0);
+    // [need][TAB_FIELDS] node fields, h[N], g[N] = h[i+1]/h[i] (last: 1/h[N-1]); see integrate_layer
+    std::vector<double> tab((size_t)need * TAB_FIELDS + 2 * (size_t)N, 0.0);
     for (int i = 0; i < need; ++i) {
         double* f = &tab[(size_t)i * TAB_FIELDS];
         if (m->kind == ESB_CYLINDER_DENSITY || m->kind == ESB_CYLINDER_FLOW) {
@@ -583,7 +630,11 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
             for (int q = 0; q < n_fields; ++q) f[q] = fields[q][i];
         }
     }
-    for (int i = 0; i < N; ++i) tab[(size_t)need * TAB_FIELDS + i] = nodes[(i + 1) * nps] - nodes[i * nps];
+    {
+        double* hs = &tab[(size_t)need * TAB_FIELDS];
+        for (int i = 0; i < N; ++i) hs[i] = nodes[(i + 1) * nps] - nodes[i * nps];
+        for (int i = 0; i < N; ++i) hs[N + i] = (i + 1 < N) ? hs[i + 1] / hs[i] : 1.0 / hs[i];
+    }
 
     DevModel& d = c->dm;
     memset(&d, 0, sizeof(d));
@@ -1050,13 +1101,15 @@ extern "C" int esb_rk_selftest(int32_t scheme, int32_t n_steps, double T, double
         const double t0 = i * h;
         if (scheme == ESB_RK8) {
             const double c[5] = {0.0, C8_M, 0.5, C8_P, 1.0};
-            double ha[5], hb[1][5];
+            double ha[5], h2b[1][5];
             for (int n = 0; n < 5; ++n) {
                 const double t = t0 + c[n] * h;
                 ha[n] = h * sin(t);
-                hb[0][n] = -h * (1.0 + t * t);
+                h2b[0][n] = -h * h * (1.0 + t * t);
             }
-            rk8_step<1>(y, yp, h, ha, hb);
+            double z[1] = {h * yp[0]};           // step-scaled slope, as in integrate_layer
+            rk8_step<1>(y, z, ha, h2b);
+            yp[0] = z[0] / h;
         } else {
             const double c[3] = {0.0, 0.5, 1.0};
             double a[3], b[1][3];

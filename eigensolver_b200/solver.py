@@ -194,8 +194,9 @@ def _iptr(a):
 class DispersionSolver:
     """One GPU context evaluating D(omega,k) for one equilibrium model."""
 
-    def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh="clustered",
-                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None):
+    def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh=None,
+                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None,
+                 mesh_params=None):
         """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation" |
         "cylinder_flow".
         profile: callable (medium, x) -> (rho, rho') for the density kinds, (U, U', U'') for
@@ -227,7 +228,11 @@ class DispersionSolver:
             m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, rho_A
             m.U_e = getattr(medium, "U_e", 0.0)
         m.scheme = _SCHEMES[scheme]
-        m.mesh = L.MESH_UNIFORM if mesh == "uniform" else L.MESH_CLUSTERED
+        if mesh is not None:              # None: the kind's default (graded for the cylinder density /
+            # axial-flow kinds, sin^2-clustered otherwise)
+            m.mesh = {"uniform": L.MESH_UNIFORM, "clustered": L.MESH_CLUSTERED, "graded": L.MESH_GRADED}[mesh]
+        if mesh_params is not None:       # (mesh_axis, mesh_edge, mesh_edge_width) of the graded mesh
+            m.mesh_axis, m.mesh_edge, m.mesh_edge_width = (float(v) for v in mesh_params)
         m.ext_wavelengths = ext_wavelengths
         if n_steps is not None:
             m.n_steps = int(n_steps)

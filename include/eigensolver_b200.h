@@ -77,7 +77,8 @@ typedef struct esb_model {
     int32_t kind;          /* esb_model_kind */
     int32_t scheme;        /* esb_scheme */
     int32_t n_steps;       /* integration steps across the layer */
-    int32_t mesh;          /* 0 = nodes clustered at the layer ends (default), 1 = uniform */
+    int32_t mesh;          /* 0 = sin^2 clustering at the layer ends, 1 = uniform, 2 = graded
+                              (target step size, see mesh_axis/mesh_edge below; cylinder kinds) */
     double c_i0, vA_i0, vA_e, c_e, gamma, rho_i0;
     double rho_A;          /* amplitude multiplying the density profile (reference rho_A) */
     double ext_ic_value;   /* exterior initial values at x = -3*2*pi/k: (1e-8,            */
@@ -92,6 +93,11 @@ typedef struct esb_model {
     int32_t r_sign;        /* cylinder: -1 = script written in r<0 (coronal, default), +1 = r>0
                               (photospheric: s_start=1, s_end=0.001, slope given as dP/dr)     */
     int32_t reserved;
+    /* mesh = 2: the local step is H * min(1, |r|/mesh_axis, (mesh_edge + |r - s_start|)/mesh_edge_width)
+     * with H fixed by n_steps: geometric towards the axis (where the 1/r, m^2/r^2 coefficients
+     * need h ~ r), refined towards the boundary (where a resonance just outside the layer makes
+     * the coefficients vary fastest), uniform in between. */
+    double mesh_axis, mesh_edge, mesh_edge_width;
 } esb_model;
 
 /* Defaults of the reference scripts for `kind` (coronal parameter set). */
