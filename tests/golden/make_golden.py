@@ -49,6 +49,8 @@ POINTS.update({
     "slab_flow_coronal": dict(
         ks=[0.1, 0.6, 1.5, 3.0, 4.5], Ws=[1.3, 1.6, 2.0, 2.4, -0.3, -1.0, -2.0, -0.1, 2.6, 0.1995],
         overrides={"dx": 1.0}),
+    "slab_flow_photospheric": dict(
+        ks=[0.1, 0.6, 1.5, 3.0], Ws=[0.2, 0.3, 0.45, 0.5, 0.58, -0.3, -0.5, -0.7, -0.85, 0.65, -0.95], overrides={}),
     # cylinder with an axial flow: the script ships with U_i0 = 0, dr = 1e5 (no flow at all)
     "cylinder_flow_coronal": dict(
         ks=[0.1, 0.6, 1.5, 3.0, 4.0],

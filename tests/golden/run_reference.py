@@ -70,6 +70,12 @@ SOLVERS = {
         "wavenumber = np.linspace(0.01,4.,150.)",
         {"sausage": ("sausage", "xi_diff_check"), "kink": ("kink", "xi_diff_check")},
     ),
+    "slab_flow_photospheric": (
+        # the steady (uniform) flow slab: U_i = 0 inside, U_e = -0.15 outside, vA_e = 0, 7 wavelengths
+        "Slab/Non uniform flow/Solver/flow_multiprocessor.py",
+        "wavenumber = np.linspace(0.01,3.5,350)",
+        {"sausage": ("sausage", "P_diff_check"), "kink": ("kink", "P_diff_check_kink")},
+    ),
     "slab_flow_coronal": (
         "Slab/Non uniform flow/Solver/flow_multiprocessor_coronal.py",
         "wavenumber = np.linspace(",

@@ -92,7 +92,8 @@ class Case:
 
     def __init__(self, name, kind, modes, W, width, medium_name=None, coordinate="negative",
                  roots_window=None, fixture=None, family=None, ext_wavelengths=3.0, U_i0=0.9,
-                 v_twist=0.15, power=1.25, s_end=None, tol_percent=1.0):
+                 v_twist=0.15, power=1.25, s_end=None, tol_percent=1.0, flow_medium=None):
+        self.flow_medium = dict(flow_medium or {})      # slab_flow: FlowMedium fields other than U_i0, width
         self.tol_percent = tol_percent      # the script's acceptance threshold (xi_tol / p_tol)
         self.ext_wavelengths = ext_wavelengths
         self.U_i0 = U_i0
@@ -106,7 +107,7 @@ class Case:
     # ---- oracles
     def rp_medium(self):
         if self.kind == "slab_flow":
-            return rp.FlowMedium(width=self.width, U_i0=self.U_i0)
+            return rp.FlowMedium(width=self.width, U_i0=self.U_i0, **self.flow_medium)
         if self.kind == "cylinder_flow":
             return rp.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0, width=self.width)
         return getattr(rp, self.medium_name)
@@ -132,7 +133,12 @@ class Case:
                                500 if fast else None)
             m.ext_wavelengths = self.ext_wavelengths
             return m
-        return rp.SlabFlow(rp.FlowMedium(width=w, U_i0=self.U_i0), "sausage" if mode == 0 else "kink")
+        m = rp.SlabFlow(rp.FlowMedium(width=w, U_i0=self.U_i0, **self.flow_medium),
+                        "sausage" if mode == 0 else "kink")
+        m.ext_wavelengths = self.ext_wavelengths
+        if self.flow_medium:
+            m.slope_guess = 0.5            # flow_multiprocessor.py:575  fsolve(objective_dvxi, 0.5)
+        return m
 
     def c_model(self, width=None, **kw):
         w = self.width if width is None else width
@@ -140,7 +146,8 @@ class Case:
             return ork.make_model("cylinder_rotation", medium=self.rp_medium(), v_twist=self.v_twist,
                                   power=self.power, s_end=self.s_end, **kw)
         if self.kind == "slab_flow":
-            return ork.make_model("slab_flow", medium=rp.FlowMedium(width=w, U_i0=self.U_i0), width=w, **kw)
+            return ork.make_model("slab_flow", medium=rp.FlowMedium(width=w, U_i0=self.U_i0, **self.flow_medium),
+                                  width=w, ext_wavelengths=self.ext_wavelengths, **kw)
         if self.kind == "cylinder_flow":
             return ork.make_model("cylinder_flow", medium=rp.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0),
                                   width=w, **kw)
@@ -150,7 +157,7 @@ class Case:
     def intervals(self, width=None):
         w = self.width if width is None else width
         if self.kind == "slab_flow":
-            return flow_continua(rp.FlowMedium(width=w, U_i0=self.U_i0))
+            return flow_continua(rp.FlowMedium(width=w, U_i0=self.U_i0, **self.flow_medium))
         if self.kind == "cylinder_flow":
             return axial_flow_continua(rp.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0, width=w))
         if self.kind == "cylinder_density":
@@ -183,8 +190,8 @@ class Case:
                                         profile=esb.PowerLawRotation(self.v_twist, self.power),
                                         s_end=self.s_end, **kw)
         if self.kind == "slab_flow":
-            return esb.DispersionSolver("slab_flow", medium=esb.FlowMedium(U_i0=self.U_i0),
-                                        profile=esb.GaussianFlow(w), **kw)
+            return esb.DispersionSolver("slab_flow", medium=esb.FlowMedium(U_i0=self.U_i0, **self.flow_medium),
+                                        profile=esb.GaussianFlow(w), ext_wavelengths=self.ext_wavelengths, **kw)
         if self.kind == "cylinder_flow":
             return esb.DispersionSolver("cylinder_flow",
                                         medium=esb.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0),
@@ -208,6 +215,11 @@ CASES = {c.name: c for c in [
          ext_wavelengths=7.0),
     Case("slab_flow", "slab_flow", (0, 1), (-2.7, 2.7), 1.0, None,
          roots_window=(1.25, 2.45), fixture="slab_flow_coronal"),
+    # the steady-flow slab of flow_multiprocessor.py (photospheric set): U = 0 inside, U_e = -0.15 outside,
+    # vA_e = 0, 7-wavelength exterior; m_e >= 0 only for |W - U_e| <= c_e
+    Case("slab_flow_photospheric", "slab_flow", (0, 1), (-0.88, 0.58), 1e5, None,
+         roots_window=(0.2, 0.53), fixture="slab_flow_photospheric", U_i0=0.0, ext_wavelengths=7.0,
+         flow_medium=dict(vA_i=1.0, c_i=2.0 / 3.0, vA_e=0.0, c_e=0.75, U_e=-0.15)),
     # cylinder with an axial flow v_z(r) (Cylinder_method_flow_testing.py); D is not even in omega
     Case("cylinder_flow", "cylinder_flow", (0, 1, 2), (-5.2, 5.2), 1.0, None,
          roots_window=(2.95, 4.95), fixture="cylinder_flow_coronal", U_i0=0.35),

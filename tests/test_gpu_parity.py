@@ -132,10 +132,18 @@ def test_against_executed_reference_fixture(solvers, golden_dir, name):
         ok = ~np.isnan(Dref) & regular_mask(w / k, iv) & (np.abs(D) > 1e-3 * scale)
         if name == "slab_density":
             ok &= w / k < 2.9
+        if name == "slab_flow_photospheric":
+            # that script starts fsolve at 0.5 while its 7-wavelength exterior makes the slope 1e6-1e9:
+            # where the reference's own fsolve gave up (its D differs from the value linear shooting
+            # gives at the same solver settings) the fixture value is termination noise
+            m = case.scipy_model(mode)
+            for j in np.nonzero(ok)[0]:
+                el, il = rp.dispersion(m, k[j], w[j], shoot="linear")
+                ok[j] = abs((el - il) - Dref[j]) <= 1e-4 * max(abs(el), abs(il))
         assert ok.sum() >= 12, ok.sum()
         assert np.array_equal(np.sign(D[ok]), np.sign(Dref[ok]))
         ratio = D[ok] / Dref[ok]
-        if name != "slab_photospheric":
+        if name not in ("slab_photospheric", "slab_flow_photospheric"):
             # (that script's 7-wavelength exterior amplifies the reference's start-up error to
             #  factors of 4-100 for small W: only the sign is meaningful there)
             assert ratio.min() > 0.5 and ratio.max() < 1.6, (ratio.min(), ratio.max())

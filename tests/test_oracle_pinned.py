@@ -27,7 +27,7 @@ TIGHT = dict(rtol=1e-12, atol="scaled", shoot="linear")
 @pytest.mark.parametrize("name,tol,stride", [("cylinder_density", 1e-7, 3), ("slab_density", 1e-8, 4),
                                              ("cylinder_photospheric", 1e-7, 1),
                                              ("slab_photospheric", 1e-7, 3), ("slab_flow", 1e-7, 2),
-                                             ("cylinder_flow", 1e-7, 3)])
+                                             ("cylinder_flow", 1e-7, 3), ("slab_flow_photospheric", 1e-7, 2)])
 def test_oracle_equals_executed_reference(golden_dir, name, tol, stride):
     """D from the reference's own sausage()/kink() vs the restatement at the SAME solver
     settings (scipy defaults, fsolve, the reference's output grids): agreement is at the
@@ -53,6 +53,10 @@ def test_oracle_equals_executed_reference(golden_dir, name, tol, stride):
         # its D is termination noise; the linear-shooting value exposes those points
         el, il = rp.dispersion(models[int(mode)], k, w, shoot="linear")
         if abs((el - il) - Dor) > 1e-4 * max(abs(el), abs(il)):
+            continue
+        if name == "slab_flow_photospheric" and abs((el - il) - Dref) > 1e-4 * max(abs(el), abs(il)):
+            # that script starts fsolve at 0.5 while the 7-wavelength exterior makes the slope ~1e6-1e9:
+            # at some points the reference's own fsolve gives up where the restatement's converges
             continue
         assert np.sign(Dor) == np.sign(Dref)
         assert abs(Dor - Dref) <= tol * max(abs(el), abs(il)), (mode, k, w, Dref, Dor)
