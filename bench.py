@@ -166,7 +166,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     import eigensolver_b200 as esb
-    from eigensolver_b200.distributed import gather_root_tables, gather_root_tables_device
+    from eigensolver_b200.distributed import gather_root_tables_device, shard_k
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,9 +178,10 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # weak scaling: rank r owns wavenumbers [r*NK, (r+1)*NK) of a world*NK grid over K_RANGE
+    # weak scaling: a world*NK wavenumber grid over K_RANGE, rank r owns rows r, r+world, ... (strided:
+    # the number of modes grows with k, contiguous slabs would leave the step time to the busiest rank)
     k_all = np.linspace(K_RANGE[0], K_RANGE[1], NK * world)
-    k = np.ascontiguousarray(k_all[rank * NK:(rank + 1) * NK])
+    k, k_off, k_stride = shard_k(k_all, rank, world, layout="strided")
     W = np.linspace(W_RANGE[0], W_RANGE[1], NW)
     # pinned host staging for the end-to-end leg
     k_pin = torch.from_numpy(k.copy()).pin_memory()
@@ -197,31 +198,37 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def gather(tables):
-        if world == 1:
-            return sum(len(t.omega) for t in tables)
-        n = 0
-        for t in tables:
-            gk, gw, ga = gather_root_tables(t.k_index, t.omega, t.accepted, rank * NK, device=dev)
-            n += len(gw)
-        return n
-
     def step_resident():
         """axes resident in HBM; root tables stay on the device until the gather."""
         ns = solver.sweep_resident_multi(MODES)
         kms = [solver.last_kernel_ms()]
-        if world > 1:       # NCCL gather of the root tables straight from the device buffers
+        if world > 1:       # NCCL gather of the modes straight from the device buffers
             for slot in range(len(MODES)):
-                gather_root_tables_device(solver, slot, rank * NK, dev)
+                gather_root_tables_device(solver, slot, k_off, dev, k_stride=k_stride, accepted_only=True,
+                                          sort=True)
         return kms, ns
 
     def step_e2e():
-        """public host API: pinned k/omega in, root tables (host) out, every mode."""
-        tables = solver.find_roots_multi(MODES, k_pin.numpy(), W_pin.numpy())
+        """Host buffers in, root tables on the host out.  One GPU: the public host call
+        (find_roots_multi = esb_upload_axes + esb_sweep_resident_multi + esb_download_roots_slot).
+        Several GPUs: every rank uploads its pinned k/omega, sweeps, the modes (what the reference's
+        sol_ks / sol_omegas hold) are gathered over NCCL and rank 0 copies the global table to the host."""
         h2d = k_pin.numel() * 8 + W_pin.numel() * 8
-        d2h = sum(len(t.omega) * (8 * 3 + 4 * 4) for t in tables)
-        nroots = gather(tables)
-        return h2d, d2h, tables, nroots
+        if world == 1:
+            tables = solver.find_roots_multi(MODES, k_pin.numpy(), W_pin.numpy())
+            d2h = sum(len(t.omega) * (8 * 3 + 4 * 4) for t in tables)
+            return h2d, d2h, sum(int(t.accepted.sum()) for t in tables), sum(len(t.omega) for t in tables)
+        solver.upload_axes(k_pin.numpy(), W_pin.numpy())
+        ns = solver.sweep_resident_multi(MODES)
+        d2h = n_modes = 0
+        for slot in range(len(MODES)):
+            g = gather_root_tables_device(solver, slot, k_off, dev, k_stride=k_stride, accepted_only=True,
+                                          sort=True)
+            n_modes += g.shape[0]
+            if rank == 0:
+                host = g.cpu()
+                d2h += host.numel() * 8
+        return h2d, d2h, n_modes, sum(ns)
 
     # ---- device-resident timing ----
     solver.upload_axes(k, W)
@@ -249,7 +256,7 @@ def run_gpu_arm(args):
     e0.record(stream)
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        h2d, d2h, tabs, nroots = step_e2e()
+        h2d, d2h, n_modes, n_brackets = step_e2e()
     e1.record(stream)
     barrier()
     ms_e2e_dev = e0.elapsed_time(e1)
@@ -264,8 +271,6 @@ def run_gpu_arm(args):
     evals_per_step = len(MODES) * NK * NW * world
     value = evals_per_step * args.steps / (ms * 1e-3)
     e2e = evals_per_step * args.steps / (ms_e2e * 1e-3)
-    n_modes = int(sum(tb.accepted.sum() for tb in tabs))
-    n_brackets = int(sum(len(tb.omega) for tb in tabs))
 
     if rank == 0:
         kms = float(np.mean(kernel_ms))                      # one fused launch = 3 modes x NK*NW evals
@@ -285,11 +290,11 @@ def run_gpu_arm(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "modes": list(MODES), "nk_per_gpu": NK, "nw": NW,
+            "config": {"workload": WORKLOAD, "modes": list(MODES), "nk_per_gpu": NK, "nw": NW, "k_shards": "strided",
                        "n_steps": N_STEPS, "mesh": "graded", "scheme": "rk8", "profile": "inverted Gaussian, width 0.95",
                        "l2": "working set 480 MB of D written per step > 126 MB L2; inputs are 88 KB"},
             "roots_per_sec": n_brackets * world * args.steps / (ms * 1e-3),
-            "modes_found_rank0": n_modes, "brackets_rank0": n_brackets,
+            "modes_found": n_modes, "brackets_rank0": n_brackets,
             "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

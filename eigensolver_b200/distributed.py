@@ -3,10 +3,15 @@
 The reference parallelises by starting one OS process per (k, speed interval)
 (Density_cylinder.py:1142-1159) and collecting the per-process lists through
 multiprocessing queues (:1161-1171).  Here the same decomposition is one process
-per GPU: every rank sweeps its own contiguous slab of wavenumbers - no data-path
+per GPU: every rank sweeps its own share of the wavenumbers - no data-path
 collective, the (k, omega) points are independent - and the only exchange is the
 gather of the (small) root tables, done with torch.distributed (NCCL over NVLink on
 GPUs, gloo in the CPU tests).
+
+Sharding: "strided" (rank r owns k[r::world]) is the default of the bench - the number of
+modes grows with k, so contiguous slabs give the last rank ~2x the brackets of the first and
+the step time is the maximum over ranks; "contiguous" slabs are kept for callers that want
+them.  Either way a local row i of rank r is the global row  k_offset + i * k_stride.
 """
 from __future__ import annotations
 
@@ -20,17 +25,28 @@ def shard_bounds(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_k(k, rank, world):
+def shard_k(k, rank, world, layout="contiguous"):
+    """-> (k of this rank, k_offset, k_stride): local row i is global row k_offset + i*k_stride."""
+    k = np.asarray(k)
+    if layout == "strided":
+        return np.ascontiguousarray(k[rank::world]), rank, world
     lo, hi = shard_bounds(len(k), rank, world)
-    return np.asarray(k)[lo:hi], lo
+    return k[lo:hi], lo, 1
 
 
-def gather_root_tables(k_index, omega, accepted, k_offset, device=None, group=None):
-    """All-gather variable-length root tables.
+def _sorted_by_global_row(allp):
+    """Rows of [global k index, omega, ...] ordered by (k index, omega): the order of the
+    single-process table (brackets of one k-row are already ascending in omega)."""
+    order = np.lexsort((allp[:, 1], allp[:, 0]))
+    return allp[order]
 
-    k_index is local to the rank's shard; `k_offset` (the shard's first global row) makes
-    it global.  Returns (k_index, omega, accepted) of ALL ranks, ordered by rank, i.e.
-    sorted by global k index.  Every rank receives the full table."""
+
+def gather_root_tables(k_index, omega, accepted, k_offset, device=None, group=None, k_stride=1):
+    """All-gather variable-length root tables (host arrays in, host arrays out).
+
+    k_index is local to the rank's shard; global row = k_offset + k_index * k_stride.
+    Returns (k_index, omega, accepted) of ALL ranks sorted by global k index, then omega,
+    i.e. the single-process table.  Every rank receives the full table."""
     import torch
     import torch.distributed as dist
 
@@ -44,13 +60,16 @@ def gather_root_tables(k_index, omega, accepted, k_offset, device=None, group=No
     # one packed fp64 payload per rank: [global k index, omega, accepted]
     pay = torch.zeros((cap, 3), dtype=torch.float64, device=dev)
     if len(omega):
-        pay[: len(omega), 0] = torch.as_tensor(np.asarray(k_index, dtype=np.float64) + k_offset, device=dev)
+        gk = np.asarray(k_index, dtype=np.float64) * k_stride + k_offset
+        pay[: len(omega), 0] = torch.as_tensor(gk, device=dev)
         pay[: len(omega), 1] = torch.as_tensor(np.asarray(omega, dtype=np.float64), device=dev)
         pay[: len(omega), 2] = torch.as_tensor(np.asarray(accepted, dtype=np.float64), device=dev)
     bufs = [torch.zeros_like(pay) for _ in range(world)]
     dist.all_gather(bufs, pay, group=group)
     parts = [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
     allp = np.concatenate(parts, axis=0) if parts else np.zeros((0, 3))
+    if k_stride != 1:
+        allp = _sorted_by_global_row(allp)
     return allp[:, 0].astype(np.int64), allp[:, 1].copy(), allp[:, 2].astype(np.int32)
 
 
@@ -62,30 +81,48 @@ class _DevArray:
                                          "version": 2, "strides": None}
 
 
-def gather_root_tables_device(solver, slot, k_offset, device, group=None):
+def gather_root_tables_device(solver, slot, k_offset, device, group=None, k_stride=1, accepted_only=False,
+                              sort=False):
     """All-gather the root table of mode slot `slot` straight from the solver's device buffers
     (no host round trip): NCCL over NVLink moves (global k index, omega, accepted) of every rank.
-    Returns a float64 tensor [total, 3] on `device`, ordered by rank = sorted by global k index."""
+
+    accepted_only: gather only the modes (what the reference's sol_ks / sol_omegas hold), payload
+    [global k index, omega]; otherwise every bracket with its accepted flag, payload
+    [global k index, omega, accepted].  sort: order by (global k index, omega) on the device
+    (needed for strided shards; contiguous shards are already in that order).
+    Returns a float64 tensor [total, 2 or 3] on `device`."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     info = solver.roots_device(slot)
     n = info["n"]
-    cnt = torch.tensor([n], dtype=torch.int64, device=device)
-    counts = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, cnt, group=group)
-    counts = counts.tolist()
-    cap = max(max(counts), 1)
-    pay = torch.zeros((cap, 3), dtype=torch.float64, device=device)
+    cols = 2 if accepted_only else 3
     if n:
         ki = torch.as_tensor(_DevArray(info["k_index"][0], n, "<i4"), device=device)
         om = torch.as_tensor(_DevArray(info["omega"][0], n, "<f8"), device=device)
         ac = torch.as_tensor(_DevArray(info["accepted"][0], n, "<i4"), device=device)
-        pay[:n, 0] = ki.to(torch.float64) + float(k_offset)
-        pay[:n, 1] = om
-        pay[:n, 2] = ac.to(torch.float64)
-    out = torch.empty((world * cap, 3), dtype=torch.float64, device=device)
+        gk = ki.to(torch.float64) * float(k_stride) + float(k_offset)
+        if accepted_only:
+            m = ac == 1
+            mine = torch.stack((gk[m], om[m]), dim=1)
+        else:
+            mine = torch.stack((gk, om, ac.to(torch.float64)), dim=1)
+    else:
+        mine = torch.zeros((0, cols), dtype=torch.float64, device=device)
+    cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device=device)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts = counts.tolist()
+    cap = max(max(counts), 1)
+    pay = torch.zeros((cap, cols), dtype=torch.float64, device=device)
+    pay[: mine.shape[0]] = mine
+    out = torch.empty((world * cap, cols), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(out, pay, group=group)
     parts = [out[r * cap: r * cap + c] for r, c in enumerate(counts)]
-    return torch.cat(parts, dim=0)
+    full = torch.cat(parts, dim=0)
+    if sort and full.shape[0]:
+        # stable two-key sort: omega first, then the global row
+        full = full[torch.argsort(full[:, 1], stable=True)]
+        full = full[torch.argsort(full[:, 0], stable=True)]
+    return full

@@ -37,15 +37,17 @@ def _local_table(k, W, offset_unused=0):
     return ki, omega, acc
 
 
-def _worker(rank, world, port, k, W, out):
+def _worker(rank, world, port, k, W, out, layout="contiguous"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        ks, off = shard_k(k, rank, world)
+        ks, off, stride = shard_k(k, rank, world, layout)
         ki, om, acc = _local_table(ks, W)
-        gk, gw, ga = gather_root_tables(ki, om, acc, off)
+        # the accepted flag of this test is a function of the GLOBAL row so that it survives re-sharding
+        acc = ((ki * stride + off) % 2).astype(np.int32)
+        gk, gw, ga = gather_root_tables(ki, om, acc, off, k_stride=stride)
         if rank == 0:
             np.savez(out, k=gk, w=gw, a=ga)
         else:
@@ -55,15 +57,28 @@ def _worker(rank, world, port, k, W, out):
         dist.destroy_process_group()
 
 
+def test_strided_shards_cover_exactly():
+    k = np.arange(11.0)
+    seen = []
+    for r in range(3):
+        ks, off, stride = shard_k(k, r, 3, "strided")
+        assert (off, stride) == (r, 3)
+        seen += list(off + stride * np.arange(len(ks)))
+        assert np.array_equal(ks, k[off + stride * np.arange(len(ks))])
+    assert sorted(seen) == list(range(11))
+
+
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_gather_equals_single_process(tmp_path):
+@pytest.mark.parametrize("layout", ["contiguous", "strided"])
+def test_two_rank_gloo_gather_equals_single_process(tmp_path, layout):
     import torch.multiprocessing as mp
     k = np.linspace(0.5, 4.0, 9)          # odd: uneven shards
     W = np.linspace(2.95, 4.95, 48)
     out = str(tmp_path / "gathered.npz")
-    mp.spawn(_worker, args=(2, _free_port(), k, W, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), k, W, out, layout), nprocs=2, join=True)
     g = np.load(out)
     ki, om, acc = _local_table(k, W)
+    acc = (ki % 2).astype(np.int32)
     assert len(ki) > 0
     assert np.array_equal(g["k"], ki)
     assert np.array_equal(g["w"], om)

@@ -354,6 +354,12 @@ def test_device_side_gather_equals_host_table(solvers):
             assert np.array_equal(g[:, 0], host.k_index + 1000.0)
             assert np.array_equal(g[:, 1], host.omega)
             assert np.array_equal(g[:, 2], host.accepted.astype(np.float64))
+            # modes only, strided global rows, sorted: what the multi-GPU bench gathers
+            a = gather_root_tables_device(s, slot, 3, dev, k_stride=8, accepted_only=True, sort=True).cpu().numpy()
+            acc = host.accepted == 1
+            assert a.shape == (int(acc.sum()), 2)
+            assert np.array_equal(a[:, 0], host.k_index[acc] * 8.0 + 3.0)
+            assert np.array_equal(a[:, 1], host.omega[acc])
     finally:
         dist.destroy_process_group()
 
