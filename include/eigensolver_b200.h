@@ -78,7 +78,7 @@ typedef struct esb_model {
     int32_t scheme;        /* esb_scheme */
     int32_t n_steps;       /* integration steps across the layer */
     int32_t mesh;          /* 0 = sin^2 clustering at the layer ends, 1 = uniform, 2 = graded
-                              (target step size, see mesh_axis/mesh_edge below; cylinder kinds) */
+                              (target step size, see mesh_axis/mesh_edge below) */
     double c_i0, vA_i0, vA_e, c_e, gamma, rho_i0;
     double rho_A;          /* amplitude multiplying the density profile (reference rho_A) */
     double ext_ic_value;   /* exterior initial values at x = -3*2*pi/k: (1e-8,            */
@@ -96,7 +96,8 @@ typedef struct esb_model {
     /* mesh = 2: the local step is H * min(1, |r|/mesh_axis, (mesh_edge + |r - s_start|)/mesh_edge_width)
      * with H fixed by n_steps: geometric towards the axis (where the 1/r, m^2/r^2 coefficients
      * need h ~ r), refined towards the boundary (where a resonance just outside the layer makes
-     * the coefficients vary fastest), uniform in between. */
+     * the coefficients vary fastest), uniform in between.  Slab kinds: no axis term, refined
+     * towards both boundaries. */
     double mesh_axis, mesh_edge, mesh_edge_width;
 } esb_model;
 

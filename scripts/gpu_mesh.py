@@ -25,10 +25,17 @@ for name in names:
         d = np.where(ok, d, 0)
         return [float(np.nanmax(d[i])) for i in range(len(modes))]
 
-    for n in (128, 160, 192, 256):
+    slab = case.kind.startswith("slab")
+    for n in (128, 160, 192, 256, 384):
         print("%-22s clustered N=%d  %s" % (name, n, " ".join("%.1e" % v for v in dev(n_steps=n))), flush=True)
-    for n in (128, 144, 160, 176):
-        for ax, (ed, ew) in itertools.product((0.08, 0.12, 0.16, 0.25, 0.4), ((0, 0), (0.02, 0.1), (0.01, 0.05), (0.04, 0.1), (0.03, 0.2))):
+    if slab:
+        Ns = (128, 160, 192, 224, 256, 288, 320, 352, 384)
+        combos = [(0.0, e) for e in ((0, 0), (0.04, 0.1), (0.05, 0.2), (0.1, 0.5))]
+    else:
+        Ns = (64, 80, 96, 112, 128)
+        combos = list(itertools.product((0.08, 0.16, 0.3), ((0, 0), (0.02, 0.1))))
+    for n in Ns:
+        for ax, (ed, ew) in combos:
             d = dev(n_steps=n, mesh="graded", mesh_params=(ax, ed, ew))
             print("%-22s graded N=%d axis=%.2f edge=(%.2f,%.2f)  %s  max %.1e" % (
                 name, n, ax, ed, ew, " ".join("%.1e" % v for v in d), max(d)), flush=True)
