@@ -328,6 +328,86 @@ def test_full_size_properties(solvers):
     assert np.array_equal(np.concatenate([lo_half.k_index, hi_half.k_index + 500]), tab.k_index)
 
 
+def _check_table_against_grid(tab, k, W, D, tol_percent=1.0):
+    """Size-independent root-table invariants: brackets == numpy's on the grid, sorted, every refined
+    root inside its bracket, acceptance flag == the reference's test on the stored (ext, int)."""
+    bk, bw = ork.brackets(D)
+    assert np.array_equal(bk, tab.k_index) and np.array_equal(bw, tab.w_index)
+    key = tab.k_index.astype(np.int64) * len(W) + tab.w_index
+    assert np.all(np.diff(key) > 0)
+    a = k[tab.k_index] * W[tab.w_index]; b = k[tab.k_index] * W[tab.w_index + 1]
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    assert np.all((tab.omega >= lo) & (tab.omega <= hi))
+    pct = np.abs(tab.ext - tab.intq) * 100 / np.maximum(np.abs(tab.ext), np.abs(tab.intq))
+    fin = np.isfinite(pct)
+    assert np.array_equal(tab.accepted[fin] == 1, pct[fin] < tol_percent)
+
+
+def _leaky(md, W):
+    """Columns the reference skips: m_e^2 (W) < 0 (Density_cylinder.py:699,760)."""
+    W2 = W * W
+    cT2 = md.cT_e**2
+    return (md.vA_e**2 - W2) * (md.c_e**2 - W2) / (cT2 - W2) < 0
+
+
+def test_full_size_slab_flow_properties():
+    """BASELINE configs[2] size: slab with a sheared flow, backward and forward branches,
+    2000 k x 20000 omega."""
+    k = np.linspace(0.01, 4.5, 2000)
+    W = np.linspace(-2.7, 2.7, 20000)
+    md = esb.FlowMedium(U_i0=0.35)
+    with esb.DispersionSolver("slab_flow", medium=md, profile=esb.GaussianFlow(1.0)) as s:
+        e, i = s.dispersion_grid(0, k, W)
+        # skip rule m_e < 0 (flow script :205), here with U_e = 0
+        assert np.array_equal(np.isnan(e).all(axis=0), _leaky(md, W))
+        tab = s.find_roots(0, k, W)
+        _check_table_against_grid(tab, k, W, e - i)
+        assert tab.accepted.sum() > 2000
+        # both branches are populated
+        assert (tab.omega[tab.accepted == 1] > 0).sum() > 500 and (tab.omega[tab.accepted == 1] < 0).sum() > 500
+        # sausage and kink share one integration: the fused scan returns the single-mode grids
+        E, I = s.dispersion_grid_multi([0, 1], k[::40], W[::20])
+        assert np.array_equal(E[0], e[::40, ::20], equal_nan=True) and np.array_equal(I[0], i[::40, ::20], equal_nan=True)
+    # flow reversal: the backward branch of U is the forward branch of -U; every factor is odd or
+    # even in (omega - k U), so (ext, int)(-omega; -U) = -(ext, int)(omega; U) bit for bit
+    with esb.DispersionSolver("slab_flow", medium=esb.FlowMedium(U_i0=-0.35), profile=esb.GaussianFlow(1.0)) as r:
+        er, ir = r.dispersion_grid(0, k[::40], -W[::20])
+    assert np.array_equal(er, -e[::40, ::20], equal_nan=True) and np.array_equal(ir, -i[::40, ::20], equal_nan=True)
+
+
+def test_full_size_rotation_properties():
+    """BASELINE configs[3] size: cylinder with rotational flow, n = 0..3, 2000 k x 20000 omega
+    (n = 0, 1, 2 in one fused scan, n = 3 on its own)."""
+    k = np.linspace(0.25, 4.0, 2000)
+    W = np.linspace(0.40, 1.6, 20000)
+    rot = esb.PowerLawRotation(0.15, 1.25)
+    sub = (slice(None, None, 50), slice(None, None, 25))
+    with esb.DispersionSolver("cylinder_rotation", profile=rot, s_end=0.01) as s:
+        tabs = s.find_roots_multi([0, 1, 2], k, W)
+        e3, i3 = s.dispersion_grid(3, k, W)
+        t3 = s.find_roots(3, k, W)
+        _check_table_against_grid(t3, k, W, e3 - i3)
+        assert np.array_equal(np.isnan(e3).all(axis=0), _leaky(s.medium, W))
+        for m, t in enumerate(tabs):
+            e, i = s.dispersion_grid(m, k[sub[0]], W)
+            one = s.find_roots(m, k[sub[0]], W)
+            rows = np.isin(t.k_index, np.arange(len(k))[sub[0]])
+            # the fused scan's table restricted to those rows == the single-mode table of the rows
+            assert rows.sum() > 0 and abs(int(rows.sum()) - len(one.omega)) <= 0.02 * len(one.omega) + 2
+            _check_table_against_grid(one, k[sub[0]], W, e - i)
+            assert t.accepted.sum() > 200
+        e0, i0 = s.dispersion_grid(0, k[sub[0]], W[sub[1]])
+        em, im = s.dispersion_grid(0, k[sub[0]], -W[sub[1]])
+        # n = 0 carries no Doppler shift: D is even in omega
+        assert np.array_equal(e0, em, equal_nan=True) and np.array_equal(i0, im, equal_nan=True)
+        e1, i1 = s.dispersion_grid(1, k[sub[0]], W[sub[1]])
+    # reversing the rotation maps the forward branch onto the backward one: (omega, v_phi) -> (-omega, -v_phi)
+    # leaves Om^2, T, Q, C1, C2, C3 unchanged, bit for bit
+    with esb.DispersionSolver("cylinder_rotation", profile=esb.PowerLawRotation(-0.15, 1.25), s_end=0.01) as r:
+        er, ir = r.dispersion_grid(1, k[sub[0]], -W[sub[1]])
+    assert np.array_equal(er, e1, equal_nan=True) and np.array_equal(ir, i1, equal_nan=True)
+
+
 def test_device_side_gather_equals_host_table(solvers):
     """The NCCL gather used by the multi-GPU bench reads the root table straight from the
     library's device buffers; with one rank it must reproduce the host-side table."""
