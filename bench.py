@@ -210,12 +210,13 @@ def run_gpu_arm(args):
 
     def step_e2e():
         """Host buffers in, root tables on the host out.  One GPU: the public host call
-        (find_roots_multi = esb_upload_axes + esb_sweep_resident_multi + esb_download_roots_slot).
+        (find_roots_multi = esb_upload_axes + esb_sweep_resident_multi + esb_roots_pinned: pinned k/omega
+        in, the full root tables of the three modes out into page-locked buffers).
         Several GPUs: every rank uploads its pinned k/omega, sweeps, the modes (what the reference's
         sol_ks / sol_omegas hold) are gathered over NCCL and rank 0 copies the global table to the host."""
         h2d = k_pin.numel() * 8 + W_pin.numel() * 8
         if world == 1:
-            tables = solver.find_roots_multi(MODES, k_pin.numpy(), W_pin.numpy())
+            tables = solver.find_roots_multi(MODES, k_pin.numpy(), W_pin.numpy(), pinned=True)
             d2h = sum(len(t.omega) * (8 * 3 + 4 * 4) for t in tables)
             return h2d, d2h, sum(int(t.accepted.sum()) for t in tables), sum(len(t.omega) for t in tables)
         solver.upload_axes(k_pin.numpy(), W_pin.numpy())

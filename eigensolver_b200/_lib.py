@@ -75,6 +75,7 @@ SYMBOLS = {
                                             _dp, _dp]),
     "esb_sweep_resident_multi": (C.c_int, [_ctx, C.c_int32, _ip, C.c_double, _ip, _ip]),
     "esb_download_roots_slot": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), C.c_int32]),
+    "esb_roots_pinned": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), _ip]),
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "esb_fp64_peak": (C.c_int, [_ctx, _dp]),
     "esb_rk_selftest": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _dp]),

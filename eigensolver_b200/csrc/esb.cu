@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -89,23 +90,30 @@ __device__ __forceinline__ bool is_bracket(double d0, double d1) {
     return isfinite(d0) && isfinite(d1) && ((d0 < 0.0 && d1 > 0.0) || (d0 > 0.0 && d1 < 0.0));
 }
 
-// one warp per row; pass 0 counts, pass 1 fills at row_offset
+// One warp per (row, segment of BRACKET_SEG omega intervals); pass 0 counts, pass 1 fills at the
+// segment's offset.  Segments are ordered (row, segment), so the filled list is sorted by
+// (k index, omega index) whatever the number of segments.
+constexpr int BRACKET_SEG = 1024;
+
 __global__ void bracket_kernel(const double* __restrict__ ext, const double* __restrict__ intq, int nk,
-                               int nw, int* __restrict__ row_count, const int* __restrict__ row_offset,
-                               int* __restrict__ bk, int* __restrict__ bw, int capacity, int fill) {
+                               int nw, int nseg, int* __restrict__ seg_count,
+                               const int* __restrict__ seg_offset, int* __restrict__ bk,
+                               int* __restrict__ bw, int capacity, int fill) {
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= nk) return;
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= nk * nseg) return;
+    const int row = item / nseg, seg = item - row * nseg;
     const double* e = ext + (size_t)row * nw;
     const double* q = intq + (size_t)row * nw;
-    int base = fill ? row_offset[row] : 0;
+    const int base = fill ? seg_offset[item] : 0;
+    const int j_begin = seg * BRACKET_SEG;
+    const int j_end = min(j_begin + BRACKET_SEG, nw - 1);
     int count = 0;
-    for (int j0 = 0; j0 < nw - 1; j0 += 32) {
+    for (int j0 = j_begin; j0 < j_end; j0 += 32) {
         const int j = j0 + lane;
         bool hit = false;
-        if (j < nw - 1) {
+        if (j < j_end) {
             const double d0 = e[j] - q[j];
-            // neighbour value: lane+1 holds it except for the last lane of the chunk
             const double d1 = e[j + 1] - q[j + 1];
             hit = is_bracket(d0, d1);
         }
@@ -119,7 +127,13 @@ __global__ void bracket_kernel(const double* __restrict__ ext, const double* __r
         }
         count += __popc(ballot);
     }
-    if (!fill && lane == 0) row_count[row] = count;
+    if (!fill && lane == 0) seg_count[item] = count;
+}
+
+// row_offset[row] = seg_offset[row * nseg]  (row = nk gives the total)
+__global__ void row_offset_kernel(const int* __restrict__ seg_offset, int nk, int nseg, int* __restrict__ row_offset) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row <= nk) row_offset[row] = seg_offset[(size_t)row * nseg];
 }
 
 // exclusive scan of row counts -> offsets[nk+1]; single block
@@ -201,8 +215,8 @@ __device__ __forceinline__ double mismatch_pct(double e, double i) {
 // whose best point keeps a mismatch above 50 % while |D| grows or the bracket has shrunk
 // to 1e-7 relative is a pole of D (sign change through infinity): it is reported,
 // unaccepted, without being bisected to machine precision.
-template <int KIND, int SCHEME>
-__global__ void __launch_bounds__(128) refine_kernel(RefineArgs r) {
+template <int KIND, int SCHEME, int MINB>
+__global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
     stage_table(r.tab, stab, r.tab_doubles);
     const double eps = 2.220446049250313e-16;
@@ -318,11 +332,16 @@ struct esb_context {
     size_t cap_k = 0, cap_w = 0, cap_grid = 0;
     int *d_rowcount = nullptr, *d_rowoff = nullptr;
     size_t cap_rows = 0, cap_rowoff = 0;
+    // one packed device allocation per slot: [om | e | i] doubles then [bk | bw | acc | it] ints, each
+    // `cap` long, so that the whole table moves in ONE copy; `pin` = page-locked host mirror
     struct RootBuf {
         int *bk = nullptr, *bw = nullptr, *acc = nullptr, *it = nullptr;
         double *om = nullptr, *e = nullptr, *i = nullptr;
+        void* base = nullptr;
         size_t cap = 0;
         int n = 0;
+        void* pin = nullptr;
+        size_t pin_cap = 0;
     } slots[ESB_MAX_MODES];
     int* d_counter = nullptr;
     size_t cap_counter = 0;
@@ -582,9 +601,8 @@ extern "C" int esb_destroy(esb_context* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& sl : c->slots) {
-        void* ps[] = {sl.bk, sl.bw, sl.acc, sl.it, sl.om, sl.e, sl.i};
-        for (void* p : ps)
-            if (p) cudaFree(p);
+        if (sl.base) cudaFree(sl.base);
+        if (sl.pin) cudaFreeHost(sl.pin);
     }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -741,20 +759,31 @@ static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
     }
 }
 
-template <int KIND, int SCHEME>
-static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
+template <int KIND, int SCHEME, int MINB>
+static cudaError_t launch_refine_b(const RefineArgs& r, cudaStream_t s) {
     const size_t smem = (size_t)r.tab_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME>,
+    cudaError_t e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel<KIND, SCHEME, MINB>, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
     int blocks = (r.n_total + 127) / 128;
-    const int cap = 148 * 4;           // persistent: 4 CTAs of 128 threads per SM (register limit)
+    const int cap = 148 * per_sm;      // persistent: as many CTAs as are resident at once
     if (blocks > cap) blocks = cap;
-    refine_kernel<KIND, SCHEME><<<blocks, 128, smem, s>>>(r);
+    refine_kernel<KIND, SCHEME, MINB><<<blocks, 128, smem, s>>>(r);
     return cudaGetLastError();
+}
+
+// 4 resident CTAs per SM: measured on the B200 (scripts/gpu_refine_time.py) - compiling the kernel
+// for 5..8 CTAs/SM spills the evaluation loop and is 5-30 % slower
+template <int KIND, int SCHEME>
+static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
+    return launch_refine_b<KIND, SCHEME, 4>(r, s);
 }
 
 // (kind, scheme) of the uploaded model -> template instantiation.  The rotational kind exists for
@@ -831,32 +860,56 @@ extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const doubl
                           stream ? (cudaStream_t)stream : cur_stream(c));
 }
 
+static int bracket_segments(int nw) { return (nw - 1 + BRACKET_SEG - 1) / BRACKET_SEG > 0 ? (nw - 1 + BRACKET_SEG - 1) / BRACKET_SEG : 1; }
+
+// count pass + scan: segment offsets in c->d_rowoff [nk*nseg + 1], total copied to the host (one sync)
+static int brackets_count(esb_context* c, const double* d_ext, const double* d_int, int nk, int nw,
+                          cudaStream_t s, int* total) {
+    const int nseg = bracket_segments(nw);
+    const size_t items = (size_t)nk * nseg;
+    int rc;
+    if ((rc = ensure(c, c->d_rowcount, c->cap_rows, items + 1))) return rc;
+    if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, items + 1))) return rc;
+    const int threads = 128, per_block = threads / 32;
+    const int blocks = (int)((items + per_block - 1) / per_block);
+    bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, nseg, c->d_rowcount, nullptr, nullptr,
+                                              nullptr, 0, 0);
+    CUDA_TRY(c, cudaGetLastError());
+    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, c->d_rowoff, (int)items);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches += 2;
+    CUDA_TRY(c, cudaMemcpyAsync(total, c->d_rowoff + items, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    return ESB_OK;
+}
+
+static int brackets_fill(esb_context* c, const double* d_ext, const double* d_int, int nk, int nw,
+                         int* d_bk, int* d_bw, int capacity, cudaStream_t s) {
+    const int nseg = bracket_segments(nw);
+    const size_t items = (size_t)nk * nseg;
+    const int threads = 128, per_block = threads / 32;
+    const int blocks = (int)((items + per_block - 1) / per_block);
+    bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, nseg, c->d_rowcount, c->d_rowoff, d_bk,
+                                              d_bw, capacity, 1);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches += 1;
+    return ESB_OK;
+}
+
 extern "C" int esb_brackets_dev(esb_context* c, const double* d_ext, const double* d_int, int32_t nk,
                                 int32_t nw, int32_t* d_row_offset, int32_t* d_bk, int32_t* d_bw,
                                 int32_t capacity, int32_t* n_host, void* stream) {
     if (!c || !d_ext || !d_int || !d_row_offset || nk <= 0 || nw <= 0) return ESB_ERR_ARG;
     cudaStream_t s = stream ? (cudaStream_t)stream : (c->use_user_stream ? c->user_stream : c->stream);
     CUDA_TRY(c, cudaSetDevice(c->device));
-    int rc = ensure(c, c->d_rowcount, c->cap_rows, (size_t)nk + 1);
-    if (rc) return rc;
-    const int threads = 128, rows_per_block = threads / 32;
-    const int blocks = (nk + rows_per_block - 1) / rows_per_block;
-    bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, c->d_rowcount, nullptr, nullptr, nullptr,
-                                              0, 0);
+    int total = 0, rc;
+    if ((rc = brackets_count(c, d_ext, d_int, nk, nw, s, &total))) return rc;
+    row_offset_kernel<<<(nk + 1 + 255) / 256, 256, 0, s>>>(c->d_rowoff, nk, bracket_segments(nw), d_row_offset);
     CUDA_TRY(c, cudaGetLastError());
-    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, d_row_offset, nk);
-    CUDA_TRY(c, cudaGetLastError());
-    c->launches += 2;
-    int total = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(&total, d_row_offset + nk, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(c, cudaStreamSynchronize(s));
+    c->launches += 1;
     if (n_host) *n_host = total;
-    if (d_bk && d_bw && capacity > 0 && total > 0) {
-        bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, c->d_rowcount, d_row_offset, d_bk,
-                                                  d_bw, capacity, 1);
-        CUDA_TRY(c, cudaGetLastError());
-        c->launches += 1;
-    }
+    if (d_bk && d_bw && capacity > 0 && total > 0)
+        if ((rc = brackets_fill(c, d_ext, d_int, nk, nw, d_bk, d_bw, capacity, s))) return rc;
     return total > capacity && d_bk ? ESB_ERR_CAPACITY : ESB_OK;
 }
 
@@ -928,21 +981,32 @@ extern "C" int esb_upload_axes(esb_context* c, const double* k, int32_t nk, cons
     return ESB_OK;
 }
 
+static size_t slot_bytes(size_t cap) { return cap * (3 * sizeof(double) + 4 * sizeof(int)); }
+
+static void slot_carve(esb_context::RootBuf& sl, void* base, size_t cap, esb_roots* out) {
+    double* d = (double*)base;
+    int* q = (int*)(d + 3 * cap);
+    if (out) {
+        out->omega = d; out->ext = d + cap; out->intq = d + 2 * cap;
+        out->k_index = q; out->w_index = q + cap; out->accepted = q + 2 * cap; out->iterations = q + 3 * cap;
+    } else {
+        sl.om = d; sl.e = d + cap; sl.i = d + 2 * cap;
+        sl.bk = q; sl.bw = q + cap; sl.acc = q + 2 * cap; sl.it = q + 3 * cap;
+    }
+}
+
 static int ensure_slot(esb_context* c, esb_context::RootBuf& sl, size_t total) {
     if (sl.cap >= total) return ESB_OK;
-    void* ps[] = {sl.bk, sl.bw, sl.acc, sl.it, sl.om, sl.e, sl.i};
-    for (void* p : ps)
-        if (p) cudaFree(p);
+    if (sl.base) cudaFree(sl.base);
+    void* pin = sl.pin;
+    const size_t pin_cap = sl.pin_cap;
     sl = esb_context::RootBuf();
-    const size_t cap = total + total / 4 + 64;
-    CUDA_TRY(c, cudaMalloc((void**)&sl.bk, cap * sizeof(int)));
-    CUDA_TRY(c, cudaMalloc((void**)&sl.bw, cap * sizeof(int)));
-    CUDA_TRY(c, cudaMalloc((void**)&sl.acc, cap * sizeof(int)));
-    CUDA_TRY(c, cudaMalloc((void**)&sl.it, cap * sizeof(int)));
-    CUDA_TRY(c, cudaMalloc((void**)&sl.om, cap * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc((void**)&sl.e, cap * sizeof(double)));
-    CUDA_TRY(c, cudaMalloc((void**)&sl.i, cap * sizeof(double)));
+    sl.pin = pin;
+    sl.pin_cap = pin_cap;
+    const size_t cap = ((total + total / 4 + 64) + 1) & ~(size_t)1;      // even: the int block stays 8-byte aligned
+    CUDA_TRY(c, cudaMalloc(&sl.base, slot_bytes(cap)));
     sl.cap = cap;
+    slot_carve(sl, sl.base, cap, nullptr);
     return ESB_OK;
 }
 
@@ -963,7 +1027,6 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     if ((rc = ensure_grid(c, plane * n_modes))) return rc;
     if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
         return rc;
-    if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, (size_t)nk + 1))) return rc;
     if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)ESB_MAX_MODES))) return rc;
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, ESB_MAX_MODES * sizeof(int), s));
     RefineArgs r;
@@ -981,8 +1044,7 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         const double* gint = c->d_int + m * plane;
         // pass 1: count (one 4-byte D2H + sync: buffer sizes and the refine launch need the count)
         int total = 0;
-        rc = esb_brackets_dev(c, gext, gint, nk, nw, c->d_rowoff, nullptr, nullptr, 0, &total, s);
-        if (rc) return rc;
+        if ((rc = brackets_count(c, gext, gint, nk, nw, s, &total))) return rc;
         sl.n = 0;
         if (n_brackets) n_brackets[m] = total;
         if (n_roots) n_roots[m] = total;
@@ -990,14 +1052,7 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         if ((rc = ensure_slot(c, sl, (size_t)total))) return rc;
         sl.n = total;
         // pass 2: fill (sorted by row, then omega index)
-        {
-            const int threads = 128, rows_per_block = threads / 32;
-            const int blocks = (nk + rows_per_block - 1) / rows_per_block;
-            bracket_kernel<<<blocks, threads, 0, s>>>(gext, gint, nk, nw, c->d_rowcount, c->d_rowoff, sl.bk,
-                                                      sl.bw, total, 1);
-            CUDA_TRY(c, cudaGetLastError());
-            c->launches += 1;
-        }
+        if ((rc = brackets_fill(c, gext, gint, nk, nw, sl.bk, sl.bw, total, s))) return rc;
         RefineSlot& q = r.slot[r.n_slots++];
         q.gext = gext; q.gint = gint; q.bk = sl.bk; q.bw = sl.bw;
         q.omega = sl.om; q.ext = sl.e; q.intq = sl.i; q.accepted = sl.acc; q.iters = sl.it;
@@ -1038,6 +1093,37 @@ extern "C" int esb_download_roots_slot(esb_context* c, int32_t slot, esb_roots* 
         if (out->iterations) CUDA_TRY(c, cudaMemcpyAsync(out->iterations, sl.it, nb * 4, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(c, cudaStreamSynchronize(s));
+    return ESB_OK;
+}
+
+extern "C" int esb_roots_pinned(esb_context* c, int32_t slot, esb_roots* out, int32_t* n_roots) {
+    if (!c || !out || slot < 0 || slot >= ESB_MAX_MODES) return ESB_ERR_ARG;
+    esb_context::RootBuf& sl = c->slots[slot];
+    memset(out, 0, sizeof(*out));
+    if (n_roots) *n_roots = sl.n;
+    if (sl.n == 0) return ESB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (sl.pin_cap < sl.cap) {
+        if (sl.pin) cudaFreeHost(sl.pin);
+        sl.pin = nullptr;
+        sl.pin_cap = 0;
+        CUDA_TRY(c, cudaHostAlloc(&sl.pin, slot_bytes(sl.cap), cudaHostAllocDefault));
+        sl.pin_cap = sl.cap;
+    }
+    // the pinned mirror has the layout of a table of capacity pin_cap; copy the 7 used prefixes
+    esb_roots h;
+    slot_carve(sl, sl.pin, sl.pin_cap, &h);
+    cudaStream_t s = cur_stream(c);
+    const size_t nb = (size_t)sl.n;
+    CUDA_TRY(c, cudaMemcpyAsync(h.omega, sl.om, nb * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(h.ext, sl.e, nb * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(h.intq, sl.i, nb * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(h.k_index, sl.bk, nb * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(h.w_index, sl.bw, nb * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(h.accepted, sl.acc, nb * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(h.iterations, sl.it, nb * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    *out = h;
     return ESB_OK;
 }
 

@@ -399,11 +399,30 @@ class DispersionSolver:
                                                   _iptr(nb)), "esb_sweep_resident_multi")
         return [int(x) for x in n]
 
-    def find_roots_multi(self, modes, k, w, layout="phase_speed", tol_percent=1.0):
-        """Host arrays in, one RootTable per mode out (one fused scan)."""
+    def find_roots_multi(self, modes, k, w, layout="phase_speed", tol_percent=1.0, pinned=False):
+        """Host arrays in, one RootTable per mode out (one fused scan).  pinned=True: the tables are
+        views of page-locked buffers owned by the context (see download_roots_pinned)."""
         self.upload_axes(k, w, layout)
         ns = self.sweep_resident_multi(modes, tol_percent)
+        if pinned:
+            return [self.download_roots_pinned(slot) for slot in range(len(ns))]
         return [self.download_roots(n, slot) for slot, n in enumerate(ns)]
+
+    def download_roots_pinned(self, slot=0):
+        """Root table of mode slot `slot` copied into page-locked host buffers owned by the context
+        (esb_roots_pinned): numpy VIEWS, valid until the next call for the same slot or close()."""
+        out = L.esb_roots()
+        n = C.c_int32(0)
+        L.check(self.lib, self.ctx, self.lib.esb_roots_pinned(self.ctx, int(slot), C.byref(out), C.byref(n)),
+                "esb_roots_pinned")
+        n = n.value
+        if n == 0:
+            z4, z8 = np.zeros(0, np.int32), np.zeros(0, np.float64)
+            return RootTable(z4, z4, z8, z8, z8, z8, z4, z4, 0)
+        view = lambda p: np.ctypeslib.as_array(p, shape=(n,))
+        ki = view(out.k_index)
+        return RootTable(ki, view(out.w_index), self._k_host[ki], view(out.omega), view(out.ext),
+                         view(out.intq), view(out.accepted), view(out.iterations), n)
 
     def download_roots(self, n, slot=0):
         ki = np.empty(n, np.int32); wi = np.empty(n, np.int32)

@@ -180,6 +180,12 @@ int esb_sweep_resident_multi(esb_context* ctx, int32_t n_modes, const int32_t* m
                              int32_t* n_brackets /* [n_modes] */);
 int esb_download_roots_slot(esb_context* ctx, int32_t slot, esb_roots* out, int32_t max_roots);
 
+/* D2H copy of the root table of `slot` into page-locked host buffers OWNED BY THE CONTEXT; *out
+ * receives their addresses, *n_roots the entry count.  One packed copy at full PCIe rate, no
+ * pageable staging.  The buffers stay valid until the next esb_roots_pinned call for the same slot
+ * or esb_destroy.  Synchronises the stream. */
+int esb_roots_pinned(esb_context* ctx, int32_t slot, esb_roots* out, int32_t* n_roots);
+
 /* Run every launch and copy of this context on `stream` (a cudaStream_t, e.g. the
  * caller's torch stream) instead of the context's own stream. */
 int esb_set_stream(esb_context* ctx, void* stream);
