@@ -440,9 +440,13 @@ ESB_HD void exterior_cyl_order(const DevModel& M, const ExtCyl& E, int n, double
 //   cylinder: modes = azimuthal orders; one staged-coefficient evaluation per node and one
 //             Bessel set serve all of them, each order integrates its own solution;
 //   slab:     sausage and kink are two closures of the same two fundamental solutions.
+// den_q[s] = the denominator of int_q[s]: the interior quantity is a ratio whose denominator (the
+// boundary value of the integrated solution) passes through zero at the poles of D.  G = D * den_q
+// has the roots of D and no such poles; the refinement iterates on G (esb.cu refine_kernel).
 template <int KIND, int SCHEME, int NM>
 ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, double k, double w,
-                             const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM]) {
+                             const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM],
+                             double (&den_q)[NM]) {
     const double nanv = nan("");
     const Point pt = make_point(M, k, w);
     // exterior Doppler shift (flow script :207): (w - k U_e)
@@ -451,7 +455,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
     const double me = m_e2(M, pt.K, Ae);
     if (!(me >= 0.0)) {                       // "if m_e < 0: pass"  (Density_cylinder.py:760)
 #pragma unroll
-        for (int s = 0; s < NM; ++s) { ext_q[s] = nanv; int_q[s] = nanv; }
+        for (int s = 0; s < NM; ++s) { ext_q[s] = nanv; int_q[s] = nanv; den_q[s] = nanv; }
         return;
     }
     if constexpr (KIND == KIND_CYL_ROTATION) {
@@ -473,9 +477,11 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             double xi_b;
             if (modes[s] == 0) {
                 // sausage: P'(end) = 0  <=>  C3 xi - C1 P = 0 at the end node   (sausage script :306)
-                xi_b = -Pb * fma(ce.C3, X[0], -ce.C1 * P[0]) / fma(ce.C3, X[1], -ce.C1 * P[1]);
+                den_q[s] = fma(ce.C3, X[1], -ce.C1 * P[1]);
+                xi_b = -Pb * fma(ce.C3, X[0], -ce.C1 * P[0]) / den_q[s];
             } else {
                 // kink (:308): P(end) + (B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1) = 0
+                den_q[s] = P[1];
                 xi_b = (M.rho_vb2 * xi_e - Pb * P[0]) / P[1];
             }
             ext_q[s] = xi_e;
@@ -514,6 +520,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             const double slope = yb[s] * yp[s] / y[s];       // dPi that fsolve finds (:790)
             // xi_i(-1) = (C1 P + D P')/C3 = P'/(rho (w^2 - k^2 vA^2))    (:798)
             int_q[s] = slope * den;
+            den_q[s] = y[s];
         }
     } else {
         double yb, ypb;
@@ -542,18 +549,20 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             const double slope = yb * (target - y[0]) / y[1];
             ext_q[s] = p_e_const * ypb;
             int_q[s] = P_Ti * slope;
+            den_q[s] = y[1];
         }
     }
 }
 
 template <int KIND, int SCHEME>
 ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
-                       double& ext_q, double& int_q) {
+                       double& ext_q, double& int_q, double& den_q) {
     const int modes[1] = {mode};
-    double e[1], i[1];
-    eval_point_multi<KIND, SCHEME, 1>(M, tab, k, w, modes, e, i);
+    double e[1], i[1], d[1];
+    eval_point_multi<KIND, SCHEME, 1>(M, tab, k, w, modes, e, i, d);
     ext_q = e[0];
     int_q = i[0];
+    den_q = d[0];
 }
 
 }  // namespace esb

@@ -37,6 +37,7 @@ struct GridArgs {
     int modes[4];
     double* ext;            // [n_modes][nk][nw]
     double* intq;
+    double* den;            // optional [n_modes][nk][nw]: denominator of intq (sweep path; see refine_kernel)
 };
 
 __device__ __forceinline__ double omega_at(const double* __restrict__ k, const double* __restrict__ w,
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
     for (int ik = blockIdx.y; ik < g.nk; ik += gridDim.y) {
         const double k = g.k[ik];
         const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
-        double e[NM], i[NM];
-        eval_point_multi<KIND, SCHEME, NM>(g.M, stab, k, w, modes, e, i);
+        double e[NM], i[NM], d[NM];
+        eval_point_multi<KIND, SCHEME, NM>(g.M, stab, k, w, modes, e, i, d);
         const size_t o = (size_t)ik * g.nw + iw;
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
             const bool fin = isfinite(e[s]) && isfinite(i[s]);
             g.ext[s * plane + o] = fin ? e[s] : nan("");
             g.intq[s * plane + o] = fin ? i[s] : nan("");
+            if (g.den) g.den[s * plane + o] = d[s];
         }
     }
 }
@@ -177,6 +179,7 @@ __global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ of
 struct RefineSlot {
     const double* gext;     // D grid of the scan (end-point values of every bracket)
     const double* gint;
+    const double* gden;     // denominator of gint at the same points
     const int* bk;
     const int* bw;
     double* omega;
@@ -211,9 +214,18 @@ __device__ __forceinline__ double mismatch_pct(double e, double i) {
 // the next bracket from a global queue as soon as its own has converged, so a warp
 // never idles behind its slowest lane.  The D evaluation (the expensive part) is executed
 // by all 32 lanes together each round; __any_sync on the "trial pending" flags ends the
-// loop.  End-point values come from the scan grid, not from new evaluations.  A bracket
-// whose best point keeps a mismatch above 50 % while |D| grows or the bracket has shrunk
-// to 1e-7 relative is a pole of D (sign change through infinity): it is reported,
+// loop.  End-point values come from the scan grid, not from new evaluations.
+//
+// Pole-free iteration.  D = ext - int with int = N/Y, Y the boundary value of the integrated
+// interior solution: D changes sign through infinity wherever Y crosses zero (the reference bisects
+// such brackets 150 levels deep and then drops them).  The scan stores Y next to (ext, int), so
+//   * a bracket whose end points have Y of opposite sign is a pole of D: it is reported at once
+//     (omega = the zero of Y by linear interpolation, ext = int = NaN, unaccepted) - no evaluation;
+//   * every other bracket is refined on G = D * Y, which has the roots of D and no such poles, so
+//     Brent's interpolation steps are not thrown off by a pole next to the root.
+// The acceptance test is the reference's, on (ext, int) at the converged root.  Poles of the
+// prefactors (e.g. omega = k U for the flow slab) survive in G: a bracket whose best point keeps a
+// mismatch above 50 % while |G| grows or the bracket has shrunk to 1e-7 relative is reported,
 // unaccepted, without being bisected to machine precision.
 template <int KIND, int SCHEME, int MINB>
 __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
@@ -222,8 +234,10 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
     const double eps = 2.220446049250313e-16;
     bool have = false, pending = false, exhausted = false;
     int t = 0, it = 0, sl = 0, mode = 0;
-    double k = 1.0, a = 0, b = 1.0, c = 0, ea = 0, ia = 0, eb = 0, ib = 0, ec = 0, ic = 0, d = 0, e = 0,
-           f0min = 0;
+    // Brent state: a = previous iterate, b = best iterate, c = the other end of the bracket;
+    // (e?, i?) = (ext, int) there, f? = G there
+    double k = 1.0, a = 0, b = 1.0, c = 0, ea = 0, ia = 0, eb = 0, ib = 0, ec = 0, ic = 0, fa = 0, fb = 0,
+           fc = 0, d = 0, e = 0, f0min = 0;
     for (;;) {
         while (!pending && !exhausted) {
             if (!have) {
@@ -243,22 +257,33 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
                 const size_t o = (size_t)ik * r.nw + jw;
                 ea = r.slot[sl].gext[o]; ia = r.slot[sl].gint[o];
                 eb = r.slot[sl].gext[o + 1]; ib = r.slot[sl].gint[o + 1];
-                c = a; ec = ea; ic = ia;
+                const double ya = r.slot[sl].gden[o], yb = r.slot[sl].gden[o + 1];
+                if ((ya < 0.0 && yb > 0.0) || (ya > 0.0 && yb < 0.0)) {
+                    // the denominator changes sign: D changes sign through infinity
+                    const double wp = a - ya * (b - a) / (yb - ya);
+                    r.slot[sl].omega[t] = fmin(fmax(wp, fmin(a, b)), fmax(a, b));
+                    r.slot[sl].ext[t] = nan("");
+                    r.slot[sl].intq[t] = nan("");
+                    r.slot[sl].iters[t] = 0;
+                    r.slot[sl].accepted[t] = 0;
+                    continue;
+                }
+                fa = (ea - ia) * ya;
+                fb = (eb - ib) * yb;
+                c = a; ec = ea; ic = ia; fc = fa;
                 d = b - a; e = d;
-                f0min = fmin(fabs(ea - ia), fabs(eb - ib));
+                f0min = fmin(fabs(fa), fabs(fb));
                 it = 0;
                 have = true;
             }
-            double fa = ea - ia, fb = eb - ib, fc = ec - ic;
             if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
                 c = a; ec = ea; ic = ia; fc = fa;
                 d = b - a; e = d;
             }
             if (fabs(fc) < fabs(fb)) {
-                a = b; ea = eb; ia = ib;
-                b = c; eb = ec; ib = ic;
-                c = a; ec = ea; ic = ia;
-                fa = fb; fb = fc; fc = fa;
+                a = b; ea = eb; ia = ib; fa = fb;
+                b = c; eb = ec; ib = ic; fb = fc;
+                c = a; ec = ea; ic = ia; fc = fa;
             }
             const double tol1 = 2.0 * eps * fabs(b);
             const double xm = 0.5 * (c - b);
@@ -300,16 +325,17 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
                 d = xm;
                 e = d;
             }
-            a = b; ea = eb; ia = ib;
+            a = b; ea = eb; ia = ib; fa = fb;
             b += (fabs(d) > tol1) ? d : (xm > 0.0 ? tol1 : -tol1);
             pending = true;
         }
         if (!__any_sync(0xffffffffu, pending)) break;
-        double en, in_;
-        eval_point<KIND, SCHEME>(r.M, stab, k, b, mode, en, in_);
+        double en, in_, yn;
+        eval_point<KIND, SCHEME>(r.M, stab, k, b, mode, en, in_, yn);
         if (pending) {
             eb = en;
             ib = in_;
+            fb = (en - in_) * yn;
             ++it;
             pending = false;
         }
@@ -328,8 +354,8 @@ struct esb_context {
     double* d_tab = nullptr;
     int tab_doubles = 0;
     // scratch for the host-pointer entry points
-    double *d_k = nullptr, *d_w = nullptr, *d_ext = nullptr, *d_int = nullptr;
-    size_t cap_k = 0, cap_w = 0, cap_grid = 0;
+    double *d_k = nullptr, *d_w = nullptr, *d_ext = nullptr, *d_int = nullptr, *d_den = nullptr;
+    size_t cap_k = 0, cap_w = 0, cap_grid = 0, cap_den = 0;
     int *d_rowcount = nullptr, *d_rowoff = nullptr;
     size_t cap_rows = 0, cap_rowoff = 0;
     // one packed device allocation per slot: [om | e | i] doubles then [bk | bw | acc | it] ints, each
@@ -597,7 +623,7 @@ extern "C" int esb_create(int32_t device, esb_context** out) {
 extern "C" int esb_destroy(esb_context* c) {
     if (!c) return ESB_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_rowcount, c->d_rowoff, c->d_counter};
+    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_den, c->d_rowcount, c->d_rowoff, c->d_counter};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& sl : c->slots) {
@@ -825,7 +851,7 @@ static int check_modes(const esb_context* c, int n_modes, const int32_t* modes) 
 // one fused launch: every requested mode at every (k, omega); outputs mode-slot major
 static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, const double* d_k, int nk,
                           const double* d_w, int nw, int layout, double* d_ext, double* d_int,
-                          cudaStream_t s) {
+                          cudaStream_t s, double* d_den = nullptr) {
     if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
     if (nk <= 0 || nw <= 0 || !d_k || !d_w || !d_ext || !d_int || layout < 0 || layout > 2 ||
         check_modes(c, n_modes, modes))
@@ -837,7 +863,7 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
     g.k = d_k; g.w = d_w; g.nk = nk; g.nw = nw; g.layout = layout;
     g.n_modes = n_modes;
     for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
-    g.ext = d_ext; g.intq = d_int;
+    g.ext = d_ext; g.intq = d_int; g.den = d_den;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
@@ -1025,7 +1051,9 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     int rc;
     const size_t plane = (size_t)nk * nw;
     if ((rc = ensure_grid(c, plane * n_modes))) return rc;
-    if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
+    if ((rc = ensure(c, c->d_den, c->cap_den, plane * n_modes))) return rc;
+    if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s,
+                             c->d_den)))
         return rc;
     if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)ESB_MAX_MODES))) return rc;
     CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, ESB_MAX_MODES * sizeof(int), s));
@@ -1042,6 +1070,7 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         esb_context::RootBuf& sl = c->slots[m];
         const double* gext = c->d_ext + m * plane;
         const double* gint = c->d_int + m * plane;
+        const double* gden = c->d_den + m * plane;
         // pass 1: count (one 4-byte D2H + sync: buffer sizes and the refine launch need the count)
         int total = 0;
         if ((rc = brackets_count(c, gext, gint, nk, nw, s, &total))) return rc;
@@ -1054,7 +1083,7 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         // pass 2: fill (sorted by row, then omega index)
         if ((rc = brackets_fill(c, gext, gint, nk, nw, sl.bk, sl.bw, total, s))) return rc;
         RefineSlot& q = r.slot[r.n_slots++];
-        q.gext = gext; q.gint = gint; q.bk = sl.bk; q.bw = sl.bw;
+        q.gext = gext; q.gint = gint; q.gden = gden; q.bk = sl.bk; q.bw = sl.bw;
         q.omega = sl.om; q.ext = sl.e; q.intq = sl.i; q.accepted = sl.acc; q.iters = sl.it;
         q.mode = modes[m];
         q.begin = r.n_total;

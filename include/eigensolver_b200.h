@@ -148,7 +148,9 @@ typedef struct esb_roots {
     double* ext;          /* [max_roots] exterior quantity at the root                 */
     double* intq;         /* [max_roots] interior quantity at the root                 */
     int32_t* accepted;    /* [max_roots] 1 = passes acceptance test (a mode), 0 = pole */
-    int32_t* iterations;  /* [max_roots] Brent iterations used                         */
+    int32_t* iterations;  /* [max_roots] Brent iterations used (0: a pole recognised from the
+                             scan itself - the denominator of the interior quantity changes sign
+                             across the bracket; omega = its interpolated zero, ext = int = NaN) */
 } esb_roots;
 
 int esb_find_roots(esb_context* ctx, int32_t mode, const double* k, int32_t nk, const double* w,
