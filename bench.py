@@ -166,7 +166,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     import eigensolver_b200 as esb
-    from eigensolver_b200.distributed import gather_root_tables_device, shard_k
+    from eigensolver_b200.distributed import gather_modes_device, shard_k
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,14 +198,21 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    _pin = {}
+
+    def pinned_out(n):
+        """page-locked host buffer for the gathered table (grown geometrically, reused across steps)"""
+        if _pin.get("cap", 0) < n:
+            _pin["cap"] = int(n * 1.25) + 1024
+            _pin["buf"] = torch.empty((_pin["cap"], 3), dtype=torch.float64).pin_memory()
+        return _pin["buf"][:n]
+
     def step_resident():
         """axes resident in HBM; root tables stay on the device until the gather."""
         ns = solver.sweep_resident_multi(MODES)
         kms = [solver.last_kernel_ms()]
-        if world > 1:       # NCCL gather of the modes straight from the device buffers
-            for slot in range(len(MODES)):
-                gather_root_tables_device(solver, slot, k_off, dev, k_stride=k_stride, accepted_only=True,
-                                          sort=True)
+        if world > 1:       # NCCL gather of the modes of all slots straight from the device buffers
+            gather_modes_device(solver, len(MODES), k_off, dev, k_stride=k_stride)
         return kms, ns
 
     def step_e2e():
@@ -221,15 +228,14 @@ def run_gpu_arm(args):
             return h2d, d2h, sum(int(t.accepted.sum()) for t in tables), sum(len(t.omega) for t in tables)
         solver.upload_axes(k_pin.numpy(), W_pin.numpy())
         ns = solver.sweep_resident_multi(MODES)
-        d2h = n_modes = 0
-        for slot in range(len(MODES)):
-            g = gather_root_tables_device(solver, slot, k_off, dev, k_stride=k_stride, accepted_only=True,
-                                          sort=True)
-            n_modes += g.shape[0]
-            if rank == 0:
-                host = g.cpu()
-                d2h += host.numel() * 8
-        return h2d, d2h, n_modes, sum(ns)
+        g = gather_modes_device(solver, len(MODES), k_off, dev, k_stride=k_stride)
+        d2h = 0
+        if rank == 0:       # the parent process of the reference: it alone holds the collected lists
+            host_buf = pinned_out(g.shape[0])
+            host_buf.copy_(g, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            d2h = host_buf.numel() * 8
+        return h2d, d2h, g.shape[0], sum(ns)
 
     # ---- device-resident timing ----
     solver.upload_axes(k, W)

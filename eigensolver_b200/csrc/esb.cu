@@ -352,6 +352,7 @@ struct esb_context {
     esb_model model{};
     DevModel dm{};
     double* d_tab = nullptr;
+    size_t cap_tab = 0;
     int tab_doubles = 0;
     // scratch for the host-pointer entry points
     double *d_k = nullptr, *d_w = nullptr, *d_ext = nullptr, *d_int = nullptr, *d_den = nullptr;
@@ -735,15 +736,16 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     }
 
     CUDA_TRY(c, cudaSetDevice(c->device));
-    if (c->d_tab) cudaFree(c->d_tab);
-    c->d_tab = nullptr;
-    c->tab_doubles = (int)tab.size();
-    if ((size_t)c->tab_doubles * sizeof(double) > 200 * 1024)
+    if (tab.size() * sizeof(double) > 200 * 1024)
         return fail(c, ESB_ERR_ARG, "n_steps too large for the shared-memory table (200 KB)");
-    CUDA_TRY(c, cudaMalloc((void**)&c->d_tab, tab.size() * sizeof(double)));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    // a parameter scan re-uploads a table of the same size: keep the allocation.  The copy goes on the
+    // sweep stream, so it is ordered after the kernels of the previous equilibrium that still read it.
+    int rc;
+    if ((rc = ensure(c, c->d_tab, c->cap_tab, tab.size()))) return rc;
+    c->tab_doubles = (int)tab.size();
+    cudaStream_t s = c->use_user_stream ? c->user_stream : c->stream;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));      // `tab` is a stack-owned pageable buffer
     c->model = *m;
     c->model_set = true;
     return ESB_OK;

@@ -126,3 +126,45 @@ def gather_root_tables_device(solver, slot, k_offset, device, group=None, k_stri
         full = full[torch.argsort(full[:, 1], stable=True)]
         full = full[torch.argsort(full[:, 0], stable=True)]
     return full
+
+
+def gather_modes_device(solver, n_slots, k_offset, device, group=None, k_stride=1, sort=False):
+    """All-gather the accepted modes of ALL mode slots in one exchange: the concatenation of the
+    reference's sol_ks / sol_omegas lists of every rank, read straight from the solver's device
+    buffers.  Returns a float64 tensor [total, 3] = (global k row, omega, slot) on `device`, ordered
+    by rank (like the reference's queue output, which is in process order) or, with sort=True, by
+    (slot, global k row, omega).  One mask compaction, one count exchange, one payload exchange."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    gks, oms, acs, sls = [], [], [], []
+    for slot in range(n_slots):
+        info = solver.roots_device(slot)
+        n = info["n"]
+        if not n:
+            continue
+        ki = torch.as_tensor(_DevArray(info["k_index"][0], n, "<i4"), device=device)
+        gks.append(ki.to(torch.float64) * float(k_stride) + float(k_offset))
+        oms.append(torch.as_tensor(_DevArray(info["omega"][0], n, "<f8"), device=device))
+        acs.append(torch.as_tensor(_DevArray(info["accepted"][0], n, "<i4"), device=device))
+        sls.append(torch.full((n,), float(slot), dtype=torch.float64, device=device))
+    if gks:
+        m = torch.cat(acs) == 1
+        mine = torch.stack((torch.cat(gks)[m], torch.cat(oms)[m], torch.cat(sls)[m]), dim=1)
+    else:
+        mine = torch.zeros((0, 3), dtype=torch.float64, device=device)
+    cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device=device)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts = counts.tolist()
+    cap = max(max(counts), 1)
+    pay = torch.zeros((cap, 3), dtype=torch.float64, device=device)
+    pay[: mine.shape[0]] = mine
+    out = torch.empty((world * cap, 3), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, pay, group=group)
+    full = torch.cat([out[r * cap: r * cap + c] for r, c in enumerate(counts)], dim=0)
+    if sort and full.shape[0]:
+        for col in (1, 0, 2):            # stable sorts, least significant key first
+            full = full[torch.argsort(full[:, col], stable=True)]
+    return full

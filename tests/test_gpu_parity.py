@@ -414,7 +414,7 @@ def test_device_side_gather_equals_host_table(solvers):
     import socket
     import torch
     import torch.distributed as dist
-    from eigensolver_b200.distributed import gather_root_tables_device
+    from eigensolver_b200.distributed import gather_modes_device, gather_root_tables_device
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
@@ -440,6 +440,13 @@ def test_device_side_gather_equals_host_table(solvers):
             assert a.shape == (int(acc.sum()), 2)
             assert np.array_equal(a[:, 0], host.k_index[acc] * 8.0 + 3.0)
             assert np.array_equal(a[:, 1], host.omega[acc])
+        # all slots in one exchange: (global row, omega, slot), sorted by (slot, row, omega)
+        allm = gather_modes_device(s, len(ns), 3, dev, k_stride=8, sort=True).cpu().numpy()
+        hosts = [s.download_roots(n, slot) for slot, n in enumerate(ns)]
+        want = np.concatenate([np.stack([h.k_index[h.accepted == 1] * 8.0 + 3.0, h.omega[h.accepted == 1],
+                                         np.full(int((h.accepted == 1).sum()), float(slot))], axis=1)
+                               for slot, h in enumerate(hosts)])
+        assert np.array_equal(allm, want)
     finally:
         dist.destroy_process_group()
 
