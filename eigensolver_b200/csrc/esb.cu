@@ -677,6 +677,16 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
             f[1] = 1.0 / (r * r);
             f[2] = fields[0][i];
             f[3] = fields[1][i];
+            if (m->scheme == ESB_RK8) {
+                // pre-scaled layout (core.cuh integrate_layer_prescaled): node j >= 1 belongs to step
+                // (j-1)/4 and is stored as {h/r, h^2/r^2, field, h field'} with that step's h; the
+                // step-end node is shared by the next step, which rescales the carried coefficients
+                const int step = i == 0 ? 0 : (i - 1) / nps;
+                const double h = nodes[(step + 1) * nps] - nodes[step * nps];
+                f[0] *= h;
+                f[1] *= h * h;
+                f[3] *= h;
+            }
         } else if (m->kind == ESB_CYLINDER_ROTATION) {
             // fields = {v_phi, v_phi', c^2};  r d/dr(-rho v_phi^2/r^2) = -2 rho v_phi (r v_phi' - v_phi)/r^2
             const double r = nodes[i], v = fields[0][i], dv = fields[1][i];

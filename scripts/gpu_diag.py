@@ -16,7 +16,7 @@ for name in names:
     for mode in case.modes:
         e0, i0 = ork.grid(model, mode, k, W)
         ok = case.regular(k, W, mode) & ~np.isnan(e0)
-        for n in (128, 192, 256, 384, 512):
+        for n in (128, 144, 192, 256):
             with case.gpu_solver(esb, n_steps=n) as s:
                 e, i = s.dispersion_grid(mode, k, W)
             nanmis = (np.isnan(e) != np.isnan(e0)).sum()
