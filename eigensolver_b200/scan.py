@@ -49,9 +49,13 @@ def parameter_scan(solver: DispersionSolver, points, k, W, modes, layout="phase_
     for p in points[lo:hi]:
         solver.reconfigure(medium=p.get("medium"), profile=p.get("profile"))
         ns = solver.sweep_resident_multi(modes, tol_percent)
-        tabs = [solver.download_roots(n, slot) for slot, n in enumerate(ns)]
-        out.append(ScanPoint(p.get("label", {}), ns, [int(t.accepted.sum()) for t in tabs],
-                             tabs if keep_tables else None))
+        # page-locked views (one packed copy per slot); copied out only if the caller keeps them
+        tabs = [solver.download_roots_pinned(slot) for slot in range(len(ns))]
+        n_modes = [int(t.accepted.sum()) for t in tabs]
+        kept = [dataclasses.replace(t, **{f.name: np.array(getattr(t, f.name)) for f in dataclasses.fields(t)
+                                          if isinstance(getattr(t, f.name), np.ndarray)})
+                for t in tabs] if keep_tables else None
+        out.append(ScanPoint(p.get("label", {}), ns, n_modes, kept))
     return out
 
 

@@ -279,6 +279,31 @@ def test_fused_modes_equal_single_mode(solvers, kind):
         assert np.nanmax(dev[reg]) < D_TOL
 
 
+def test_pinned_download_equals_pageable(solvers):
+    """esb_roots_pinned (one packed copy into page-locked buffers owned by the context) returns the
+    table esb_download_roots_slot returns; the views survive further grid calls, not the next download."""
+    s = solvers["cylinder_density"]
+    k = np.linspace(0.5, 4.0, 17); W = np.linspace(0.55, 4.95, 700)
+    s.upload_axes(k, W)
+    ns = s.sweep_resident_multi([0, 1, 2])
+    for slot, n in enumerate(ns):
+        a = s.download_roots(n, slot)
+        b = s.download_roots_pinned(slot)
+        assert len(b.omega) == n > 0
+        for name in ("k_index", "w_index", "k", "omega", "ext", "intq", "accepted", "iterations"):
+            assert np.array_equal(getattr(a, name), getattr(b, name), equal_nan=True), name
+    # poles recognised from the scan: no evaluation, NaN quantities, position inside the bracket
+    t = s.download_roots(ns[1], 1)
+    poles = t.iterations == 0
+    assert poles.sum() > 0 and np.isnan(t.ext[poles]).all() and (t.accepted[poles] == 0).all()
+    lo = k[t.k_index] * W[t.w_index]; hi = k[t.k_index] * W[t.w_index + 1]
+    assert np.all((t.omega >= lo) & (t.omega <= hi))
+    # an empty slot
+    s.upload_axes([1.0, 2.0], np.linspace(5.1, 6.0, 33))
+    assert s.sweep_resident_multi([1]) == [0]
+    assert len(s.download_roots_pinned(0).omega) == 0
+
+
 def test_rk4_and_rk8_agree():
     k = np.linspace(0.3, 4.0, 6); W = np.linspace(3.0, 4.9, 40)
     with esb.DispersionSolver("cylinder_density", scheme="rk8") as a, \
