@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -448,7 +449,37 @@ static void graded_breakpoints(const esb_model* m, bool slab, std::vector<double
     if (slab && N % 2 == 0) out[N / 2] = 0.5 * (a + b);
 }
 
+static int build_breakpoints_uncached(const esb_model* m, std::vector<double>& bp);
+
+// The breakpoints depend on the discretisation fields of the model only; a parameter scan calls
+// esb_set_model_fields once per equilibrium with the same mesh, so the last mesh is kept.
 static int build_breakpoints(const esb_model* m, std::vector<double>& bp) {
+    struct Key {
+        int32_t kind, scheme, n_steps, mesh;
+        double s_start, s_end, axis, edge, width;
+        bool operator==(const Key& o) const {
+            return kind == o.kind && scheme == o.scheme && n_steps == o.n_steps && mesh == o.mesh &&
+                   s_start == o.s_start && s_end == o.s_end && axis == o.axis && edge == o.edge && width == o.width;
+        }
+    };
+    static std::mutex mu;
+    static Key last{-1, 0, 0, 0, 0, 0, 0, 0, 0};
+    static std::vector<double> last_bp;
+    const Key key{m->kind, m->scheme, m->n_steps, m->mesh, m->s_start, m->s_end,
+                  m->mesh_axis, m->mesh_edge, m->mesh_edge_width};
+    std::lock_guard<std::mutex> lock(mu);
+    if (!(key == last)) {
+        std::vector<double> fresh;
+        const int rc = build_breakpoints_uncached(m, fresh);
+        if (rc) return rc;
+        last = key;
+        last_bp.swap(fresh);
+    }
+    bp = last_bp;
+    return ESB_OK;
+}
+
+static int build_breakpoints_uncached(const esb_model* m, std::vector<double>& bp) {
     const int N = m->n_steps;
     bp.resize(N + 1);
     const bool cyl = m->kind == ESB_CYLINDER_ROTATION || m->kind == ESB_CYLINDER_DENSITY ||
