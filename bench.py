@@ -88,7 +88,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nk, nw = 8, max(8, 2 * cores)
+    nk, nw = 8, max(8, 4 * cores)           # ~4 s of work on all cores per step
     with mp.get_context("fork").Pool(cores, initializer=_cpu_init) as pool:
         for _ in range(args.warmup):
             time_cpu(pool, cores, 2, cores, 1)
@@ -288,10 +288,11 @@ def run_gpu_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             with mp.get_context("fork").Pool(cores, initializer=_cpu_init) as pool:
                 time_cpu(pool, cores, 2, cores, 1)
-                n, dt = time_cpu(pool, cores, 8, max(8, 2 * cores), 5)
+                n, dt = time_cpu(pool, cores, 16, max(8, 8 * cores), 5)      # ~15 s on all cores
             cpu = {"value": n / dt, "unit": "evals/s", "cores": cores, "kind": "port",
-                   "sample": "8 k x %d omega x 3 modes, uniform random in the workload's box; oracle/"
-                             "reference_path.py (scipy odeint + fsolve, the reference's algorithm)" % max(8, 2 * cores)}
+                   "sample": "16 k x %d omega x 3 modes, uniform random in the workload's box (%.0f s); oracle/"
+                             "reference_path.py (scipy odeint + fsolve, the reference's algorithm)"
+                             % (max(8, 8 * cores), dt)}
         line = {
             "metric": "dispersion_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
