@@ -36,26 +36,65 @@ class ScanPoint:
     tables: list = None       # RootTable per mode if keep_tables
 
 
+def _scan_point(solver, p, modes, tol_percent, keep_tables):
+    solver.reconfigure(medium=p.get("medium"), profile=p.get("profile"))
+    ns = solver.sweep_resident_multi(modes, tol_percent)
+    # page-locked views (one packed copy per slot); copied out only if the caller keeps them
+    tabs = [solver.download_roots_pinned(slot) for slot in range(len(ns))]
+    n_modes = [int(t.accepted.sum()) for t in tabs]
+    kept = [dataclasses.replace(t, **{f.name: np.array(getattr(t, f.name)) for f in dataclasses.fields(t)
+                                      if isinstance(getattr(t, f.name), np.ndarray)})
+            for t in tabs] if keep_tables else None
+    return ScanPoint(p.get("label", {}), ns, n_modes, kept)
+
+
 def parameter_scan(solver: DispersionSolver, points, k, W, modes, layout="phase_speed", tol_percent=1.0,
-                   rank=0, world=1, keep_tables=False):
+                   rank=0, world=1, keep_tables=False, streams=1):
     """Sweep every equilibrium in `points` (list of dicts with optional keys 'medium', 'profile' and
     a free-form 'label') over the same (k, W) grid on this rank's share of the list.
 
-    Returns the list of ScanPoint for THIS rank (use torch.distributed.all_gather_object or
-    eigensolver_b200.distributed to combine ranks)."""
+    streams > 1: that many contexts (clones of `solver`, each with its own CUDA stream and buffers)
+    are driven by one host thread each, so that the latency-bound tail of one equilibrium (the
+    bracket-count synchronisations and the sequential Brent iterations of a small bracket list)
+    overlaps the scan of the next.  Worth it when one equilibrium is a few milliseconds of GPU work.
+
+    Returns the list of ScanPoint for THIS rank, in the order of `points` (use
+    torch.distributed.all_gather_object or eigensolver_b200.distributed to combine ranks)."""
     lo, hi = shard_bounds(len(points), rank, world)
-    solver.upload_axes(k, W, layout)
-    out = []
-    for p in points[lo:hi]:
-        solver.reconfigure(medium=p.get("medium"), profile=p.get("profile"))
-        ns = solver.sweep_resident_multi(modes, tol_percent)
-        # page-locked views (one packed copy per slot); copied out only if the caller keeps them
-        tabs = [solver.download_roots_pinned(slot) for slot in range(len(ns))]
-        n_modes = [int(t.accepted.sum()) for t in tabs]
-        kept = [dataclasses.replace(t, **{f.name: np.array(getattr(t, f.name)) for f in dataclasses.fields(t)
-                                          if isinstance(getattr(t, f.name), np.ndarray)})
-                for t in tabs] if keep_tables else None
-        out.append(ScanPoint(p.get("label", {}), ns, n_modes, kept))
+    mine = points[lo:hi]
+    if streams <= 1 or len(mine) <= 1:
+        solver.upload_axes(k, W, layout)
+        return [_scan_point(solver, p, modes, tol_percent, keep_tables) for p in mine]
+    import queue
+    import threading
+    solvers = [solver] + [solver.clone() for _ in range(min(streams, len(mine)) - 1)]
+    todo = queue.SimpleQueue()
+    for item in enumerate(mine):
+        todo.put(item)
+    out = [None] * len(mine)
+    errors = []
+
+    def worker(s):
+        try:
+            s.upload_axes(k, W, layout)
+            while True:
+                try:
+                    i, p = todo.get_nowait()
+                except queue.Empty:
+                    return
+                out[i] = _scan_point(s, p, modes, tol_percent, keep_tables)
+        except Exception as exc:          # surfaced in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in solvers]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for s in solvers[1:]:
+        s.close()
+    if errors:
+        raise errors[0]
     return out
 
 
