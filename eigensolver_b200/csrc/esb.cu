@@ -227,7 +227,7 @@ __device__ __forceinline__ double mismatch_pct(double e, double i) {
 // The acceptance test is the reference's, on (ext, int) at the converged root.  Poles of the
 // prefactors (e.g. omega = k U for the flow slab) survive in G: a bracket whose best point keeps a
 // mismatch above 50 % while |G| grows or the bracket has shrunk to 1e-7 relative is reported,
-// unaccepted, without being bisected to machine precision.
+// unaccepted, without being bisected to machine precision; so is a jump of G (see below).
 template <int KIND, int SCHEME, int MINB>
 __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
     // Brent state: a = previous iterate, b = best iterate, c = the other end of the bracket;
     // (e?, i?) = (ext, int) there, f? = G there
     double k = 1.0, a = 0, b = 1.0, c = 0, ea = 0, ia = 0, eb = 0, ib = 0, ec = 0, ic = 0, fa = 0, fb = 0,
-           fc = 0, d = 0, e = 0, f0min = 0;
+           fc = 0, d = 0, e = 0, f0min = 0, f0max = 0, w0 = 0, hw0 = 0;
     for (;;) {
         while (!pending && !exhausted) {
             if (!have) {
@@ -274,6 +274,11 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
                 c = a; ec = ea; ic = ia; fc = fa;
                 d = b - a; e = d;
                 f0min = fmin(fabs(fa), fabs(fb));
+                f0max = fmax(fabs(fa), fabs(fb));
+                // scales of the bracket as found: they keep the tolerances meaningful for a bracket
+                // that straddles omega = 0 (the backward/forward scans of the flow kinds have one per k)
+                w0 = fmax(fabs(a), fabs(b));
+                hw0 = 0.5 * fabs(b - a);
                 it = 0;
                 have = true;
             }
@@ -286,12 +291,18 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
                 b = c; eb = ec; ib = ic; fb = fc;
                 c = a; ec = ea; ic = ia; fc = fa;
             }
-            const double tol1 = 2.0 * eps * fabs(b);
+            const double tol1 = 2.0 * eps * fmax(fabs(b), 0.5 * w0);
             const double xm = 0.5 * (c - b);
             const bool converged = fabs(xm) <= tol1 || fb == 0.0 || !isfinite(fb) || it >= 120;
             const bool pole = it >= 2 && mismatch_pct(eb, ib) > 50.0 &&
-                              (fabs(fb) > 4.0 * f0min || fabs(xm) < 1e-7 * fabs(b));
-            if (converged || pole) {
+                              (fabs(fb) > 4.0 * f0min || fabs(xm) < fmax(1e-7 * fabs(b), 1e-3 * hw0));
+            // a jump: inside a continuum the integration crosses a singular point and G changes sign
+            // discontinuously (the reference bisects such brackets 150 levels deep).  Once the bracket
+            // has shrunk a million-fold a root would have |G| ~ 1e-6 of its end-point values; a best
+            // value still above 1e-4 of them is a discontinuity.  (Were a genuine root ever caught by
+            // this, it is already located to 1e-6 of a grid interval, ~1e-10 relative.)
+            const bool jump = fabs(xm) < 1e-6 * hw0 && fabs(fb) > 100.0 * f0max * (fabs(xm) / hw0);
+            if (converged || pole || jump) {
                 r.slot[sl].omega[t] = b;
                 r.slot[sl].ext[t] = eb;
                 r.slot[sl].intq[t] = ib;
@@ -645,7 +656,7 @@ extern "C" int esb_create(int32_t device, esb_context** out) {
     }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
-        delete c;
+        esb_destroy(c);
         return ESB_ERR_CUDA;
     }
     *out = c;

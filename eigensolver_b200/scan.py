@@ -49,53 +49,15 @@ def _scan_point(solver, p, modes, tol_percent, keep_tables):
 
 
 def parameter_scan(solver: DispersionSolver, points, k, W, modes, layout="phase_speed", tol_percent=1.0,
-                   rank=0, world=1, keep_tables=False, streams=1):
+                   rank=0, world=1, keep_tables=False):
     """Sweep every equilibrium in `points` (list of dicts with optional keys 'medium', 'profile' and
     a free-form 'label') over the same (k, W) grid on this rank's share of the list.
-
-    streams > 1: that many contexts (clones of `solver`, each with its own CUDA stream and buffers)
-    are driven by one host thread each, so that the latency-bound tail of one equilibrium (the
-    bracket-count synchronisations and the sequential Brent iterations of a small bracket list)
-    overlaps the scan of the next.  Worth it when one equilibrium is a few milliseconds of GPU work.
 
     Returns the list of ScanPoint for THIS rank, in the order of `points` (use
     torch.distributed.all_gather_object or eigensolver_b200.distributed to combine ranks)."""
     lo, hi = shard_bounds(len(points), rank, world)
-    mine = points[lo:hi]
-    if streams <= 1 or len(mine) <= 1:
-        solver.upload_axes(k, W, layout)
-        return [_scan_point(solver, p, modes, tol_percent, keep_tables) for p in mine]
-    import queue
-    import threading
-    solvers = [solver] + [solver.clone() for _ in range(min(streams, len(mine)) - 1)]
-    todo = queue.SimpleQueue()
-    for item in enumerate(mine):
-        todo.put(item)
-    out = [None] * len(mine)
-    errors = []
-
-    def worker(s):
-        try:
-            s.upload_axes(k, W, layout)
-            while True:
-                try:
-                    i, p = todo.get_nowait()
-                except queue.Empty:
-                    return
-                out[i] = _scan_point(s, p, modes, tol_percent, keep_tables)
-        except Exception as exc:          # surfaced in the caller's thread
-            errors.append(exc)
-
-    threads = [threading.Thread(target=worker, args=(s,)) for s in solvers]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    for s in solvers[1:]:
-        s.close()
-    if errors:
-        raise errors[0]
-    return out
+    solver.upload_axes(k, W, layout)
+    return [_scan_point(solver, p, modes, tol_percent, keep_tables) for p in points[lo:hi]]
 
 
 def density_flow_grid(contrasts, flow_amplitudes, base_density: Medium = None, base_flow: FlowMedium = None,

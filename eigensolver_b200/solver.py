@@ -208,9 +208,6 @@ class DispersionSolver:
         layer 1 -> 0.001, exterior slope given as dP/dr)."""
         self.lib = L.load()
         self.kind = kind
-        self._init_kw = dict(kind=kind, medium=medium, profile=profile, n_steps=n_steps, scheme=scheme, mesh=mesh,
-                             device=device, rho_A=rho_A, ext_ic=ext_ic, ext_wavelengths=ext_wavelengths,
-                             coordinate=coordinate, s_end=s_end, mesh_params=mesh_params)
         m = L.esb_model()
         L.check(self.lib, None, self.lib.esb_model_defaults(_KINDS[kind], C.byref(m)), "esb_model_defaults")
         if medium is None:
@@ -274,13 +271,6 @@ class DispersionSolver:
         L.check(self.lib, self.ctx,
                 self.lib.esb_set_model_fields(self.ctx, C.byref(m), fptr, len(fields), self.nodes.size,
                                               _dptr(boundary), boundary.size), "esb_set_model_fields")
-
-    def clone(self):
-        """A second context (own stream, own buffers) for the same model on the same device: what a
-        parameter scan uses to keep several equilibria in flight (scan.parameter_scan, streams > 1)."""
-        kw = dict(self._init_kw)
-        kw["medium"], kw["profile"] = self.medium, self.profile
-        return DispersionSolver(**kw)
 
     def reconfigure(self, medium=None, profile=None):
         """Swap the equilibrium (speeds and/or profile) on the same context and mesh: one small

@@ -48,7 +48,6 @@ for name, kind, kw, modes, k, W in CONFIGS:
 
 # configs[4]: parameter scan, density contrast x flow amplitude x k; 1e9 evaluations in total on 8 GPUs =
 # 1.25e8 per GPU: here the one-GPU share (25 cylinder equilibria x 3 modes + 25 slab-flow equilibria x 2 modes)
-STREAMS = int(os.environ.get("SCAN_STREAMS", "4"))
 dens, flow = density_flow_grid(np.linspace(0.12, 0.35, 25), np.linspace(0.05, 0.9, 25))
 k = np.linspace(0.01, 4.5, 500)
 tot = 0
@@ -57,14 +56,14 @@ with esb.DispersionSolver("cylinder_density") as sd, esb.DispersionSolver("slab_
     parameter_scan(sd, dens[:1], k, Wd, [0, 1, 2]); parameter_scan(sf, flow[:1], k, Wf, [0, 1])    # warm-up
     torch.cuda.synchronize()
     t = time.perf_counter()
-    r1 = parameter_scan(sd, dens, k, Wd, [0, 1, 2], streams=STREAMS)
+    r1 = parameter_scan(sd, dens, k, Wd, [0, 1, 2])
     tot += len(dens) * 3 * len(k) * 2000
-    r2 = parameter_scan(sf, flow, k, Wf, [0, 1], streams=STREAMS)
+    r2 = parameter_scan(sf, flow, k, Wf, [0, 1])
     tot += len(flow) * 2 * len(k) * 2000
     torch.cuda.synchronize()
     dt = time.perf_counter() - t
 rec = {"config": "configs[4] parameter scan: 25 density contrasts (cylinder, 3 modes) + 25 flow amplitudes (slab, 2 modes), "
-                 "500 k x 2000 omega each, incl. per-point table upload and root-table download; %d contexts in flight" % STREAMS,
+                 "500 k x 2000 omega each, incl. per-point table upload and root-table download",
        "evals": tot, "s_total": dt, "evals_per_sec": tot / dt,
        "modes_found": int(sum(sum(p.n_modes) for p in r1 + r2))}
 print(json.dumps(rec), flush=True)

@@ -487,13 +487,6 @@ def test_parameter_scan_matches_fresh_solvers():
         with esb.DispersionSolver(kind) as s:
             res = parameter_scan(s, pts, k, W, modes, keep_tables=True)
             halves = [parameter_scan(s, pts, k, W, modes, rank=r, world=2) for r in range(2)]
-            # several contexts in flight (one host thread and one CUDA stream each): same tables, same order
-            conc = parameter_scan(s, pts, k, W, modes, keep_tables=True, streams=3)
-        assert [p.label for p in conc] == [p.label for p in res]
-        for a, b in zip(conc, res):
-            assert a.n_brackets == b.n_brackets and a.n_modes == b.n_modes
-            for ta, tb in zip(a.tables, b.tables):
-                assert np.array_equal(ta.omega, tb.omega, equal_nan=True) and np.array_equal(ta.k_index, tb.k_index)
         assert [p.label for p in halves[0] + halves[1]] == [p.label for p in res]
         assert [p.n_brackets for p in halves[0] + halves[1]] == [p.n_brackets for p in res]
         for p, r in zip(pts, res):
