@@ -72,6 +72,20 @@ class GaussianDensity:
 
 
 @dataclasses.dataclass(frozen=True)
+class EpsteinDensity:
+    """(rho_i0 - rho_e)/cosh((x-x0)/a)^8 + rho_e: the reference's alternative profile
+    (Density_cylinder.py:139-142, `a` = inhomogeneity width).  Like any other callable
+    (medium, x) -> (rho, rho') it is simply sampled at the mesh nodes."""
+    a: float = 1.0
+    x0: float = 0.0
+
+    def __call__(self, medium, x):
+        t = (np.asarray(x, dtype=np.float64) - self.x0) / self.a
+        d = medium.rho_i0 - medium.rho_e
+        return d / np.cosh(t) ** 8 + medium.rho_e, d * (-8.0 / self.a) * np.sinh(t) / np.cosh(t) ** 9
+
+
+@dataclasses.dataclass(frozen=True)
 class FlowMedium:
     """Speeds of the slab flow script (flow_multiprocessor_coronal.py:47-56): uniform density and
     field inside the slab, exterior at rest or streaming with U_e."""

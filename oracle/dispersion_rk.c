@@ -44,6 +44,9 @@ typedef struct {
                             rho_i0 are then the uniform interior values */
     double r_sign;       /* cylinder: -1 scripts in r<0 (coronal), +1 scripts in r>0 (photospheric) */
     double v_twist, power; /* kind 3: v_phi = v_twist r^power (uniform rho_i0, vA_i0; r > 0) */
+    int profile_kind;      /* density kinds: 0 inverted Gaussian, 1 Epstein (Density_cylinder.py:139-142):
+                              (rho_i0 - rho_e)/cosh((x-x0)/width)^8 + rho_e */
+    int pad2;
 } ork_model;
 
 /* ---- Cooper-Verner 8th order tableau, table driven -------------------- */
@@ -122,9 +125,17 @@ static double rho_e_of(const ork_model* m) {
 static void profile(const pt_ctx* p, double x, double* rho, double* drho, double* c2, double* dc2,
                     double* vA2, double* dvA2) {
     const ork_model* m = p->m;
-    const double g = exp(-(x - m->x0) * (x - m->x0) / (m->width * m->width));
-    const double prof = p->rho_e + (m->rho_i0 - p->rho_e) * g;
-    const double dprof = (m->rho_i0 - p->rho_e) * g * (-2.0 * (x - m->x0) / (m->width * m->width));
+    double prof, dprof;
+    if (m->profile_kind == 1) {
+        const double t = (x - m->x0) / m->width, ch = cosh(t);
+        const double ch8 = pow(ch, 8.0);
+        prof = (m->rho_i0 - p->rho_e) / ch8 + p->rho_e;
+        dprof = (m->rho_i0 - p->rho_e) * (-8.0 / m->width) * sinh(t) / (ch8 * ch);
+    } else {
+        const double g = exp(-(x - m->x0) * (x - m->x0) / (m->width * m->width));
+        prof = p->rho_e + (m->rho_i0 - p->rho_e) * g;
+        dprof = (m->rho_i0 - p->rho_e) * g * (-2.0 * (x - m->x0) / (m->width * m->width));
+    }
     *rho = m->rho_A * prof;
     *drho = m->rho_A * dprof;
     if (m->kind == 1) { /* B_i = B_0: vA^2 = B_0^2/rho */

@@ -153,6 +153,21 @@ class GaussianDensity:
         return rho, drho, c2, dc2, vA2, dvA2
 
 
+@dataclasses.dataclass
+class EpsteinDensity(GaussianDensity):
+    """The reference's alternative profile (Density_cylinder.py:139-142, commented out in the shipped
+    file): rho = (rho_i0 - rho_e)/(cosh(x/a)^4)^2 + rho_e, `width` = the inhomogeneity width a."""
+
+    def rho(self, x):
+        m = self.medium
+        return self.rho_A * ((m.rho_i0 - m.rho_e) / np.cosh((x - self.x0) / self.width) ** 8 + m.rho_e)
+
+    def drho(self, x):
+        m = self.medium
+        t = (x - self.x0) / self.width
+        return self.rho_A * (m.rho_i0 - m.rho_e) * (-8.0 / self.width) * np.sinh(t) / np.cosh(t) ** 9
+
+
 # --------------------------------------------------------------------------
 # the four geometry/mode closures
 # --------------------------------------------------------------------------

@@ -21,7 +21,7 @@ class ork_model(C.Structure):
                 ("width", C.c_double), ("x0", C.c_double), ("ic_v", C.c_double), ("ic_s", C.c_double),
                 ("ext_wavelengths", C.c_double), ("s_start", C.c_double), ("s_end", C.c_double),
                 ("U_i0", C.c_double), ("U_e", C.c_double), ("r_sign", C.c_double),
-                ("v_twist", C.c_double), ("power", C.c_double)]
+                ("v_twist", C.c_double), ("power", C.c_double), ("profile_kind", C.c_int), ("pad2", C.c_int)]
 
 
 def build():
@@ -49,7 +49,8 @@ def lib():
 
 
 def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rho_A=1.0,
-               coordinate="negative", ext_wavelengths=3.0, v_twist=0.25, power=0.8, s_end=None):
+               coordinate="negative", ext_wavelengths=3.0, v_twist=0.25, power=0.8, s_end=None,
+               profile="gaussian"):
     """kind: 'slab_density' | 'cylinder_density' | 'slab_flow'; medium: any object with c_i0, vA_i0,
     vA_e, c_e, gamma, rho_i0 attributes (flow: vA_i, c_i, vA_e, c_e, U_i0, U_e, gamma, rho_i);
     defaults: the reference's coronal sets.  coordinate='positive': cylinder scripts in r > 0."""
@@ -58,6 +59,7 @@ def make_model(kind, medium=None, width=None, x0=0.0, n_ext=None, n_int=None, rh
     m.kind = {"slab_density": 0, "cylinder_density": 1, "slab_flow": 2, "cylinder_rotation": 3,
               "cylinder_flow": 4}[kind]
     m.r_sign = -1.0
+    m.profile_kind = {"gaussian": 0, "epstein": 1}[profile]
     if kind == "cylinder_flow":
         # Cylinder_method_flow_testing.py:66-69 (coronal speeds), r < 0, P0 = [1e-8, 1e-8] (:774)
         md = medium

@@ -65,6 +65,17 @@ POINTS.update({
         overrides={"v_twist": 0.15, "power": 1.25}),
 })
 
+# the Epstein profile the cylinder script carries as a comment (:139-142), switched on the way its author would
+EPSTEIN_PATCH = [(
+    "def profile(r):       # Define the internal profile as a function of variable x   (Inverted Gaussian)\n"
+    "    return (rho_e + ((rho_i0 - rho_e)*sym.exp(-(r-r0)**2/dr**2)))",
+    "a = 1.   #inhomogeneity width for epstein profile\n"
+    "def profile(x):       # Define the internal profile as a function of variable x   (Epstein Profile)\n"
+    "    return ((rho_i0 - rho_e)/(sym.cosh(x/a)**4)**2 + rho_e)")]
+POINTS["cylinder_density_epstein"] = dict(
+    solver="cylinder_density_coronal", patches=EPSTEIN_PATCH,
+    ks=[0.1, 0.5, 1.0, 2.0, 3.2, 4.5], Ws=[0.52, 0.6, 0.75, 0.88, 1.35, 1.6, 1.95, 2.95, 3.3, 4.0, 4.9, 0.45, 5.2])
+
 SCANS = {
     # (mode, k, W_lo, W_hi, n)  - intervals that contain a mode
     "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),
@@ -97,7 +108,7 @@ def main():
         if only and name not in only:
             continue
         t0 = time.time()
-        ref = ReferenceSolver(name, overrides=spec.get("overrides"))
+        ref = ReferenceSolver(spec.get("solver", name), overrides=spec.get("overrides"), patches=spec.get("patches"))
         rows = []
         for mode_id, mode in ((0, "sausage"), (1, "kink")):
             if mode not in ref.modes:

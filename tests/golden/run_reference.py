@@ -154,7 +154,9 @@ def _legacy_odeint():
 class ReferenceSolver:
     """The reference's physics set-up + sausage()/kink() functions, exec'd as-is."""
 
-    def __init__(self, name, overrides=None, max_interior=None):
+    def __init__(self, name, overrides=None, max_interior=None, patches=None):
+        """patches: (old, new) source replacements for edits that are not single assignment lines -
+        e.g. switching to one of the alternative profile definitions the script carries as comments."""
         path, marker, modes = SOLVERS[name]
         self.name = name
         self.modes = modes
@@ -167,6 +169,9 @@ class ReferenceSolver:
             cut = src.rfind(marker)
         assert cut > 0, "driver marker not found"
         src = src[:cut]
+        for old, new in (patches or []):
+            assert src.count(old) == 1, old
+            src = src.replace(old, new)
         # parameter overrides (e.g. profile width) are applied by rewriting the
         # single assignment line, exactly what a user of the scripts edits by hand.
         for key, val in (overrides or {}).items():

@@ -41,8 +41,9 @@ def regular_mask(W, intervals, margin=0.01):
     return ok
 
 
-def cyl_profile(width=0.95, medium=rp.CYL_CORONAL):
-    return rp.GaussianDensity(medium, width=width, const_B=True)
+def cyl_profile(width=0.95, medium=rp.CYL_CORONAL, shape="gaussian"):
+    cls = rp.EpsteinDensity if shape == "epstein" else rp.GaussianDensity
+    return cls(medium, width=width, const_B=True)
 
 
 def slab_profile(width=0.9, medium=rp.SLAB_CORONAL):
@@ -92,7 +93,8 @@ class Case:
 
     def __init__(self, name, kind, modes, W, width, medium_name=None, coordinate="negative",
                  roots_window=None, fixture=None, family=None, ext_wavelengths=3.0, U_i0=0.9,
-                 v_twist=0.15, power=1.25, s_end=None, tol_percent=1.0, flow_medium=None):
+                 v_twist=0.15, power=1.25, s_end=None, tol_percent=1.0, flow_medium=None, shape="gaussian"):
+        self.shape = shape                              # density kinds: "gaussian" | "epstein"
         self.flow_medium = dict(flow_medium or {})      # slab_flow: FlowMedium fields other than U_i0, width
         self.tol_percent = tol_percent      # the script's acceptance threshold (xi_tol / p_tol)
         self.ext_wavelengths = ext_wavelengths
@@ -127,7 +129,7 @@ class Case:
                 cache[key] = rp.CylinderFlow(rp.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0, width=w), mode)
             return cache[key]
         if self.kind == "cylinder_density":
-            return rp.CylinderDensity(cyl_profile(w, self.rp_medium()), mode, coordinate=self.coordinate)
+            return rp.CylinderDensity(cyl_profile(w, self.rp_medium(), self.shape), mode, coordinate=self.coordinate)
         if self.kind == "slab_density":
             m = rp.SlabDensity(slab_profile(w, self.rp_medium()), "sausage" if mode == 0 else "kink",
                                500 if fast else None)
@@ -152,7 +154,7 @@ class Case:
             return ork.make_model("cylinder_flow", medium=rp.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0),
                                   width=w, **kw)
         return ork.make_model(self.kind, medium=self.rp_medium(), width=w, coordinate=self.coordinate,
-                              ext_wavelengths=self.ext_wavelengths, **kw)
+                              ext_wavelengths=self.ext_wavelengths, profile=self.shape, **kw)
 
     def intervals(self, width=None):
         w = self.width if width is None else width
@@ -162,7 +164,7 @@ class Case:
             return axial_flow_continua(rp.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=self.U_i0, width=w))
         if self.kind == "cylinder_density":
             s0, s1 = (1.0, 0.001) if self.coordinate == "positive" else (-1.0, -0.001)
-            return continua(cyl_profile(w, self.rp_medium()), s0, s1, False)
+            return continua(cyl_profile(w, self.rp_medium(), self.shape), s0, s1, False)
         return continua(slab_profile(w, self.rp_medium()), -1.0, 1.0, True)
 
     def regular(self, k, W, mode, margin=0.02, width=None):
@@ -198,13 +200,18 @@ class Case:
                                         profile=esb.GaussianAxialFlow(w), **kw)
         medium = {"CYL_CORONAL": esb.CYLINDER_CORONAL, "CYL_PHOTOSPHERIC": esb.CYLINDER_PHOTOSPHERIC,
                   "SLAB_CORONAL": esb.SLAB_CORONAL, "SLAB_PHOTOSPHERIC": esb.SLAB_PHOTOSPHERIC}[self.medium_name]
-        return esb.DispersionSolver(self.kind, medium=medium, profile=esb.GaussianDensity(w),
+        profile = esb.EpsteinDensity(w) if self.shape == "epstein" else esb.GaussianDensity(w)
+        return esb.DispersionSolver(self.kind, medium=medium, profile=profile,
                                     coordinate=self.coordinate, ext_wavelengths=self.ext_wavelengths, **kw)
 
 
 CASES = {c.name: c for c in [
     Case("cylinder_density", "cylinder_density", (0, 1, 2), (0.40, 5.2), 0.95, "CYL_CORONAL",
          roots_window=(2.95, 4.95), fixture="cylinder_density_coronal", family="cyl_coronal"),
+    # the same script with the Epstein profile it carries as a comment: a non-Gaussian profile through
+    # the "sample any profile at the mesh nodes" interface
+    Case("cylinder_epstein", "cylinder_density", (0, 1, 2), (0.40, 5.2), 1.0, "CYL_CORONAL",
+         roots_window=(2.95, 4.95), fixture="cylinder_density_epstein", shape="epstein"),
     Case("slab_density", "slab_density", (0, 1), (0.30, 3.2), 0.9, "SLAB_CORONAL",
          roots_window=(1.75, 2.95), fixture="slab_density_coronal", family="slab_coronal"),
     Case("cylinder_photospheric", "cylinder_density", (0, 1, 2), (0.40, 1.6), 0.9, "CYL_PHOTOSPHERIC",

@@ -24,7 +24,8 @@ warnings.filterwarnings("ignore")
 TIGHT = dict(rtol=1e-12, atol="scaled", shoot="linear")
 
 
-@pytest.mark.parametrize("name,tol,stride", [("cylinder_density", 1e-7, 3), ("slab_density", 1e-8, 4),
+@pytest.mark.parametrize("name,tol,stride", [("cylinder_density", 1e-7, 3), ("cylinder_epstein", 1e-7, 3),
+                                             ("slab_density", 1e-8, 4),
                                              ("cylinder_photospheric", 1e-7, 1),
                                              ("slab_photospheric", 1e-7, 3), ("slab_flow", 1e-7, 2),
                                              ("cylinder_flow", 1e-7, 3), ("slab_flow_photospheric", 1e-7, 2)])
