@@ -81,6 +81,10 @@ SCANS = {
     "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),
                                  ("kink", 3.0, 0.52, 0.88, 30)],
     "slab_density_coronal": [("kink", 0.75, 0.42, 0.76, 25), ("sausage", 1.5, 1.75, 2.95, 25)],
+    "cylinder_flow_coronal": [("kink", 3.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),
+                              ("sausage", 3.0, -4.9, -2.95, 30), ("kink", 3.0, -4.9, -2.95, 30)],
+    "slab_flow_coronal": [("kink", 1.5, 1.25, 2.45, 30), ("sausage", 1.5, 1.25, 2.45, 30),
+                          ("kink", 1.5, -2.45, -1.25, 30)],
 }
 
 PICKLES = {

@@ -65,24 +65,31 @@ def test_oracle_equals_executed_reference(golden_dir, name, tol, stride):
     assert n_checked >= 6 and n_skipped >= 2
 
 
-@pytest.mark.parametrize("name", ["cylinder_density", "slab_density"])
+@pytest.mark.parametrize("name", ["cylinder_density", "slab_density", "cylinder_flow", "slab_flow"])
 def test_reference_scan_and_bisection(golden_dir, name):
     """The reference's own scan+bisection output (sol_ks/sol_omegas) over a few intervals:
-    every mode it reports is a root of the oracle's D to within its 1 % acceptance band."""
+    every mode it reports is a root of the oracle's D to within its acceptance band (1 %; 6 % for
+    the axial-flow cylinder script)."""
     case = CASES[name]
+    tol = 6.0 if name == "cylinder_flow" else 1.0          # the script's xi_tol / p_tol
     g = np.load(os.path.join(golden_dir, "ref_scan_%s.npz" % case.fixture))
-    n = 0
+    n = found = 0
     while "scan%d_k" % n in g.files:
         mode = int(g["scan%d_mode" % n][0]); k = float(g["scan%d_k" % n][0])
         freq = g["scan%d_freq" % n]; ws = g["scan%d_sol_ws" % n]
         model = case.scipy_model(mode)
         mine = rp.find_roots(model, k, freq, **TIGHT)
         for w in ws:
-            e, i = rp.dispersion(model, k, float(w), **TIGHT)
-            assert rp.mismatch_percent(e, i) < 1.5
-            assert np.min(np.abs(mine - w)) < 5e-3 * abs(w)
+            # at the reference's own solver settings the restatement reproduces its decision to accept ...
+            e, i = rp.dispersion(case.scipy_model(mode, fast=False), k, float(w))
+            assert rp.mismatch_percent(e, i) < tol
+            # ... and the accepted point sits next to a converged root (the reference stops anywhere inside
+            # its band, and its D carries the solver noise described in DESIGN.md: up to 0.5 % in omega for
+            # the steep sausage branch of the flow slab)
+            assert np.min(np.abs(mine - w)) < 1e-2 * tol * abs(w)
+            found += 1
         n += 1
-    assert n >= 2
+    assert n >= 2 and found >= 1
 
 
 def test_shipped_root_tables_pass_acceptance_under_oracle(golden_dir):
