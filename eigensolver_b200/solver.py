@@ -174,10 +174,11 @@ class PowerLawRotation:
 @dataclasses.dataclass
 class RootTable:
     """Result of a root search.  `k`, `omega` of accepted modes are what the
-    reference stores in sol_ks / sol_omegas."""
+    reference stores in sol_ks / sol_omegas.  `k_axis` is the wavenumber axis the table's
+    `k_index` refers to; `k` (= k_axis[k_index]) is evaluated on access."""
     k_index: np.ndarray
     w_index: np.ndarray
-    k: np.ndarray
+    k_axis: np.ndarray
     omega: np.ndarray
     ext: np.ndarray
     intq: np.ndarray
@@ -185,9 +186,13 @@ class RootTable:
     iterations: np.ndarray
     n_brackets: int = 0
 
+    @property
+    def k(self):
+        return self.k_axis[self.k_index]
+
     def modes(self):
         m = self.accepted.astype(bool)
-        return self.k[m], self.omega[m]
+        return self.k_axis[self.k_index[m]], self.omega[m]
 
 
 _KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY, "slab_flow": L.SLAB_FLOW,
@@ -378,7 +383,7 @@ class DispersionSolver:
                                          float(tol_percent), cap, C.byref(out), C.byref(n), C.byref(nb))
             L.check(self.lib, self.ctx, rc, "esb_find_roots")
             n = n.value
-            return RootTable(ki[:n].copy(), wi[:n].copy(), k[ki[:n]], om[:n].copy(), ex[:n].copy(),
+            return RootTable(ki[:n].copy(), wi[:n].copy(), k, om[:n].copy(), ex[:n].copy(),
                              iq[:n].copy(), ac[:n].copy(), it[:n].copy(), nb.value)
         self.upload_axes(k, w, layout)
         n, nb = self.sweep_resident(mode, tol_percent)
@@ -435,7 +440,7 @@ class DispersionSolver:
             return RootTable(z4, z4, z8, z8, z8, z8, z4, z4, 0)
         view = lambda p: np.ctypeslib.as_array(p, shape=(n,))
         ki = view(out.k_index)
-        return RootTable(ki, view(out.w_index), self._k_host[ki], view(out.omega), view(out.ext),
+        return RootTable(ki, view(out.w_index), self._k_host, view(out.omega), view(out.ext),
                          view(out.intq), view(out.accepted), view(out.iterations), n)
 
     def download_roots(self, n, slot=0):
@@ -445,7 +450,7 @@ class DispersionSolver:
         out = L.esb_roots(_iptr(ki), _iptr(wi), _dptr(om), _dptr(ex), _dptr(iq), _iptr(ac), _iptr(it))
         L.check(self.lib, self.ctx, self.lib.esb_download_roots_slot(self.ctx, int(slot), C.byref(out), n),
                 "esb_download_roots_slot")
-        return RootTable(ki, wi, self._k_host[ki], om, ex, iq, ac, it, n)
+        return RootTable(ki, wi, self._k_host, om, ex, iq, ac, it, n)
 
     def roots_device(self, slot=0):
         """Device pointers of the root table of mode slot `slot` (valid until the next sweep):
