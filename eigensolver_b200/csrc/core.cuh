@@ -280,21 +280,25 @@ ESB_HD void rk4_step(double (&y)[NS], double (&yp)[NS], double h, const double (
 // m2[s] = (azimuthal order)^2 of solution s (cylinder); the node coefficients are evaluated
 // once per node and shared by all solutions.  RK8 runs in the step-scaled variables (y, z = h y'):
 // g[i] rescales z from one step to the next and back to y' after the last one.
-template <int KIND, int SCHEME, int NS>
+template <int KIND, int SCHEME, int NS, bool RANGE = false>
 ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __restrict__ tab,
-                            const double (&m2)[NS], double (&y)[NS], double (&yp)[NS]) {
+                            const double (&m2)[NS], double (&y)[NS], double (&yp)[NS], int r0 = 0,
+                            int r1 = 0) {
+    // RANGE: steps [r0, r1) of the mesh, else all of it; (y, y') in and out are unscaled
+    const int i0 = RANGE ? r0 : 0;
+    const int iend = RANGE ? r1 : M.n_steps;
     const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
     const double* gs = hs + M.n_steps;
     constexpr int NPS = (SCHEME == SCHEME_RK8) ? 4 : 2;
     constexpr int NN = NPS + 1;
     double a0, b0, bm0;
-    node_coeffs<KIND>(M, pt, tab, a0, b0, bm0);
+    node_coeffs<KIND>(M, pt, tab + (size_t)(i0 * NPS) * TAB_FIELDS, a0, b0, bm0);
     if constexpr (SCHEME == SCHEME_RK8) {
-        const double h0 = hs[0];
+        const double h0 = hs[i0];
 #pragma unroll
         for (int s = 0; s < NS; ++s) yp[s] *= h0;
     }
-    for (int i = 0; i < M.n_steps; ++i) {
+    for (int i = i0; i < iend; ++i) {
         const double* f = tab + (size_t)(i * NPS) * TAB_FIELDS;
         const double h = hs[i];
         double ca[NN], cb[NN], bm[NN], cbs[NS][NN];
@@ -319,6 +323,13 @@ ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __
             for (int s = 0; s < NS; ++s) yp[s] *= g;
         } else {
             rk4_step<NS>(y, yp, h, ca, cbs);
+        }
+    }
+    if constexpr (SCHEME == SCHEME_RK8 && RANGE) {
+        if (iend < M.n_steps) {          // z is in the scale of step iend: back to y'
+            const double ih = 1.0 / hs[iend];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) yp[s] *= ih;
         }
     }
 }
@@ -375,21 +386,34 @@ ESB_HD void node_coeffs_scaled(const DevModel& M, const Point& pt, const ScaledP
     }
 }
 
-template <int KIND, int NS>
+template <int KIND, int NS, bool RANGE = false>
 ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const double* __restrict__ tab,
-                                      const double (&m2)[NS], double (&y)[NS], double (&yp)[NS]) {
+                                      const double (&m2)[NS], double (&y)[NS], double (&yp)[NS], int r0 = 0,
+                                      int r1 = 0) {
+    // RANGE: steps [r0, r1) of the mesh, else all of it; (y, y') in and out are unscaled
+    const int i0 = RANGE ? r0 : 0;
+    const int iend = RANGE ? r1 : M.n_steps;
     const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
     const double* gs = hs + M.n_steps;
     const ScaledPoint sp = make_scaled_point<KIND>(M, pt);
     const double cc = (KIND == KIND_CYL_DENSITY) ? sp.AS : sp.inv_s;
     double ha0, h2b0, h2bm0;
-    {
+    if (!RANGE || i0 == 0) {
         const double h0 = hs[0], h2 = h0 * h0;
         node_coeffs_scaled<KIND>(M, pt, sp, h2 * cc, h2 * pt.K, tab, ha0, h2b0, h2bm0);
+    } else {
+        // node 4 i0 is stored in the scale of the step it ends: evaluate it there, rescale like the carry
+        const double hp = hs[i0 - 1], h2 = hp * hp, g = gs[i0 - 1], g2 = g * g;
+        node_coeffs_scaled<KIND>(M, pt, sp, h2 * cc, h2 * pt.K, tab + (size_t)(i0 * 4) * TAB_FIELDS, ha0, h2b0,
+                                 h2bm0);
+        ha0 *= g; h2b0 *= g2; h2bm0 *= g2;
+    }
+    {
+        const double h0 = hs[i0];
 #pragma unroll
         for (int s = 0; s < NS; ++s) yp[s] *= h0;
     }
-    for (int i = 0; i < M.n_steps; ++i) {
+    for (int i = i0; i < iend; ++i) {
         const double* f = tab + (size_t)(i * 4) * TAB_FIELDS;
         const double h = hs[i], h2 = h * h;
         const double c1 = h2 * cc, h2K = h2 * pt.K;
@@ -407,6 +431,11 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
         ha0 = ha[4] * g; h2b0 = h2b[4] * g2; h2bm0 = h2bm[4] * g2;        // the shared node, in the next step's scale
 #pragma unroll
         for (int s = 0; s < NS; ++s) yp[s] *= g;
+    }
+    if (RANGE && iend < M.n_steps) {     // z is in the scale of step iend: back to y'
+        const double ih = 1.0 / hs[iend];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) yp[s] *= ih;
     }
 }
 
@@ -449,11 +478,14 @@ ESB_HD RotCoef node_rot(const DevModel& M, const Point& p, double m, const doubl
 
 // two fundamental solutions of the (P, xi) system along the staged mesh; `end` = coefficients
 // at the last node (needed by the sausage end condition)
+template <bool RANGE = false>
 ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, const double* __restrict__ tab,
-                               double (&P)[2], double (&X)[2], RotCoef& end) {
+                               double (&P)[2], double (&X)[2], RotCoef& end, int r0 = 0, int r1 = 0) {
+    const int i0 = RANGE ? r0 : 0;
+    const int iend = RANGE ? r1 : M.n_steps;
     const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
-    RotCoef c0 = node_rot(M, pt, m, tab);
-    for (int i = 0; i < M.n_steps; ++i) {
+    RotCoef c0 = node_rot(M, pt, m, tab + (size_t)(i0 * 4) * TAB_FIELDS);
+    for (int i = i0; i < iend; ++i) {
         const double* f = tab + (size_t)(i * 4) * TAB_FIELDS;
         const double h = hs[i];
         double m11[5], m12[5], m21[5], m22[5];
@@ -521,6 +553,39 @@ ESB_HD void exterior_cyl_order(const DevModel& M, const ExtCyl& E, int n, double
     ypb = M.r_sign * E.kap * (As * dI1 * E.ea + Bs * dK1 * E.eb);
 }
 
+// ------------------------------------------------- warp-cooperative layer ----
+// One warp evaluates ONE point: the ODE is linear, so lane j integrates the two fundamental solutions
+// over its own sub-interval of the mesh (steps [j per, (j+1) per)) and the 32 transfer matrices are
+// multiplied in order by a shuffle tree.  Twice the arithmetic of the one-solution cylinder scheme,
+// 1/32 of its latency: used by the refinement when there are fewer brackets than lanes to fill
+// (esb.cu refine_warp_kernel), where the sequential Brent iterations are latency bound.
+// T = {T00, T01, T10, T11}: (u, v)_end = T (u, v)_start.
+#ifdef __CUDA_ARCH__
+template <class F>
+__device__ __forceinline__ void warp_transfer(int n_steps, F&& integrate_range, double (&T)[4]) {
+    const int lane = threadIdx.x & 31;
+    const int per = (n_steps + 31) >> 5;
+    const int i0 = lane * per;
+    const int i1 = i0 + per < n_steps ? i0 + per : n_steps;
+    double u[2] = {1.0, 0.0}, v[2] = {0.0, 1.0};             // images of (1,0) and (0,1)
+    if (i0 < n_steps) integrate_range(i0, i1, u, v);
+    T[0] = u[0]; T[1] = u[1]; T[2] = v[0]; T[3] = v[1];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        double B[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) B[q] = __shfl_down_sync(0xffffffffu, T[q], off);
+        if ((lane & (2 * off - 1)) == 0) {                    // B (later sub-interval) after T (earlier)
+            const double t0 = fma(B[0], T[0], B[1] * T[2]), t1 = fma(B[0], T[1], B[1] * T[3]);
+            const double t2 = fma(B[2], T[0], B[3] * T[2]), t3 = fma(B[2], T[1], B[3] * T[3]);
+            T[0] = t0; T[1] = t1; T[2] = t2; T[3] = t3;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) T[q] = __shfl_sync(0xffffffffu, T[q], 0);
+}
+#endif
+
 // ------------------------------------------------------------ full point ----
 // NM evaluations of the reference's scan-loop body at one (k, omega), one per requested
 // mode, sharing everything that does not depend on the mode:
@@ -530,10 +595,13 @@ ESB_HD void exterior_cyl_order(const DevModel& M, const ExtCyl& E, int n, double
 // den_q[s] = the denominator of int_q[s]: the interior quantity is a ratio whose denominator (the
 // boundary value of the integrated solution) passes through zero at the poles of D.  G = D * den_q
 // has the roots of D and no such poles; the refinement iterates on G (esb.cu refine_kernel).
-template <int KIND, int SCHEME, int NM>
+// WARP (device only, NM = 1, all 32 lanes of the warp call it with the same arguments): the layer is
+// integrated cooperatively (warp_transfer); every lane returns the same values.
+template <int KIND, int SCHEME, int NM, bool WARP = false>
 ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, double k, double w,
                              const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM],
                              double (&den_q)[NM]) {
+    static_assert(!WARP || NM == 1, "the warp-cooperative evaluation handles one mode");
     const double nanv = nan("");
     const Point pt = make_point(M, k, w);
     // exterior Doppler shift (flow script :207): (w - k U_e)
@@ -560,6 +628,18 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             // fundamental solutions (P, xi) = (1, 0), (0, 1) at the boundary r = s_start
             double P[2] = {1.0, 0.0}, X[2] = {0.0, 1.0};
             RotCoef ce;
+#ifdef __CUDA_ARCH__
+            if constexpr (WARP) {
+                const double mm = double(modes[s]);
+                double T[4];
+                warp_transfer(M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+                    RotCoef unused;
+                    integrate_rotation<true>(M, pt, mm, tab, u, v, unused, i0, i1);
+                }, T);
+                P[0] = T[0]; P[1] = T[1]; X[0] = T[2]; X[1] = T[3];
+                ce = node_rot(M, pt, mm, tab + (size_t)(M.n_steps * 4) * TAB_FIELDS);
+            } else
+#endif
             integrate_rotation(M, pt, double(modes[s]), tab, P, X, ce);
             double xi_b;
             if (modes[s] == 0) {
@@ -593,6 +673,20 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             yp[s] = modes[s] == 0 ? 0.0 : 1.0;
             m2[s] = double(modes[s]) * double(modes[s]);
         }
+#ifdef __CUDA_ARCH__
+        if constexpr (WARP) {
+            const double mm2[2] = {m2[0], m2[0]};
+            double T[4];
+            warp_transfer(M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+                if constexpr (SCHEME == SCHEME_RK8) integrate_layer_prescaled<KIND, 2, true>(M, pt, tab, mm2, u, v, i0, i1);
+                else integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, mm2, u, v, i0, i1);
+            }, T);
+            // the solution that satisfies the axis condition: (y, y')(axis) = (1, 0) or (0, 1)
+            const double y0 = y[0], yp0 = yp[0];
+            y[0] = fma(T[0], y0, T[1] * yp0);
+            yp[0] = fma(T[2], y0, T[3] * yp0);
+        } else
+#endif
         if constexpr (SCHEME == SCHEME_RK8) integrate_layer_prescaled<KIND, NM>(M, pt, tab, m2, y, yp);
         else integrate_layer<KIND, SCHEME, NM>(M, pt, tab, m2, y, yp);
         double den;
@@ -617,6 +711,15 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
         const double p_e_const = M.rho_e * M.se2 * (pt.K * M.cTe2 - Ae) / (We * (pt.K * M.ce2 - Ae));
         double y[2] = {1.0, 0.0}, yp[2] = {0.0, 1.0};
         const double m2[2] = {0.0, 0.0};
+#ifdef __CUDA_ARCH__
+        if constexpr (WARP) {
+            double T[4];
+            warp_transfer(M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+                integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, u, v, i0, i1);
+            }, T);
+            y[0] = T[0]; y[1] = T[1]; yp[0] = T[2]; yp[1] = T[3];
+        } else
+#endif
         integrate_layer<KIND, SCHEME, 2>(M, pt, tab, m2, y, yp);
         double P_Ti;
         if (KIND == KIND_SLAB_FLOW) {
@@ -642,12 +745,12 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
     }
 }
 
-template <int KIND, int SCHEME>
+template <int KIND, int SCHEME, bool WARP = false>
 ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
                        double& ext_q, double& int_q, double& den_q) {
     const int modes[1] = {mode};
     double e[1], i[1], d[1];
-    eval_point_multi<KIND, SCHEME, 1>(M, tab, k, w, modes, e, i, d);
+    eval_point_multi<KIND, SCHEME, 1, WARP>(M, tab, k, w, modes, e, i, d);
     ext_q = e[0];
     int_q = i[0];
     den_q = d[0];

@@ -211,146 +211,220 @@ __device__ __forceinline__ double mismatch_pct(double e, double i) {
     return fabs(e - i) * 100.0 / fmax(fabs(e), fabs(i));
 }
 
-// Persistent kernel: every lane runs Brent's method on one bracket at a time and pulls
-// the next bracket from a global queue as soon as its own has converged, so a warp
-// never idles behind its slowest lane.  The D evaluation (the expensive part) is executed
-// by all 32 lanes together each round; __any_sync on the "trial pending" flags ends the
-// loop.  End-point values come from the scan grid, not from new evaluations.
-//
+// ---- Brent's method on G = D * Y, one bracket -------------------------------------------------
 // Pole-free iteration.  D = ext - int with int = N/Y, Y the boundary value of the integrated
 // interior solution: D changes sign through infinity wherever Y crosses zero (the reference bisects
 // such brackets 150 levels deep and then drops them).  The scan stores Y next to (ext, int), so
-//   * a bracket whose end points have Y of opposite sign is a pole of D: it is reported at once
-//     (omega = the zero of Y by linear interpolation, ext = int = NaN, unaccepted) - no evaluation;
+//   * a bracket whose end points have Y of opposite sign AND int of opposite sign (the numerator
+//     N = int * Y keeps its sign) is a pole of D: it is reported at once (omega = the zero of Y by
+//     linear interpolation, ext = int = NaN, unaccepted) - no evaluation;
 //   * every other bracket is refined on G = D * Y, which has the roots of D and no such poles, so
 //     Brent's interpolation steps are not thrown off by a pole next to the root.
 // The acceptance test is the reference's, on (ext, int) at the converged root.  Poles of the
 // prefactors (e.g. omega = k U for the flow slab) survive in G: a bracket whose best point keeps a
 // mismatch above 50 % while |G| grows or the bracket has shrunk to 1e-7 relative is reported,
 // unaccepted, without being bisected to machine precision; so is a jump of G (see below).
+struct Brent {
+    // a = previous iterate, b = best iterate, c = the other end of the bracket; (e?, i?) = (ext, int)
+    // there, f? = G there
+    double a, b, c, ea, ia, eb, ib, ec, ic, fa, fb, fc, d, e, f0min, f0max, w0, hw0;
+    int it;
+    bool on_g;      // iterate on G = D * Y (else on D itself)
+};
+
+// false: the bracket is a pole of D (S.b = its interpolated position)
+__device__ __forceinline__ bool brent_init(Brent& S, double a, double b, double ea, double ia, double eb,
+                                           double ib, double ya, double yb) {
+    S.on_g = true;
+    if ((ya < 0.0 && yb > 0.0) || (ya > 0.0 && yb < 0.0)) {
+        if ((ia < 0.0 && ib > 0.0) || (ia > 0.0 && ib < 0.0)) {
+            // the denominator changes sign and the numerator N = int * Y does not: int, hence D,
+            // changes sign through infinity
+            const double wp = a - ya * (b - a) / (yb - ya);
+            S.b = fmin(fmax(wp, fmin(a, b)), fmax(a, b));
+            return false;
+        }
+        // numerator and denominator vanish together (slab: for even coefficients y2(1) = 0 implies
+        // y1(1) = +-1, which is the sausage or the kink target): int = N/Y stays finite, D is smooth
+        // and G would have a spurious root at the zero of Y - iterate on D itself
+        S.on_g = false;
+    }
+    S.a = a; S.b = b; S.ea = ea; S.ia = ia; S.eb = eb; S.ib = ib;
+    S.fa = (ea - ia) * (S.on_g ? ya : 1.0);
+    S.fb = (eb - ib) * (S.on_g ? yb : 1.0);
+    S.c = a; S.ec = ea; S.ic = ia; S.fc = S.fa;
+    S.d = b - a; S.e = S.d;
+    S.f0min = fmin(fabs(S.fa), fabs(S.fb));
+    S.f0max = fmax(fabs(S.fa), fabs(S.fb));
+    // scales of the bracket as found: they keep the tolerances meaningful for a bracket
+    // that straddles omega = 0 (the backward/forward scans of the flow kinds have one per k)
+    S.w0 = fmax(fabs(a), fabs(b));
+    S.hw0 = 0.5 * fabs(b - a);
+    S.it = 0;
+    return true;
+}
+
+// true: evaluate at S.b and hand the values to brent_feed; false: finished, the result is (S.b, S.eb, S.ib)
+__device__ __forceinline__ bool brent_next(Brent& S) {
+    const double eps = 2.220446049250313e-16;
+    if ((S.fb > 0.0 && S.fc > 0.0) || (S.fb < 0.0 && S.fc < 0.0)) {
+        S.c = S.a; S.ec = S.ea; S.ic = S.ia; S.fc = S.fa;
+        S.d = S.b - S.a; S.e = S.d;
+    }
+    if (fabs(S.fc) < fabs(S.fb)) {
+        S.a = S.b; S.ea = S.eb; S.ia = S.ib; S.fa = S.fb;
+        S.b = S.c; S.eb = S.ec; S.ib = S.ic; S.fb = S.fc;
+        S.c = S.a; S.ec = S.ea; S.ic = S.ia; S.fc = S.fa;
+    }
+    const double tol1 = 2.0 * eps * fmax(fabs(S.b), 0.5 * S.w0);
+    const double xm = 0.5 * (S.c - S.b);
+    const bool converged = fabs(xm) <= tol1 || S.fb == 0.0 || !isfinite(S.fb) || S.it >= 120;
+    const bool pole = S.it >= 2 && mismatch_pct(S.eb, S.ib) > 50.0 &&
+                      (fabs(S.fb) > 4.0 * S.f0min || fabs(xm) < fmax(1e-7 * fabs(S.b), 1e-3 * S.hw0));
+    // a jump: inside a continuum the integration crosses a singular point and G changes sign
+    // discontinuously (the reference bisects such brackets 150 levels deep).  Once the bracket
+    // has shrunk a million-fold a root would have |G| ~ 1e-6 of its end-point values; a best
+    // value still above 1e-4 of them is a discontinuity.  (Were a genuine root ever caught by
+    // this, it is already located to 1e-6 of a grid interval, ~1e-10 relative.)
+    const bool jump = fabs(xm) < 1e-6 * S.hw0 && fabs(S.fb) > 100.0 * S.f0max * (fabs(xm) / S.hw0);
+    if (converged || pole || jump) return false;
+    if (fabs(S.e) >= tol1 && fabs(S.fa) > fabs(S.fb)) {
+        const double s = S.fb / S.fa;
+        double p, q;
+        if (S.a == S.c) {
+            p = 2.0 * xm * s;
+            q = 1.0 - s;
+        } else {
+            const double qq = S.fa / S.fc, rr = S.fb / S.fc;
+            p = s * (2.0 * xm * qq * (qq - rr) - (S.b - S.a) * (rr - 1.0));
+            q = (qq - 1.0) * (rr - 1.0) * (s - 1.0);
+        }
+        if (p > 0.0) q = -q;
+        p = fabs(p);
+        const double m1 = 3.0 * xm * q - fabs(tol1 * q);
+        const double m2 = fabs(S.e * q);
+        if (2.0 * p < (m1 < m2 ? m1 : m2)) {
+            S.e = S.d;
+            S.d = p / q;
+        } else {
+            S.d = xm;
+            S.e = S.d;
+        }
+    } else {
+        S.d = xm;
+        S.e = S.d;
+    }
+    S.a = S.b; S.ea = S.eb; S.ia = S.ib; S.fa = S.fb;
+    S.b += (fabs(S.d) > tol1) ? S.d : (xm > 0.0 ? tol1 : -tol1);
+    return true;
+}
+
+__device__ __forceinline__ void brent_feed(Brent& S, double en, double in_, double yn) {
+    S.eb = en;
+    S.ib = in_;
+    S.fb = (en - in_) * (S.on_g ? yn : 1.0);
+    ++S.it;
+}
+
+// bracket t of the single queue over all mode slots -> slot, local index, point data, Brent state.
+// false: classified as a pole from the scan (result already written).
+__device__ __forceinline__ bool refine_pickup(const RefineArgs& r, int tq, bool writer, int& sl, int& t, int& mode,
+                                              double& k, Brent& S) {
+    sl = (r.n_slots > 2 && tq >= r.slot[2].begin) ? 2 : (r.n_slots > 1 && tq >= r.slot[1].begin) ? 1 : 0;
+    t = tq - r.slot[sl].begin;
+    mode = r.slot[sl].mode;
+    const int ik = r.slot[sl].bk[t], jw = r.slot[sl].bw[t];
+    k = r.k[ik];
+    const double a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
+    const double b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
+    const size_t o = (size_t)ik * r.nw + jw;
+    if (brent_init(S, a, b, r.slot[sl].gext[o], r.slot[sl].gint[o], r.slot[sl].gext[o + 1],
+                   r.slot[sl].gint[o + 1], r.slot[sl].gden[o], r.slot[sl].gden[o + 1]))
+        return true;
+    if (writer) {
+        r.slot[sl].omega[t] = S.b;
+        r.slot[sl].ext[t] = nan("");
+        r.slot[sl].intq[t] = nan("");
+        r.slot[sl].iters[t] = 0;
+        r.slot[sl].accepted[t] = 0;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void refine_store(const RefineArgs& r, int sl, int t, const Brent& S) {
+    r.slot[sl].omega[t] = S.b;
+    r.slot[sl].ext[t] = S.eb;
+    r.slot[sl].intq[t] = S.ib;
+    r.slot[sl].iters[t] = S.it;
+    r.slot[sl].accepted[t] = (mismatch_pct(S.eb, S.ib) < r.tol_percent) ? 1 : 0;
+}
+
+// Persistent kernel, one LANE per bracket: every lane runs Brent's method on one bracket at a time
+// and pulls the next bracket from a global queue as soon as its own has converged, so a warp
+// never idles behind its slowest lane.  The D evaluation (the expensive part) is executed
+// by all 32 lanes together each round; __any_sync on the "trial pending" flags ends the
+// loop.  End-point values come from the scan grid, not from new evaluations.
 template <int KIND, int SCHEME, int MINB>
 __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
     stage_table(r.tab, stab, r.tab_doubles);
-    const double eps = 2.220446049250313e-16;
     bool have = false, pending = false, exhausted = false;
-    int t = 0, it = 0, sl = 0, mode = 0;
-    // Brent state: a = previous iterate, b = best iterate, c = the other end of the bracket;
-    // (e?, i?) = (ext, int) there, f? = G there
-    double k = 1.0, a = 0, b = 1.0, c = 0, ea = 0, ia = 0, eb = 0, ib = 0, ec = 0, ic = 0, fa = 0, fb = 0,
-           fc = 0, d = 0, e = 0, f0min = 0, f0max = 0, w0 = 0, hw0 = 0;
+    int t = 0, sl = 0, mode = 0;
+    double k = 1.0;
+    Brent S;
+    S.b = 1.0;
     for (;;) {
         while (!pending && !exhausted) {
             if (!have) {
-                t = atomicAdd(r.counter, 1);
-                if (t >= r.n_total) {
+                const int tq = atomicAdd(r.counter, 1);
+                if (tq >= r.n_total) {
                     exhausted = true;
                     break;
                 }
-                // one queue over the brackets of all mode slots
-                sl = (r.n_slots > 2 && t >= r.slot[2].begin) ? 2 : (r.n_slots > 1 && t >= r.slot[1].begin) ? 1 : 0;
-                t -= r.slot[sl].begin;
-                mode = r.slot[sl].mode;
-                const int ik = r.slot[sl].bk[t], jw = r.slot[sl].bw[t];
-                k = r.k[ik];
-                a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
-                b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
-                const size_t o = (size_t)ik * r.nw + jw;
-                ea = r.slot[sl].gext[o]; ia = r.slot[sl].gint[o];
-                eb = r.slot[sl].gext[o + 1]; ib = r.slot[sl].gint[o + 1];
-                const double ya = r.slot[sl].gden[o], yb = r.slot[sl].gden[o + 1];
-                if ((ya < 0.0 && yb > 0.0) || (ya > 0.0 && yb < 0.0)) {
-                    // the denominator changes sign: D changes sign through infinity
-                    const double wp = a - ya * (b - a) / (yb - ya);
-                    r.slot[sl].omega[t] = fmin(fmax(wp, fmin(a, b)), fmax(a, b));
-                    r.slot[sl].ext[t] = nan("");
-                    r.slot[sl].intq[t] = nan("");
-                    r.slot[sl].iters[t] = 0;
-                    r.slot[sl].accepted[t] = 0;
-                    continue;
-                }
-                fa = (ea - ia) * ya;
-                fb = (eb - ib) * yb;
-                c = a; ec = ea; ic = ia; fc = fa;
-                d = b - a; e = d;
-                f0min = fmin(fabs(fa), fabs(fb));
-                f0max = fmax(fabs(fa), fabs(fb));
-                // scales of the bracket as found: they keep the tolerances meaningful for a bracket
-                // that straddles omega = 0 (the backward/forward scans of the flow kinds have one per k)
-                w0 = fmax(fabs(a), fabs(b));
-                hw0 = 0.5 * fabs(b - a);
-                it = 0;
+                if (!refine_pickup(r, tq, true, sl, t, mode, k, S)) continue;
                 have = true;
             }
-            if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
-                c = a; ec = ea; ic = ia; fc = fa;
-                d = b - a; e = d;
-            }
-            if (fabs(fc) < fabs(fb)) {
-                a = b; ea = eb; ia = ib; fa = fb;
-                b = c; eb = ec; ib = ic; fb = fc;
-                c = a; ec = ea; ic = ia; fc = fa;
-            }
-            const double tol1 = 2.0 * eps * fmax(fabs(b), 0.5 * w0);
-            const double xm = 0.5 * (c - b);
-            const bool converged = fabs(xm) <= tol1 || fb == 0.0 || !isfinite(fb) || it >= 120;
-            const bool pole = it >= 2 && mismatch_pct(eb, ib) > 50.0 &&
-                              (fabs(fb) > 4.0 * f0min || fabs(xm) < fmax(1e-7 * fabs(b), 1e-3 * hw0));
-            // a jump: inside a continuum the integration crosses a singular point and G changes sign
-            // discontinuously (the reference bisects such brackets 150 levels deep).  Once the bracket
-            // has shrunk a million-fold a root would have |G| ~ 1e-6 of its end-point values; a best
-            // value still above 1e-4 of them is a discontinuity.  (Were a genuine root ever caught by
-            // this, it is already located to 1e-6 of a grid interval, ~1e-10 relative.)
-            const bool jump = fabs(xm) < 1e-6 * hw0 && fabs(fb) > 100.0 * f0max * (fabs(xm) / hw0);
-            if (converged || pole || jump) {
-                r.slot[sl].omega[t] = b;
-                r.slot[sl].ext[t] = eb;
-                r.slot[sl].intq[t] = ib;
-                r.slot[sl].iters[t] = it;
-                r.slot[sl].accepted[t] = (mismatch_pct(eb, ib) < r.tol_percent) ? 1 : 0;
+            if (!brent_next(S)) {
+                refine_store(r, sl, t, S);
                 have = false;
                 continue;
             }
-            if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
-                const double s = fb / fa;
-                double p, q;
-                if (a == c) {
-                    p = 2.0 * xm * s;
-                    q = 1.0 - s;
-                } else {
-                    const double qq = fa / fc, rr = fb / fc;
-                    p = s * (2.0 * xm * qq * (qq - rr) - (b - a) * (rr - 1.0));
-                    q = (qq - 1.0) * (rr - 1.0) * (s - 1.0);
-                }
-                if (p > 0.0) q = -q;
-                p = fabs(p);
-                const double m1 = 3.0 * xm * q - fabs(tol1 * q);
-                const double m2 = fabs(e * q);
-                if (2.0 * p < (m1 < m2 ? m1 : m2)) {
-                    e = d;
-                    d = p / q;
-                } else {
-                    d = xm;
-                    e = d;
-                }
-            } else {
-                d = xm;
-                e = d;
-            }
-            a = b; ea = eb; ia = ib; fa = fb;
-            b += (fabs(d) > tol1) ? d : (xm > 0.0 ? tol1 : -tol1);
             pending = true;
         }
         if (!__any_sync(0xffffffffu, pending)) break;
         double en, in_, yn;
-        eval_point<KIND, SCHEME>(r.M, stab, k, b, mode, en, in_, yn);
+        eval_point<KIND, SCHEME>(r.M, stab, k, S.b, mode, en, in_, yn);
         if (pending) {
-            eb = en;
-            ib = in_;
-            fb = (en - in_) * yn;
-            ++it;
+            brent_feed(S, en, in_, yn);
             pending = false;
         }
+    }
+}
+
+// Persistent kernel, one WARP per bracket: the 32 lanes integrate the layer cooperatively
+// (core.cuh warp_transfer), so one evaluation has 1/32 of the latency.  Used when there are fewer
+// brackets than lanes to fill, where the lane-per-bracket kernel lasts as long as the sequential
+// evaluations of its slowest bracket.  The Brent state is replicated (uniform) across the warp.
+template <int KIND, int SCHEME>
+__global__ void __launch_bounds__(128) refine_warp_kernel(RefineArgs r) {
+    extern __shared__ __align__(16) double stab[];
+    stage_table(r.tab, stab, r.tab_doubles);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int tq = 0;
+        if (lane == 0) tq = atomicAdd(r.counter, 1);
+        tq = __shfl_sync(0xffffffffu, tq, 0);
+        if (tq >= r.n_total) break;
+        int t, sl, mode;
+        double k;
+        Brent S;
+        if (!refine_pickup(r, tq, lane == 0, sl, t, mode, k, S)) continue;
+        while (brent_next(S)) {
+            double en, in_, yn;
+            eval_point<KIND, SCHEME, true>(r.M, stab, k, S.b, mode, en, in_, yn);
+            brent_feed(S, en, in_, yn);
+        }
+        if (lane == 0) refine_store(r, sl, t, S);
     }
 }
 
@@ -389,6 +463,7 @@ struct esb_context {
     int64_t launches = 0;
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
+    int refine_mode = 0;       // 0 = by bracket count, 1 = lane per bracket, 2 = warp per bracket
     int ax_nk = 0, ax_nw = 0, ax_layout = 0;
     std::string err;
 };
@@ -859,6 +934,26 @@ static cudaError_t launch_refine_b(const RefineArgs& r, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+template <int KIND, int SCHEME>
+static cudaError_t launch_refine_warp(const RefineArgs& r, cudaStream_t s) {
+    const size_t smem = (size_t)r.tab_doubles * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(refine_warp_kernel<KIND, SCHEME>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(refine_warp_kernel<KIND, SCHEME>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_warp_kernel<KIND, SCHEME>, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int blocks = (r.n_total + 3) / 4;             // 4 warps = 4 brackets per CTA at a time
+    const int cap = 148 * per_sm;
+    if (blocks > cap) blocks = cap;
+    refine_warp_kernel<KIND, SCHEME><<<blocks, 128, smem, s>>>(r);
+    return cudaGetLastError();
+}
+
 // 4 resident CTAs per SM: measured on the B200 (scripts/gpu_refine_time.py) - compiling the kernel
 // for 5..8 CTAs/SM spills the evaluation loop and is 5-30 % slower
 template <int KIND, int SCHEME>
@@ -1039,6 +1134,12 @@ extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k
     return esb_dispersion_grid_multi(c, 1, &mode, k, nk, w, nw, layout, ext, intq);
 }
 
+extern "C" int esb_set_refine_mode(esb_context* c, int32_t mode) {
+    if (!c || mode < 0 || mode > 2) return ESB_ERR_ARG;
+    c->refine_mode = mode;
+    return ESB_OK;
+}
+
 extern "C" int esb_set_stream(esb_context* c, void* stream) {
     if (!c) return ESB_ERR_ARG;
     c->user_stream = (cudaStream_t)stream;
@@ -1145,7 +1246,13 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     }
     if (r.n_total > 0) {
         // ONE persistent launch refines the brackets of every mode (single work queue)
+        // fewer brackets than lanes to keep busy: one warp per bracket (1/32 of the evaluation latency,
+        // twice the arithmetic for the one-solution cylinder kinds); else one lane per bracket
+        const bool one_solution = c->dm.kind == KIND_CYL_DENSITY || c->dm.kind == KIND_CYL_FLOW;
+        const bool warp_path = c->refine_mode == 2 ||
+                               (c->refine_mode == 0 && r.n_total <= (one_solution ? 24000 : 48000));
         const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
+            if (warp_path) return launch_refine_warp<decltype(kind)::value, decltype(scheme)::value>(r, s);
             return launch_refine<decltype(kind)::value, decltype(scheme)::value>(r, s);
         });
         CUDA_TRY(c, e);

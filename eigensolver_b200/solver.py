@@ -469,6 +469,12 @@ class DispersionSolver:
         L.check(self.lib, self.ctx, self.lib.esb_set_stream(self.ctx, C.c_void_p(int(stream_ptr))),
                 "esb_set_stream")
 
+    def set_refine_mode(self, mode):
+        """"auto" (by bracket count) | "lane" (one lane per bracket) | "warp" (one warp per bracket)."""
+        L.check(self.lib, self.ctx,
+                self.lib.esb_set_refine_mode(self.ctx, {"auto": 0, "lane": 1, "warp": 2}[mode]),
+                "esb_set_refine_mode")
+
     def fp64_peak_tflops(self):
         v = C.c_double(0.0)
         L.check(self.lib, self.ctx, self.lib.esb_fp64_peak(self.ctx, C.byref(v)), "esb_fp64_peak")

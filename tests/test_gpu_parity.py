@@ -331,6 +331,36 @@ def test_pinned_download_equals_pageable(solvers):
     assert len(s.download_roots_pinned(0).omega) == 0
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_refine_lane_and_warp_kernels_agree(solvers, name):
+    """One lane per bracket (throughput) and one warp per bracket (latency: sub-interval transfer
+    matrices multiplied by a shuffle tree) are two schedules of the same iteration."""
+    s = solvers[name]
+    case = CASES[name]
+    k, W = _grid_case(name, nk=11, nw=400)
+    try:
+        tabs = {}
+        for mode_name in ("lane", "warp"):
+            s.set_refine_mode(mode_name)
+            tabs[mode_name] = [s.find_roots(m, k, W) for m in case.modes]
+    finally:
+        s.set_refine_mode("auto")
+    n_acc = 0
+    for m, a, b in zip(case.modes, tabs["lane"], tabs["warp"]):
+        assert np.array_equal(a.k_index, b.k_index) and np.array_equal(a.w_index, b.w_index)
+        reg = case.regular(k, W, m)
+        ok = reg[a.k_index, a.w_index] & reg[a.k_index, a.w_index + 1]
+        # outside the continua: the same classification and the same roots to rounding
+        assert np.array_equal(a.accepted[ok], b.accepted[ok])
+        acc = ok & (a.accepted == 1)
+        n_acc += int(acc.sum())
+        if acc.any():
+            assert np.max(np.abs(a.omega[acc] - b.omega[acc]) / np.abs(a.omega[acc])) < 1e-11
+        # inside them D is solver noise: the two summation orders may file a noise bracket differently
+        assert (a.accepted != b.accepted).sum() <= 0.05 * len(a.accepted) + 2
+    assert n_acc >= 5
+
+
 def test_rk4_and_rk8_agree():
     k = np.linspace(0.3, 4.0, 6); W = np.linspace(3.0, 4.9, 40)
     with esb.DispersionSolver("cylinder_density", scheme="rk8") as a, \
