@@ -1246,11 +1246,16 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     }
     if (r.n_total > 0) {
         // ONE persistent launch refines the brackets of every mode (single work queue)
-        // fewer brackets than lanes to keep busy: one warp per bracket (1/32 of the evaluation latency,
-        // twice the arithmetic for the one-solution cylinder kinds); else one lane per bracket
-        const bool one_solution = c->dm.kind == KIND_CYL_DENSITY || c->dm.kind == KIND_CYL_FLOW;
-        const bool warp_path = c->refine_mode == 2 ||
-                               (c->refine_mode == 0 && r.n_total <= (one_solution ? 24000 : 48000));
+        // one warp per bracket (1/32 of the evaluation latency) or one lane per bracket.  Measured
+        // crossovers (scripts/gpu_refine_modes.py, profiles/r01o_refine_modes.log): the cylinder
+        // second-order kinds integrate ONE solution per lane but two per warp lane, so the warp kernel
+        // wins only while the lanes cannot be filled (< ~24 k brackets); the two-solution kinds do the
+        // same arithmetic either way and the warp kernel has a 32x shorter tail: ahead up to > 100 k
+        // (rotation, whose per-lane exterior Bessel work is replicated 32 times: ~100 k)
+        const int kind = c->dm.kind;
+        const int limit = (kind == KIND_CYL_DENSITY || kind == KIND_CYL_FLOW) ? 24000
+                          : kind == KIND_CYL_ROTATION ? 100000 : 250000;
+        const bool warp_path = c->refine_mode == 2 || (c->refine_mode == 0 && r.n_total <= limit);
         const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
             if (warp_path) return launch_refine_warp<decltype(kind)::value, decltype(scheme)::value>(r, s);
             return launch_refine<decltype(kind)::value, decltype(scheme)::value>(r, s);
