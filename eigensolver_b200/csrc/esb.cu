@@ -87,6 +87,34 @@ __global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
     }
 }
 
+// One WARP per (mode, k, omega): the warp-cooperative evaluation (core.cuh warp_transfer) for grids too
+// small to fill the lanes - a reference-style worker call is one k and ~90 frequencies - where the
+// one-thread-per-point kernel lasts as long as one full integration.
+template <int KIND, int SCHEME>
+__global__ void __launch_bounds__(128) grid_warp_kernel(GridArgs g) {
+    extern __shared__ __align__(16) double stab[];
+    stage_table(g.tab, stab, g.tab_doubles);
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const size_t plane = (size_t)g.nk * g.nw;
+    const size_t total = plane * g.n_modes;
+    for (size_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < total; p += n_warps) {
+        const int slot = (int)(p / plane);
+        const size_t o = p - slot * plane;
+        const int ik = (int)(o / g.nw), iw = (int)(o - (size_t)ik * g.nw);
+        const double k = g.k[ik];
+        const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
+        double e, i, d;
+        eval_point<KIND, SCHEME, true>(g.M, stab, k, w, g.modes[slot], e, i, d);
+        if (lane == 0) {
+            const bool fin = isfinite(e) && isfinite(i);
+            g.ext[p] = fin ? e : nan("");
+            g.intq[p] = fin ? i : nan("");
+            if (g.den) g.den[p] = d;
+        }
+    }
+}
+
 // ---- brackets: sign change of D = ext - int between neighbours along omega ----
 __device__ __forceinline__ bool is_bracket(double d0, double d1) {
     // both evaluated (finite) and strictly opposite signs
@@ -904,8 +932,24 @@ static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+constexpr size_t GRID_WARP_MAX_POINTS = 8192;     // (mode, k, omega) triples; above it one thread per point
+
+template <int KIND, int SCHEME>
+static cudaError_t launch_grid_warp(const GridArgs& g, cudaStream_t s) {
+    const size_t smem = (size_t)g.tab_doubles * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(grid_warp_kernel<KIND, SCHEME>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const size_t total = (size_t)g.nk * g.nw * g.n_modes;
+    int blocks = (int)((total + 3) / 4);           // 4 warps = 4 points per CTA at a time
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    grid_warp_kernel<KIND, SCHEME><<<blocks, 128, smem, s>>>(g);
+    return cudaGetLastError();
+}
+
 template <int KIND, int SCHEME>
 static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
+    if ((size_t)g.nk * g.nw * g.n_modes <= GRID_WARP_MAX_POINTS) return launch_grid_warp<KIND, SCHEME>(g, s);
     switch (g.n_modes) {
         case 1: return launch_grid_nm<KIND, SCHEME, 1>(g, s);
         case 2: return launch_grid_nm<KIND, SCHEME, 2>(g, s);
