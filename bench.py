@@ -300,7 +300,7 @@ def run_gpu_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "modes": list(MODES), "nk_per_gpu": NK, "nw": NW, "k_shards": "strided",
                        "n_steps": N_STEPS, "mesh": "graded", "scheme": "rk8", "profile": "inverted Gaussian, width 0.95",
-                       "l2": "working set 480 MB of D written per step > 126 MB L2; inputs are 88 KB"},
+                       "l2": "working set 720 MB of (ext, int, Y) written per step > 126 MB L2; inputs are 88 KB"},
             "roots_per_sec": n_brackets * world * args.steps / (ms * 1e-3),
             "modes_found": n_modes, "brackets_rank0": n_brackets,
             "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
