@@ -361,6 +361,55 @@ def test_refine_lane_and_warp_kernels_agree(solvers, name):
     assert n_acc >= 5
 
 
+def test_device_pointer_entry_points(solvers):
+    """esb_dispersion_grid_dev / esb_brackets_dev on caller-owned device buffers (torch tensors) and a
+    caller-owned stream: the same grids and the same sorted bracket list as the host entry points."""
+    import ctypes as C
+    import torch
+    s = solvers["cylinder_density"]
+    lib = s.lib
+    dev = torch.device("cuda", 0)
+    for nk, nw in ((7, 300), (40, 2500)):          # warp-per-point and thread-per-point scan kernels
+        k = np.linspace(0.5, 4.0, nk); W = np.linspace(0.55, 4.95, nw)
+        e_host, i_host = s.dispersion_grid(1, k, W)
+        tab = s.find_roots(1, k, W)
+        stream = torch.cuda.Stream(dev)
+        d_k = torch.from_numpy(k).to(dev); d_w = torch.from_numpy(W).to(dev)
+        d_e = torch.empty((nk, nw), dtype=torch.float64, device=dev); d_i = torch.empty_like(d_e)
+        torch.cuda.synchronize()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        rc = lib.esb_dispersion_grid_dev(s.ctx, 1, p(d_k), nk, p(d_w), nw, 1, p(d_e), p(d_i),
+                                         C.c_void_p(stream.cuda_stream))
+        assert rc == 0
+        d_off = torch.empty(nk + 1, dtype=torch.int32, device=dev)
+        cap = len(tab.omega) + 8
+        d_bk = torch.empty(cap, dtype=torch.int32, device=dev); d_bw = torch.empty_like(d_bk)
+        n = C.c_int32(-1)
+        rc = lib.esb_brackets_dev(s.ctx, p(d_e), p(d_i), nk, nw, p(d_off), p(d_bk), p(d_bw), cap, C.byref(n),
+                                  C.c_void_p(stream.cuda_stream))
+        assert rc == 0
+        stream.synchronize()
+        assert np.array_equal(d_e.cpu().numpy(), e_host, equal_nan=True)
+        assert np.array_equal(d_i.cpu().numpy(), i_host, equal_nan=True)
+        assert n.value == len(tab.omega)
+        assert np.array_equal(d_bk[:n.value].cpu().numpy(), tab.k_index)
+        assert np.array_equal(d_bw[:n.value].cpu().numpy(), tab.w_index)
+        off = d_off.cpu().numpy()
+        assert off[0] == 0 and off[-1] == n.value
+        assert np.array_equal(np.diff(off), np.bincount(tab.k_index, minlength=nk))
+        # too small a capacity is reported, the count is still returned
+        rc = lib.esb_brackets_dev(s.ctx, p(d_e), p(d_i), nk, nw, p(d_off), p(d_bk), p(d_bw), 3, C.byref(n),
+                                  C.c_void_p(stream.cuda_stream))
+        assert rc == -3 and n.value == len(tab.omega)
+    # a context can be moved onto the caller's stream
+    st = torch.cuda.Stream(dev)
+    with esb.DispersionSolver("slab_density") as t:
+        a = t.find_roots(0, np.linspace(0.3, 1.5, 9), np.linspace(1.75, 2.95, 200))
+        t.set_stream(st.cuda_stream)
+        b = t.find_roots(0, np.linspace(0.3, 1.5, 9), np.linspace(1.75, 2.95, 200))
+        assert np.array_equal(a.omega, b.omega, equal_nan=True) and np.array_equal(a.accepted, b.accepted)
+
+
 def test_rk4_and_rk8_agree():
     k = np.linspace(0.3, 4.0, 6); W = np.linspace(3.0, 4.9, 40)
     with esb.DispersionSolver("cylinder_density", scheme="rk8") as a, \
@@ -369,6 +418,16 @@ def test_rk4_and_rk8_agree():
         eb, ib = b.dispersion_grid(1, k, W)
     assert np.array_equal(ea, eb)
     assert np.max(np.abs(ia - ib) / np.abs(ia)) < 5e-9
+    # the classical scheme on the other second-order kinds (generic, unscaled coefficient path)
+    for kind, kw, W in (("slab_density", {}, np.linspace(1.75, 2.95, 40)),
+                        ("cylinder_flow", {}, np.linspace(3.0, 4.9, 40)),
+                        ("slab_flow", dict(profile=esb.GaussianFlow(1.0)), np.linspace(1.25, 2.45, 40))):
+        with esb.DispersionSolver(kind, scheme="rk8", **kw) as a, \
+                esb.DispersionSolver(kind, scheme="rk4", n_steps=4096, **kw) as b:
+            ea, ia = a.dispersion_grid(1, k, W)
+            eb, ib = b.dispersion_grid(1, k, W)
+        assert np.array_equal(ea, eb, equal_nan=True)
+        assert np.nanmax(np.abs(ia - ib) / np.abs(ia)) < 2e-8, kind
 
 
 def test_full_size_properties(solvers):
