@@ -423,11 +423,11 @@ def test_rk4_and_rk8_agree():
                         ("cylinder_flow", {}, np.linspace(3.0, 4.9, 40)),
                         ("slab_flow", dict(profile=esb.GaussianFlow(1.0)), np.linspace(1.25, 2.45, 40))):
         with esb.DispersionSolver(kind, scheme="rk8", **kw) as a, \
-                esb.DispersionSolver(kind, scheme="rk4", n_steps=4096, **kw) as b:
+                esb.DispersionSolver(kind, scheme="rk4", n_steps=2048, **kw) as b:    # 200 KB table limit
             ea, ia = a.dispersion_grid(1, k, W)
             eb, ib = b.dispersion_grid(1, k, W)
         assert np.array_equal(ea, eb, equal_nan=True)
-        assert np.nanmax(np.abs(ia - ib) / np.abs(ia)) < 2e-8, kind
+        assert np.nanmax(np.abs(ia - ib) / np.abs(ia)) < 1e-6, kind           # 4th order at 2048 steps
 
 
 def test_full_size_properties(solvers):
