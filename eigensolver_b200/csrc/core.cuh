@@ -1,7 +1,7 @@
 // Device core of the dispersion-function hot path: exterior closed forms,
 // per-node ODE coefficients from the staged profile table, fixed-step RK4 / RK8
 // shooting integrator and the matching closures.  One thread evaluates one
-// (k, omega) point.
+// (k, omega) point (eval_point_multi), or one warp does (WARP = true, warp_transfer).
 //
 // Reference path restated (file:line in /root/reference):
 //   cylinder  Cylinder/Non-uniform density/Coronal/solvers/Density_cylinder.py:694-821

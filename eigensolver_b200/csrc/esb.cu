@@ -1,13 +1,16 @@
 // eigensolver_b200: kernels + C ABI (see include/eigensolver_b200.h).
 //
 // Kernels (all FP64, sm_100a):
-//   grid_kernel      one thread per (k, omega): exterior closed form + RK shooting
-//                    across the layer with the profile table staged in shared memory.
-//   bracket_count /  one warp per k-row: warp-ballot sign-change detection along omega,
-//   bracket_fill     popc prefix -> deterministic, sorted bracket list.
-//   refine_kernel    persistent; one lane per bracket at a time, brackets pulled from a
-//                    queue: Brent iteration on D(omega), warp-level vote (__any_sync) on the
-//                    pending flags, pole early-out, acceptance test.
+//   grid_kernel        one thread per (k, omega), up to 3 modes fused per thread: exterior closed form +
+//                      RK shooting across the layer with the profile table staged in shared memory.
+//   grid_warp_kernel   one warp per (mode, k, omega) for small grids: the lanes integrate sub-intervals
+//                      of the layer and multiply their transfer matrices (core.cuh warp_transfer).
+//   bracket_kernel /   one warp per (k-row, omega segment): warp-ballot sign-change detection along
+//   scan_kernel        omega, popc prefix -> deterministic, sorted bracket list.
+//   refine_kernel      persistent, one lane per bracket, brackets pulled from a queue: Brent iteration
+//                      on the pole-free function G = D * Y, warp-level vote (__any_sync) on the pending
+//                      flags, poles classified from the scan, acceptance test.
+//   refine_warp_kernel the same iteration, one warp per bracket (short bracket lists: latency).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
