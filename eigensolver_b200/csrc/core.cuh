@@ -37,7 +37,7 @@ struct DevModel {
     double ic_v, ic_s;        // exterior initial values
     double ext_len;           // exterior start = -ext_len / k
     // interior: c^2 = alpha/rho, vA^2 = beta/rho, cT^2 = tau/rho, S = alpha + beta
-    double alpha, beta, tau, S;
+    double alpha, beta, tau, S, invS;
     double rho_b;             // density at the boundary s_start
     double s_start;           // boundary position (-1)
     double r_sign;            // cylinder: -1 scripts written in r<0 (coronal), +1 in r>0 (photospheric)
@@ -169,7 +169,7 @@ ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, doub
         const double p1 = p.Kalpha - u, p2 = p.Kbeta - u, p3 = p.Ktau - u;
         const double inv = 1.0 / (p1 * p3);
         a = p.AKc * drho * inv;
-        b = (p1 * p1) * p2 * inv / M.S;
+        b = (p1 * p1) * p2 * inv * M.invS;
         bm = 0.0;
     }
 }

@@ -889,6 +889,7 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
         d.beta = m->vA_i0 * m->vA_i0 * m->rho_i0 * (m->kind == ESB_SLAB_DENSITY ? m->rho_A : 1.0);
         d.alpha = d.rho_e * (d.ce2 + 0.5 * g * d.vAe2) - 0.5 * g * d.beta;
         d.S = d.alpha + d.beta;
+        d.invS = 1.0 / d.S;
         d.tau = d.alpha * d.beta / d.S;
         d.rho_b = boundary[0];
     }
