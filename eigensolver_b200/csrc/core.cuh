@@ -450,30 +450,41 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
 // first-order pair in (P, xi) directly - the same solutions, no coefficient derivatives:
 //   P'  = -(C1/D) P + (C3/D) xi          xi' = -(C2/D) P + (C1/D - 1/r) xi
 // staged node f = {1/r, v_phi, r d/dr(-rho v_phi^2/r^2), c^2}.
-struct RotCoef { double m11, m12, m21, m22, C1, C3; };
+// The staged rotation node holds the (k, omega, m)-independent products, 8 doubles:
+//   {1/r, 1/r^2, v_phi/r, c^2 + vA^2, c^2, rho v_phi, rho v_phi^2/r, r d/dr(-rho v_phi^2/r^2)}
+constexpr int ROT_FIELDS = 8;
+
+// unscaled pieces of the system matrix: m11 = -C1/D, m12 = C3/D, m21 = -C2/D, m22 = C1/D - 1/r
+struct RotCoef { double C1, C2, C3, invD, invr; };
 
 ESB_HD RotCoef node_rot(const DevModel& M, const Point& p, double m, const double* f) {
-    const double invr = f[0], vphi = f[1], f2 = f[2], c2 = f[3];
-    const double Om = fma(-m * vphi, invr, p.w);
+    const double invr = f[0], invr2 = f[1], vr = f[2], s = f[3], c2 = f[4], rv = f[5], q0 = f[6], f2 = f[7];
+    const double Om = fma(-m, vr, p.w);
     const double O2 = Om * Om;
-    const double s = c2 + M.vAi2;
     const double wA2 = p.K * M.vAi2;
     const double a1 = O2 - wA2;
     const double A2 = fma(O2, s, -wA2 * c2);             // s (Om^2 - w_c^2), w_c^2 = w_A^2 c^2/s
-    const double Dd = M.rho_i * a1 * A2;
-    const double Q = -a1 * M.rho_i * vphi * vphi * invr;
-    const double T = M.rho_i * vphi * Om;
-    const double invr2 = invr * invr;
+    const double ra1 = M.rho_i * a1;
+    const double Dd = ra1 * A2;
+    const double Q = -a1 * q0;
+    const double T = rv * Om;
+    const double TA = (A2 * T) * invr2;
     RotCoef c;
-    c.C1 = fma(Q, O2, -2.0 * m * A2 * T * invr2);
-    const double C2 = fma(O2, O2, -A2 * fma(m * m, invr2, p.K));
-    c.C3 = fma(Dd, fma(M.rho_i, a1, f2), fma(Q, Q, -4.0 * A2 * T * T * invr2));
-    const double invD = 1.0 / Dd;
-    c.m11 = -c.C1 * invD;
-    c.m12 = c.C3 * invD;
-    c.m21 = -C2 * invD;
-    c.m22 = fma(c.C1, invD, -invr);
+    c.C1 = fma(Q, O2, -2.0 * m * TA);
+    c.C2 = fma(O2, O2, -A2 * fma(m * m, invr2, p.K));
+    c.C3 = fma(Dd, ra1 + f2, fma(Q, Q, -4.0 * TA * T));
+    c.invD = 1.0 / Dd;
+    c.invr = invr;
     return c;
+}
+
+// the four entries of the system matrix at one node, multiplied by the step h
+ESB_HD void rot_scaled(const RotCoef& c, double h, double& m11, double& m12, double& m21, double& m22) {
+    const double hD = h * c.invD;
+    m11 = -c.C1 * hD;
+    m12 = c.C3 * hD;
+    m21 = -c.C2 * hD;
+    m22 = fma(c.C1, hD, -h * c.invr);
 }
 
 // two fundamental solutions of the (P, xi) system along the staged mesh; `end` = coefficients
@@ -483,17 +494,17 @@ ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, con
                                double (&P)[2], double (&X)[2], RotCoef& end, int r0 = 0, int r1 = 0) {
     const int i0 = RANGE ? r0 : 0;
     const int iend = RANGE ? r1 : M.n_steps;
-    const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
-    RotCoef c0 = node_rot(M, pt, m, tab + (size_t)(i0 * 4) * TAB_FIELDS);
+    const double* hs = tab + (size_t)M.n_nodes * ROT_FIELDS;
+    RotCoef c0 = node_rot(M, pt, m, tab + (size_t)(i0 * 4) * ROT_FIELDS);
     for (int i = i0; i < iend; ++i) {
-        const double* f = tab + (size_t)(i * 4) * TAB_FIELDS;
+        const double* f = tab + (size_t)(i * 4) * ROT_FIELDS;
         const double h = hs[i];
         double m11[5], m12[5], m21[5], m22[5];
-        m11[0] = h * c0.m11; m12[0] = h * c0.m12; m21[0] = h * c0.m21; m22[0] = h * c0.m22;
+        rot_scaled(c0, h, m11[0], m12[0], m21[0], m22[0]);
 #pragma unroll
         for (int n = 1; n < 5; ++n) {
-            c0 = node_rot(M, pt, m, f + n * TAB_FIELDS);
-            m11[n] = h * c0.m11; m12[n] = h * c0.m12; m21[n] = h * c0.m21; m22[n] = h * c0.m22;
+            c0 = node_rot(M, pt, m, f + n * ROT_FIELDS);
+            rot_scaled(c0, h, m11[n], m12[n], m21[n], m22[n]);
         }
         const RhsSystem rhs{m11, m12, m21, m22};
         rk8_generic<2>(P, X, rhs);
@@ -637,7 +648,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
                     integrate_rotation<true>(M, pt, mm, tab, u, v, unused, i0, i1);
                 }, T);
                 P[0] = T[0]; P[1] = T[1]; X[0] = T[2]; X[1] = T[3];
-                ce = node_rot(M, pt, mm, tab + (size_t)(M.n_steps * 4) * TAB_FIELDS);
+                ce = node_rot(M, pt, mm, tab + (size_t)(M.n_steps * 4) * ROT_FIELDS);
             } else
 #endif
             integrate_rotation(M, pt, double(modes[s]), tab, P, X, ce);

@@ -815,10 +815,11 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     std::vector<double> nodes(need);
     if (esb_mesh_nodes(m, nodes.data())) return fail(c, ESB_ERR_ARG, "mesh");
     const int N = m->n_steps, nps = nodes_per_step(m->scheme);
-    // [need][TAB_FIELDS] node fields, h[N], g[N] = h[i+1]/h[i] (last: 1/h[N-1]); see integrate_layer
-    std::vector<double> tab((size_t)need * TAB_FIELDS + 2 * (size_t)N, 0.0);
+    // [need][fields per node] node fields, h[N], g[N] = h[i+1]/h[i] (last: 1/h[N-1]); see integrate_layer
+    const int tf = m->kind == ESB_CYLINDER_ROTATION ? ROT_FIELDS : TAB_FIELDS;
+    std::vector<double> tab((size_t)need * tf + 2 * (size_t)N, 0.0);
     for (int i = 0; i < need; ++i) {
-        double* f = &tab[(size_t)i * TAB_FIELDS];
+        double* f = &tab[(size_t)i * tf];
         if (m->kind == ESB_CYLINDER_DENSITY || m->kind == ESB_CYLINDER_FLOW) {
             const double r = nodes[i];
             f[0] = 1.0 / r;
@@ -837,17 +838,23 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
             }
         } else if (m->kind == ESB_CYLINDER_ROTATION) {
             // fields = {v_phi, v_phi', c^2};  r d/dr(-rho v_phi^2/r^2) = -2 rho v_phi (r v_phi' - v_phi)/r^2
-            const double r = nodes[i], v = fields[0][i], dv = fields[1][i];
+            // staged: the (k, omega, m)-independent products node_rot needs (core.cuh ROT_FIELDS)
+            const double r = nodes[i], v = fields[0][i], dv = fields[1][i], c2 = fields[2][i];
+            const double rho = m->rho_i0;
             f[0] = 1.0 / r;
-            f[1] = v;
-            f[2] = -2.0 * m->rho_i0 * v * (r * dv - v) / (r * r);
-            f[3] = fields[2][i];
+            f[1] = 1.0 / (r * r);
+            f[2] = v / r;
+            f[3] = c2 + m->vA_i0 * m->vA_i0;
+            f[4] = c2;
+            f[5] = rho * v;
+            f[6] = rho * v * v / r;
+            f[7] = -2.0 * rho * v * (r * dv - v) / (r * r);
         } else {
             for (int q = 0; q < n_fields; ++q) f[q] = fields[q][i];
         }
     }
     {
-        double* hs = &tab[(size_t)need * TAB_FIELDS];
+        double* hs = &tab[(size_t)need * tf];
         for (int i = 0; i < N; ++i) hs[i] = nodes[(i + 1) * nps] - nodes[i * nps];
         for (int i = 0; i < N; ++i) hs[N + i] = (i + 1 < N) ? hs[i + 1] / hs[i] : 1.0 / hs[i];
     }
