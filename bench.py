@@ -131,35 +131,71 @@ def ncu_traffic():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process (every 5 ms), the
+    `nvidia-smi` query of the profiling recipe as a fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm = []
+        self.sm_max = None
+        self.seen = set()
+        self.source = None
         self.stop = threading.Event()
 
-    def run(self):
+    def _nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        uuid = None
+        try:      # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES, NVML indexes the machine
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis else self.index
+        except Exception:
+            phys = self.index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.source = "nvml"
+        while not self.stop.is_set():
+            self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.seen.update(n for n, b in bits.items() if r & b)
+            self.stop.wait(0.005)
+
+    def _smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.source = "nvidia-smi"
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                      timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if r and r[0].isdigit():
+                    self.sm.append(int(r[0]))
+                    self.sm_max = int(r[1]) if r[1].isdigit() else self.sm_max
+                    self.seen.update(n for j, n in enumerate(self.NAMES) if len(r) > 2 + j and r[2 + j] == "Active")
             except Exception:
                 pass
             self.stop.wait(0.1)
 
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
+
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(r[2 + j] == "Active" for r in self.rows if len(r) > 2 + j)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max,
+                "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(sm), "source": self.source}
 
 
 def run_gpu_arm(args):
