@@ -77,7 +77,7 @@ SYMBOLS = {
     "esb_download_roots_slot": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), C.c_int32]),
     "esb_roots_pinned": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), _ip]),
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
-    "esb_set_refine_mode": (C.c_int, [_ctx, C.c_int32]),
+    "esb_set_schedule": (C.c_int, [_ctx, C.c_int32]),
     "esb_fp64_peak": (C.c_int, [_ctx, _dp]),
     "esb_rk_selftest": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _dp]),
     "esb_bessel_ik_scaled": (C.c_int, [C.c_int32, C.c_double, _dp]),

@@ -42,6 +42,7 @@ struct GridArgs {
     double* ext;            // [n_modes][nk][nw]
     double* intq;
     double* den;            // optional [n_modes][nk][nw]: denominator of intq (sweep path; see refine_kernel)
+    int schedule;           // 0 = by size, 1 = one thread per point, 2 = one warp per point
 };
 
 __device__ __forceinline__ double omega_at(const double* __restrict__ k, const double* __restrict__ w,
@@ -494,7 +495,7 @@ struct esb_context {
     int64_t launches = 0;
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
-    int refine_mode = 0;       // 0 = by bracket count, 1 = lane per bracket, 2 = warp per bracket
+    int schedule = 0;          // 0 = by size, 1 = one lane per point / bracket, 2 = one warp per point / bracket
     int ax_nk = 0, ax_nw = 0, ax_layout = 0;
     std::string err;
 };
@@ -960,7 +961,8 @@ static cudaError_t launch_grid_warp(const GridArgs& g, cudaStream_t s) {
 
 template <int KIND, int SCHEME>
 static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
-    if ((size_t)g.nk * g.nw * g.n_modes <= GRID_WARP_MAX_POINTS) return launch_grid_warp<KIND, SCHEME>(g, s);
+    if (g.schedule == 2 || (g.schedule == 0 && (size_t)g.nk * g.nw * g.n_modes <= GRID_WARP_MAX_POINTS))
+        return launch_grid_warp<KIND, SCHEME>(g, s);
     switch (g.n_modes) {
         case 1: return launch_grid_nm<KIND, SCHEME, 1>(g, s);
         case 2: return launch_grid_nm<KIND, SCHEME, 2>(g, s);
@@ -1068,6 +1070,7 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
     g.n_modes = n_modes;
     for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
     g.ext = d_ext; g.intq = d_int; g.den = d_den;
+    g.schedule = c->schedule;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
@@ -1189,9 +1192,9 @@ extern "C" int esb_dispersion_grid(esb_context* c, int32_t mode, const double* k
     return esb_dispersion_grid_multi(c, 1, &mode, k, nk, w, nw, layout, ext, intq);
 }
 
-extern "C" int esb_set_refine_mode(esb_context* c, int32_t mode) {
+extern "C" int esb_set_schedule(esb_context* c, int32_t mode) {
     if (!c || mode < 0 || mode > 2) return ESB_ERR_ARG;
-    c->refine_mode = mode;
+    c->schedule = mode;
     return ESB_OK;
 }
 
@@ -1310,7 +1313,7 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         const int kind = c->dm.kind;
         const int limit = (kind == KIND_CYL_DENSITY || kind == KIND_CYL_FLOW) ? 24000
                           : kind == KIND_CYL_ROTATION ? 100000 : 250000;
-        const bool warp_path = c->refine_mode == 2 || (c->refine_mode == 0 && r.n_total <= limit);
+        const bool warp_path = c->schedule == 2 || (c->schedule == 0 && r.n_total <= limit);
         const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
             if (warp_path) return launch_refine_warp<decltype(kind)::value, decltype(scheme)::value>(r, s);
             return launch_refine<decltype(kind)::value, decltype(scheme)::value>(r, s);

@@ -469,11 +469,12 @@ class DispersionSolver:
         L.check(self.lib, self.ctx, self.lib.esb_set_stream(self.ctx, C.c_void_p(int(stream_ptr))),
                 "esb_set_stream")
 
-    def set_refine_mode(self, mode):
-        """"auto" (by bracket count) | "lane" (one lane per bracket) | "warp" (one warp per bracket)."""
+    def set_schedule(self, mode):
+        """Scan and refinement kernels: "auto" (by size) | "lane" (one lane per point / bracket) |
+        "warp" (one warp per point / bracket).  Each is bit-reproducible; they agree to rounding."""
         L.check(self.lib, self.ctx,
-                self.lib.esb_set_refine_mode(self.ctx, {"auto": 0, "lane": 1, "warp": 2}[mode]),
-                "esb_set_refine_mode")
+                self.lib.esb_set_schedule(self.ctx, {"auto": 0, "lane": 1, "warp": 2}[mode]),
+                "esb_set_schedule")
 
     def fp64_peak_tflops(self):
         v = C.c_double(0.0)

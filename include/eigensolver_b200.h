@@ -188,11 +188,12 @@ int esb_download_roots_slot(esb_context* ctx, int32_t slot, esb_roots* out, int3
  * or esb_destroy.  Synchronises the stream. */
 int esb_roots_pinned(esb_context* ctx, int32_t slot, esb_roots* out, int32_t* n_roots);
 
-/* Refinement kernel: 0 (default) = chosen by the number of brackets, 1 = one lane per bracket
- * (throughput: every lane integrates its own point), 2 = one warp per bracket (latency: the 32
- * lanes integrate sub-intervals of the layer and multiply their transfer matrices).  Both give
- * the same roots to rounding. */
-int esb_set_refine_mode(esb_context* ctx, int32_t mode);
+/* Schedule of the scan and refinement kernels: 0 (default) = chosen by size, 1 = one lane per
+ * (k, omega) point / per bracket (throughput: every lane integrates its own point), 2 = one warp per
+ * point / per bracket (latency: the 32 lanes integrate sub-intervals of the layer and multiply their
+ * transfer matrices).  A schedule is bit-reproducible; the two agree to rounding (~1e-14 relative),
+ * so force one of them when grids of different sizes are to be compared bit for bit. */
+int esb_set_schedule(esb_context* ctx, int32_t mode);
 
 /* Run every launch and copy of this context on `stream` (a cudaStream_t, e.g. the
  * caller's torch stream) instead of the context's own stream. */

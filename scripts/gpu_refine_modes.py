@@ -16,7 +16,7 @@ for kind, modes, W, kw in (("cylinder_density", [0, 1, 2], np.linspace(0.5, 5.0,
             s.upload_axes(k, W)
             row = []
             for mode in ("lane", "warp"):
-                s.set_refine_mode(mode)
+                s.set_schedule(mode)
                 s.sweep_resident_multi(modes); torch.cuda.synchronize()
                 ts = []
                 for _ in range(3):

@@ -15,7 +15,7 @@ for kind, kw, modes, (lo, hi) in CASES:
         for nk, nw in ((3, 129), (12, 900)):            # warp-per-point / thread-per-point scan
             k = np.linspace(0.6, 3.5, nk); W = np.linspace(lo, hi, nw)
             for mode in ("lane", "warp"):
-                s.set_refine_mode(mode)
+                s.set_schedule(mode)
                 tabs = s.find_roots_multi(modes, k, W)
                 t1 = s.find_roots(modes[-1], k, W, max_roots=4096)
                 p = s.download_roots_pinned(0)
