@@ -375,6 +375,24 @@ def test_refine_lane_and_warp_kernels_agree(solvers, name):
     assert np.max(np.abs(i1[ok] - i3[ok]) / np.maximum(np.abs(i3[ok]), np.abs(e3[ok]))) < 1e-9
 
 
+def test_convergence_check_flags_sharp_profiles():
+    """The fixed-step integrator reports its own discretisation error: negligible for the shipped
+    profile width, visible for a much sharper profile, and cured by more steps."""
+    k = np.linspace(0.5, 4.5, 9); W = np.linspace(3.0, 4.9, 120)          # above the Alfven continuum
+    with esb.DispersionSolver("cylinder_density") as s:
+        err, where = s.convergence_check([0, 1, 2], k, W)
+        assert err < 1e-9 and where["n_steps_fine"] == 2 * where["n_steps"]
+    # a dense shell of width 0.05 at r = 0.5, in the uniform part of the mesh (6 steps per width)
+    sharp = esb.GaussianDensity(0.05, x0=-0.5)
+    W2 = np.linspace(4.6, 4.95, 60)           # above the Alfven continuum (vA = 4.41 outside the shell)
+    with esb.DispersionSolver("cylinder_density", profile=sharp) as s:
+        err_default, _ = s.convergence_check([1], k, W2)
+    with esb.DispersionSolver("cylinder_density", profile=sharp, n_steps=576) as s:
+        err_fine, _ = s.convergence_check([1], k, W2)
+    assert err_default > 1e-10                # the default step count is visibly too coarse for it ...
+    assert err_fine < 1e-3 * err_default      # ... and 4x the steps (8th order) cure it
+
+
 def test_device_pointer_entry_points(solvers):
     """esb_dispersion_grid_dev / esb_brackets_dev on caller-owned device buffers (torch tensors) and a
     caller-owned stream: the same grids and the same sorted bracket list as the host entry points."""
