@@ -88,7 +88,8 @@ SCRIPTS = {
         ref=_REF["flow_p"], kind="slab_flow",
         medium=FlowMedium(vA_i=1.0, c_i=2.0 / 3.0, vA_e=0.0, c_e=0.75, U_i0=0.0, U_e=-0.15),
         profile=GaussianFlow(1e5), solver=dict(ext_wavelengths=7.0), tol=1e-6, n_freq=100,
-        wavenumber=(0.01, 3.5, 350), speeds=lambda md, prof: sorted([md.cT_i, md.c_e + md.U_e])),
+        wavenumber=(0.01, 3.5, 350), speeds=lambda md, prof: sorted([md.cT_i, md.c_e + md.U_e]),
+        freq=lambda: np.logspace(0.001, 0.55, 80) - 1.0),       # :813, the same frequencies for every k
     # Cylinder_method_flow_testing.py: xi_tol :530 (6 %), speeds :243, driver :1134,:1153; ships with U_i0 = 0
     "cylinder_flow": dict(
         ref=_REF["cylflow"], kind="cylinder_flow", medium=CYLINDER_FLOW_CORONAL, profile=GaussianAxialFlow(1e5),
@@ -210,6 +211,13 @@ class ReferenceScript:
             for i in range(len(speeds) - 1):
                 W = np.linspace(speeds[i], speeds[i + 1], n_freq)
                 tab = self.solver.find_roots(mode, wavenumber, W, layout="phase_speed",
+                                             tol_percent=self.tol)
+                k_ok, w_ok = self._modes_of(tab)
+                ks.append(k_ok)
+                ws.append(w_ok)
+            if "freq" in self.spec and speeds == sorted(self.default_speeds()):
+                # a script whose driver also scans one absolute frequency array for every k
+                tab = self.solver.find_roots(mode, wavenumber, self.spec["freq"](), layout="shared",
                                              tol_percent=self.tol)
                 k_ok, w_ok = self._modes_of(tab)
                 ks.append(k_ok)
