@@ -76,6 +76,14 @@ POINTS["cylinder_density_epstein"] = dict(
     solver="cylinder_density_coronal", patches=EPSTEIN_PATCH,
     ks=[0.1, 0.5, 1.0, 2.0, 3.2, 4.5], Ws=[0.52, 0.6, 0.75, 0.88, 1.35, 1.6, 1.95, 2.95, 3.3, 4.0, 4.9, 0.45, 5.2])
 
+# a second width per density script (the widths of the shipped root tables)
+POINTS["cylinder_density_coronal_w15"] = dict(
+    solver="cylinder_density_coronal", overrides={"dr": 1.5},
+    ks=[0.3, 1.0, 2.0, 3.2, 4.5], Ws=[0.52, 0.7, 0.88, 1.5, 1.95, 3.3, 4.0, 4.9, 0.45, 5.2])
+POINTS["slab_density_coronal_w3"] = dict(
+    solver="slab_density_coronal", overrides={"dx": 3.0},
+    ks=[0.05, 0.3, 0.75, 1.5, 3.0], Ws=[0.42, 0.6, 0.74, 1.75, 2.0, 2.5, 2.95, 0.398, 3.1])
+
 SCANS = {
     # (mode, k, W_lo, W_hi, n)  - intervals that contain a mode
     "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),

@@ -208,6 +208,11 @@ class Case:
 CASES = {c.name: c for c in [
     Case("cylinder_density", "cylinder_density", (0, 1, 2), (0.40, 5.2), 0.95, "CYL_CORONAL",
          roots_window=(2.95, 4.95), fixture="cylinder_density_coronal", family="cyl_coronal"),
+    # a second profile width per density script
+    Case("cylinder_density_w15", "cylinder_density", (0, 1, 2), (0.40, 5.2), 1.5, "CYL_CORONAL",
+         roots_window=(2.95, 4.95), fixture="cylinder_density_coronal_w15"),
+    Case("slab_density_w3", "slab_density", (0, 1), (0.30, 3.2), 3.0, "SLAB_CORONAL",
+         roots_window=(1.75, 2.95), fixture="slab_density_coronal_w3"),
     # the same script with the Epstein profile it carries as a comment: a non-Gaussian profile through
     # the "sample any profile at the mesh nodes" interface
     Case("cylinder_epstein", "cylinder_density", (0, 1, 2), (0.40, 5.2), 1.0, "CYL_CORONAL",

@@ -25,6 +25,7 @@ TIGHT = dict(rtol=1e-12, atol="scaled", shoot="linear")
 
 
 @pytest.mark.parametrize("name,tol,stride", [("cylinder_density", 1e-7, 3), ("cylinder_epstein", 1e-7, 3),
+                                             ("cylinder_density_w15", 1e-7, 3), ("slab_density_w3", 1e-8, 2),
                                              ("slab_density", 1e-8, 4),
                                              ("cylinder_photospheric", 1e-7, 1),
                                              ("slab_photospheric", 1e-7, 3), ("slab_flow", 1e-7, 2),
