@@ -44,6 +44,9 @@ struct DevModel {
     // slab with a sheared flow U(x) / cylinder with an axial flow v_z(r): uniform interior c_i,
     // vA_i, rho_i; U_b = flow speed at the boundary s_start
     double ci2, vAi2, cTi2, si, rho_i, U_e, U_b;
+    // slab kinds: the staged profile is mirror-symmetric about the mid-plane (checked by the host when the
+    // model is set): the even and the odd solution are integrated from the mid-plane over HALF the layer
+    int symmetric;
     // cylinder with rotational flow v_phi(r): uniform rho_i, vA_i (vAi2, rho_i above);
     // rho v_phi^2 at the boundary enters the kink end condition
     double rho_vb2;
@@ -573,10 +576,11 @@ ESB_HD void exterior_cyl_order(const DevModel& M, const ExtCyl& E, int n, double
 // T = {T00, T01, T10, T11}: (u, v)_end = T (u, v)_start.
 #ifdef __CUDA_ARCH__
 template <class F>
-__device__ __forceinline__ void warp_transfer(int n_steps, F&& integrate_range, double (&T)[4]) {
+__device__ __forceinline__ void warp_transfer(int first, int n_steps, F&& integrate_range, double (&T)[4]) {
+    // steps [first, n_steps) shared out over the 32 lanes
     const int lane = threadIdx.x & 31;
-    const int per = (n_steps + 31) >> 5;
-    const int i0 = lane * per;
+    const int per = (n_steps - first + 31) >> 5;
+    const int i0 = first + lane * per;
     const int i1 = i0 + per < n_steps ? i0 + per : n_steps;
     double u[2] = {1.0, 0.0}, v[2] = {0.0, 1.0};             // images of (1,0) and (0,1)
     if (i0 < n_steps) integrate_range(i0, i1, u, v);
@@ -643,7 +647,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             if constexpr (WARP) {
                 const double mm = double(modes[s]);
                 double T[4];
-                warp_transfer(M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+                warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
                     RotCoef unused;
                     integrate_rotation<true>(M, pt, mm, tab, u, v, unused, i0, i1);
                 }, T);
@@ -688,7 +692,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
         if constexpr (WARP) {
             const double mm2[2] = {m2[0], m2[0]};
             double T[4];
-            warp_transfer(M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+            warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
                 if constexpr (SCHEME == SCHEME_RK8) integrate_layer_prescaled<KIND, 2, true>(M, pt, tab, mm2, u, v, i0, i1);
                 else integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, mm2, u, v, i0, i1);
             }, T);
@@ -720,18 +724,23 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
         exterior_slab(M, k, me, yb, ypb);
         // P_e = p_e_const vx'   (..._coronal.py:221,250 / flow :209,291)
         const double p_e_const = M.rho_e * M.se2 * (pt.K * M.cTe2 - Ae) / (We * (pt.K * M.ce2 - Ae));
+        // General layer: the two fundamental solutions at the near boundary, integrated across.
+        // Mirror-symmetric layer (every shipped script: x0 = 0): the even and the odd solution,
+        // (1, 0) and (0, 1) at the mid-plane, integrated over the far half only - the sausage condition
+        // vx(1) = -vx(-1) selects the odd one, the kink condition the even one.  Half the steps.
         double y[2] = {1.0, 0.0}, yp[2] = {0.0, 1.0};
         const double m2[2] = {0.0, 0.0};
+        const int first = M.symmetric ? M.n_steps / 2 : 0;
 #ifdef __CUDA_ARCH__
         if constexpr (WARP) {
             double T[4];
-            warp_transfer(M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+            warp_transfer(first, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
                 integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, u, v, i0, i1);
             }, T);
             y[0] = T[0]; y[1] = T[1]; yp[0] = T[2]; yp[1] = T[3];
         } else
 #endif
-        integrate_layer<KIND, SCHEME, 2>(M, pt, tab, m2, y, yp);
+        integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, y, yp, first, M.n_steps);
         double P_Ti;
         if (KIND == KIND_SLAB_FLOW) {
             // displacement continuity: vx_i(-1) = vx_e(-1) (w - k U(-1))/(w - k U_e)   (flow :290)
@@ -747,11 +756,20 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
             // sausage: vx(1) = -vx(-1) (:259); kink: vx(1) = +vx(-1) (:696)
-            const double target = (modes[s] == 0) ? -1.0 : 1.0;
-            const double slope = yb * (target - y[0]) / y[1];
+            double slope;
+            if (M.symmetric) {
+                // vx = yb Sol(x)/Sol(-1), Sol = odd (sausage) or even (kink): Sol(-1) = -+Sol(1),
+                // Sol'(-1) = +-Sol'(1)  ->  vx'(-1) = -yb Sol'(1)/Sol(1)
+                const int c = (modes[s] == 0) ? 1 : 0;
+                slope = -yb * yp[c] / y[c];
+                den_q[s] = y[c];
+            } else {
+                const double target = (modes[s] == 0) ? -1.0 : 1.0;
+                slope = yb * (target - y[0]) / y[1];
+                den_q[s] = y[1];
+            }
             ext_q[s] = p_e_const * ypb;
             int_q[s] = P_Ti * slope;
-            den_q[s] = y[1];
         }
     }
 }

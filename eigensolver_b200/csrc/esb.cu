@@ -564,7 +564,12 @@ static void graded_breakpoints(const esb_model* m, bool slab, std::vector<double
     }
     out[0] = a;
     out[N] = b;
-    if (slab && N % 2 == 0) out[N / 2] = 0.5 * (a + b);
+    if (slab && N % 2 == 0) {
+        // exactly mirror-symmetric about the mid-plane (the accumulated sum above is so only to ~1e-11):
+        // a symmetric profile then takes the half-layer path of eval_point_multi
+        out[N / 2] = 0.5 * (a + b);
+        for (int i = 0; i < N / 2; ++i) out[N - i] = (a + b) - out[i];
+    }
 }
 
 static int build_breakpoints_uncached(const esb_model* m, std::vector<double>& bp);
@@ -878,6 +883,22 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     d.ext_len = m->ext_wavelengths * 2.0 * M_PI;
     d.s_start = m->s_start;
     d.r_sign = m->r_sign >= 0 ? 1.0 : -1.0;
+    if (m->kind == ESB_SLAB_DENSITY || m->kind == ESB_SLAB_FLOW) {
+        // mirror symmetry of the staged profile about the mid-plane: even fields (rho; U, U'') equal,
+        // odd fields (rho'; U') opposite at mirrored nodes (the mesh itself is symmetric for even N)
+        bool sym = (N % 2 == 0);
+        for (int q = 0; q < n_fields && sym; ++q) {
+            const double parity = (q == 1) ? -1.0 : 1.0;
+            double scale = 0.0;
+            for (int i = 0; i < need; ++i) scale = fmax(scale, fabs(fields[q][i]));
+            for (int i = 0; i < need && sym; ++i)
+                sym = fabs(fields[q][i] - parity * fields[q][need - 1 - i]) <= 1e-12 * scale;
+        }
+        for (int i = 0; i < need && sym; ++i)
+            sym = fabs((nodes[i] - nodes[0]) - (nodes[need - 1] - nodes[need - 1 - i])) <=
+                  1e-12 * fabs(nodes[need - 1] - nodes[0]);
+        d.symmetric = sym ? 1 : 0;
+    }
     if (m->kind == ESB_SLAB_FLOW || m->kind == ESB_CYLINDER_FLOW) {
         d.ci2 = m->c_i0 * m->c_i0;
         d.vAi2 = m->vA_i0 * m->vA_i0;

@@ -375,6 +375,35 @@ def test_refine_lane_and_warp_kernels_agree(solvers, name):
     assert np.max(np.abs(i1[ok] - i3[ok]) / np.maximum(np.abs(i3[ok]), np.abs(e3[ok]))) < 1e-9
 
 
+def test_slab_symmetric_and_general_layers():
+    """Mirror-symmetric slabs (x0 = 0, every shipped script) integrate the even and the odd solution over
+    half the layer; a profile centred off the mid-plane takes the general two-point path.  Both against
+    the C oracle, which always integrates the full layer with the reference's two-point condition."""
+    k = np.linspace(0.3, 4.0, 10)
+    for kind, x0, W, prof, mk in (
+            ("slab_density", 0.3, np.linspace(1.75, 2.95, 160), lambda x0: esb.GaussianDensity(0.9, x0),
+             lambda x0: ork.make_model("slab_density", width=0.9, x0=x0)),
+            ("slab_flow", 0.25, np.linspace(1.25, 2.45, 160), lambda x0: esb.GaussianFlow(1.0, x0),
+             lambda x0: ork.make_model("slab_flow", medium=rp.FlowMedium(width=1.0, x0=x0), width=1.0, x0=x0))):
+        for shift in (0.0, x0):
+            model = mk(shift)
+            with esb.DispersionSolver(kind, profile=prof(shift)) as s:
+                for mode in (0, 1):
+                    e, i = s.dispersion_grid(mode, k, W)
+                    e0, i0 = ork.grid(model, mode, k, W)
+                    ok = np.isfinite(e0) & np.isfinite(i0)
+                    assert np.array_equal(np.isnan(e), ~ok)
+                    dev = np.abs((e - i) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+                    assert np.nanmax(dev[ok]) < D_TOL, (kind, shift, mode, np.nanmax(dev[ok]))
+                    tab = s.find_roots(mode, k, W)
+                    bk, bw = ork.brackets(e0 - i0)
+                    assert np.array_equal(bk, tab.k_index) and np.array_equal(bw, tab.w_index)
+                    for j in np.nonzero(tab.accepted == 1)[0][:6]:
+                        kk = k[tab.k_index[j]]
+                        r, _, _ = ork.refine(model, mode, kk, kk * W[tab.w_index[j]], kk * W[tab.w_index[j] + 1])
+                        assert abs(tab.omega[j] - r) <= ROOT_TOL * abs(r)
+
+
 def test_convergence_check_flags_sharp_profiles():
     """The fixed-step integrator reports its own discretisation error: negligible for the shipped
     profile width, visible for a much sharper profile, and cured by more steps."""
