@@ -490,11 +490,10 @@ ESB_HD void rot_scaled(const RotCoef& c, double h, double& m11, double& m12, dou
     m22 = fma(c.C1, hD, -h * c.invr);
 }
 
-// two fundamental solutions of the (P, xi) system along the staged mesh; `end` = coefficients
-// at the last node (needed by the sausage end condition)
-template <bool RANGE = false>
+// NS solutions of the (P, xi) system along the staged mesh (axis end -> boundary)
+template <int NS, bool RANGE = false>
 ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, const double* __restrict__ tab,
-                               double (&P)[2], double (&X)[2], RotCoef& end, int r0 = 0, int r1 = 0) {
+                               double (&P)[NS], double (&X)[NS], int r0 = 0, int r1 = 0) {
     const int i0 = RANGE ? r0 : 0;
     const int iend = RANGE ? r1 : M.n_steps;
     const double* hs = tab + (size_t)M.n_nodes * ROT_FIELDS;
@@ -510,9 +509,8 @@ ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, con
             rot_scaled(c0, h, m11[n], m12[n], m21[n], m22[n]);
         }
         const RhsSystem rhs{m11, m12, m21, m22};
-        rk8_generic<2>(P, X, rhs);
+        rk8_generic<NS>(P, X, rhs);
     }
-    end = c0;
 }
 
 // --------------------------------------------------------------- exterior ----
@@ -640,31 +638,48 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             double Pb, ypb;
             exterior_cyl_order(M, E, modes[s], Pb, ypb);
             const double xi_e = xi_e_const * ypb;
-            // fundamental solutions (P, xi) = (1, 0), (0, 1) at the boundary r = s_start
-            double P[2] = {1.0, 0.0}, X[2] = {0.0, 1.0};
-            RotCoef ce;
-#ifdef __CUDA_ARCH__
-            if constexpr (WARP) {
-                const double mm = double(modes[s]);
-                double T[4];
-                warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
-                    RotCoef unused;
-                    integrate_rotation<true>(M, pt, mm, tab, u, v, unused, i0, i1);
-                }, T);
-                P[0] = T[0]; P[1] = T[1]; X[0] = T[2]; X[1] = T[3];
-                ce = node_rot(M, pt, mm, tab + (size_t)(M.n_steps * 4) * ROT_FIELDS);
-            } else
-#endif
-            integrate_rotation(M, pt, double(modes[s]), tab, P, X, ce);
+            // The layer is integrated from the axis end (where the scripts impose their end condition)
+            // out to the boundary r = s_start, where P = P_e fixes the scale.
+            const double mm = double(modes[s]);
             double xi_b;
             if (modes[s] == 0) {
-                // sausage: P'(end) = 0  <=>  C3 xi - C1 P = 0 at the end node   (sausage script :306)
-                den_q[s] = fma(ce.C3, X[1], -ce.C1 * P[1]);
-                xi_b = -Pb * fma(ce.C3, X[0], -ce.C1 * P[0]) / den_q[s];
+                // sausage: P'(axis end) = 0  <=>  C3 xi - C1 P = 0 there (sausage script :306): ONE
+                // solution, started with (P, xi) proportional to (C3, C1)
+                const RotCoef ca = node_rot(M, pt, mm, tab);
+                const double nrm = 1.0 / fmax(fabs(ca.C3), fabs(ca.C1));
+                double P[1] = {ca.C3 * nrm}, X[1] = {ca.C1 * nrm};
+#ifdef __CUDA_ARCH__
+                if constexpr (WARP) {
+                    double T[4];
+                    warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+                        integrate_rotation<2, true>(M, pt, mm, tab, u, v, i0, i1);
+                    }, T);
+                    const double p0 = P[0], x0 = X[0];
+                    P[0] = fma(T[0], p0, T[1] * x0);
+                    X[0] = fma(T[2], p0, T[3] * x0);
+                } else
+#endif
+                integrate_rotation<1>(M, pt, mm, tab, P, X);
+                den_q[s] = P[0];
+                xi_b = Pb * X[0] / P[0];
             } else {
-                // kink (:308): P(end) + (B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1) = 0
+                // kink (:308): P(axis end) = c = -(B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1), xi(axis end) free:
+                // the two fundamental solutions (1, 0), (0, 1) from there; P(1) = c P1 + alpha P2 = P_e
+                double P[2] = {1.0, 0.0}, X[2] = {0.0, 1.0};
+#ifdef __CUDA_ARCH__
+                if constexpr (WARP) {
+                    double T[4];
+                    warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+                        integrate_rotation<2, true>(M, pt, mm, tab, u, v, i0, i1);
+                    }, T);
+                    P[0] = T[0]; P[1] = T[1]; X[0] = T[2]; X[1] = T[3];
+                } else
+#endif
+                integrate_rotation<2>(M, pt, mm, tab, P, X);
+                const double c = M.rho_vb2 * xi_e;
+                const double alpha = (Pb - c * P[0]) / P[1];
                 den_q[s] = P[1];
-                xi_b = (M.rho_vb2 * xi_e - Pb * P[0]) / P[1];
+                xi_b = fma(c, X[0], alpha * X[1]);
             }
             ext_q[s] = xi_e;
             int_q[s] = xi_b;      // xi_i(1) = (C1 P + D P')/C3 at r = 1   (:314)

@@ -609,21 +609,10 @@ static int build_breakpoints_uncached(const esb_model* m, std::vector<double>& b
                      m->kind == ESB_CYLINDER_FLOW;
     if (m->mesh == 2) {
         graded_breakpoints(m, !cyl, bp);                          // cylinder: axis -> boundary
-        if (m->kind == ESB_CYLINDER_ROTATION)                     // integrates boundary -> axis
-            for (int i = 0; i < (N + 1) / 2; ++i) std::swap(bp[i], bp[N - i]);
         return ESB_OK;
     }
-    if (m->kind == ESB_CYLINDER_ROTATION) {
-        // forward, boundary (s_start) -> axis end (s_end): the kink end condition is inhomogeneous
-        for (int i = 0; i <= N; ++i) {
-            const double t = double(i) / N;
-            const double f = m->mesh == 1 ? t : cluster(t);
-            bp[i] = m->s_start + (m->s_end - m->s_start) * f;
-        }
-        bp[0] = m->s_start;
-        bp[N] = m->s_end;
-    } else if (m->kind == ESB_CYLINDER_DENSITY || m->kind == ESB_CYLINDER_FLOW) {
-        // from the axis end (s_end) out to the boundary (s_start)
+    if (cyl) {
+        // every cylinder kind: from the axis end (s_end) out to the boundary (s_start)
         for (int i = 0; i <= N; ++i) {
             const double t = double(i) / N;
             const double f = m->mesh == 1 ? t : cluster(t);
