@@ -755,7 +755,16 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             y[0] = T[0]; y[1] = T[1]; yp[0] = T[2]; yp[1] = T[3];
         } else
 #endif
-        integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, y, yp, first, M.n_steps);
+        if (NM == 1 && M.symmetric) {
+            // one mode of a symmetric layer needs only its own solution (odd: sausage, even: kink)
+            const int c = (modes[0] == 0) ? 1 : 0;
+            double y1[1] = {c == 0 ? 1.0 : 0.0}, yp1[1] = {c == 0 ? 0.0 : 1.0};
+            const double m21[1] = {0.0};
+            integrate_layer<KIND, SCHEME, 1, true>(M, pt, tab, m21, y1, yp1, first, M.n_steps);
+            y[c] = y1[0]; yp[c] = yp1[0];
+        } else {
+            integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, y, yp, first, M.n_steps);
+        }
         double P_Ti;
         if (KIND == KIND_SLAB_FLOW) {
             // displacement continuity: vx_i(-1) = vx_e(-1) (w - k U(-1))/(w - k U_e)   (flow :290)
