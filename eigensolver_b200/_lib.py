@@ -51,6 +51,7 @@ _ctx = C.c_void_p
 #: every symbol include/eigensolver_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "esb_version": (C.c_int, []),
+    "esb_sizeof_model": (C.c_int, []),
     "esb_model_defaults": (C.c_int, [C.c_int32, C.POINTER(esb_model)]),
     "esb_mesh_size": (C.c_int, [C.POINTER(esb_model), _ip]),
     "esb_mesh_nodes": (C.c_int, [C.POINTER(esb_model), _dp]),

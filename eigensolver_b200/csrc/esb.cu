@@ -650,6 +650,7 @@ static int check_model(const esb_model* m) {
 }
 
 extern "C" int esb_version(void) { return ESB_VERSION; }
+extern "C" int esb_sizeof_model(void) { return (int)sizeof(esb_model); }
 
 extern "C" int esb_model_defaults(int32_t kind, esb_model* out) {
     if (!out) return ESB_ERR_ARG;

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ESB_VERSION 100
+#define ESB_VERSION 110   /* 1.1: esb_model grew the mesh_* fields; pinned tables, schedules */
 
 typedef struct esb_context esb_context;
 
@@ -100,6 +100,9 @@ typedef struct esb_model {
      * towards both boundaries. */
     double mesh_axis, mesh_edge, mesh_edge_width;
 } esb_model;
+
+/* sizeof(esb_model) as compiled into the library: a binding checks its own struct against it. */
+int esb_sizeof_model(void);
 
 /* Defaults of the reference scripts for `kind` (coronal parameter set). */
 int esb_model_defaults(int32_t kind, esb_model* out);

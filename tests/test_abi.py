@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_defaults():
     lib = esb.load()
-    assert lib.esb_version() == 100
+    assert lib.esb_version() == 110
+    assert lib.esb_sizeof_model() == C.sizeof(L.esb_model)        # the ctypes mirror of the struct
     m = L.esb_model()
     assert lib.esb_model_defaults(L.CYLINDER_DENSITY, C.byref(m)) == 0
     # Density_cylinder.py:69-72,120,768
@@ -44,6 +45,19 @@ def test_version_and_defaults():
     assert (m.c_i0, m.vA_i0, m.vA_e, m.c_e) == (1.0, 1.2, 3.0, 0.4)
     assert (m.s_start, m.s_end) == (-1.0, 1.0)
     assert (m.ext_ic_value, m.ext_ic_slope) == (1e-8, 1e-8)
+    # every kind has defaults with a usable discretisation
+    for kind in (L.SLAB_DENSITY, L.CYLINDER_DENSITY, L.SLAB_FLOW, L.CYLINDER_ROTATION, L.CYLINDER_FLOW):
+        assert lib.esb_model_defaults(kind, C.byref(m)) == 0
+        n = C.c_int32()
+        assert lib.esb_mesh_size(C.byref(m), C.byref(n)) == 0 and n.value == 4 * m.n_steps + 1
+        x = np.empty(n.value)
+        assert lib.esb_mesh_nodes(C.byref(m), x.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        d = np.diff(x)
+        assert np.all(d > 0) or np.all(d < 0)                      # monotone along the integration
+        ends = sorted([x[0], x[-1]])
+        assert ends == sorted([m.s_start, m.s_end])
+        if kind in (L.SLAB_DENSITY, L.SLAB_FLOW):                  # exactly mirror-symmetric slab meshes
+            assert np.array_equal(x - x[0], (x[-1] - x[::-1]))
     assert lib.esb_model_defaults(7, C.byref(m)) == L.ESB_ERR_ARG
 
 
