@@ -6,15 +6,16 @@
 A "step" is one pass of the hot path over the workload BASELINE.json quotes the metric
 on (configs[1]): the cylinder with non-uniform density, modes n = 0, 1, 2, on a
 1000 k x 10000 omega grid - 3e7 evaluations of D(omega,k) followed by bracket detection
-and root refinement.  With N > 1 every rank sweeps its own 1000-wavenumber slab of an
-N*1000 k grid (weak scaling, no data-path collective) and the root tables are gathered
+and root refinement.  With N > 1 every rank sweeps its own 1000 wavenumbers (rows r, r+N, ...) of
+an N*1000 k grid (weak scaling, no data-path collective) and the modes found are gathered
 with NCCL inside the timed region.
 
   value  whole-job D evaluations per second, axes already resident in HBM
-  e2e    the same through the public host API (pinned host k/omega in, root tables out)
-  roofline.bound = "fp64": the kernel is an FP64-pipe kernel (no tensor cores, ~16 B of
-         HBM traffic per 7.7e4 flops), so the bound is the FP64 FMA rate, measured in the
-         same process with a DFMA-chain kernel (esb_fp64_peak).
+  e2e    the same through the public host API: pinned host k/omega in, the root tables of the
+         three modes out into page-locked host memory (N > 1: gathered modes on rank 0)
+  roofline.bound = "fp64": the kernel is an FP64-pipe kernel (no tensor cores, 24 B of HBM
+         traffic per 4.3e4 flops), so the bound is the FP64 FMA rate, measured in the same
+         process with a DFMA-chain kernel (esb_fp64_peak); traffic = ncu DRAM bytes per launch.
   cpu_baseline  the oracle port of the reference's scipy path (odeint + fsolve) timed on a
          bounded sample with all host cores.
 """
