@@ -262,6 +262,7 @@ struct Brent {
     double a, b, c, ea, ia, eb, ib, ec, ic, fa, fb, fc, d, e, f0min, f0max, w0, hw0;
     int it;
     bool on_g;      // iterate on G = D * Y (else on D itself)
+    double guess;   // first trial point from the scan grid (NaN: none, start with the secant step)
 };
 
 // false: the bracket is a pole of D (S.b = its interpolated position)
@@ -293,7 +294,27 @@ __device__ __forceinline__ bool brent_init(Brent& S, double a, double b, double 
     S.w0 = fmax(fabs(a), fabs(b));
     S.hw0 = 0.5 * fabs(b - a);
     S.it = 0;
+    S.guess = nan("");
     return true;
+}
+
+// Inverse cubic interpolation through four neighbouring scan points (w_i, G_i), evaluated at G = 0:
+// the first trial point of a bracket whose neighbourhood is smooth (G strictly monotone over the four,
+// no sign change of Y).  The scan grid is fine against the scale of G, so this lands within ~1e-9 of
+// the bracket width of the root and the iteration needs ~4 evaluations instead of ~8.
+__device__ __forceinline__ double inverse_cubic_guess(const double (&w)[4], const double (&g)[4]) {
+    const double d01 = g[0] - g[1], d12 = g[1] - g[2], d23 = g[2] - g[3];
+    if (!((d01 > 0.0 && d12 > 0.0 && d23 > 0.0) || (d01 < 0.0 && d12 < 0.0 && d23 < 0.0))) return nan("");
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double l = w[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j != i) l *= g[j] / (g[j] - g[i]);
+        x += l;
+    }
+    return x;
 }
 
 // true: evaluate at S.b and hand the values to brent_feed; false: finished, the result is (S.b, S.eb, S.ib)
@@ -320,7 +341,12 @@ __device__ __forceinline__ bool brent_next(Brent& S) {
     // this, it is already located to 1e-6 of a grid interval, ~1e-10 relative.)
     const bool jump = fabs(xm) < 1e-6 * S.hw0 && fabs(S.fb) > 100.0 * S.f0max * (fabs(xm) / S.hw0);
     if (converged || pole || jump) return false;
-    if (fabs(S.e) >= tol1 && fabs(S.fa) > fabs(S.fb)) {
+    if (S.it == 0 && isfinite(S.guess) && (S.guess - S.b) * (S.c - S.guess) > 0.0 &&
+        fabs(S.guess - S.b) > tol1) {
+        // first trial from the scan grid; Brent's bookkeeping takes over from the next step on
+        S.d = S.guess - S.b;
+        S.e = S.d;
+    } else if (fabs(S.e) >= tol1 && fabs(S.fa) > fabs(S.fb)) {
         const double s = S.fb / S.fa;
         double p, q;
         if (S.a == S.c) {
@@ -371,8 +397,23 @@ __device__ __forceinline__ bool refine_pickup(const RefineArgs& r, int tq, bool 
     const double b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
     const size_t o = (size_t)ik * r.nw + jw;
     if (brent_init(S, a, b, r.slot[sl].gext[o], r.slot[sl].gint[o], r.slot[sl].gext[o + 1],
-                   r.slot[sl].gint[o + 1], r.slot[sl].gden[o], r.slot[sl].gden[o + 1]))
+                   r.slot[sl].gint[o + 1], r.slot[sl].gden[o], r.slot[sl].gden[o + 1])) {
+        if (S.on_g && jw >= 1 && jw + 2 < r.nw) {
+            double w4[4], g4[4];
+            bool smooth = true;
+            const double y_ref = r.slot[sl].gden[o];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const size_t oq = o + q - 1;
+                const double y = r.slot[sl].gden[oq];
+                w4[q] = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + q - 1);
+                g4[q] = (r.slot[sl].gext[oq] - r.slot[sl].gint[oq]) * y;
+                smooth = smooth && isfinite(g4[q]) && ((y > 0.0) == (y_ref > 0.0));
+            }
+            if (smooth) S.guess = inverse_cubic_guess(w4, g4);
+        }
         return true;
+    }
     if (writer) {
         r.slot[sl].omega[t] = S.b;
         r.slot[sl].ext[t] = nan("");
