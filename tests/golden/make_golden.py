@@ -84,6 +84,14 @@ POINTS["slab_density_coronal_w3"] = dict(
     solver="slab_density_coronal", overrides={"dx": 3.0},
     ks=[0.05, 0.3, 0.75, 1.5, 3.0], Ws=[0.42, 0.6, 0.74, 1.75, 2.0, 2.5, 2.95, 0.398, 3.1])
 
+# rotational flow, a second (linear) rotation law: the shipped root tables of that law are checked too
+POINTS["cylinder_rotation_sausage_p1"] = dict(
+    solver="cylinder_rotation_sausage", overrides={"v_twist": 0.1, "power": 1.0},
+    ks=[0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.55, 0.8, 0.97, 1.1, 1.2, 1.3, 1.45, 0.49, 1.6])
+POINTS["cylinder_rotation_kink_p1"] = dict(
+    solver="cylinder_rotation_kink", overrides={"v_twist": 0.1, "power": 1.0},
+    ks=[0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.55, 0.8, 0.97, 1.1, 1.2, 1.3, 1.45, 0.49, 1.6])
+
 SCANS = {
     # (mode, k, W_lo, W_hi, n)  - intervals that contain a mode
     "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),

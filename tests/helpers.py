@@ -240,6 +240,9 @@ CASES = {c.name: c for c in [
     # r ~ 0.007 for every (k, omega) it scans: there the reference's output is solver noise.
     Case("cylinder_rotation", "cylinder_rotation", (0, 1, 2), (0.40, 1.6), None, "CYL_PHOTOSPHERIC",
          roots_window=(0.9, 1.49), v_twist=0.15, power=1.25, s_end=0.01),
+    # a second, linear rotation law (the v01_p1 family of the shipped root tables); fixture = file suffix
+    Case("cylinder_rotation_p1", "cylinder_rotation", (0, 1, 2), (0.40, 1.6), None, "CYL_PHOTOSPHERIC",
+         roots_window=(0.9, 1.49), v_twist=0.1, power=1.0, s_end=0.01, fixture="_p1"),
 ]}
 
 # The shipped flow root tables (Example data/flow_width*_coronal.pickle) were produced with

@@ -113,13 +113,14 @@ def test_against_executed_reference_fixture(solvers, golden_dir, name):
     atol = 1.5e-8), so its D carries a common amplitude error of 10-25 %; sign, skip pattern
     and the ext/int ratio are what it determines, and those must agree."""
     case = CASES[name]
-    iv = None if name == "cylinder_rotation" else case.intervals()
+    iv = None if case.kind == "cylinder_rotation" else case.intervals()
     s = solvers[name]
     n = 0
     for mode in (0, 1):
-        if name == "cylinder_rotation":
+        if case.kind == "cylinder_rotation":
             # one fixture per script: the sausage script stops at r = 0.01, the kink script at 0.001
-            g = np.load(os.path.join(golden_dir, "ref_D_cylinder_rotation_%s.npz" % ("sausage", "kink")[mode]))
+            g = np.load(os.path.join(golden_dir, "ref_D_cylinder_rotation_%s%s.npz" % (("sausage", "kink")[mode],
+                                                                                  case.fixture or "")))
             k, w, Dref = g["k"], g["w"], g["D"]
             rot = esb.DispersionSolver("cylinder_rotation", profile=esb.PowerLawRotation(case.v_twist, case.power),
                                        s_end=0.01 if mode == 0 else 0.001)

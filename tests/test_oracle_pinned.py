@@ -155,14 +155,27 @@ def test_c_oracle_equals_converged_scipy_path(name):
     assert worst < 5e-9, worst     # the scipy path at rtol 1e-12 is itself good to ~1e-9 in amplitude
 
 
-@pytest.mark.parametrize("fixture,mode", [("cylinder_rotation_sausage", 0), ("cylinder_rotation_kink", 1)])
-def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode):
+@pytest.mark.parametrize("fixture,mode,v_twist,power", [
+    ("cylinder_rotation_sausage", 0, 0.15, 1.25), ("cylinder_rotation_kink", 1, 0.15, 1.25),
+    ("cylinder_rotation_sausage_p1", 0, 0.1, 1.0), ("cylinder_rotation_kink_p1", 1, 0.1, 1.0)])
+def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode, v_twist, power):
     """Rotational-flow cylinder: D from the reference's own sausage()/kink() (scipy defaults, sympy
-    coefficients rebuilt per point) vs the restatement (sympy coefficients built once)."""
-    case = CASES["cylinder_rotation"]
+    coefficients rebuilt per point) vs the restatement (sympy coefficients built once), for the two
+    rotation laws v_phi = 0.15 r^1.25 and v_phi = 0.1 r."""
+    import helpers
+    md = rp.CYL_PHOTOSPHERIC
+    s_end = 0.01 if mode == 0 else 0.001
     g = np.load(os.path.join(golden_dir, "ref_D_%s.npz" % fixture))
-    model = rp.CylinderRotation(rp.CYL_PHOTOSPHERIC, mode, case.v_twist, case.power,
-                                s_end=0.01 if mode == 0 else 0.001)
+    model = rp.CylinderRotation(md, mode, v_twist, power, s_end=s_end)
+    c_model = ork.make_model("cylinder_rotation", medium=md, v_twist=v_twist, power=power, s_end=s_end)
+
+    def regular(k, W, margin=0.03):
+        ok = helpers.regular_mask(np.array([W]), helpers.rotation_continua(md, v_twist, power, s_end, mode, k),
+                                  margin)[0]
+        for dW in (-margin, 0.0, margin):
+            ok = ok and helpers.rotation_regular(md, v_twist, power, s_end, mode, k, np.array([W + dW]))[0]
+        return ok
+
     n_checked = n_skipped = 0
     for k, w, Dref in list(zip(g["k"], g["w"], g["D"]))[::2]:
         Dor = rp.D(model, k, w)
@@ -170,7 +183,7 @@ def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode):
             assert np.isnan(Dor)
             n_skipped += 1
             continue
-        if not case.regular(k, np.array([w / k]), mode, margin=0.03)[0, 0]:
+        if not regular(k, w / k):
             continue
         el, il = rp.dispersion(model, k, w, shoot="linear")
         if abs((el - il) - Dor) > 1e-4 * max(abs(el), abs(il)):
@@ -179,6 +192,10 @@ def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode):
         # steer LSODA through different step sequences: agreement at its 1e-8 tolerance amplified
         # by the 1/r^2 growth towards the axis, not at rounding level
         assert abs(Dor - Dref) <= 2e-3 * max(abs(el), abs(il)), (k, w, Dref, Dor)
+        # and the C restatement (first-order system, no coefficient derivatives) agrees with the converged path
+        e2, i2 = ork.point(c_model, mode, k, w)
+        et, it_ = rp.dispersion(model, k, w, **TIGHT)
+        assert abs((e2 - i2) - (et - it_)) <= 1e-7 * max(abs(et), abs(it_)), (k, w)
         n_checked += 1
     assert n_checked >= 6 and n_skipped >= 2
 
