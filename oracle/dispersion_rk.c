@@ -12,7 +12,9 @@
  *     (what fsolve does on a linear problem: Density_cylinder.py:785-790);
  *   - the coefficients are written from c_i^2(x), vA_i^2(x), cT_i^2(x) and their
  *     derivatives exactly as the reference composes them (F, dF/F, m0 / g/F), with the
- *     profile evaluated analytically at every stage - no tables.
+ *     profile evaluated analytically at every stage - no tables; where the reference differentiates
+ *     F and r C1/C3 with sympy (rotational and axial-flow cylinder) the derivative is taken by
+ *     forward-mode automatic differentiation of the same expression tree.
  *
  * The CUDA path uses closed-form exteriors, a backward one-solution integration
  * for the cylinder, algebraically reduced coefficients and a staged table; that the two
@@ -204,59 +206,81 @@ static void coef_int_flow(const void* c, double x, double* a, double* b) {
 /* cylinder with rotational flow: Twisted_photospheric_nonlinear_flow_kink_fast.py:264-297.
  * D, C1, C2, C3 are written as the reference writes them; F = r D/C3 and r C1/C3 are
  * differentiated numerically (8th-order central differences) where the reference uses sympy. */
-typedef struct { double D, C1, C2, C3; } rot_c;
-static rot_c rot_coeffs(const pt_ctx* p, double r) {
+/* Forward-mode automatic differentiation in r (value, d/dr): the exact derivative of the same expression
+ * tree, where the reference calls sympy.diff.  (A finite-difference version of this oracle was wrong by
+ * up to 3e-3 at k = 0.05 for the linear rotation law, where C3 comes close to zero and F = r D/C3 varies
+ * rapidly; the scipy oracle with sympy derivatives and an independent integration of the first-order
+ * system agreed with each other there to 1e-9, and with this version.) */
+typedef struct { double v, d; } dual;
+static dual dc(double c) { dual r = {c, 0.0}; return r; }
+static dual dadd(dual a, dual b) { dual r = {a.v + b.v, a.d + b.d}; return r; }
+static dual dsub(dual a, dual b) { dual r = {a.v - b.v, a.d - b.d}; return r; }
+static dual dmul(dual a, dual b) { dual r = {a.v * b.v, a.d * b.v + a.v * b.d}; return r; }
+static dual ddiv(dual a, dual b) { dual r = {a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)}; return r; }
+static dual dscale(double c, dual a) { dual r = {c * a.v, c * a.d}; return r; }
+static dual dpow(dual a, double p) { dual r = {pow(a.v, p), p * pow(a.v, p - 1.0) * a.d}; return r; }
+static dual dexp(dual a) { const double e = exp(a.v); dual r = {e, e * a.d}; return r; }
+
+typedef struct { dual D, C1, C2, C3; } rot_c;
+static rot_c rot_coeffs(const pt_ctx* p, double rv) {
     const ork_model* m = p->m;
     const double rho = m->rho_i0, mm = (double)p->mode;
+    const dual r = {rv, 1.0};
+    const dual r2 = dmul(r, r);
+    const double vA2 = m->vA_i0 * m->vA_i0;
+    const double alf2 = p->k * p->k * vA2;                          /* alfven_freq^2 (B_phi = 0) */
     rot_c c;
     if (m->kind == 4) {
         /* Cylinder_method_flow_testing.py:711-746 with v_phi = B_phi = 0 (:190-196): Q = T = 0 */
-        const double vz = m->U_e + (m->U_i0 - m->U_e) * exp(-(r - m->x0) * (r - m->x0) / (m->width * m->width));
-        const double c2f = m->c_i0 * m->c_i0, vA2f = m->vA_i0 * m->vA_i0;
-        const double sh = p->w - p->k * vz;                       /* shift_freq  :713 */
-        const double al = p->k * sqrt(vA2f);                      /* alfven_freq :716 */
-        const double cu2 = al * al * c2f / (c2f + vA2f);          /* cusp_freq^2 :719 */
-        c.D = rho * (c2f + vA2f) * (sh * sh - al * al) * (sh * sh - cu2);
-        c.C1 = 0.0;
-        c.C2 = sh * sh * sh * sh - (c2f + vA2f) * (mm * mm / (r * r) + p->k * p->k) * (sh * sh - cu2);
-        c.C3 = c.D * rho * (sh * sh - al * al);
+        const dual arg = dscale(-1.0 / (m->width * m->width), dmul(dsub(r, dc(m->x0)), dsub(r, dc(m->x0))));
+        const dual vz = dadd(dc(m->U_e), dscale(m->U_i0 - m->U_e, dexp(arg)));
+        const double c2f = m->c_i0 * m->c_i0;
+        const dual sh = dsub(dc(p->w), dscale(p->k, vz));           /* shift_freq  :713 */
+        const dual s2 = dmul(sh, sh);
+        const double cu2 = alf2 * c2f / (c2f + vA2);                /* cusp_freq^2 :719 */
+        c.D = dscale(rho * (c2f + vA2), dmul(dsub(s2, dc(alf2)), dsub(s2, dc(cu2))));
+        c.C1 = dc(0.0);
+        c.C2 = dsub(dmul(s2, s2), dscale(c2f + vA2, dmul(dadd(ddiv(dc(mm * mm), r2), dc(p->k * p->k)),
+                                                          dsub(s2, dc(cu2)))));
+        c.C3 = dscale(rho, dmul(c.D, dsub(s2, dc(alf2))));
         return c;
     }
-    const double vphi = m->v_twist * pow(r, m->power);
+    /* Twisted_photospheric_nonlinear_flow_kink_fast.py:105-111, 264-297 */
+    const dual vphi = dscale(m->v_twist, dpow(r, m->power));
     const double P0 = m->c_i0 * m->c_i0 * rho / m->gamma;
-    const double Pi = rho * m->v_twist * m->v_twist * pow(r, 2.0 * m->power) / (2.0 * m->power) + P0;
-    const double c2 = m->gamma * Pi / rho, vA2 = m->vA_i0 * m->vA_i0;
-    const double shift = p->w - mm * vphi / r;
-    const double alf = p->k * sqrt(vA2);
-    const double cusp2 = alf * alf * c2 / (c2 + vA2);
-    const double s2 = shift * shift;
-    c.D = rho * (c2 + vA2) * (s2 - alf * alf) * (s2 - cusp2);
-    const double Q = -(s2 - alf * alf) * rho * vphi * vphi / r;
-    const double T = rho * vphi * shift;
-    c.C1 = Q * s2 - 2.0 * mm * (c2 + vA2) * (s2 - cusp2) * T / (r * r);
-    c.C2 = s2 * s2 - (c2 + vA2) * (mm * mm / (r * r) + p->k * p->k) * (s2 - cusp2);
-    /* C3_diff = -rho (v_phi/r)^2 ; r d/dr C3_diff = -rho v_twist^2 (2 power - 2) r^(2 power - 2) */
-    const double rdC3 = -rho * m->v_twist * m->v_twist * (2.0 * m->power - 2.0) * pow(r, 2.0 * m->power - 2.0);
-    c.C3 = c.D * (rho * (s2 - alf * alf) + rdC3) + (Q * Q - 4.0 * (c2 + vA2) * (s2 - cusp2) * T * T / (r * r));
+    const dual Pi = dadd(dscale(rho * m->v_twist * m->v_twist / (2.0 * m->power), dpow(r, 2.0 * m->power)), dc(P0));
+    const dual c2 = dscale(m->gamma / rho, Pi);
+    const dual s = dadd(c2, dc(vA2));                               /* c^2 + vA^2 */
+    const dual shift = dsub(dc(p->w), dscale(mm, ddiv(vphi, r)));
+    const dual s2 = dmul(shift, shift);
+    const dual cusp2 = ddiv(dscale(alf2, c2), s);
+    const dual a1 = dsub(s2, dc(alf2));
+    const dual A2 = dmul(s, dsub(s2, cusp2));                       /* (c^2+vA^2)(shift^2 - cusp^2) */
+    c.D = dscale(rho, dmul(a1, A2));
+    const dual Q = dscale(-rho, ddiv(dmul(a1, dmul(vphi, vphi)), r));
+    const dual T = dscale(rho, dmul(vphi, shift));
+    c.C1 = dsub(dmul(Q, s2), dscale(2.0 * mm, ddiv(dmul(A2, T), r2)));
+    c.C2 = dsub(dmul(s2, s2), dmul(A2, dadd(ddiv(dc(mm * mm), r2), dc(p->k * p->k))));
+    /* C3_diff = -rho (v_phi/r)^2 ; r d/dr C3_diff, itself differentiated once more below */
+    const dual q = ddiv(vphi, r);
+    const dual C3diff = dscale(-rho, dmul(q, q));
+    /* r * d(C3diff)/dr as a dual needs the second derivative of C3diff: for v_phi = v r^p it is closed form */
+    const double pw = 2.0 * m->power - 2.0;
+    const dual rdC3 = dscale(-rho * m->v_twist * m->v_twist * pw, dpow(r, pw));
+    (void)C3diff;
+    c.C3 = dadd(dmul(c.D, dadd(dscale(rho, a1), rdC3)),
+                dsub(dmul(Q, Q), dscale(4.0, ddiv(dmul(A2, dmul(T, T)), r2))));
     return c;
 }
 static void coef_int_rot(const void* cv, double r, double* a, double* b) {
     const pt_ctx* p = (const pt_ctx*)cv;
-    static const double w8[4] = {4.0 / 5.0, -1.0 / 5.0, 4.0 / 105.0, -1.0 / 280.0};
-    const double h = 2e-3 * r;
-    double dF = 0.0, dG = 0.0;
-    for (int j = 1; j <= 4; ++j) {
-        const rot_c cp = rot_coeffs(p, r + j * h), cm = rot_coeffs(p, r - j * h);
-        dF += w8[j - 1] * ((r + j * h) * cp.D / cp.C3 - (r - j * h) * cm.D / cm.C3);
-        dG += w8[j - 1] * ((r + j * h) * cp.C1 / cp.C3 - (r - j * h) * cm.C1 / cm.C3);
-    }
-    dF /= h;
-    dG /= h;
     const rot_c c = rot_coeffs(p, r);
-    const double F = r * c.D / c.C3;
-    const double g = -dG - r * (c.C2 - c.C1 * c.C1 / c.C3) / c.D;
-    *a = -dF / F;                                       /* dP_dr_i  (:304) */
-    *b = g / F;
+    const dual rr = {r, 1.0};
+    const dual F = ddiv(dmul(rr, c.D), c.C3);                       /* F = r D/C3  (:288) */
+    const dual G = ddiv(dmul(rr, c.C1), c.C3);                      /* r C1/C3 */
+    const double g = -G.d - r * (c.C2.v - c.C1.v * c.C1.v / c.C3.v) / c.D.v;   /* (:294) */
+    *a = -F.d / F.v;                                                /* dP_dr_i  (:304) */
+    *b = g / F.v;
 }
 
 static double cluster(double t) {
@@ -316,7 +340,7 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
         const double slope = (mode == 0) ? -yb * Yp[0] / Yp[1] : (rv2 * xi_e - yb * Y[0]) / Y[1];
         const rot_c cb = rot_coeffs(&p, m->s_start);
         *ext_q = xi_e;
-        *int_q = (cb.C1 * yb + cb.D * slope) / cb.C3;       /* inside_xi_solution[0]  (:314) */
+        *int_q = (cb.C1.v * yb + cb.D.v * slope) / cb.C3.v;       /* inside_xi_solution[0]  (:314) */
     } else if (m->kind != 1) {
         const coef_fn cf = (m->kind == 2) ? coef_int_flow : coef_int_slab;
         const int H = N / 2;
