@@ -39,15 +39,19 @@ NK, NW = 1000, 10000
 MODES = (0, 1, 2)
 K_RANGE = (0.01, 4.5)          # Density_cylinder.py:1126  wavenumber = linspace(0.01, 4.5, ...)
 W_RANGE = (0.5, 5.0)           # c_e .. vA_e : the phase-speed window in which m_e >= 0
-N_STEPS = 144                  # the cylinder kind's default: graded mesh, see DESIGN.md
-# algorithmic FP64 flops (fma = 2, mul/add/div = 1), see DESIGN.md.  Per RK8 step in the step-scaled
-# variables (y, h y'):
-#   shared by the modes evaluated together: 4 node-coefficient evaluations x 14 flop + 16 (h a, h^2 b)
-#   per mode: 176 (88 FMAs of the 11 stage sums) + 33 (11 x mul + fma right-hand sides)
-#             + 10 (b + m^2/r^2 at 5 nodes) + 1 (rescaling h y' to the next step) = 220
-# one D evaluation alone: 72 + 220 = 292 flop/step; three fused: (72 + 3*220)/3 = 244 flop/step/eval
-FLOPS_PER_EVAL = 292 * N_STEPS + 700
-FLOPS_FUSED_LAUNCH = ((72 + 3 * 220) * N_STEPS + 3 * 500) * NK * NW
+N_STEPS = 152                  # the cylinder kind's default: normal-form scheme, graded mesh, see DESIGN.md
+# algorithmic FP64 flops (fma = 2, mul/add/div = 1), see DESIGN.md.  Per step of the Cooper-Verner method
+# in Nystrom form on u'' = q u (scheme "rk8n"), step-scaled variables (u, h u'):
+#   shared by the modes evaluated together: 4 node evaluations of h^2 q x 17 flop + 6 (step scalings) = 74
+#   per mode: 52 FMAs (3 stage bases, 40 + 4 + 5 tableau products) + 1 add + 11 products q_i U_i
+#             + 5 FMAs (n^2 - 1/4) h^2/r^2 + 1 (rescaling h u') = 127
+# one D evaluation alone: 201 flop/step; three fused: (74 + 3*127)/3 = 152 flop/step/eval
+# (round 1, first-derivative form "rk8": 292 and 244 flop/step, 144 steps)
+FLOPS_PER_EVAL = 201 * N_STEPS + 700
+FLOPS_FUSED_LAUNCH = ((74 + 3 * 127) * N_STEPS + 3 * 500) * NK * NW
+# FP64-pipe instructions of the same launch, from the SASS of the step loop (tools/sass_loop_count.py:
+# 291 per step for three modes) - the pipe-utilisation view of the same roofline
+FP64_INSTR_FUSED_LAUNCH = (291 * N_STEPS + 3 * 300) * NK * NW
 WORKLOAD = "cylinder non-uniform density, n=0,1,2, 1000 k x 10000 omega per GPU"
 
 
@@ -224,7 +228,7 @@ def run_gpu_arm(args):
     k_pin = torch.from_numpy(k.copy()).pin_memory()
     W_pin = torch.from_numpy(W.copy()).pin_memory()
 
-    solver = esb.DispersionSolver("cylinder_density", n_steps=N_STEPS, scheme="rk8", device=local)
+    solver = esb.DispersionSolver("cylinder_density", n_steps=N_STEPS, scheme="rk8n", device=local)
     stream = torch.cuda.current_stream(dev)
     solver.set_stream(stream.cuda_stream)
     fp64_peak = solver.fp64_peak_tflops()
@@ -336,7 +340,7 @@ def run_gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "modes": list(MODES), "nk_per_gpu": NK, "nw": NW, "k_shards": "strided",
-                       "n_steps": N_STEPS, "mesh": "graded", "scheme": "rk8", "profile": "inverted Gaussian, width 0.95",
+                       "n_steps": N_STEPS, "mesh": "graded", "scheme": "rk8n", "profile": "inverted Gaussian, width 0.95",
                        "l2": "working set 720 MB of (ext, int, Y) written per step > 126 MB L2; inputs are 88 KB"},
             "roots_per_sec": n_brackets * world * args.steps / (ms * 1e-3),
             "modes_found": n_modes, "brackets_rank0": n_brackets,
@@ -345,8 +349,10 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": ncu_traffic(),
-                         "kernel": "grid_kernel<cylinder,rk8,3 modes fused>", "kernel_ms": kms,
+                         "kernel": "grid_kernel<cylinder,rk8n,3 modes fused>", "kernel_ms": kms,
                          "flops_per_launch": FLOPS_FUSED_LAUNCH,
+                         "fp64_instr_per_launch": FP64_INSTR_FUSED_LAUNCH,
+                         "pipe_frac": FP64_INSTR_FUSED_LAUNCH / (kms * 1e-3) / (fp64_peak * 1e12 / 2.0),
                          "peak_source": "esb_fp64_peak: DFMA-chain kernel measured in this process "
                                         "(nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s)" % nominal,
                          "kernel_share_of_step": kms / (ms / args.steps)},

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libeigensolver_b200.so")
 
 ESB_OK, ESB_ERR_ARG, ESB_ERR_CUDA, ESB_ERR_CAPACITY, ESB_ERR_ALLOC = 0, -1, -2, -3, -4
 SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW, CYLINDER_ROTATION, CYLINDER_FLOW = 0, 1, 2, 3, 4
-RK4, RK8 = 0, 1
+RK4, RK8, RK8N = 0, 1, 2
 OMEGA_SHARED, OMEGA_PHASE_SPEED, OMEGA_PER_K = 0, 1, 2
 MESH_CLUSTERED, MESH_UNIFORM, MESH_GRADED = 0, 1, 2
 
@@ -55,6 +55,7 @@ SYMBOLS = {
     "esb_model_defaults": (C.c_int, [C.c_int32, C.POINTER(esb_model)]),
     "esb_mesh_size": (C.c_int, [C.POINTER(esb_model), _ip]),
     "esb_mesh_nodes": (C.c_int, [C.POINTER(esb_model), _dp]),
+    "esb_model_n_fields": (C.c_int, [C.POINTER(esb_model), _ip]),
     "esb_create": (C.c_int, [C.c_int32, C.POINTER(_ctx)]),
     "esb_destroy": (C.c_int, [_ctx]),
     "esb_last_error": (C.c_char_p, [_ctx]),

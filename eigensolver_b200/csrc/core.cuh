@@ -20,15 +20,38 @@
 #include "bessel.cuh"
 
 namespace esb {
+#define ESB_RKN_ENUM
+#include "rkn_tableau.h"
+#undef ESB_RKN_ENUM
+#if defined(__CUDACC__)
+// NOT const-qualified: nvcc would fold the values back into 64-bit immediates
+#define ESB_TABLE_QUAL __device__ __constant__
+namespace dev_tables {
+#include "rkn_tableau.h"
+}
+#undef ESB_TABLE_QUAL
+#endif
+#define ESB_TABLE_QUAL static const
+namespace host_tables {
+#include "rkn_tableau.h"
+}
+#undef ESB_TABLE_QUAL
+#define RKN(name) ESB_TAB(esb_rkn8)[RKN_##name]
+}  // namespace esb
+
+namespace esb {
 
 enum { KIND_SLAB_DENSITY = 0, KIND_CYL_DENSITY = 1, KIND_SLAB_FLOW = 2, KIND_CYL_ROTATION = 3, KIND_CYL_FLOW = 4 };
 
 template <int KIND>
 constexpr bool is_cyl_second_order = (KIND == KIND_CYL_DENSITY || KIND == KIND_CYL_FLOW);
-enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1 };
+// SCHEME_RK8N: the same Cooper-Verner method in Nystrom form on the normal form u'' = q u of the
+// second-order kinds (integrate_layer_nform below)
+enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1, SCHEME_RK8N = 2 };
 enum { OMEGA_SHARED = 0, OMEGA_PHASE_SPEED = 1, OMEGA_PER_K = 2 };
 
 constexpr int TAB_FIELDS = 4;   // doubles per node in the staged table
+constexpr int NF_FIELDS = 6;    // ... for the normal-form scheme (SCHEME_RK8N)
 
 struct DevModel {
     int kind, scheme, n_steps, n_nodes;
@@ -50,6 +73,8 @@ struct DevModel {
     // cylinder with rotational flow v_phi(r): uniform rho_i, vA_i (vAi2, rho_i above);
     // rho v_phi^2 at the boundary enters the kink end condition
     double rho_vb2;
+    double r_axis;            // cylinder kinds: position of the first node (the axis end of the layer)
+    double f_lo, f_hi;        // range of the first profile field (rho / v_z) over the layer (normal-form scheme)
 };
 
 // ---------------------------------------------------------------- tableau ----
@@ -79,7 +104,7 @@ constexpr double a115 = (-42.0 + 7.0 * SQ21) / 18.0, a116 = (-18.0 + 28.0 * SQ21
 constexpr double b8_1 = 1.0 / 20.0, b8_8 = 49.0 / 180.0, b8_9 = 16.0 / 45.0, b8_10 = 49.0 / 180.0,
                  b8_11 = 1.0 / 20.0;
 
-ESB_HD int nodes_per_step(int scheme) { return scheme == SCHEME_RK8 ? 4 : 2; }
+ESB_HD int nodes_per_step(int scheme) { return scheme == SCHEME_RK4 ? 2 : 4; }
 
 // ------------------------------------------------------------- point data ----
 struct Point {
@@ -234,7 +259,7 @@ template <int NS>
 struct RhsSecondOrder {
     const double (&ha)[5];
     const double (&h2bs)[NS][5];
-    ESB_HD void operator()(int s, int n, double U, double Z, double& FU, double& FZ) const {
+    ESB_HDM void operator()(int s, int n, double U, double Z, double& FU, double& FZ) const {
         FU = Z;
         FZ = fma(ha[n], Z, h2bs[s][n] * U);
     }
@@ -247,7 +272,7 @@ struct RhsSystem {
     const double (&m12)[5];
     const double (&m21)[5];
     const double (&m22)[5];
-    ESB_HD void operator()(int, int n, double U, double V, double& FU, double& FV) const {
+    ESB_HDM void operator()(int, int n, double U, double V, double& FU, double& FV) const {
         FU = fma(m11[n], U, m12[n] * V);
         FV = fma(m21[n], U, m22[n] * V);
     }
@@ -354,61 +379,78 @@ struct ScaledPoint {
 
 template <int KIND>
 ESB_HD ScaledPoint make_scaled_point(const DevModel& M, const Point& pt) {
-    ScaledPoint sp;
-    // w = 0: q, p -> 1e280-ish, X Y overflows to +inf, 1/(X Y) = 0 and a = -1/r, b = k^2, the w -> 0 limit
-    const double A = pt.A > 1e-280 ? pt.A : 1e-280;
-    sp.q = pt.Kbeta / A;
-    sp.p = pt.Ktau / A;
-    sp.AS = A / M.S;
-    sp.m2k = -2.0 * pt.k;
-    sp.inv_s = 1.0 / M.si;
+    ScaledPoint sp{};
+    if constexpr (KIND == KIND_CYL_DENSITY) {
+        // w = 0: q, p -> 1e280-ish, X Y overflows to +inf, 1/(X Y) = 0 and a = -1/r, b = k^2, the w -> 0 limit
+        const double A = pt.A > 1e-280 ? pt.A : 1e-280;
+        sp.q = pt.Kbeta / A;
+        sp.p = pt.Ktau / A;
+        sp.AS = A / M.S;
+    } else if constexpr (KIND == KIND_CYL_FLOW) {
+        sp.m2k = -2.0 * pt.k;
+        sp.inv_s = 1.0 / M.si;
+    }
     return sp;
 }
 
-template <int KIND>
+// NFTAB: the node is read from the normal-form table (NF_FIELDS doubles: {-h/(2r) | h^2, h^2/r^2, field,
+// h field', ...}) instead of the 4-field pre-scaled one - the normal-form scheme integrates the points
+// next to a resonance in these variables (shoot_layer) from its own table.
+template <int KIND, bool NFTAB = false>
 ESB_HD void node_coeffs_scaled(const DevModel& M, const Point& pt, const ScaledPoint& sp, double c1, double h2K,
                                const double* f, double& ha, double& h2b, double& h2bm) {
-    const double hinvr = f[0];
-    h2bm = f[1];
-    if (KIND == KIND_CYL_DENSITY) {
-        const double rho = f[2], hdrho = f[3];
-        const double X = rho - sp.q;
-        const double Y = rho - sp.p;
-        const double inv = 1.0 / (X * Y);
-        ha = fma(hdrho * Y, inv, -hinvr);
-        h2b = fma(-((rho * rho) * X) * c1, inv, h2K);         // c1 = h^2 w^2/S
+    if constexpr (KIND == KIND_SLAB_DENSITY) {
+        // f = {h^2, -, rho, h rho'} (normal-form table only)
+        const double u = f[2] * pt.A;
+        const double p1 = pt.Kalpha - u, p2 = pt.Kbeta - u, p3 = pt.Ktau - u;
+        const double inv = 1.0 / (p1 * p3);
+        ha = (pt.AKc * f[3]) * inv;
+        h2b = ((p1 * p1) * p2) * (inv * c1);                  // c1 = h^2/S
+        h2bm = 0.0;
     } else {
-        const double vz = f[2], hdvz = f[3];
-        const double Om = fma(-pt.k, vz, pt.w);
-        const double O2 = Om * Om;
-        const double X = fma(-pt.K, M.vAi2, O2);
-        const double Y = fma(-pt.K, M.cTi2, O2);
-        const double inv = 1.0 / (X * Y);
-        ha = fma((sp.m2k * hdvz) * Om * Y, inv, -hinvr);
-        h2b = fma(-((O2 * O2) * X) * c1, inv, h2K);           // c1 = h^2/s
+        const double nhinvr = NFTAB ? f[0] + f[0] : -f[0];    // -h/r
+        h2bm = f[1];
+        if constexpr (KIND == KIND_CYL_DENSITY) {
+            const double rho = f[2], hdrho = f[3];
+            const double X = rho - sp.q;
+            const double Y = rho - sp.p;
+            const double inv = 1.0 / (X * Y);
+            ha = fma(hdrho * Y, inv, nhinvr);
+            h2b = fma(-((rho * rho) * X) * c1, inv, h2K);         // c1 = h^2 w^2/S
+        } else {
+            const double vz = f[2], hdvz = f[3];
+            const double Om = fma(-pt.k, vz, pt.w);
+            const double O2 = Om * Om;
+            const double X = fma(-pt.K, M.vAi2, O2);
+            const double Y = fma(-pt.K, M.cTi2, O2);
+            const double inv = 1.0 / (X * Y);
+            ha = fma((sp.m2k * hdvz) * Om * Y, inv, nhinvr);
+            h2b = fma(-((O2 * O2) * X) * c1, inv, h2K);           // c1 = h^2/s
+        }
     }
 }
 
-template <int KIND, int NS, bool RANGE = false>
+template <int KIND, int NS, bool RANGE = false, bool NFTAB = false>
 ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const double* __restrict__ tab,
                                       const double (&m2)[NS], double (&y)[NS], double (&yp)[NS], int r0 = 0,
                                       int r1 = 0) {
     // RANGE: steps [r0, r1) of the mesh, else all of it; (y, y') in and out are unscaled
+    constexpr int TF = NFTAB ? NF_FIELDS : TAB_FIELDS;
     const int i0 = RANGE ? r0 : 0;
     const int iend = RANGE ? r1 : M.n_steps;
-    const double* hs = tab + (size_t)M.n_nodes * TAB_FIELDS;
+    const double* hs = tab + (size_t)M.n_nodes * TF;
     const double* gs = hs + M.n_steps;
     const ScaledPoint sp = make_scaled_point<KIND>(M, pt);
-    const double cc = (KIND == KIND_CYL_DENSITY) ? sp.AS : sp.inv_s;
+    const double cc = (KIND == KIND_CYL_DENSITY) ? sp.AS : (KIND == KIND_SLAB_DENSITY) ? M.invS : sp.inv_s;
     double ha0, h2b0, h2bm0;
     if (!RANGE || i0 == 0) {
         const double h0 = hs[0], h2 = h0 * h0;
-        node_coeffs_scaled<KIND>(M, pt, sp, h2 * cc, h2 * pt.K, tab, ha0, h2b0, h2bm0);
+        node_coeffs_scaled<KIND, NFTAB>(M, pt, sp, h2 * cc, h2 * pt.K, tab, ha0, h2b0, h2bm0);
     } else {
         // node 4 i0 is stored in the scale of the step it ends: evaluate it there, rescale like the carry
         const double hp = hs[i0 - 1], h2 = hp * hp, g = gs[i0 - 1], g2 = g * g;
-        node_coeffs_scaled<KIND>(M, pt, sp, h2 * cc, h2 * pt.K, tab + (size_t)(i0 * 4) * TAB_FIELDS, ha0, h2b0,
-                                 h2bm0);
+        node_coeffs_scaled<KIND, NFTAB>(M, pt, sp, h2 * cc, h2 * pt.K, tab + (size_t)(i0 * 4) * TF, ha0, h2b0,
+                                        h2bm0);
         ha0 *= g; h2b0 *= g2; h2bm0 *= g2;
     }
     {
@@ -417,18 +459,19 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
         for (int s = 0; s < NS; ++s) yp[s] *= h0;
     }
     for (int i = i0; i < iend; ++i) {
-        const double* f = tab + (size_t)(i * 4) * TAB_FIELDS;
+        const double* f = tab + (size_t)(i * 4) * TF;
         const double h = hs[i], h2 = h * h;
         const double c1 = h2 * cc, h2K = h2 * pt.K;
         double ha[5], h2b[5], h2bm[5], h2bs[NS][5];
         ha[0] = ha0; h2b[0] = h2b0; h2bm[0] = h2bm0;
 #pragma unroll
         for (int n = 1; n < 5; ++n)
-            node_coeffs_scaled<KIND>(M, pt, sp, c1, h2K, f + n * TAB_FIELDS, ha[n], h2b[n], h2bm[n]);
+            node_coeffs_scaled<KIND, NFTAB>(M, pt, sp, c1, h2K, f + n * TF, ha[n], h2b[n], h2bm[n]);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
-            for (int n = 0; n < 5; ++n) h2bs[s][n] = fma(m2[s], h2bm[n], h2b[n]);
+            for (int n = 0; n < 5; ++n)
+                h2bs[s][n] = is_cyl_second_order<KIND> ? fma(m2[s], h2bm[n], h2b[n]) : h2b[n];
         rk8_step<NS>(y, yp, ha, h2bs);
         const double g = gs[i], g2 = g * g;
         ha0 = ha[4] * g; h2b0 = h2b[4] * g2; h2bm0 = h2bm[4] * g2;        // the shared node, in the next step's scale
@@ -440,6 +483,214 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
 #pragma unroll
         for (int s = 0; s < NS; ++s) yp[s] *= ih;
     }
+}
+
+// ---- normal form u'' = q u, Cooper-Verner in Nystrom form (SCHEME_RK8N) ------------------------
+// Every second-order kind is (F y')' = g y, i.e. y'' = a y' + b y with a = -F'/F.  The substitution
+// u = sqrt|F| y removes the first-derivative term:
+//     u'' = q u,    q = b - a'/2 + a^2/4
+// and a Runge-Kutta method applied to (u, u')' = (u', q u) never needs the stages of u' on their own
+// (tools/gen_rkn_tableau.py): the SAME 8th-order method costs 64 FP64 instructions per solution and
+// step instead of 110 (40 + 4 + 5 products with (A A), b^T A, b; four "c_i z" bases shared by the
+// stages on the same node; 11 products q_i U_i), with the same four stage nodes.
+//   cylinder density  F = r/(rho w^2 - k^2 beta):  X = rho - qh, Y = rho - ph, L = rho'/X
+//       q = k^2 + (n^2 - 1/4)/r^2 - (w^2/S) rho^2/Y - rho''/(2X) + 3/4 L^2 - L/(2r)
+//   cylinder axial flow  F = r/(rho (Om^2 - k^2 vA^2)):  X = Om^2 - k^2 vA^2, Y = Om^2 - k^2 cT^2,
+//       X' = -2 k Om v', X'' = 2 k^2 v'^2 - 2 k Om v'', L = X'/X
+//       q = k^2 + (n^2 - 1/4)/r^2 - Om^4/(s Y) - X''/(2X) + 3/4 L^2 - L/(2r)
+//   slab density  F = P3/P1, P_j = {alpha, beta, tau} k^2/w^2 - rho, i_j = 1/P_j, a = rho' (i3 - i1)
+//       q = (w^2/S) P1 P2 i3 - (i3 - i1)(rho'' + rho'^2 (i3 + i1))/2 + a^2/4
+// The staged node holds the step-scaled (k, omega)-independent pieces (model_host.h):
+//   cylinder {-h/(2r), h^2/r^2, field, h field', -h^2 field''/2, h^2 field^2}
+//   slab     {h^2,     -,       rho,   h rho',   -h^2 rho''/2,   -}
+// The end conditions and the matching are stated for (y, y'); nform_edge gives a and the factor of F
+// that varies along the layer at a node, so that (y, y') = (u, u' + a u/2)/sqrt|F| at both ends.
+struct NPoint {
+    double q, p, t;      // density kinds: k^2 {beta, tau, alpha}/w^2
+    double AS;           // density kinds: w^2/S
+    double dd;           // slab: (alpha - tau) k^2/w^2
+    double m2k;          // flow: -2 k
+    double inv_s;        // flow: 1/(c^2 + vA^2)
+};
+
+template <int KIND>
+ESB_HD NPoint make_npoint(const DevModel& M, const Point& pt) {
+    static_assert(KIND == KIND_CYL_DENSITY || KIND == KIND_CYL_FLOW || KIND == KIND_SLAB_DENSITY,
+                  "kinds with a normal form");
+    NPoint sp{};
+    if constexpr (KIND == KIND_CYL_FLOW) {
+        sp.m2k = -2.0 * pt.k;
+        sp.inv_s = 1.0 / M.si;
+    } else {
+        // w = 0: the ratios -> 1e280-ish, the products overflow to +inf, their reciprocal is 0 and
+        // q = k^2 (+ the azimuthal term), the w -> 0 limit
+        const double A = pt.A > 1e-280 ? pt.A : 1e-280;
+        sp.q = pt.Kbeta / A;
+        sp.p = pt.Ktau / A;
+        sp.t = pt.Kalpha / A;
+        sp.AS = A / M.S;
+        sp.dd = sp.t - sp.p;
+    }
+    return sp;
+}
+
+// h^2 q (without the azimuthal term) and its azimuthal factor h^2/r^2 at one staged node.
+// c1 = h^2 w^2/S (density), h^2/s (flow); h2K = h^2 k^2.
+template <int KIND>
+ESB_HD void node_q(const DevModel& M, const Point& pt, const NPoint& sp, double c1, double h2K, const double* f,
+                   double& h2q, double& h2m) {
+    if constexpr (KIND == KIND_CYL_DENSITY) {
+        const double rho = f[2];
+        const double X = rho - sp.q;
+        const double Y = rho - sp.p;
+        const double inv = 1.0 / (X * Y);
+        const double iX = inv * Y, iY = inv * X;
+        const double L = f[3] * iX;
+        double acc = fma(-(sp.AS * f[5]), iY, h2K);
+        acc = fma(f[4], iX, acc);
+        acc = fma(0.75 * L, L, acc);
+        h2q = fma(L, f[0], acc);
+        h2m = f[1];
+    } else if constexpr (KIND == KIND_CYL_FLOW) {
+        const double hdv = f[3];
+        const double Om = fma(-pt.k, f[2], pt.w);
+        const double O2 = Om * Om;
+        const double X = fma(-pt.K, M.vAi2, O2);
+        const double Y = fma(-pt.K, M.cTi2, O2);
+        const double inv = 1.0 / (X * Y);
+        const double iX = inv * Y, iY = inv * X;
+        const double kO = sp.m2k * Om;                         // -2 k Om
+        const double L = (kO * hdv) * iX;                      // h X'/X
+        const double W = fma(pt.K * hdv, hdv, -kO * f[4]);     // h^2 X''/2 = k^2 (h v')^2 - k Om h^2 v''
+        double acc = fma(-((O2 * O2) * c1), iY, h2K);
+        acc = fma(-W, iX, acc);
+        acc = fma(0.75 * L, L, acc);
+        h2q = fma(L, f[0], acc);
+        h2m = f[1];
+    } else {
+        const double rho = f[2], hdr = f[3];
+        const double P1 = sp.t - rho, P2 = sp.q - rho, P3 = sp.p - rho;
+        const double I = 1.0 / (P1 * P3);
+        const double i3 = I * P1;
+        const double d = I * sp.dd;                            // i3 - i1
+        const double sm = I * (P1 + P3);                       // i3 + i1
+        const double E = hdr * d;                              // h a
+        double acc = ((c1 * P1) * P2) * i3;                    // h^2 b, c1 = h^2 w^2/S
+        acc = fma(f[4], d, acc);
+        acc = fma(-0.5 * (E * hdr), sm, acc);
+        h2q = fma(0.25 * E, E, acc);
+        h2m = 0.0;
+    }
+}
+
+// h a (h = the step the node is stored in) and the varying factor of F at a node:
+// F = r/(rho_0 Xf) (cylinder), F = Xf (slab: P3/P1)
+template <int KIND>
+ESB_HD void nform_edge(const DevModel& M, const Point& pt, const NPoint& sp, const double* f, double& ha, double& Xf) {
+    if constexpr (KIND == KIND_CYL_DENSITY) {
+        const double X = f[2] - sp.q;
+        ha = fma(f[3], 1.0 / X, 2.0 * f[0]);
+        Xf = X;
+    } else if constexpr (KIND == KIND_CYL_FLOW) {
+        const double Om = fma(-pt.k, f[2], pt.w);
+        const double X = fma(-pt.K, M.vAi2, Om * Om);
+        ha = fma((sp.m2k * Om) * f[3], 1.0 / X, 2.0 * f[0]);
+        Xf = X;
+    } else {
+        const double P1 = sp.t - f[2], P3 = sp.p - f[2];
+        ha = f[3] * (sp.dd / (P1 * P3));
+        Xf = P3 / P1;
+    }
+}
+
+// One step for NS solutions in the step-scaled variables (u, z = h u'); q[s][n] = h^2 q_s at the five
+// stage nodes {0, (7-sqrt21)/14, 1/2, (7+sqrt21)/14, 1}.  stage -> node as in rk8_generic.
+template <int NS>
+ESB_HD void rkn8_step(double (&u)[NS], double (&z)[NS], const double (&q)[NS][5]) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const double U = u[s], Z = z[s];
+        const double(&Q)[5] = q[s];
+        const double BH = fma(0.5, Z, U), BM = fma(RKN(c_m), Z, U), BP = fma(RKN(c_p), Z, U), B1 = U + Z;
+        const double F1 = Q[0] * U;
+        const double F2 = Q[2] * BH;
+        const double F3 = Q[2] * fma(RKN(n3_1), F1, BH);
+        const double F4 = Q[3] * fma(RKN(n4_2), F2, fma(RKN(n4_1), F1, BP));
+        const double F5 = Q[3] * fma(RKN(n5_3), F3, fma(RKN(n5_2), F2, fma(RKN(n5_1), F1, BP)));
+        const double F6 = Q[2] * fma(RKN(n6_4), F4, fma(RKN(n6_3), F3, fma(RKN(n6_2), F2, fma(RKN(n6_1), F1, BH))));
+        const double F7 = Q[1] * fma(RKN(n7_5), F5, fma(RKN(n7_4), F4, fma(RKN(n7_3), F3, fma(RKN(n7_2), F2, fma(RKN(n7_1), F1, BM)))));
+        const double F8 = Q[1] * fma(RKN(n8_6), F6, fma(RKN(n8_5), F5, fma(RKN(n8_4), F4, fma(RKN(n8_3), F3, fma(RKN(n8_1), F1, BM)))));
+        const double F9 = Q[2] * fma(RKN(n9_7), F7, fma(RKN(n9_6), F6, fma(RKN(n9_5), F5, fma(RKN(n9_4), F4, fma(RKN(n9_3), F3,
+                                 fma(RKN(n9_1), F1, BH))))));
+        const double F10 = Q[3] * fma(RKN(n10_8), F8, fma(RKN(n10_7), F7, fma(RKN(n10_6), F6, fma(RKN(n10_5), F5, fma(RKN(n10_4), F4,
+                                  fma(RKN(n10_3), F3, fma(RKN(n10_1), F1, BP)))))));
+        const double F11 = Q[4] * fma(RKN(n11_9), F9, fma(RKN(n11_8), F8, fma(RKN(n11_7), F7, fma(RKN(n11_6), F6, fma(RKN(n11_5), F5,
+                                  fma(RKN(n11_4), F4, fma(RKN(n11_3), F3, B1)))))));
+        u[s] = fma(RKN(nb_10), F10, fma(RKN(nb_9), F9, fma(RKN(nb_8), F8, fma(RKN(nb_1), F1, B1))));
+        z[s] = fma(RKN(b_11), F11, fma(RKN(b_10), F10, fma(RKN(b_9), F9, fma(RKN(b_8), F8, fma(RKN(b_1), F1, Z)))));
+    }
+}
+
+// NS solutions of u'' = (q + m2[s] bm) u along the staged mesh; (u, u') in and out unscaled.
+// m2[s] = n^2 - 1/4 (cylinder), unused for the slab.  RANGE: steps [r0, r1), else all of the mesh.
+template <int KIND, int NS, bool RANGE = false>
+ESB_HD void integrate_layer_nform(const DevModel& M, const Point& pt, const NPoint& sp, const double* __restrict__ tab,
+                                  const double (&m2)[NS], double (&u)[NS], double (&up)[NS], int r0 = 0,
+                                  int r1 = 0) {
+    constexpr bool CYL = is_cyl_second_order<KIND>;
+    const int i0 = RANGE ? r0 : 0;
+    const int iend = RANGE ? r1 : M.n_steps;
+    const double* hs = tab + (size_t)M.n_nodes * NF_FIELDS;
+    const double* gs = hs + M.n_steps;
+    const double cc = (KIND == KIND_CYL_FLOW) ? sp.inv_s : sp.AS;
+    double q0, bm0;
+    if (!RANGE || i0 == 0) {
+        const double h2 = hs[0] * hs[0];
+        node_q<KIND>(M, pt, sp, h2 * cc, h2 * pt.K, tab, q0, bm0);
+    } else {
+        // node 4 i0 is stored in the scale of the step it ends: evaluate it there, rescale like the carry
+        const double hp = hs[i0 - 1], h2 = hp * hp, g = gs[i0 - 1], g2 = g * g;
+        node_q<KIND>(M, pt, sp, h2 * cc, h2 * pt.K, tab + (size_t)(i0 * 4) * NF_FIELDS, q0, bm0);
+        q0 *= g2; bm0 *= g2;
+    }
+    {
+        const double h0 = hs[i0];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) up[s] *= h0;
+    }
+    for (int i = i0; i < iend; ++i) {
+        const double* f = tab + (size_t)(i * 4) * NF_FIELDS;
+        const double h = hs[i], h2 = h * h;
+        const double c1 = h2 * cc, h2K = h2 * pt.K;
+        double q[5], bm[5], qs[NS][5];
+        q[0] = q0; bm[0] = bm0;
+#pragma unroll
+        for (int n = 1; n < 5; ++n) node_q<KIND>(M, pt, sp, c1, h2K, f + n * NF_FIELDS, q[n], bm[n]);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int n = 0; n < 5; ++n) qs[s][n] = CYL ? fma(m2[s], bm[n], q[n]) : q[n];
+        rkn8_step<NS>(u, up, qs);
+        const double g = gs[i], g2 = g * g;
+        q0 = q[4] * g2; bm0 = bm[4] * g2;                      // the shared node, in the next step's scale
+#pragma unroll
+        for (int s = 0; s < NS; ++s) up[s] *= g;
+    }
+    if (RANGE && iend < M.n_steps) {     // z is in the scale of step iend: back to u'
+        const double ih = 1.0 / hs[iend];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) up[s] *= ih;
+    }
+}
+
+// (a, varying factor of F) at breakpoint `step` of the mesh (node 4 step), a unscaled
+template <int KIND>
+ESB_HD void nform_end_values(const DevModel& M, const Point& pt, const NPoint& sp, const double* __restrict__ tab,
+                             int step, double& a, double& Xf) {
+    const double* hs = tab + (size_t)M.n_nodes * NF_FIELDS;
+    double ha;
+    nform_edge<KIND>(M, pt, sp, tab + (size_t)(step * 4) * NF_FIELDS, ha, Xf);
+    a = ha / hs[step > 0 ? step - 1 : 0];
 }
 
 // ------------------------------------------------- rotational-flow cylinder ----
@@ -599,6 +850,110 @@ __device__ __forceinline__ void warp_transfer(int first, int n_steps, F&& integr
 }
 #endif
 
+// ------------------------------------------------------------- shoot_layer ----
+// The normal form has a DOUBLE pole where the first-derivative form has a simple one (q contains
+// a^2/4): a point whose resonance lies just outside the layer - the analytic continuation of the profile
+// reaches the resonant value a little beyond an end of the layer, or the profile comes close to it
+// without reaching it - is integrated less accurately in u than in y on the same mesh (measured: 1e-5
+// instead of 1e-10 at 0.02 in phase speed above the Alfven continuum, equal beyond ~0.1).  Such points
+// (resonant value within NF_BAND, relative, of the range the profile spans in the layer, but outside
+// it) take the (y, h y') variables on the same table.  Inside the range (a resonance in the layer: the
+// continua, below the noise floor) any form returns noise; they stay on the cheaper one.
+constexpr double NF_BAND = 0.15;
+
+ESB_HD bool in_band(double v, double lo, double hi) {
+    return (v > hi && v < hi * (1.0 + NF_BAND)) || (v < lo && v > lo * (1.0 - NF_BAND));
+}
+
+template <int KIND>
+ESB_HD bool near_resonance(const DevModel& M, const Point& pt, const NPoint& sp) {
+    if constexpr (KIND == KIND_CYL_DENSITY) {
+        return in_band(sp.q, M.f_lo, M.f_hi);                            // Alfven: rho = k^2 beta/w^2
+    } else if constexpr (KIND == KIND_SLAB_DENSITY) {
+        return in_band(sp.t, M.f_lo, M.f_hi) || in_band(sp.p, M.f_lo, M.f_hi);   // sound point of F, cusp
+    } else {
+        // Alfven: (w - k v_z)^2 = k^2 vA^2 with v_z in [f_lo, f_hi]
+        const double Oa = fma(-pt.k, M.f_lo, pt.w), Ob = fma(-pt.k, M.f_hi, pt.w);
+        const double a2 = Oa * Oa, b2 = Ob * Ob;
+        const double hi = fmax(a2, b2), lo = (Oa * Ob <= 0.0) ? 0.0 : fmin(a2, b2);
+        return in_band(pt.K * M.vAi2, lo, hi);
+    }
+}
+
+constexpr int SCHEME_RK8_NTAB = 3;      // internal: the (y, h y') variables read from the normal-form table
+
+// steps [i0, i1) of the mesh by the scheme; FULL: the whole mesh (compile-time bounds)
+template <int KIND, int SCHEME, int NS, bool FULL>
+ESB_HD void layer_range(const DevModel& M, const Point& pt, const NPoint& sp, const double* __restrict__ tab,
+                        const double (&m2)[NS], double (&y)[NS], double (&yp)[NS], int i0, int i1) {
+    if constexpr (SCHEME == SCHEME_RK8N) integrate_layer_nform<KIND, NS, !FULL>(M, pt, sp, tab, m2, y, yp, i0, i1);
+    else if constexpr (SCHEME == SCHEME_RK8_NTAB)
+        integrate_layer_prescaled<KIND, NS, !FULL, true>(M, pt, tab, m2, y, yp, i0, i1);
+    else if constexpr (SCHEME == SCHEME_RK8 && is_cyl_second_order<KIND>)
+        integrate_layer_prescaled<KIND, NS, !FULL>(M, pt, tab, m2, y, yp, i0, i1);
+    else integrate_layer<KIND, SCHEME, NS, !FULL>(M, pt, tab, m2, y, yp, i0, i1);
+}
+
+// start vectors -> end of the mesh in the variables of SCHEME.  WARP (all 32 lanes together, same
+// arguments): the transfer matrix of the layer is built cooperatively (warp_transfer) and applied to the
+// start vectors; all solutions then share m2[0].
+template <int KIND, int SCHEME, int NS, bool WARP, bool FULL>
+ESB_HD void shoot_vars(const DevModel& M, const Point& pt, const NPoint& sp, const double* __restrict__ tab,
+                       const double (&m2)[NS], double (&y)[NS], double (&yp)[NS], int first) {
+#ifdef __CUDA_ARCH__
+    if constexpr (WARP) {
+        const double mm2[2] = {m2[0], m2[0]};
+        double T[4];
+        warp_transfer(first, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
+            layer_range<KIND, SCHEME, 2, false>(M, pt, sp, tab, mm2, u, v, i0, i1);
+        }, T);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const double y0 = y[s], yp0 = yp[s];
+            y[s] = fma(T[0], y0, T[1] * yp0);
+            yp[s] = fma(T[2], y0, T[3] * yp0);
+        }
+    } else
+#endif
+    layer_range<KIND, SCHEME, NS, FULL>(M, pt, sp, tab, m2, y, yp, first, M.n_steps);
+}
+
+// NS solutions given as (y, y') at breakpoint `first` of the mesh -> (y, y') at its end.  m2[s] = the
+// square of the azimuthal order of solution s (cylinder).  SCHEME_RK8N integrates u = sqrt|F| y and
+// converts at both ends (points next to a resonance: see near_resonance).  FULL: first == 0 known at
+// compile time.
+template <int KIND, int SCHEME, int NS, bool WARP, bool FULL>
+ESB_HD void shoot_layer(const DevModel& M, const Point& pt, const double* __restrict__ tab, const double (&m2)[NS],
+                        double (&y)[NS], double (&yp)[NS], int first) {
+    if constexpr (SCHEME == SCHEME_RK8N) {
+        const NPoint sp = make_npoint<KIND>(M, pt);
+        if (near_resonance<KIND>(M, pt, sp)) {
+            shoot_vars<KIND, SCHEME_RK8_NTAB, NS, WARP, FULL>(M, pt, sp, tab, m2, y, yp, first);
+            return;
+        }
+        double a0, X0, a_end, XN, mq[NS];
+        nform_end_values<KIND>(M, pt, sp, tab, first, a0, X0);
+        nform_end_values<KIND>(M, pt, sp, tab, M.n_steps, a_end, XN);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            yp[s] = fma(-0.5 * a0, y[s], yp[s]);          // u' = y' - a y/2 (the common factor sqrt|F| is restored in sf)
+            mq[s] = m2[s] - 0.25;
+        }
+        shoot_vars<KIND, SCHEME_RK8N, NS, WARP, FULL>(M, pt, sp, tab, mq, y, yp, first);
+        const double ratio = is_cyl_second_order<KIND> ? (M.r_axis / M.s_start) * (XN / X0) : X0 / XN;
+        double sf = sqrt(fabs(ratio));                    // sqrt|F(first)/F(end)|
+        if (!(sf <= 1.7e308)) sf = 1.0;                   // a resonance exactly on an end node (inside a continuum)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            yp[s] = fma(0.5 * a_end, y[s], yp[s]) * sf;   // y' = (u' + a u/2)/sqrt|F|
+            y[s] *= sf;
+        }
+    } else {
+        const NPoint sp{};
+        shoot_vars<KIND, SCHEME, NS, WARP, FULL>(M, pt, sp, tab, m2, y, yp, first);
+    }
+}
+
 // ------------------------------------------------------------ full point ----
 // NM evaluations of the reference's scan-loop body at one (k, omega), one per requested
 // mode, sharing everything that does not depend on the mode:
@@ -703,22 +1058,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             yp[s] = modes[s] == 0 ? 0.0 : 1.0;
             m2[s] = double(modes[s]) * double(modes[s]);
         }
-#ifdef __CUDA_ARCH__
-        if constexpr (WARP) {
-            const double mm2[2] = {m2[0], m2[0]};
-            double T[4];
-            warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
-                if constexpr (SCHEME == SCHEME_RK8) integrate_layer_prescaled<KIND, 2, true>(M, pt, tab, mm2, u, v, i0, i1);
-                else integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, mm2, u, v, i0, i1);
-            }, T);
-            // the solution that satisfies the axis condition: (y, y')(axis) = (1, 0) or (0, 1)
-            const double y0 = y[0], yp0 = yp[0];
-            y[0] = fma(T[0], y0, T[1] * yp0);
-            yp[0] = fma(T[2], y0, T[3] * yp0);
-        } else
-#endif
-        if constexpr (SCHEME == SCHEME_RK8) integrate_layer_prescaled<KIND, NM>(M, pt, tab, m2, y, yp);
-        else integrate_layer<KIND, SCHEME, NM>(M, pt, tab, m2, y, yp);
+        shoot_layer<KIND, SCHEME, NM, WARP, true>(M, pt, tab, m2, y, yp, 0);
         double den;
         if constexpr (KIND == KIND_CYL_FLOW) {
             // (C1 P + D P')/C3 at r = -1 with C1 = 0: P'/(rho (Om_b^2 - k^2 vA^2)), Om_b = w - k v_z(-1)
@@ -746,24 +1086,15 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
         double y[2] = {1.0, 0.0}, yp[2] = {0.0, 1.0};
         const double m2[2] = {0.0, 0.0};
         const int first = M.symmetric ? M.n_steps / 2 : 0;
-#ifdef __CUDA_ARCH__
-        if constexpr (WARP) {
-            double T[4];
-            warp_transfer(first, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
-                integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, u, v, i0, i1);
-            }, T);
-            y[0] = T[0]; y[1] = T[1]; yp[0] = T[2]; yp[1] = T[3];
-        } else
-#endif
-        if (NM == 1 && M.symmetric) {
+        if (!WARP && NM == 1 && M.symmetric) {
             // one mode of a symmetric layer needs only its own solution (odd: sausage, even: kink)
             const int c = (modes[0] == 0) ? 1 : 0;
             double y1[1] = {c == 0 ? 1.0 : 0.0}, yp1[1] = {c == 0 ? 0.0 : 1.0};
             const double m21[1] = {0.0};
-            integrate_layer<KIND, SCHEME, 1, true>(M, pt, tab, m21, y1, yp1, first, M.n_steps);
+            shoot_layer<KIND, SCHEME, 1, false, false>(M, pt, tab, m21, y1, yp1, first);
             y[c] = y1[0]; yp[c] = yp1[0];
         } else {
-            integrate_layer<KIND, SCHEME, 2, true>(M, pt, tab, m2, y, yp, first, M.n_steps);
+            shoot_layer<KIND, SCHEME, 2, WARP, false>(M, pt, tab, m2, y, yp, first);
         }
         double P_Ti;
         if (KIND == KIND_SLAB_FLOW) {

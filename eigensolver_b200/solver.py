@@ -59,16 +59,17 @@ SLAB_PHOTOSPHERIC = Medium(1.0, 1.9, 0.8, 1.3)
 
 @dataclasses.dataclass(frozen=True)
 class GaussianDensity:
-    """rho_e + (rho_i0 - rho_e) exp(-(x-x0)^2/width^2)   (Density_cylinder.py:135)."""
+    """rho_e + (rho_i0 - rho_e) exp(-(x-x0)^2/width^2)   (Density_cylinder.py:135).
+    Returns (rho, rho', rho''): the normal-form scheme ("rk8n") needs the second derivative."""
     width: float = 0.95
     x0: float = 0.0
 
     def __call__(self, medium, x):
         x = np.asarray(x, dtype=np.float64)
         g = np.exp(-((x - self.x0) ** 2) / self.width**2)
-        rho = medium.rho_e + (medium.rho_i0 - medium.rho_e) * g
-        drho = (medium.rho_i0 - medium.rho_e) * g * (-2.0 * (x - self.x0) / self.width**2)
-        return rho, drho
+        d = medium.rho_i0 - medium.rho_e
+        t = -2.0 * (x - self.x0) / self.width**2
+        return medium.rho_e + d * g, d * g * t, d * g * (t * t - 2.0 / self.width**2)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -82,7 +83,9 @@ class EpsteinDensity:
     def __call__(self, medium, x):
         t = (np.asarray(x, dtype=np.float64) - self.x0) / self.a
         d = medium.rho_i0 - medium.rho_e
-        return d / np.cosh(t) ** 8 + medium.rho_e, d * (-8.0 / self.a) * np.sinh(t) / np.cosh(t) ** 9
+        ch, sh = np.cosh(t), np.sinh(t)
+        return (d / ch**8 + medium.rho_e, d * (-8.0 / self.a) * sh / ch**9,
+                d * (8.0 / self.a**2) * (9.0 * sh * sh - ch * ch) / ch**10)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -151,7 +154,8 @@ class GaussianAxialFlow:
         r = np.asarray(r, dtype=np.float64)
         g = np.exp(-((r - self.r0) ** 2) / self.width**2)
         dU0 = medium.U_i0 - medium.U_e
-        return medium.U_e + dU0 * g, dU0 * g * (-2.0 * (r - self.r0) / self.width**2)
+        t = -2.0 * (r - self.r0) / self.width**2
+        return medium.U_e + dU0 * g, dU0 * g * t, dU0 * g * (t * t - 2.0 / self.width**2)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -197,7 +201,8 @@ class RootTable:
 
 _KINDS = {"slab_density": L.SLAB_DENSITY, "cylinder_density": L.CYLINDER_DENSITY, "slab_flow": L.SLAB_FLOW,
           "cylinder_rotation": L.CYLINDER_ROTATION, "cylinder_flow": L.CYLINDER_FLOW}
-_SCHEMES = {"rk4": L.RK4, "rk8": L.RK8}
+_SCHEMES = {"rk4": L.RK4, "rk8": L.RK8, "rk8n": L.RK8N}
+_SCHEME_NAMES = {v: k for k, v in _SCHEMES.items()}
 _LAYOUTS = {"shared": L.OMEGA_SHARED, "phase_speed": L.OMEGA_PHASE_SPEED, "per_k": L.OMEGA_PER_K}
 _MODES = {"sausage": 0, "kink": 1, "fluting": 2, "fluting2": 2, "fluting3": 3}
 
@@ -210,52 +215,50 @@ def _iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
-class DispersionSolver:
-    """One GPU context evaluating D(omega,k) for one equilibrium model."""
+_DEFAULT_MEDIA = {"cylinder_density": CYLINDER_CORONAL, "slab_density": SLAB_CORONAL,
+                  "slab_flow": SLAB_FLOW_CORONAL, "cylinder_rotation": CYLINDER_PHOTOSPHERIC,
+                  "cylinder_flow": CYLINDER_FLOW_CORONAL}
+_DEFAULT_PROFILES = {"cylinder_density": GaussianDensity(0.95), "slab_density": GaussianDensity(0.9),
+                     "slab_flow": GaussianFlow(1e5), "cylinder_rotation": PowerLawRotation(),
+                     "cylinder_flow": GaussianAxialFlow(1.0)}
 
-    def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme="rk8", mesh=None,
-                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None,
-                 mesh_params=None):
-        """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation" |
-        "cylinder_flow".
-        profile: callable (medium, x) -> (rho, rho') for the density kinds, (U, U', U'') for
-        "slab_flow", (v_phi, v_phi', c_i^2) for "cylinder_rotation", (v_z, v_z') for
-        "cylinder_flow"; any function may be given (this
-        replaces the reference's sympy profile).  s_end: far end of the layer (the rotational sausage
-        script stops at r = 0.01, the kink one at 0.001).
-        coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
-        layer 1 -> 0.001, exterior slope given as dP/dr)."""
+
+#: (n_steps, mesh_axis) measured for "rk8" on the kinds whose library default is "rk8n"
+_RK8_TUNED = {"cylinder_density": (144, 0.16), "cylinder_flow": (144, 0.16)}
+
+
+class ModelSpec:
+    """Host description of one equilibrium + discretisation: the `esb_model` struct, the mesh nodes and
+    the profile sampled there - everything `esb_set_model_fields` takes.  Needs no GPU (the mesh
+    functions of the library are host code); `DispersionSolver` uploads it, the CPU tests hand the same
+    arguments to the host build of the kernels' arithmetic (tests/host_harness)."""
+
+    def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme=None, mesh=None, rho_A=1.0,
+                 ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None, mesh_params=None):
         self.lib = L.load()
         self.kind = kind
         m = L.esb_model()
         L.check(self.lib, None, self.lib.esb_model_defaults(_KINDS[kind], C.byref(m)), "esb_model_defaults")
-        if medium is None:
-            medium = {"cylinder_density": CYLINDER_CORONAL, "slab_density": SLAB_CORONAL,
-                      "slab_flow": SLAB_FLOW_CORONAL, "cylinder_rotation": CYLINDER_PHOTOSPHERIC,
-                      "cylinder_flow": CYLINDER_FLOW_CORONAL}[kind]
-        self.medium = medium
-        if profile is None:
-            profile = {"cylinder_density": GaussianDensity(0.95), "slab_density": GaussianDensity(0.9),
-                       "slab_flow": GaussianFlow(1e5), "cylinder_rotation": PowerLawRotation(),
-                       "cylinder_flow": GaussianAxialFlow(1.0)}[kind]
-        self.profile = profile
-        if kind == "slab_flow":
-            m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
-            m.gamma, m.rho_i0, m.rho_A, m.U_e = medium.gamma, medium.rho_i, 1.0, medium.U_e
-        else:
-            m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
-            m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, rho_A
-            m.U_e = getattr(medium, "U_e", 0.0)
-        m.scheme = _SCHEMES[scheme]
-        if mesh is not None:              # None: the kind's default (graded for the cylinder density /
-            # axial-flow kinds, sin^2-clustered otherwise)
+        self.medium = _DEFAULT_MEDIA[kind] if medium is None else medium
+        self.profile = _DEFAULT_PROFILES[kind] if profile is None else profile
+        self.rho_A = rho_A
+        self._set_medium(m, self.medium)
+        if scheme is not None:            # None: the kind's default ("rk8n" where the kind has a normal form)
+            m.scheme = _SCHEMES[scheme]
+        elif m.scheme == L.RK8N and len(self.profile(self.medium, np.array([m.s_start]))) < 3:
+            m.scheme = L.RK8              # a user profile without the second derivative: the (y, y') form
+        if m.scheme == L.RK8 and kind in _RK8_TUNED:
+            # the discretisation tuned for the first-derivative form (the library's defaults are the
+            # normal-form scheme's)
+            m.n_steps, m.mesh_axis = _RK8_TUNED[kind]
+        if mesh is not None:              # None: the kind's default (graded)
             m.mesh = {"uniform": L.MESH_UNIFORM, "clustered": L.MESH_CLUSTERED, "graded": L.MESH_GRADED}[mesh]
         if mesh_params is not None:       # (mesh_axis, mesh_edge, mesh_edge_width) of the graded mesh
             m.mesh_axis, m.mesh_edge, m.mesh_edge_width = (float(v) for v in mesh_params)
         m.ext_wavelengths = ext_wavelengths
         if n_steps is not None:
             m.n_steps = int(n_steps)
-        elif scheme == "rk4":
+        elif m.scheme == L.RK4:
             m.n_steps = 2048
         if coordinate == "positive":
             if kind != "cylinder_density":
@@ -267,11 +270,85 @@ class DispersionSolver:
         if s_end is not None:
             m.s_end = float(s_end)
         self.model = m
-        self._rho_A = rho_A
         n = C.c_int32()
         L.check(self.lib, None, self.lib.esb_mesh_size(C.byref(m), C.byref(n)), "esb_mesh_size")
         self.nodes = np.empty(n.value, dtype=np.float64)
         L.check(self.lib, None, self.lib.esb_mesh_nodes(C.byref(m), _dptr(self.nodes)), "esb_mesh_nodes")
+        nf = C.c_int32()
+        L.check(self.lib, None, self.lib.esb_model_n_fields(C.byref(m), C.byref(nf)), "esb_model_n_fields")
+        self.n_fields = nf.value
+
+    def _set_medium(self, m, medium):
+        if self.kind == "slab_flow":
+            m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
+            m.gamma, m.rho_i0, m.rho_A, m.U_e = medium.gamma, medium.rho_i, 1.0, medium.U_e
+        else:
+            m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
+            m.gamma, m.rho_i0, m.rho_A = medium.gamma, medium.rho_i0, self.rho_A
+            m.U_e = getattr(medium, "U_e", 0.0)
+
+    def replace(self, medium=None, profile=None):
+        """Another equilibrium on the same mesh (what a parameter scan changes between sweeps)."""
+        if medium is not None:
+            self.medium = medium
+            self._set_medium(self.model, medium)
+        if profile is not None:
+            self.profile = profile
+
+    @property
+    def scheme(self):
+        return _SCHEME_NAMES[self.model.scheme]
+
+    def sampled(self):
+        """-> (fields, boundary): the profile at the mesh nodes, the first field at s_start."""
+        scale = self.rho_A if self.kind in ("cylinder_density", "slab_density") else 1.0
+        vals = self.profile(self.medium, self.nodes)
+        if len(vals) < self.n_fields:
+            raise ValueError("scheme %r needs %d profile fields (value, first and second derivative), the "
+                             "profile returned %d" % (self.scheme, self.n_fields, len(vals)))
+        fields = [np.ascontiguousarray(np.asarray(f, dtype=np.float64) * scale) for f in vals[:self.n_fields]]
+        boundary = np.array([float(self.profile(self.medium, np.array([self.model.s_start]))[0][0]) * scale])
+        return fields, boundary
+
+    def abi_args(self):
+        """The argument list (after ctx) of esb_set_model_fields; keeps the arrays alive on self."""
+        self._fields, self._boundary = self.sampled()
+        self._fptr = (C.POINTER(C.c_double) * len(self._fields))(*[_dptr(f) for f in self._fields])
+        return (C.byref(self.model), self._fptr, len(self._fields), self.nodes.size, _dptr(self._boundary),
+                self._boundary.size)
+
+    def solver_kwargs(self):
+        """Keyword arguments that rebuild this spec (convergence_check builds a finer copy)."""
+        m = self.model
+        return dict(kind=self.kind, medium=self.medium, profile=self.profile, n_steps=int(m.n_steps),
+                    scheme=self.scheme,
+                    mesh={L.MESH_CLUSTERED: "clustered", L.MESH_UNIFORM: "uniform", L.MESH_GRADED: "graded"}[m.mesh],
+                    mesh_params=(m.mesh_axis, m.mesh_edge, m.mesh_edge_width),
+                    ext_ic=(m.ext_ic_value, m.ext_ic_slope), ext_wavelengths=m.ext_wavelengths, s_end=m.s_end,
+                    rho_A=self.rho_A,
+                    coordinate="positive" if (self.kind == "cylinder_density" and m.r_sign > 0) else "negative")
+
+
+class DispersionSolver:
+    """One GPU context evaluating D(omega,k) for one equilibrium model."""
+
+    def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme=None, mesh=None,
+                 device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None,
+                 mesh_params=None):
+        """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation" |
+        "cylinder_flow".
+        profile: callable (medium, x) -> (rho, rho', rho'') for the density kinds, (U, U', U'') for
+        "slab_flow", (v_phi, v_phi', c_i^2) for "cylinder_rotation", (v_z, v_z', v_z'') for
+        "cylinder_flow"; any function may be given (this replaces the reference's sympy profile; a
+        profile that returns no second derivative runs on the "rk8" scheme).
+        scheme: "rk8n" (normal form, default where the kind has one) | "rk8" | "rk4".
+        s_end: far end of the layer (the rotational sausage script stops at r = 0.01, the kink one at 0.001).
+        coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
+        layer 1 -> 0.001, exterior slope given as dP/dr)."""
+        self.spec = ModelSpec(kind, medium, profile, n_steps, scheme, mesh, rho_A, ext_ic, ext_wavelengths,
+                              coordinate, s_end, mesh_params)
+        self.lib = self.spec.lib
+        self.kind = kind
         self.ctx = L._ctx()
         rc = self.lib.esb_create(int(device), C.byref(self.ctx))
         if rc != L.ESB_OK:
@@ -280,32 +357,20 @@ class DispersionSolver:
                              "eigensolver_b200 has no CPU fallback" % (rc, device))
         self._upload_model()
 
+    # the spec's fields under their old names
+    model = property(lambda self: self.spec.model)
+    medium = property(lambda self: self.spec.medium)
+    profile = property(lambda self: self.spec.profile)
+    nodes = property(lambda self: self.spec.nodes)
+
     def _upload_model(self):
-        m, medium, kind = self.model, self.medium, self.kind
-        scale = self._rho_A if kind in ("cylinder_density", "slab_density") else 1.0
-        fields = [np.ascontiguousarray(np.asarray(f, dtype=np.float64) * scale)
-                  for f in self.profile(medium, self.nodes)]
-        boundary = np.array([float(self.profile(medium, np.array([m.s_start]))[0][0]) * scale])
-        fptr = (C.POINTER(C.c_double) * len(fields))(*[_dptr(f) for f in fields])
-        L.check(self.lib, self.ctx,
-                self.lib.esb_set_model_fields(self.ctx, C.byref(m), fptr, len(fields), self.nodes.size,
-                                              _dptr(boundary), boundary.size), "esb_set_model_fields")
+        L.check(self.lib, self.ctx, self.lib.esb_set_model_fields(self.ctx, *self.spec.abi_args()),
+                "esb_set_model_fields")
 
     def reconfigure(self, medium=None, profile=None):
         """Swap the equilibrium (speeds and/or profile) on the same context and mesh: one small
         table upload, no reallocation.  This is what a parameter scan does between sweeps."""
-        m = self.model
-        if medium is not None:
-            self.medium = medium
-            if self.kind == "slab_flow":
-                m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i, medium.vA_i, medium.vA_e, medium.c_e
-                m.gamma, m.rho_i0, m.U_e = medium.gamma, medium.rho_i, medium.U_e
-            else:
-                m.c_i0, m.vA_i0, m.vA_e, m.c_e = medium.c_i0, medium.vA_i0, medium.vA_e, medium.c_e
-                m.gamma, m.rho_i0 = medium.gamma, medium.rho_i0
-                m.U_e = getattr(medium, "U_e", 0.0)
-        if profile is not None:
-            self.profile = profile
+        self.spec.replace(medium, profile)
         self._upload_model()
 
     # ------------------------------------------------------------------
@@ -479,13 +544,10 @@ class DispersionSolver:
         kk, ww, lay, nw = self._axes(k, w, layout)
         e0, i0 = self.dispersion_grid_multi(modes, k, w, layout)
         m = self.model
-        kw = dict(kind=self.kind, medium=self.medium, profile=self.profile, n_steps=int(m.n_steps) * int(factor),
-                  scheme={L.RK4: "rk4", L.RK8: "rk8"}[m.scheme],
-                  mesh={L.MESH_CLUSTERED: "clustered", L.MESH_UNIFORM: "uniform", L.MESH_GRADED: "graded"}[m.mesh],
-                  mesh_params=(m.mesh_axis, m.mesh_edge, m.mesh_edge_width),
-                  ext_ic=(m.ext_ic_value, m.ext_ic_slope), ext_wavelengths=m.ext_wavelengths, s_end=m.s_end,
-                  rho_A=self._rho_A, coordinate="positive" if (self.kind == "cylinder_density" and m.r_sign > 0)
-                  else "negative")
+        kw = self.spec.solver_kwargs()
+        kw["n_steps"] = int(m.n_steps) * int(factor)
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > 900:
+            kw["scheme"] = "rk8"          # the six-field table of that many steps exceeds shared memory
         with DispersionSolver(**kw) as fine:
             e1, i1 = fine.dispersion_grid_multi(modes, k, w, layout)
         ok = np.isfinite(e0) & np.isfinite(i0) & np.isfinite(e1) & np.isfinite(i1)

@@ -35,7 +35,8 @@
 extern "C" {
 #endif
 
-#define ESB_VERSION 110   /* 1.1: esb_model grew the mesh_* fields; pinned tables, schedules */
+#define ESB_VERSION 120   /* 1.1: esb_model grew the mesh_* fields; pinned tables, schedules
+                             1.2: ESB_RK8N (normal-form Nystrom scheme, needs the profile's second derivative) */
 
 typedef struct esb_context esb_context;
 
@@ -61,7 +62,11 @@ enum esb_model_kind {
 /* Fixed-step integrator used across the layer. */
 enum esb_scheme {
     ESB_RK4 = 0, /* classical 4-stage, stage nodes c = 0, 1/2, 1                              */
-    ESB_RK8 = 1  /* Cooper-Verner 11-stage 8th order, nodes c = 0, (7-/+sqrt21)/14, 1/2, 1   */
+    ESB_RK8 = 1, /* Cooper-Verner 11-stage 8th order, nodes c = 0, (7-/+sqrt21)/14, 1/2, 1   */
+    ESB_RK8N = 2 /* the same method in Nystrom form on the normal form u'' = q u (u = sqrt|F| y) of
+                    the second-order kinds (cylinder density / axial flow, slab density): 64 instead of
+                    110 FP64 instructions per solution and step.  The default of those kinds; the
+                    profile's SECOND derivative is a third field of esb_set_model_fields            */
 };
 
 /* How the omega axis is given. */
@@ -124,10 +129,12 @@ int esb_set_model(esb_context* ctx, const esb_model* m, const double* rho, const
                   int32_t n_nodes, double rho_boundary);
 
 /* Generic form: fields[f][n_nodes] sampled at esb_mesh_nodes().
- *   density kinds : fields = {rho, rho'},       boundary = {rho(s_start)}
+ *   density kinds : fields = {rho, rho'} (+ rho'' with ESB_RK8N),   boundary = {rho(s_start)}
  *   ESB_SLAB_FLOW : fields = {U, U', U''},      boundary = {U(s_start)}
  *   ESB_CYLINDER_ROTATION : fields = {v_phi, v_phi', c_i^2}, boundary = {v_phi(s_start)}
- *   ESB_CYLINDER_FLOW : fields = {v_z, v_z'},   boundary = {v_z(s_start)}                    */
+ *   ESB_CYLINDER_FLOW : fields = {v_z, v_z'} (+ v_z'' with ESB_RK8N), boundary = {v_z(s_start)}
+ * esb_model_n_fields() returns the count for a model.  A failed call leaves the previous model set. */
+int esb_model_n_fields(const esb_model* m, int32_t* n_fields);
 int esb_set_model_fields(esb_context* ctx, const esb_model* m, const double* const* fields,
                          int32_t n_fields, int32_t n_nodes, const double* boundary,
                          int32_t n_boundary);

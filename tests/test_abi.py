@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_defaults():
     lib = esb.load()
-    assert lib.esb_version() == 110
+    assert lib.esb_version() == 120
     assert lib.esb_sizeof_model() == C.sizeof(L.esb_model)        # the ctypes mirror of the struct
     m = L.esb_model()
     assert lib.esb_model_defaults(L.CYLINDER_DENSITY, C.byref(m)) == 0

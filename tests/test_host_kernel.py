@@ -1,0 +1,81 @@
+"""CPU parity tests of the kernels' arithmetic: csrc/core.cuh compiled for the host
+(tests/host_kernel.py) against the C oracle, on the grids the GPU parity tests use and on the
+BASELINE coordinates (k from 0.01, every mode incl. n = 3).  The GPU suite shows that the device
+build agrees with this host build; together they tie the GPU results to the oracle."""
+import numpy as np
+import pytest
+
+import eigensolver_b200 as esb
+import host_kernel as hk
+from helpers import CASES
+from oracle import rk_oracle as ork
+
+D_TOL = 1e-9
+
+
+def spec_of(case, **kw):
+    """the ModelSpec a GPU solver of this case would upload"""
+    class _Capture:
+        """stands in for the package: records the arguments of DispersionSolver(...)"""
+        def __getattr__(self, name):
+            return getattr(esb, name)
+
+        @staticmethod
+        def DispersionSolver(kind, **k):
+            k.pop("device", None)
+            return esb.ModelSpec(kind, **k)
+    return case.gpu_solver(_Capture(), **kw)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_build_matches_c_oracle(name):
+    case = CASES[name]
+    model = case.c_model()
+    k = np.linspace(0.05, 4.5, 20)
+    W = np.linspace(case.W[0], case.W[1], 240)
+    modes = list(case.modes)
+    e, i, _ = hk.grid(spec_of(case), modes, k, W)
+    for slot, mode in enumerate(modes):
+        e0, i0 = ork.grid(model, mode, k, W)
+        fin = np.isfinite(e0) & np.isfinite(i0)
+        assert np.array_equal(np.isfinite(e[slot]) & np.isfinite(i[slot]), fin)
+        ok = case.regular(k, W, mode) & fin
+        dev = np.abs((e[slot] - i[slot]) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+        assert ok.sum() > 0.25 * ok.size
+        assert np.nanmax(dev[ok]) < D_TOL, (mode, np.nanmax(dev[ok]))
+
+
+@pytest.mark.parametrize("kind", ["cylinder_density", "cylinder_flow", "slab_density"])
+def test_normal_form_and_first_derivative_form_agree(kind):
+    """ESB_RK8N (u = sqrt|F| y, Nystrom form) and ESB_RK8 ((y, h y') variables) are two discretisations of
+    the same problem: they agree to the discretisation error wherever the problem is regular, and the
+    scheme's own switch (near_resonance) keeps the points next to a continuum on the accurate form."""
+    case = CASES[kind]
+    k = np.linspace(0.01, 4.5, 16)
+    W = np.linspace(case.W[0], case.W[1], 600)
+    modes = list(case.modes)
+    a = spec_of(case)
+    assert a.scheme == "rk8n"
+    b = spec_of(case, scheme="rk8")
+    ea, ia, da = hk.grid(a, modes, k, W)
+    eb, ib, db = hk.grid(b, modes, k, W)
+    assert np.array_equal(np.isnan(ea), np.isnan(eb))
+    for slot, mode in enumerate(modes):
+        ok = case.regular(k, W, mode) & np.isfinite(ea[slot]) & np.isfinite(ia[slot])
+        sc = np.maximum(np.abs(eb[slot]), np.abs(ib[slot]))
+        assert np.max(np.abs(ea[slot] - eb[slot])[ok] / np.abs(eb[slot])[ok]) < 1e-13     # same exterior
+        assert np.max((np.abs(ia[slot] - ib[slot]) / sc)[ok]) < 2 * D_TOL
+        # the denominator Y (pole-free refinement) is the same quantity in both
+        assert np.max((np.abs(da[slot] - db[slot]) / np.abs(db[slot]))[ok]) < 1e-7
+
+
+def test_fused_equals_single_mode_on_host():
+    case = CASES["cylinder_density"]
+    k = np.linspace(0.3, 4.0, 7)
+    W = np.linspace(2.95, 4.95, 50)
+    sp = spec_of(case)
+    e3, i3, d3 = hk.grid(sp, [0, 1, 2], k, W)
+    for slot, m in enumerate((0, 1, 2)):
+        e1, i1, d1 = hk.grid(sp, [m], k, W)
+        assert np.allclose(e3[slot], e1[0], rtol=1e-13, equal_nan=True)
+        assert np.allclose(i3[slot], i1[0], rtol=1e-11, equal_nan=True)
