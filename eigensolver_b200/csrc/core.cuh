@@ -605,6 +605,11 @@ ESB_HD void nform_edge(const DevModel& M, const Point& pt, const NPoint& sp, con
 
 // One step for NS solutions in the step-scaled variables (u, z = h u'); q[s][n] = h^2 q_s at the five
 // stage nodes {0, (7-sqrt21)/14, 1/2, (7+sqrt21)/14, 1}.  stage -> node as in rk8_generic.
+// The tableau coefficients are 64-bit immediates: compiled for 3 resident CTAs per SM (esb.cu
+// ESB_GRID_MINB) they stay in uniform registers across the step loop (385 instructions per fused step,
+// 290 of them FP64); compiled for 4 the loop re-materialises them with two UMOVs each (527
+// instructions, issue-bound: 33.0 instead of 30.5 ms on the bench grid).  Reading them from shared
+// memory was tried: nvcc hoists the loads into ~250 registers (2 CTAs/SM, 37.2 ms) or spills them.
 template <int NS>
 ESB_HD void rkn8_step(double (&u)[NS], double (&z)[NS], const double (&q)[NS][5]) {
 #pragma unroll

@@ -64,8 +64,19 @@ __device__ __forceinline__ void stage_table(const double* __restrict__ g, double
 
 // NM modes are evaluated per thread, sharing the staged coefficients (cylinder) or the whole
 // integration (slab); outputs are mode-slot major.
+// Resident CTAs per SM the scan / refine kernels are compiled for.  Measured on the B200 with the
+// normal-form scheme (scripts/gpu_variants.py, profiles/r02b_variants.log): 3 (<= 168 registers: the
+// tableau stays in uniform registers across the step loop) beats 4 (128 registers: constants moved
+// around inside the loop) and 2: scan 30.5 / 31.6 / 37.2 ms, brackets + refinement 4.9 / 5.2 / 5.0 ms.
+// The first-derivative schemes keep round 1's 4 (128 registers; 3 was 3 % slower there).
+#ifndef ESB_GRID_MINB
+#define ESB_GRID_MINB(SCHEME) ((SCHEME) == SCHEME_RK8N ? 3 : 4)
+#endif
+#ifndef ESB_REFINE_MINB
+#define ESB_REFINE_MINB(SCHEME) ((SCHEME) == SCHEME_RK8N ? 3 : 4)
+#endif
 template <int KIND, int SCHEME, int NM>
-__global__ void __launch_bounds__(128) grid_kernel(GridArgs g) {
+__global__ void __launch_bounds__(128, ESB_GRID_MINB(SCHEME)) grid_kernel(GridArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -838,7 +849,7 @@ static cudaError_t launch_refine_warp(const RefineArgs& r, cudaStream_t s) {
 // for 5..8 CTAs/SM spills the evaluation loop and is 5-30 % slower
 template <int KIND, int SCHEME>
 static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
-    return launch_refine_b<KIND, SCHEME, 4>(r, s);
+    return launch_refine_b<KIND, SCHEME, ESB_REFINE_MINB(SCHEME)>(r, s);
 }
 
 // (kind, scheme) of the uploaded model -> template instantiation.  The rotational kind exists for
