@@ -17,6 +17,7 @@ SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW, CYLINDER_ROTATION, CYLINDER_FLOW = 0,
 RK4, RK8, RK8N = 0, 1, 2
 OMEGA_SHARED, OMEGA_PHASE_SPEED, OMEGA_PER_K = 0, 1, 2
 MESH_CLUSTERED, MESH_UNIFORM, MESH_GRADED = 0, 1, 2
+ACCEPT_CONVERGED, ACCEPT_REFERENCE = 0, 1
 
 
 class EsbError(RuntimeError):
@@ -79,6 +80,8 @@ SYMBOLS = {
     "esb_download_roots_slot": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), C.c_int32]),
     "esb_roots_pinned": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), _ip]),
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "esb_tables_wait": (C.c_int, [_ctx, C.c_void_p]),
+    "esb_set_accept_rule": (C.c_int, [_ctx, C.c_int32]),
     "esb_set_schedule": (C.c_int, [_ctx, C.c_int32]),
     "esb_fp64_peak": (C.c_int, [_ctx, _dp]),
     "esb_rk_selftest": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _dp]),

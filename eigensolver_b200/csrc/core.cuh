@@ -927,10 +927,15 @@ ESB_HD void shoot_vars(const DevModel& M, const Point& pt, const NPoint& sp, con
 // square of the azimuthal order of solution s (cylinder).  SCHEME_RK8N integrates u = sqrt|F| y and
 // converts at both ends (points next to a resonance: see near_resonance).  FULL: first == 0 known at
 // compile time.
-template <int KIND, int SCHEME, int NS, bool WARP, bool FULL>
+// YFORM: every point in the (y, h y') variables.  The lane-per-bracket refinement uses it: its 32
+// lanes hold unrelated (k, omega), so the per-point choice would make most warps run BOTH step loops.
+template <int KIND, int SCHEME, int NS, bool WARP, bool FULL, bool YFORM = false>
 ESB_HD void shoot_layer(const DevModel& M, const Point& pt, const double* __restrict__ tab, const double (&m2)[NS],
                         double (&y)[NS], double (&yp)[NS], int first) {
-    if constexpr (SCHEME == SCHEME_RK8N) {
+    if constexpr (SCHEME == SCHEME_RK8N && YFORM) {
+        const NPoint sp{};
+        shoot_vars<KIND, SCHEME_RK8_NTAB, NS, WARP, FULL>(M, pt, sp, tab, m2, y, yp, first);
+    } else if constexpr (SCHEME == SCHEME_RK8N) {
         const NPoint sp = make_npoint<KIND>(M, pt);
         if (near_resonance<KIND>(M, pt, sp)) {
             shoot_vars<KIND, SCHEME_RK8_NTAB, NS, WARP, FULL>(M, pt, sp, tab, m2, y, yp, first);
@@ -970,7 +975,7 @@ ESB_HD void shoot_layer(const DevModel& M, const Point& pt, const double* __rest
 // has the roots of D and no such poles; the refinement iterates on G (esb.cu refine_kernel).
 // WARP (device only, NM = 1, all 32 lanes of the warp call it with the same arguments): the layer is
 // integrated cooperatively (warp_transfer); every lane returns the same values.
-template <int KIND, int SCHEME, int NM, bool WARP = false>
+template <int KIND, int SCHEME, int NM, bool WARP = false, bool YFORM = false>
 ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, double k, double w,
                              const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM],
                              double (&den_q)[NM]) {
@@ -1063,7 +1068,7 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             yp[s] = modes[s] == 0 ? 0.0 : 1.0;
             m2[s] = double(modes[s]) * double(modes[s]);
         }
-        shoot_layer<KIND, SCHEME, NM, WARP, true>(M, pt, tab, m2, y, yp, 0);
+        shoot_layer<KIND, SCHEME, NM, WARP, true, YFORM>(M, pt, tab, m2, y, yp, 0);
         double den;
         if constexpr (KIND == KIND_CYL_FLOW) {
             // (C1 P + D P')/C3 at r = -1 with C1 = 0: P'/(rho (Om_b^2 - k^2 vA^2)), Om_b = w - k v_z(-1)
@@ -1096,10 +1101,10 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
             const int c = (modes[0] == 0) ? 1 : 0;
             double y1[1] = {c == 0 ? 1.0 : 0.0}, yp1[1] = {c == 0 ? 0.0 : 1.0};
             const double m21[1] = {0.0};
-            shoot_layer<KIND, SCHEME, 1, false, false>(M, pt, tab, m21, y1, yp1, first);
+            shoot_layer<KIND, SCHEME, 1, false, false, YFORM>(M, pt, tab, m21, y1, yp1, first);
             y[c] = y1[0]; yp[c] = yp1[0];
         } else {
-            shoot_layer<KIND, SCHEME, 2, WARP, false>(M, pt, tab, m2, y, yp, first);
+            shoot_layer<KIND, SCHEME, 2, WARP, false, YFORM>(M, pt, tab, m2, y, yp, first);
         }
         double P_Ti;
         if (KIND == KIND_SLAB_FLOW) {
@@ -1134,12 +1139,12 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
     }
 }
 
-template <int KIND, int SCHEME, bool WARP = false>
+template <int KIND, int SCHEME, bool WARP = false, bool YFORM = false>
 ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
                        double& ext_q, double& int_q, double& den_q) {
     const int modes[1] = {mode};
     double e[1], i[1], d[1];
-    eval_point_multi<KIND, SCHEME, 1, WARP>(M, tab, k, w, modes, e, i, d);
+    eval_point_multi<KIND, SCHEME, 1, WARP, YFORM>(M, tab, k, w, modes, e, i, d);
     ext_q = e[0];
     int_q = i[0];
     den_q = d[0];

@@ -44,6 +44,7 @@ struct GridArgs {
     double* intq;
     double* den;            // optional [n_modes][nk][nw]: denominator of intq (sweep path; see refine_kernel)
     int schedule;           // 0 = by size, 1 = one thread per point, 2 = one warp per point
+    unsigned long long* tile_counter;   // work queue head of the persistent scan kernel (zeroed before launch)
 };
 
 __device__ __forceinline__ double omega_at(const double* __restrict__ k, const double* __restrict__ w,
@@ -64,28 +65,42 @@ __device__ __forceinline__ void stage_table(const double* __restrict__ g, double
 
 // NM modes are evaluated per thread, sharing the staged coefficients (cylinder) or the whole
 // integration (slab); outputs are mode-slot major.
-// Resident CTAs per SM the scan / refine kernels are compiled for.  Measured on the B200 with the
-// normal-form scheme (scripts/gpu_variants.py, profiles/r02b_variants.log): 3 (<= 168 registers: the
-// tableau stays in uniform registers across the step loop) beats 4 (128 registers: constants moved
-// around inside the loop) and 2: scan 30.5 / 31.6 / 37.2 ms, brackets + refinement 4.9 / 5.2 / 5.0 ms.
-// The first-derivative schemes keep round 1's 4 (128 registers; 3 was 3 % slower there).
-#ifndef ESB_GRID_MINB
-#define ESB_GRID_MINB(SCHEME) ((SCHEME) == SCHEME_RK8N ? 3 : 4)
+//
+// Persistent: ONE CTA per SM stages the table once; its warps pull 32-point tiles (a row index and 32
+// consecutive omega) from a global counter until the grid is exhausted.  No CTA turnover - the
+// one-CTA-per-128-points launch re-staged the table 79 000 times per bench launch and left 10 % of
+// the warp slots idle between a CTA's first and last warp finishing (ncu: 10.8 of 12 warps active).
+// Resident warps per SM = what the register budget allows: 12 (<= 168 registers) for the normal-form
+// scheme, whose tableau then stays in uniform registers across the step loop (385 instructions per
+// fused step, 290 of them FP64; compiled for 128 registers the constants are re-materialised inside
+// the loop: 527 instructions, issue-bound: scan 30.5 / 31.6 / 37.2 ms compiled for 3 / 4 / 2 CTAs of
+// 128 threads per SM, scripts/gpu_variants.py); 16 (128 registers) for the first-derivative schemes,
+// as measured in round 1.
+#ifndef ESB_GRID_THREADS
+#define ESB_GRID_THREADS(SCHEME) ((SCHEME) == SCHEME_RK8N ? 384 : 512)
 #endif
 #ifndef ESB_REFINE_MINB
 #define ESB_REFINE_MINB(SCHEME) ((SCHEME) == SCHEME_RK8N ? 3 : 4)
 #endif
 template <int KIND, int SCHEME, int NM>
-__global__ void __launch_bounds__(128, ESB_GRID_MINB(SCHEME)) grid_kernel(GridArgs g) {
+__global__ void __launch_bounds__(ESB_GRID_THREADS(SCHEME), 1) grid_kernel(GridArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
-    const int iw = blockIdx.x * blockDim.x + threadIdx.x;
-    if (iw >= g.nw) return;
+    const int lane = threadIdx.x & 31;
     int modes[NM];
 #pragma unroll
     for (int s = 0; s < NM; ++s) modes[s] = g.modes[s];
     const size_t plane = (size_t)g.nk * g.nw;
-    for (int ik = blockIdx.y; ik < g.nk; ik += gridDim.y) {
+    const int tiles_per_row = (g.nw + 31) >> 5;
+    const unsigned long long n_tiles = (unsigned long long)g.nk * tiles_per_row;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(g.tile_counter, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tiles) break;
+        const int ik = (int)(t / tiles_per_row);
+        const int iw = (int)(t - (unsigned long long)ik * tiles_per_row) * 32 + lane;
+        if (iw >= g.nw) continue;
         const double k = g.k[ik];
         const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
         double e[NM], i[NM], d[NM];
@@ -131,30 +146,66 @@ __global__ void __launch_bounds__(128) grid_warp_kernel(GridArgs g) {
     }
 }
 
-// ---- brackets: sign change of D = ext - int between neighbours along omega ----
+// ---- brackets ------------------------------------------------------------------------------------
+__device__ __forceinline__ double mismatch_pct(double e, double i) {
+    // the reference's acceptance quantity (Density_cylinder.py:809)
+    return fabs(e - i) * 100.0 / fmax(fabs(e), fabs(i));
+}
+
 __device__ __forceinline__ bool is_bracket(double d0, double d1) {
     // both evaluated (finite) and strictly opposite signs
     return isfinite(d0) && isfinite(d1) && ((d0 < 0.0 && d1 > 0.0) || (d0 > 0.0 && d1 < 0.0));
 }
 
-// One warp per (row, segment of BRACKET_SEG omega intervals); pass 0 counts, pass 1 fills at the
-// segment's offset.  Segments are ordered (row, segment), so the filled list is sorted by
+// One sweep = up to ESB_MAX_MODES mode slots over the same (k, omega) grid.  The bracket passes and the
+// refinement of ALL slots are single launches over one descriptor; the only host round trip of a sweep
+// is the read-back of the per-slot counts (esb_sweep_resident_multi).
+#define ESB_MAX_MODES 4
+
+struct SlotDev {
+    const double* gext;     // planes of the scan: end-point values of every bracket
+    const double* gint;
+    const double* gden;     // denominator of gint at the same points
+    int* bk;                // bracket: row, lower and upper omega index (upper = lower + 1 except
+    int* bw;                //   across skipped points in the reference rule; upper == lower: a scan
+    int* bw2;               //   point the reference accepts as it stands)
+    double* omega;
+    double* ext;
+    double* intq;
+    int* accepted;
+    int* iters;
+    int mode;
+    int capacity;           // entries the slot's buffers hold; brackets beyond it are counted, not stored
+};
+
+struct SweepDev {
+    SlotDev slot[ESB_MAX_MODES];
+    int n_slots, nk, nw, nseg;
+    int* seg_count;         // [n_slots * nk * nseg]
+    int* seg_offset;        // [n_slots * nk * nseg + 1] exclusive prefix over all slots
+    int* slot_begin;        // [ESB_MAX_MODES + 1] first global work index of every slot; [n_slots] = total
+    int rule;               // ESB_ACCEPT_CONVERGED: adjacent finite points; ESB_ACCEPT_REFERENCE: the script's rule
+    double tol_percent;
+};
+
+// One warp per (slot, row, segment of BRACKET_SEG omega intervals); pass 0 counts, pass 1 fills at the
+// segment's offset.  Items are ordered (slot, row, segment), so every slot's list is sorted by
 // (k index, omega index) whatever the number of segments.
 constexpr int BRACKET_SEG = 1024;
 
-__global__ void bracket_kernel(const double* __restrict__ ext, const double* __restrict__ intq, int nk,
-                               int nw, int nseg, int* __restrict__ seg_count,
-                               const int* __restrict__ seg_offset, int* __restrict__ bk,
-                               int* __restrict__ bw, int capacity, int fill) {
+__global__ void bracket_kernel(SweepDev sw, int fill) {
     const int lane = threadIdx.x & 31;
     const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (item >= nk * nseg) return;
-    const int row = item / nseg, seg = item - row * nseg;
-    const double* e = ext + (size_t)row * nw;
-    const double* q = intq + (size_t)row * nw;
-    const int base = fill ? seg_offset[item] : 0;
+    const int per_slot = sw.nk * sw.nseg;
+    if (item >= sw.n_slots * per_slot) return;
+    const int sl = item / per_slot;
+    const int row = (item - sl * per_slot) / sw.nseg, seg = item - sl * per_slot - row * sw.nseg;
+    const SlotDev& S = sw.slot[sl];
+    const double* e = S.gext + (size_t)row * sw.nw;
+    const double* q = S.gint + (size_t)row * sw.nw;
+    const int base = fill ? sw.seg_offset[item] - sw.slot_begin[sl] : 0;
     const int j_begin = seg * BRACKET_SEG;
-    const int j_end = min(j_begin + BRACKET_SEG, nw - 1);
+    const int j_end = min(j_begin + BRACKET_SEG, sw.nw - 1);
     int count = 0;
     for (int j0 = j_begin; j0 < j_end; j0 += 32) {
         const int j = j0 + lane;
@@ -167,24 +218,82 @@ __global__ void bracket_kernel(const double* __restrict__ ext, const double* __r
         const unsigned ballot = __ballot_sync(0xffffffffu, hit);
         if (fill && hit) {
             const int pos = base + count + __popc(ballot & ((1u << lane) - 1u));
-            if (pos < capacity) {
-                bk[pos] = row;
-                bw[pos] = j;
+            if (pos < S.capacity) {
+                S.bk[pos] = row;
+                S.bw[pos] = j;
+                if (S.bw2) S.bw2[pos] = j + 1;
             }
         }
         count += __popc(ballot);
     }
-    if (!fill && lane == 0) seg_count[item] = count;
+    if (!fill && lane == 0) sw.seg_count[item] = count;
 }
 
-// row_offset[row] = seg_offset[row * nseg]  (row = nk gives the total)
-__global__ void row_offset_kernel(const int* __restrict__ seg_offset, int nk, int nseg, int* __restrict__ row_offset) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row <= nk) row_offset[row] = seg_offset[(size_t)row * nseg];
+// The reference's own scan rule, one warp per (slot, row) (Density_cylinder.py:803-821, the same in
+// every script).  Walking the EVALUATED points of a row in order (m_e < 0 points are skipped, :760):
+//   * a point whose mismatch is below the tolerance is appended to the solutions as it stands and the
+//     list of points seen (`all_ws`) is cleared (:809-812);
+//   * else, if D changed sign against the previous evaluated point AND more than two points have been
+//     seen since the list was last cleared (:814-815), the pair (previous, this) is bisected and the
+//     list is cleared (:820).
+// The state (points seen since the last clear) is sequential in omega: the warp classifies 32 points at
+// a time by ballot and every lane walks the three masks with bit operations.
+__global__ void bracket_reference_kernel(SweepDev sw, int fill) {
+    const int lane = threadIdx.x & 31;
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= sw.n_slots * sw.nk) return;
+    const int sl = item / sw.nk, row = item - sl * sw.nk;
+    const SlotDev& S = sw.slot[sl];
+    const double* e = S.gext + (size_t)row * sw.nw;
+    const double* q = S.gint + (size_t)row * sw.nw;
+    const int base = fill ? sw.seg_offset[item] - sw.slot_begin[sl] : 0;
+    int count = 0, seen = 0, prev_j = -1;
+    double prev_d = 0.0;                     // xi_diff_check = [0]: the first product is with 0
+    for (int j0 = 0; j0 < sw.nw; j0 += 32) {
+        const int j = j0 + lane;
+        double d = nan("");
+        bool ok = false;
+        if (j < sw.nw) {
+            const double ev = e[j], qv = q[j];
+            d = ev - qv;
+            ok = mismatch_pct(ev, qv) < sw.tol_percent;
+        }
+        const unsigned finite_m = __ballot_sync(0xffffffffu, isfinite(d));
+        const unsigned accept_m = __ballot_sync(0xffffffffu, ok);
+        const unsigned neg_m = __ballot_sync(0xffffffffu, d < 0.0);
+        const unsigned zero_m = __ballot_sync(0xffffffffu, d == 0.0);
+        for (int b = 0; b < 32; ++b) {
+            if (!((finite_m >> b) & 1u)) continue;
+            const int jj = j0 + b;
+            const int sgn = ((zero_m >> b) & 1u) ? 0 : ((neg_m >> b) & 1u) ? -1 : 1;
+            const int psgn = prev_d == 0.0 ? 0 : prev_d < 0.0 ? -1 : 1;
+            ++seen;
+            int lo = -1, hi = -1;
+            if ((accept_m >> b) & 1u) {
+                lo = hi = jj;                                    // a solution as it stands
+                seen = 0;
+            } else if (sgn * psgn < 0 && seen > 2) {
+                lo = prev_j; hi = jj;
+                seen = 0;
+            }
+            if (lo >= 0) {
+                if (fill && lane == 0) {
+                    const int pos = base + count;
+                    if (pos < S.capacity) { S.bk[pos] = row; S.bw[pos] = lo; S.bw2[pos] = hi; }
+                }
+                ++count;
+            }
+            prev_d = (double)sgn;
+            prev_j = jj;
+        }
+    }
+    if (!fill && lane == 0) sw.seg_count[item] = count;
 }
 
-// exclusive scan of row counts -> offsets[nk+1]; single block
-__global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int n) {
+// exclusive scan of the item counts -> offsets[n + 1]; single block.  Every `slot_items`-th offset is
+// also written to slot_begin[] (the first work index of each mode slot; slot_begin[n / slot_items] = total).
+__global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int n, int slot_items,
+                            int* __restrict__ slot_begin) {
     __shared__ int carry;
     __shared__ int warp_sums[32];
     if (threadIdx.x == 0) carry = 0;
@@ -212,48 +321,37 @@ __global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ of
         }
         __syncthreads();
         const int prefix = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
-        if (i < n) offsets[i] = prefix;
+        if (i < n) {
+            offsets[i] = prefix;
+            if (slot_begin && slot_items > 0 && i % slot_items == 0) slot_begin[i / slot_items] = prefix;
+        }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) offsets[n] = carry;
+    if (threadIdx.x == 0) {
+        offsets[n] = carry;
+        if (slot_begin && slot_items > 0) slot_begin[n / slot_items] = carry;
+    }
+}
+
+// row_offset[row] = seg_offset[row * nseg]  (row = nk gives the total)
+__global__ void row_offset_kernel(const int* __restrict__ seg_offset, int nk, int nseg, int* __restrict__ row_offset) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row <= nk) row_offset[row] = seg_offset[(size_t)row * nseg];
 }
 
 // ---- refinement ----
-struct RefineSlot {
-    const double* gext;     // D grid of the scan (end-point values of every bracket)
-    const double* gint;
-    const double* gden;     // denominator of gint at the same points
-    const int* bk;
-    const int* bw;
-    double* omega;
-    double* ext;
-    double* intq;
-    int* accepted;
-    int* iters;
-    int mode;
-    int begin;              // first global work index of this slot
-};
-
 struct RefineArgs {
     DevModel M;
     const double* tab;
     int tab_doubles;
     const double* k;
     const double* w;
-    int nk, nw, layout;
-    int n_slots;
-    int n_total;            // brackets of all slots together
-    RefineSlot slot[3];
-    int* counter;           // work queue head (zeroed before launch)
-    double tol_percent;
+    int layout;
+    SweepDev sw;
+    int* counter;           // work queue heads (zeroed before launch): [0] first pass, [1] second pass
 };
-
-__device__ __forceinline__ double mismatch_pct(double e, double i) {
-    // the reference's acceptance quantity (Density_cylinder.py:809)
-    return fabs(e - i) * 100.0 / fmax(fabs(e), fabs(i));
-}
 
 // ---- Brent's method on G = D * Y, one bracket -------------------------------------------------
 // Pole-free iteration.  D = ext - int with int = N/Y, Y the boundary value of the integrated
@@ -396,91 +494,172 @@ __device__ __forceinline__ void brent_feed(Brent& S, double en, double in_, doub
     ++S.it;
 }
 
-// bracket t of the single queue over all mode slots -> slot, local index, point data, Brent state.
-// false: classified as a pole from the scan (result already written).
-__device__ __forceinline__ bool refine_pickup(const RefineArgs& r, int tq, bool writer, int& sl, int& t, int& mode,
-                                              double& k, Brent& S) {
-    sl = (r.n_slots > 2 && tq >= r.slot[2].begin) ? 2 : (r.n_slots > 1 && tq >= r.slot[1].begin) ? 1 : 0;
-    t = tq - r.slot[sl].begin;
-    mode = r.slot[sl].mode;
-    const int ik = r.slot[sl].bk[t], jw = r.slot[sl].bw[t];
-    k = r.k[ik];
-    const double a = omega_at(r.k, r.w, r.layout, r.nw, ik, jw);
-    const double b = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + 1);
-    const size_t o = (size_t)ik * r.nw + jw;
-    if (brent_init(S, a, b, r.slot[sl].gext[o], r.slot[sl].gint[o], r.slot[sl].gext[o + 1],
-                   r.slot[sl].gint[o + 1], r.slot[sl].gden[o], r.slot[sl].gden[o + 1])) {
-        if (S.on_g && jw >= 1 && jw + 2 < r.nw) {
-            double w4[4], g4[4];
-            bool smooth = true;
-            const double y_ref = r.slot[sl].gden[o];
+// ---- the reference's own bisection (accept rule ESB_ACCEPT_REFERENCE) ---------------------------
+// locate_kink (Density_cylinder.py:548-686) evaluates omega = linspace(lo, hi, 3) in order; a point whose
+// mismatch is below the tolerance is THE solution (:671-676, no further refinement); otherwise, after the
+// third point, a sign change between the middle and the upper point recurses into (middle, upper)
+// (:678-684, the list of points seen has three entries only then), up to 150 levels (:558).  A root in
+// the LOWER half is therefore not followed - the scripts' tables hold what this rule finds, so the
+// drop-in reproduces it.  lo and hi were evaluated by the caller and are outside the band: one new
+// evaluation (the middle) per level.
+struct RefBisect {
+    double a, b, db;        // bracket, D at its upper end
+    double mid, em, im;     // last trial and (ext, int) there
+    int level;
+    bool found;
+};
+
+// true: evaluate at S.mid and hand the values to refbisect_feed; false: finished
+__device__ __forceinline__ bool refbisect_next(RefBisect& S) {
+    if (S.found || S.level > 150 || S.level < 0) return false;
+    S.mid = S.a + (S.b - S.a) * 0.5;        // numpy.linspace(a, b, 3)[1]
+    return true;
+}
+
+__device__ __forceinline__ void refbisect_feed(RefBisect& S, double en, double in_, double tol_percent) {
+    S.em = en; S.im = in_;
+    const double dm = en - in_;
+    if (mismatch_pct(en, in_) < tol_percent) {
+        S.found = true;
+    } else if (isfinite(dm) && dm * S.db < 0.0) {
+        S.a = S.mid;
+        ++S.level;
+    } else {
+        S.level = -1 - S.level;             // not followed: the reference stops here without a solution
+    }
+}
+
+// global work index -> slot and local index (slot_begin[] is ascending)
+__device__ __forceinline__ int slot_of(const SweepDev& sw, int tq) {
+    int sl = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const size_t oq = o + q - 1;
-                const double y = r.slot[sl].gden[oq];
-                w4[q] = omega_at(r.k, r.w, r.layout, r.nw, ik, jw + q - 1);
-                g4[q] = (r.slot[sl].gext[oq] - r.slot[sl].gint[oq]) * y;
-                smooth = smooth && isfinite(g4[q]) && ((y > 0.0) == (y_ref > 0.0));
-            }
-            if (smooth) S.guess = inverse_cubic_guess(w4, g4);
+    for (int s = 1; s < ESB_MAX_MODES; ++s)
+        if (s < sw.n_slots && tq >= sw.slot_begin[s]) sl = s;
+    return sl;
+}
+
+struct Pick {
+    int sl, t, mode;
+    double k;
+    bool reference;         // iterate with RefBisect, else Brent
+};
+
+enum { PICK_SKIP = 0, PICK_WORK = 1 };
+
+// Bracket tq of the single queue over all mode slots -> slot, local index, point data, iteration state.
+// pass 0 takes the brackets without a first trial from the scan grid (inside the continua: up to ~20
+// evaluations each), pass 1 the smooth ones (3-4 evaluations): the long ones start first and the queue
+// drains on short ones.  Entries finished without an evaluation (poles classified from the scan, scan
+// points the reference accepts as they stand, overflow beyond the slot capacity) are written in pass 0.
+__device__ __forceinline__ int refine_pickup(const RefineArgs& r, int tq, int pass, bool writer, Pick& P, Brent& S,
+                                             RefBisect& B) {
+    const SweepDev& sw = r.sw;
+    P.sl = slot_of(sw, tq);
+    const SlotDev& L = sw.slot[P.sl];
+    P.t = tq - sw.slot_begin[P.sl];
+    if (P.t >= L.capacity) return PICK_SKIP;
+    P.mode = L.mode;
+    P.reference = sw.rule == ESB_ACCEPT_REFERENCE;
+    const int ik = L.bk[P.t], jlo = L.bw[P.t], jhi = L.bw2[P.t];
+    P.k = r.k[ik];
+    const size_t o = (size_t)ik * sw.nw + jlo, o2 = (size_t)ik * sw.nw + jhi;
+    const double a = omega_at(r.k, r.w, r.layout, sw.nw, ik, jlo);
+    if (jhi == jlo) {                       // reference rule: a scan point inside the band
+        if (pass == 0 && writer) {
+            L.omega[P.t] = a; L.ext[P.t] = L.gext[o]; L.intq[P.t] = L.gint[o];
+            L.iters[P.t] = 0; L.accepted[P.t] = 1;
         }
-        return true;
+        return PICK_SKIP;
     }
-    if (writer) {
-        r.slot[sl].omega[t] = S.b;
-        r.slot[sl].ext[t] = nan("");
-        r.slot[sl].intq[t] = nan("");
-        r.slot[sl].iters[t] = 0;
-        r.slot[sl].accepted[t] = 0;
+    const double b = omega_at(r.k, r.w, r.layout, sw.nw, ik, jhi);
+    if (P.reference) {
+        if (pass != 0) return PICK_SKIP;
+        B.a = a; B.b = b; B.db = L.gext[o2] - L.gint[o2];
+        B.mid = b; B.em = L.gext[o2]; B.im = L.gint[o2];
+        B.level = 0; B.found = false;
+        return PICK_WORK;
     }
-    return false;
+    if (!brent_init(S, a, b, L.gext[o], L.gint[o], L.gext[o2], L.gint[o2], L.gden[o], L.gden[o2])) {
+        if (pass == 0 && writer) {          // a pole of D, classified from the scan
+            L.omega[P.t] = S.b; L.ext[P.t] = nan(""); L.intq[P.t] = nan("");
+            L.iters[P.t] = 0; L.accepted[P.t] = 0;
+        }
+        return PICK_SKIP;
+    }
+    if (S.on_g && jhi == jlo + 1 && jlo >= 1 && jlo + 2 < sw.nw) {
+        double w4[4], g4[4];
+        bool smooth = true;
+        const double y_ref = L.gden[o];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const size_t oq = o + q - 1;
+            const double y = L.gden[oq];
+            w4[q] = omega_at(r.k, r.w, r.layout, sw.nw, ik, jlo + q - 1);
+            g4[q] = (L.gext[oq] - L.gint[oq]) * y;
+            smooth = smooth && isfinite(g4[q]) && ((y > 0.0) == (y_ref > 0.0));
+        }
+        if (smooth) S.guess = inverse_cubic_guess(w4, g4);
+    }
+    return (isfinite(S.guess) ? 1 : 0) == pass ? PICK_WORK : PICK_SKIP;
 }
 
-__device__ __forceinline__ void refine_store(const RefineArgs& r, int sl, int t, const Brent& S) {
-    r.slot[sl].omega[t] = S.b;
-    r.slot[sl].ext[t] = S.eb;
-    r.slot[sl].intq[t] = S.ib;
-    r.slot[sl].iters[t] = S.it;
-    r.slot[sl].accepted[t] = (mismatch_pct(S.eb, S.ib) < r.tol_percent) ? 1 : 0;
+__device__ __forceinline__ void refine_store(const RefineArgs& r, const Pick& P, const Brent& S, const RefBisect& B) {
+    const SlotDev& L = r.sw.slot[P.sl];
+    if (P.reference) {
+        L.omega[P.t] = B.mid; L.ext[P.t] = B.em; L.intq[P.t] = B.im;
+        L.iters[P.t] = B.level < 0 ? -B.level : B.level + 1;          // evaluations used
+        L.accepted[P.t] = B.found ? 1 : 0;
+        return;
+    }
+    L.omega[P.t] = S.b; L.ext[P.t] = S.eb; L.intq[P.t] = S.ib;
+    L.iters[P.t] = S.it;
+    L.accepted[P.t] = (mismatch_pct(S.eb, S.ib) < r.sw.tol_percent) ? 1 : 0;
 }
 
-// Persistent kernel, one LANE per bracket: every lane runs Brent's method on one bracket at a time
-// and pulls the next bracket from a global queue as soon as its own has converged, so a warp
-// never idles behind its slowest lane.  The D evaluation (the expensive part) is executed
-// by all 32 lanes together each round; __any_sync on the "trial pending" flags ends the
-// loop.  End-point values come from the scan grid, not from new evaluations.
+// Persistent kernel, one LANE per bracket: every lane iterates on one bracket at a time and pulls the
+// next bracket from a global queue as soon as its own has converged, so a warp never idles behind
+// its slowest lane.  The D evaluation (the expensive part) is executed by all 32 lanes together each
+// round; __any_sync on the "trial pending" flags ends the loop.  End-point values come from the scan
+// grid, not from new evaluations.  The brackets are counted on the device (slot_begin[n_slots]).
 template <int KIND, int SCHEME, int MINB>
 __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
     stage_table(r.tab, stab, r.tab_doubles);
+    const int n_total = r.sw.slot_begin[r.sw.n_slots];
     bool have = false, pending = false, exhausted = false;
-    int t = 0, sl = 0, mode = 0;
-    double k = 1.0;
+    int pass = 0;
+    Pick P;
+    P.k = 1.0; P.mode = 0; P.reference = false;
     Brent S;
-    S.b = 1.0;
+    RefBisect B;
+    double wq = 1.0;        // trial frequency
     for (;;) {
         while (!pending && !exhausted) {
             if (!have) {
-                const int tq = atomicAdd(r.counter, 1);
-                if (tq >= r.n_total) {
+                const int tq = atomicAdd(r.counter + pass, 1);
+                if (tq >= n_total) {
+                    if (pass == 0) { pass = 1; continue; }
                     exhausted = true;
                     break;
                 }
-                if (!refine_pickup(r, tq, true, sl, t, mode, k, S)) continue;
+                if (refine_pickup(r, tq, pass, true, P, S, B) == PICK_SKIP) continue;
                 have = true;
             }
-            if (!brent_next(S)) {
-                refine_store(r, sl, t, S);
+            const bool more = P.reference ? refbisect_next(B) : brent_next(S);
+            if (!more) {
+                refine_store(r, P, S, B);
                 have = false;
                 continue;
             }
+            wq = P.reference ? B.mid : S.b;
             pending = true;
         }
         if (!__any_sync(0xffffffffu, pending)) break;
         double en, in_, yn;
-        eval_point<KIND, SCHEME>(r.M, stab, k, S.b, mode, en, in_, yn);
+        eval_point<KIND, SCHEME, false, true>(r.M, stab, P.k, wq, P.mode, en, in_, yn);
         if (pending) {
-            brent_feed(S, en, in_, yn);
+            if (P.reference) refbisect_feed(B, en, in_, r.sw.tol_percent);
+            else brent_feed(S, en, in_, yn);
             pending = false;
         }
     }
@@ -489,32 +668,37 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
 // Persistent kernel, one WARP per bracket: the 32 lanes integrate the layer cooperatively
 // (core.cuh warp_transfer), so one evaluation has 1/32 of the latency.  Used when there are fewer
 // brackets than lanes to fill, where the lane-per-bracket kernel lasts as long as the sequential
-// evaluations of its slowest bracket.  The Brent state is replicated (uniform) across the warp.
+// evaluations of its slowest bracket.  The iteration state is replicated (uniform) across the warp.
 template <int KIND, int SCHEME>
 __global__ void __launch_bounds__(128) refine_warp_kernel(RefineArgs r) {
     extern __shared__ __align__(16) double stab[];
     stage_table(r.tab, stab, r.tab_doubles);
     const int lane = threadIdx.x & 31;
-    for (;;) {
-        int tq = 0;
-        if (lane == 0) tq = atomicAdd(r.counter, 1);
-        tq = __shfl_sync(0xffffffffu, tq, 0);
-        if (tq >= r.n_total) break;
-        int t, sl, mode;
-        double k;
-        Brent S;
-        if (!refine_pickup(r, tq, lane == 0, sl, t, mode, k, S)) continue;
-        while (brent_next(S)) {
-            double en, in_, yn;
-            eval_point<KIND, SCHEME, true>(r.M, stab, k, S.b, mode, en, in_, yn);
-            brent_feed(S, en, in_, yn);
+    const int n_total = r.sw.slot_begin[r.sw.n_slots];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (;;) {
+            int tq = 0;
+            if (lane == 0) tq = atomicAdd(r.counter + pass, 1);
+            tq = __shfl_sync(0xffffffffu, tq, 0);
+            if (tq >= n_total) break;
+            Pick P;
+            Brent S;
+            RefBisect B;
+            if (refine_pickup(r, tq, pass, lane == 0, P, S, B) == PICK_SKIP) continue;
+            for (;;) {
+                const bool more = P.reference ? refbisect_next(B) : brent_next(S);
+                if (!more) break;
+                double en, in_, yn;
+                eval_point<KIND, SCHEME, true>(r.M, stab, P.k, P.reference ? B.mid : S.b, P.mode, en, in_, yn);
+                if (P.reference) refbisect_feed(B, en, in_, r.sw.tol_percent);
+                else brent_feed(S, en, in_, yn);
+            }
+            if (lane == 0) refine_store(r, P, S, B);
         }
-        if (lane == 0) refine_store(r, sl, t, S);
     }
 }
 
 // ============================================================ host side ====
-#define ESB_MAX_MODES 4
 
 struct esb_context {
     int device = 0;
@@ -533,7 +717,7 @@ struct esb_context {
     // one packed device allocation per slot: [om | e | i] doubles then [bk | bw | acc | it] ints, each
     // `cap` long, so that the whole table moves in ONE copy; `pin` = page-locked host mirror
     struct RootBuf {
-        int *bk = nullptr, *bw = nullptr, *acc = nullptr, *it = nullptr;
+        int *bk = nullptr, *bw = nullptr, *acc = nullptr, *it = nullptr, *bw2 = nullptr;
         double *om = nullptr, *e = nullptr, *i = nullptr;
         void* base = nullptr;
         size_t cap = 0;
@@ -541,9 +725,16 @@ struct esb_context {
         void* pin = nullptr;
         size_t pin_cap = 0;
     } slots[ESB_MAX_MODES];
+    // queue heads: ints [0], [1] = the two passes of the refinement, bytes 8..15 = the scan's tile counter;
+    // d_slot_begin[ESB_MAX_MODES + 1] = first work index of every slot (written by scan_kernel), h_counts =
+    // its page-locked host copy
     int* d_counter = nullptr;
-    size_t cap_counter = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int* d_slot_begin = nullptr;
+    int* h_counts = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_counts = nullptr, ev_done = nullptr;
+    bool tables_pending = false;   // a sweep's refinement may still be running: consumers wait on ev_done
+    int n_sm = 148;
+    int accept_rule = ESB_ACCEPT_CONVERGED;
     bool timed = false;
     int64_t launches = 0;
     cudaStream_t user_stream = nullptr;
@@ -683,7 +874,13 @@ extern "C" int esb_create(int32_t device, esb_context** out) {
         return ESB_ERR_CUDA;
     }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_counter, 16) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_slot_begin, (ESB_MAX_MODES + 1) * sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->h_counts, (ESB_MAX_MODES + 1) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
         esb_destroy(c);
         return ESB_ERR_CUDA;
     }
@@ -694,9 +891,13 @@ extern "C" int esb_create(int32_t device, esb_context** out) {
 extern "C" int esb_destroy(esb_context* c) {
     if (!c) return ESB_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_den, c->d_rowcount, c->d_rowoff, c->d_counter};
+    void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_den, c->d_rowcount, c->d_rowoff, c->d_counter,
+                    c->d_slot_begin};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->ev_counts) cudaEventDestroy(c->ev_counts);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (auto& sl : c->slots) {
         if (sl.base) cudaFree(sl.base);
         if (sl.pin) cudaFreeHost(sl.pin);
@@ -761,95 +962,113 @@ extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* r
 }
 
 // ---- launches ---------------------------------------------------------------
+constexpr int TABLE_SMEM_MAX = 200 * 1024;       // model_host.h refuses larger tables
+constexpr int MAX_DEVICES = 64;
+
+// Function attributes are set once per (kernel instantiation, device): the staged table is read-only
+// broadcast data, so shared memory gets the whole carve-out and the dynamic limit is the table maximum.
+template <class K>
+static cudaError_t configure_once(K kernel, bool (&done)[MAX_DEVICES]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < MAX_DEVICES && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < MAX_DEVICES) done[dev] = true;
+    return cudaSuccess;
+}
+
 template <int KIND, int SCHEME, int NM>
-static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s) {
+static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s, int n_sm) {
     const size_t smem = (size_t)g.tab_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME, NM>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool done[MAX_DEVICES] = {};
+    cudaError_t e = configure_once(grid_kernel<KIND, SCHEME, NM>, done);
     if (e != cudaSuccess) return e;
-    // the table is read-only broadcast data: give shared memory the whole carve-out so that the
-    // resident-CTA count is limited by registers, not by the default L1/shared split
-    e = cudaFuncSetAttribute(grid_kernel<KIND, SCHEME, NM>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    e = cudaMemsetAsync(g.tile_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    dim3 block(128);
-    dim3 grid((g.nw + 127) / 128, g.nk < 65535 ? g.nk : 65535);
-    grid_kernel<KIND, SCHEME, NM><<<grid, block, smem, s>>>(g);
+    constexpr int threads = ESB_GRID_THREADS(SCHEME);
+    const long long n_tiles = (long long)g.nk * ((g.nw + 31) / 32);
+    long long blocks = (n_tiles + threads / 32 - 1) / (threads / 32);
+    // one CTA per SM; a grid with fewer tiles than warp slots spreads its tiles over all SMs
+    if (n_tiles >= n_sm) blocks = n_sm;
+    grid_kernel<KIND, SCHEME, NM><<<(int)blocks, threads, smem, s>>>(g);
     return cudaGetLastError();
 }
 
 constexpr size_t GRID_WARP_MAX_POINTS = 8192;     // (mode, k, omega) triples; above it one thread per point
 
 template <int KIND, int SCHEME>
-static cudaError_t launch_grid_warp(const GridArgs& g, cudaStream_t s) {
+static cudaError_t launch_grid_warp(const GridArgs& g, cudaStream_t s, int n_sm) {
     const size_t smem = (size_t)g.tab_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(grid_warp_kernel<KIND, SCHEME>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool done[MAX_DEVICES] = {};
+    cudaError_t e = configure_once(grid_warp_kernel<KIND, SCHEME>, done);
     if (e != cudaSuccess) return e;
     const size_t total = (size_t)g.nk * g.nw * g.n_modes;
     int blocks = (int)((total + 3) / 4);           // 4 warps = 4 points per CTA at a time
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > n_sm * 4) blocks = n_sm * 4;
     grid_warp_kernel<KIND, SCHEME><<<blocks, 128, smem, s>>>(g);
     return cudaGetLastError();
 }
 
 template <int KIND, int SCHEME>
-static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s) {
+static cudaError_t launch_grid(const GridArgs& g, cudaStream_t s, int n_sm) {
     if (g.schedule == 2 || (g.schedule == 0 && (size_t)g.nk * g.nw * g.n_modes <= GRID_WARP_MAX_POINTS))
-        return launch_grid_warp<KIND, SCHEME>(g, s);
+        return launch_grid_warp<KIND, SCHEME>(g, s, n_sm);
     switch (g.n_modes) {
-        case 1: return launch_grid_nm<KIND, SCHEME, 1>(g, s);
-        case 2: return launch_grid_nm<KIND, SCHEME, 2>(g, s);
-        case 3: return launch_grid_nm<KIND, SCHEME, 3>(g, s);
+        case 1: return launch_grid_nm<KIND, SCHEME, 1>(g, s, n_sm);
+        case 2: return launch_grid_nm<KIND, SCHEME, 2>(g, s, n_sm);
+        case 3: return launch_grid_nm<KIND, SCHEME, 3>(g, s, n_sm);
+        case 4: return launch_grid_nm<KIND, SCHEME, 4>(g, s, n_sm);
         default: return cudaErrorInvalidValue;
     }
 }
 
+// Persistent refinement launches: as many CTAs as are resident at once (n_total = host copy of the
+// bracket count, for the launch size only - the kernels read the count from the device).
 template <int KIND, int SCHEME, int MINB>
-static cudaError_t launch_refine_b(const RefineArgs& r, cudaStream_t s) {
+static cudaError_t launch_refine_b(const RefineArgs& r, cudaStream_t s, int n_total, int n_sm) {
     const size_t smem = (size_t)r.tab_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME, MINB>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(refine_kernel<KIND, SCHEME, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    static bool done[MAX_DEVICES] = {};
+    cudaError_t e = configure_once(refine_kernel<KIND, SCHEME, MINB>, done);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_kernel<KIND, SCHEME, MINB>, 128, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    int blocks = (r.n_total + 127) / 128;
-    const int cap = 148 * per_sm;      // persistent: as many CTAs as are resident at once
-    if (blocks > cap) blocks = cap;
+    int blocks = (n_total + 127) / 128;
+    if (blocks > n_sm * per_sm) blocks = n_sm * per_sm;
+    if (blocks < 1) blocks = 1;
     refine_kernel<KIND, SCHEME, MINB><<<blocks, 128, smem, s>>>(r);
     return cudaGetLastError();
 }
 
 template <int KIND, int SCHEME>
-static cudaError_t launch_refine_warp(const RefineArgs& r, cudaStream_t s) {
+static cudaError_t launch_refine_warp(const RefineArgs& r, cudaStream_t s, int n_total, int n_sm) {
     const size_t smem = (size_t)r.tab_doubles * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(refine_warp_kernel<KIND, SCHEME>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(refine_warp_kernel<KIND, SCHEME>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+    static bool done[MAX_DEVICES] = {};
+    cudaError_t e = configure_once(refine_warp_kernel<KIND, SCHEME>, done);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, refine_warp_kernel<KIND, SCHEME>, 128, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    int blocks = (r.n_total + 3) / 4;             // 4 warps = 4 brackets per CTA at a time
-    const int cap = 148 * per_sm;
-    if (blocks > cap) blocks = cap;
+    int blocks = (n_total + 3) / 4;               // 4 warps = 4 brackets per CTA at a time
+    if (blocks > n_sm * per_sm) blocks = n_sm * per_sm;
+    if (blocks < 1) blocks = 1;
     refine_warp_kernel<KIND, SCHEME><<<blocks, 128, smem, s>>>(r);
     return cudaGetLastError();
 }
 
-// 4 resident CTAs per SM: measured on the B200 (scripts/gpu_refine_time.py) - compiling the kernel
-// for 5..8 CTAs/SM spills the evaluation loop and is 5-30 % slower
+// Resident CTAs per SM the lane-per-bracket kernel is compiled for (ESB_REFINE_MINB): 4 for the
+// first-derivative schemes (5..8 spill the evaluation loop and are 5-30 % slower, round 1), 3 for the
+// normal-form scheme (no spills at <= 168 registers; brackets + refinement of the bench sweep 4.9 ms
+// against 5.2 ms at 4 and 5.0 ms at 2, scripts/gpu_variants.py)
 template <int KIND, int SCHEME>
-static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s) {
-    return launch_refine_b<KIND, SCHEME, ESB_REFINE_MINB(SCHEME)>(r, s);
+static cudaError_t launch_refine(const RefineArgs& r, cudaStream_t s, int n_total, int n_sm) {
+    return launch_refine_b<KIND, SCHEME, ESB_REFINE_MINB(SCHEME)>(r, s, n_total, n_sm);
 }
 
 // (kind, scheme) of the uploaded model -> template instantiation.  The rotational kind exists for
@@ -887,7 +1106,7 @@ static int check_mode(const esb_context* c, int mode) {
 }
 
 static int check_modes(const esb_context* c, int n_modes, const int32_t* modes) {
-    if (n_modes < 1 || n_modes > 3 || !modes) return -1;
+    if (n_modes < 1 || n_modes > ESB_MAX_MODES || !modes) return -1;
     for (int i = 0; i < n_modes; ++i)
         if (check_mode(c, modes[i])) return -1;
     return 0;
@@ -910,10 +1129,11 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
     for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
     g.ext = d_ext; g.intq = d_int; g.den = d_den;
     g.schedule = c->schedule;
+    g.tile_counter = reinterpret_cast<unsigned long long*>(c->d_counter + 2);
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
     const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
-        return launch_grid<decltype(kind)::value, decltype(scheme)::value>(g, s);
+        return launch_grid<decltype(kind)::value, decltype(scheme)::value>(g, s, c->n_sm);
     });
     CUDA_TRY(c, e);
     CUDA_TRY(c, cudaEventRecord(c->ev1, s));
@@ -932,37 +1152,42 @@ extern "C" int esb_dispersion_grid_dev(esb_context* c, int32_t mode, const doubl
                           stream ? (cudaStream_t)stream : cur_stream(c));
 }
 
-static int bracket_segments(int nw) { return (nw - 1 + BRACKET_SEG - 1) / BRACKET_SEG > 0 ? (nw - 1 + BRACKET_SEG - 1) / BRACKET_SEG : 1; }
+static int bracket_segments(int nw) {
+    const int n = (nw - 1 + BRACKET_SEG - 1) / BRACKET_SEG;
+    return n > 0 ? n : 1;
+}
 
-// count pass + scan: segment offsets in c->d_rowoff [nk*nseg + 1], total copied to the host (one sync)
-static int brackets_count(esb_context* c, const double* d_ext, const double* d_int, int nk, int nw,
-                          cudaStream_t s, int* total) {
-    const int nseg = bracket_segments(nw);
-    const size_t items = (size_t)nk * nseg;
+// count pass + scan over all slots of `sw` (segment offsets in c->d_rowoff, slot_begin in c->d_slot_begin),
+// then the asynchronous copy of slot_begin[] to the page-locked c->h_counts, marked by c->ev_counts
+static int brackets_count(esb_context* c, SweepDev& sw, cudaStream_t s) {
+    const bool ref = sw.rule == ESB_ACCEPT_REFERENCE;
+    sw.nseg = ref ? 1 : bracket_segments(sw.nw);
+    const size_t per_slot = (size_t)sw.nk * sw.nseg, items = per_slot * sw.n_slots;
     int rc;
     if ((rc = ensure(c, c->d_rowcount, c->cap_rows, items + 1))) return rc;
     if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, items + 1))) return rc;
+    sw.seg_count = c->d_rowcount;
+    sw.seg_offset = c->d_rowoff;
+    sw.slot_begin = c->d_slot_begin;
     const int threads = 128, per_block = threads / 32;
     const int blocks = (int)((items + per_block - 1) / per_block);
-    bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, nseg, c->d_rowcount, nullptr, nullptr,
-                                              nullptr, 0, 0);
+    if (ref) bracket_reference_kernel<<<blocks, threads, 0, s>>>(sw, 0);
+    else bracket_kernel<<<blocks, threads, 0, s>>>(sw, 0);
     CUDA_TRY(c, cudaGetLastError());
-    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, c->d_rowoff, (int)items);
+    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, c->d_rowoff, (int)items, (int)per_slot, c->d_slot_begin);
     CUDA_TRY(c, cudaGetLastError());
     c->launches += 2;
-    CUDA_TRY(c, cudaMemcpyAsync(total, c->d_rowoff + items, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(c, cudaStreamSynchronize(s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counts, c->d_slot_begin, (sw.n_slots + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaEventRecord(c->ev_counts, s));
     return ESB_OK;
 }
 
-static int brackets_fill(esb_context* c, const double* d_ext, const double* d_int, int nk, int nw,
-                         int* d_bk, int* d_bw, int capacity, cudaStream_t s) {
-    const int nseg = bracket_segments(nw);
-    const size_t items = (size_t)nk * nseg;
+static int brackets_fill(esb_context* c, const SweepDev& sw, cudaStream_t s) {
+    const size_t items = (size_t)sw.nk * sw.nseg * sw.n_slots;
     const int threads = 128, per_block = threads / 32;
     const int blocks = (int)((items + per_block - 1) / per_block);
-    bracket_kernel<<<blocks, threads, 0, s>>>(d_ext, d_int, nk, nw, nseg, c->d_rowcount, c->d_rowoff, d_bk,
-                                              d_bw, capacity, 1);
+    if (sw.rule == ESB_ACCEPT_REFERENCE) bracket_reference_kernel<<<blocks, threads, 0, s>>>(sw, 1);
+    else bracket_kernel<<<blocks, threads, 0, s>>>(sw, 1);
     CUDA_TRY(c, cudaGetLastError());
     c->launches += 1;
     return ESB_OK;
@@ -974,14 +1199,22 @@ extern "C" int esb_brackets_dev(esb_context* c, const double* d_ext, const doubl
     if (!c || !d_ext || !d_int || !d_row_offset || nk <= 0 || nw <= 0) return ESB_ERR_ARG;
     cudaStream_t s = stream ? (cudaStream_t)stream : (c->use_user_stream ? c->user_stream : c->stream);
     CUDA_TRY(c, cudaSetDevice(c->device));
-    int total = 0, rc;
-    if ((rc = brackets_count(c, d_ext, d_int, nk, nw, s, &total))) return rc;
-    row_offset_kernel<<<(nk + 1 + 255) / 256, 256, 0, s>>>(c->d_rowoff, nk, bracket_segments(nw), d_row_offset);
+    SweepDev sw{};
+    sw.n_slots = 1; sw.nk = nk; sw.nw = nw;
+    sw.rule = ESB_ACCEPT_CONVERGED;
+    sw.slot[0].gext = d_ext; sw.slot[0].gint = d_int;
+    sw.slot[0].bk = d_bk; sw.slot[0].bw = d_bw; sw.slot[0].bw2 = nullptr;
+    sw.slot[0].capacity = (d_bk && d_bw && capacity > 0) ? capacity : 0;
+    int rc;
+    if ((rc = brackets_count(c, sw, s))) return rc;
+    row_offset_kernel<<<(nk + 1 + 255) / 256, 256, 0, s>>>(c->d_rowoff, nk, sw.nseg, d_row_offset);
     CUDA_TRY(c, cudaGetLastError());
     c->launches += 1;
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_counts));
+    const int total = c->h_counts[1];
     if (n_host) *n_host = total;
-    if (d_bk && d_bw && capacity > 0 && total > 0)
-        if ((rc = brackets_fill(c, d_ext, d_int, nk, nw, d_bk, d_bw, capacity, s))) return rc;
+    if (sw.slot[0].capacity > 0 && total > 0)
+        if ((rc = brackets_fill(c, sw, s))) return rc;
     return total > capacity && d_bk ? ESB_ERR_CAPACITY : ESB_OK;
 }
 
@@ -1059,7 +1292,7 @@ extern "C" int esb_upload_axes(esb_context* c, const double* k, int32_t nk, cons
     return ESB_OK;
 }
 
-static size_t slot_bytes(size_t cap) { return cap * (3 * sizeof(double) + 4 * sizeof(int)); }
+static size_t slot_bytes(size_t cap) { return cap * (3 * sizeof(double) + 5 * sizeof(int)); }
 
 static void slot_carve(esb_context::RootBuf& sl, void* base, size_t cap, esb_roots* out) {
     double* d = (double*)base;
@@ -1069,12 +1302,12 @@ static void slot_carve(esb_context::RootBuf& sl, void* base, size_t cap, esb_roo
         out->k_index = q; out->w_index = q + cap; out->accepted = q + 2 * cap; out->iterations = q + 3 * cap;
     } else {
         sl.om = d; sl.e = d + cap; sl.i = d + 2 * cap;
-        sl.bk = q; sl.bw = q + cap; sl.acc = q + 2 * cap; sl.it = q + 3 * cap;
+        sl.bk = q; sl.bw = q + cap; sl.acc = q + 2 * cap; sl.it = q + 3 * cap; sl.bw2 = q + 4 * cap;
     }
 }
 
 static int ensure_slot(esb_context* c, esb_context::RootBuf& sl, size_t total) {
-    if (sl.cap >= total) return ESB_OK;
+    if (sl.cap >= total && sl.base) return ESB_OK;
     if (sl.base) cudaFree(sl.base);
     void* pin = sl.pin;
     const size_t pin_cap = sl.pin_cap;
@@ -1088,9 +1321,24 @@ static int ensure_slot(esb_context* c, esb_context::RootBuf& sl, size_t total) {
     return ESB_OK;
 }
 
-// scan (ONE fused launch for all modes) -> per mode: brackets -> refinement, on the axes
-// already resident in HBM; the root tables stay on the device, one slot per mode
-// (esb_download_roots_slot / esb_roots_device copy them out).
+static void slots_to_dev(esb_context* c, SweepDev& sw, int n_modes, const int32_t* modes, size_t plane) {
+    for (int m = 0; m < n_modes; ++m) {
+        esb_context::RootBuf& sl = c->slots[m];
+        SlotDev& q = sw.slot[m];
+        q.gext = c->d_ext + m * plane; q.gint = c->d_int + m * plane; q.gden = c->d_den + m * plane;
+        q.bk = sl.bk; q.bw = sl.bw; q.bw2 = sl.bw2;
+        q.omega = sl.om; q.ext = sl.e; q.intq = sl.i; q.accepted = sl.acc; q.iters = sl.it;
+        q.mode = modes[m];
+        q.capacity = (int)sl.cap;
+    }
+}
+
+// scan (ONE fused launch for all modes) -> brackets of all modes (one count, one scan, one fill
+// launch) -> refinement of all of them (one persistent launch), on the axes already resident in HBM.
+// The root tables stay on the device, one slot per mode (esb_download_roots_slot / esb_roots_pinned /
+// esb_roots_device hand them out).  One host wait per sweep: the per-slot bracket counts, copied to
+// page-locked memory while the fill pass runs; the refinement is still in flight when the call returns
+// (every table accessor orders itself after it).
 extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const int32_t* modes,
                                         double tol_percent, int32_t* n_roots, int32_t* n_brackets) {
     if (!c) return ESB_ERR_ARG;
@@ -1102,47 +1350,50 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     cudaStream_t s = cur_stream(c);
     int rc;
     const size_t plane = (size_t)nk * nw;
+    for (int m = 0; m < ESB_MAX_MODES; ++m) c->slots[m].n = 0;      // slots of an earlier, wider sweep are void
     if ((rc = ensure_grid(c, plane * n_modes))) return rc;
     if ((rc = ensure(c, c->d_den, c->cap_den, plane * n_modes))) return rc;
     if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s,
                              c->d_den)))
         return rc;
-    if ((rc = ensure(c, c->d_counter, c->cap_counter, (size_t)ESB_MAX_MODES))) return rc;
-    CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, ESB_MAX_MODES * sizeof(int), s));
-    RefineArgs r;
-    r.M = c->dm;
-    r.tab = c->d_tab;
-    r.tab_doubles = c->tab_doubles;
-    r.k = c->d_k; r.w = c->d_w; r.nk = nk; r.nw = nw; r.layout = layout;
-    r.n_slots = 0;
-    r.n_total = 0;
-    r.counter = c->d_counter;
-    r.tol_percent = tol_percent;
+    // first sweep of a context: room for one bracket per 64 grid points (grown on demand below)
+    for (int m = 0; m < n_modes; ++m)
+        if (!c->slots[m].base && (rc = ensure_slot(c, c->slots[m], std::max<size_t>(1024, plane / 64)))) return rc;
+    SweepDev sw{};
+    sw.n_slots = n_modes; sw.nk = nk; sw.nw = nw;
+    sw.rule = c->accept_rule;
+    sw.tol_percent = tol_percent;
+    slots_to_dev(c, sw, n_modes, modes, plane);
+    if ((rc = brackets_count(c, sw, s))) return rc;
+    if ((rc = brackets_fill(c, sw, s))) return rc;                  // runs while the host waits for the counts
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_counts));
+    int n_total = c->h_counts[n_modes];
+    bool grown = false;
     for (int m = 0; m < n_modes; ++m) {
-        esb_context::RootBuf& sl = c->slots[m];
-        const double* gext = c->d_ext + m * plane;
-        const double* gint = c->d_int + m * plane;
-        const double* gden = c->d_den + m * plane;
-        // pass 1: count (one 4-byte D2H + sync: buffer sizes and the refine launch need the count)
-        int total = 0;
-        if ((rc = brackets_count(c, gext, gint, nk, nw, s, &total))) return rc;
-        sl.n = 0;
+        const int total = c->h_counts[m + 1] - c->h_counts[m];
         if (n_brackets) n_brackets[m] = total;
         if (n_roots) n_roots[m] = total;
-        if (total == 0) continue;
-        if ((rc = ensure_slot(c, sl, (size_t)total))) return rc;
-        sl.n = total;
-        // pass 2: fill (sorted by row, then omega index)
-        if ((rc = brackets_fill(c, gext, gint, nk, nw, sl.bk, sl.bw, total, s))) return rc;
-        RefineSlot& q = r.slot[r.n_slots++];
-        q.gext = gext; q.gint = gint; q.gden = gden; q.bk = sl.bk; q.bw = sl.bw;
-        q.omega = sl.om; q.ext = sl.e; q.intq = sl.i; q.accepted = sl.acc; q.iters = sl.it;
-        q.mode = modes[m];
-        q.begin = r.n_total;
-        r.n_total += total;
+        if ((size_t)total > c->slots[m].cap) {
+            if (!grown) CUDA_TRY(c, cudaStreamSynchronize(s));       // the fill pass still writes the old buffers
+            grown = true;
+            if ((rc = ensure_slot(c, c->slots[m], (size_t)total))) return rc;
+        }
+        c->slots[m].n = total;
     }
-    if (r.n_total > 0) {
-        // ONE persistent launch refines the brackets of every mode (single work queue)
+    if (grown) {                                                    // rare: a table outgrew its slot
+        slots_to_dev(c, sw, n_modes, modes, plane);
+        if ((rc = brackets_fill(c, sw, s))) return rc;
+    }
+    if (n_total > 0) {
+        CUDA_TRY(c, cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(int), s));
+        RefineArgs r;
+        r.M = c->dm;
+        r.tab = c->d_tab;
+        r.tab_doubles = c->tab_doubles;
+        r.k = c->d_k; r.w = c->d_w; r.layout = layout;
+        r.sw = sw;
+        r.counter = c->d_counter;
+        // ONE persistent launch refines the brackets of every mode (single work queue):
         // one warp per bracket (1/32 of the evaluation latency) or one lane per bracket.  Measured
         // crossovers (scripts/gpu_refine_modes.py, profiles/r01o_refine_modes.log): the cylinder
         // second-order kinds integrate ONE solution per lane but two per warp lane, so the warp kernel
@@ -1152,14 +1403,17 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         const int kind = c->dm.kind;
         const int limit = (kind == KIND_CYL_DENSITY || kind == KIND_CYL_FLOW) ? 24000
                           : kind == KIND_CYL_ROTATION ? 100000 : 250000;
-        const bool warp_path = c->schedule == 2 || (c->schedule == 0 && r.n_total <= limit);
+        const bool warp_path = c->schedule == 2 || (c->schedule == 0 && n_total <= limit);
         const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
-            if (warp_path) return launch_refine_warp<decltype(kind)::value, decltype(scheme)::value>(r, s);
-            return launch_refine<decltype(kind)::value, decltype(scheme)::value>(r, s);
+            if (warp_path)
+                return launch_refine_warp<decltype(kind)::value, decltype(scheme)::value>(r, s, n_total, c->n_sm);
+            return launch_refine<decltype(kind)::value, decltype(scheme)::value>(r, s, n_total, c->n_sm);
         });
         CUDA_TRY(c, e);
         c->launches += 1;
     }
+    CUDA_TRY(c, cudaEventRecord(c->ev_done, s));
+    c->tables_pending = true;
     return ESB_OK;
 }
 
@@ -1175,6 +1429,7 @@ extern "C" int esb_download_roots_slot(esb_context* c, int32_t slot, esb_roots* 
     if ((int64_t)nb > (int64_t)max_roots) return fail(c, ESB_ERR_CAPACITY, "max_roots too small");
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t s = cur_stream(c);
+    if (c->tables_pending) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_done, 0));
     if (nb) {
         if (out->k_index) CUDA_TRY(c, cudaMemcpyAsync(out->k_index, sl.bk, nb * 4, cudaMemcpyDeviceToHost, s));
         if (out->w_index) CUDA_TRY(c, cudaMemcpyAsync(out->w_index, sl.bw, nb * 4, cudaMemcpyDeviceToHost, s));
@@ -1206,6 +1461,7 @@ extern "C" int esb_roots_pinned(esb_context* c, int32_t slot, esb_roots* out, in
     esb_roots h;
     slot_carve(sl, sl.pin, sl.pin_cap, &h);
     cudaStream_t s = cur_stream(c);
+    if (c->tables_pending) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_done, 0));
     const size_t nb = (size_t)sl.n;
     CUDA_TRY(c, cudaMemcpyAsync(h.omega, sl.om, nb * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(c, cudaMemcpyAsync(h.ext, sl.e, nb * 8, cudaMemcpyDeviceToHost, s));
@@ -1229,6 +1485,28 @@ extern "C" int esb_roots_device(esb_context* c, int32_t slot, esb_roots* out, in
     out->k_index = sl.bk; out->w_index = sl.bw; out->omega = sl.om; out->ext = sl.e;
     out->intq = sl.i; out->accepted = sl.acc; out->iterations = sl.it;
     if (n_roots) *n_roots = sl.n;
+    return ESB_OK;
+}
+
+// The sweep returns with its refinement still in flight.  stream = a cudaStream_t that will read the
+// tables handed out by esb_roots_device: it is made to wait (on the device) for the sweep; NULL: the
+// calling host thread waits instead.
+extern "C" int esb_tables_wait(esb_context* c, void* stream) {
+    if (!c) return ESB_ERR_ARG;
+    if (!c->tables_pending) return ESB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (stream) {
+        CUDA_TRY(c, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_done, 0));
+    } else {
+        CUDA_TRY(c, cudaEventSynchronize(c->ev_done));
+        c->tables_pending = false;
+    }
+    return ESB_OK;
+}
+
+extern "C" int esb_set_accept_rule(esb_context* c, int32_t rule) {
+    if (!c || (rule != ESB_ACCEPT_CONVERGED && rule != ESB_ACCEPT_REFERENCE)) return ESB_ERR_ARG;
+    c->accept_rule = rule;
     return ESB_OK;
 }
 

@@ -73,6 +73,16 @@ def gather_root_tables(k_index, omega, accepted, k_offset, device=None, group=No
     return allp[:, 0].astype(np.int64), allp[:, 1].copy(), allp[:, 2].astype(np.int32)
 
 
+def _consumer_stream(device):
+    """cudaStream_t of torch's current stream on `device` (None on a CPU device: the call blocks)."""
+    import torch
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return None
+    # the legacy default stream has handle 0, which esb_tables_wait reads as "block the host"
+    return torch.cuda.current_stream(dev).cuda_stream or None
+
+
 class _DevArray:
     """Zero-copy view of library-owned device memory for torch.as_tensor (CUDA array interface)."""
 
@@ -95,7 +105,8 @@ def gather_root_tables_device(solver, slot, k_offset, device, group=None, k_stri
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    info = solver.roots_device(slot)
+    # torch reads the library's buffers on its current stream: order that stream after the sweep
+    info = solver.roots_device(slot, stream=_consumer_stream(device))
     n = info["n"]
     cols = 2 if accepted_only else 3
     if n:
@@ -139,8 +150,9 @@ def gather_modes_device(solver, n_slots, k_offset, device, group=None, k_stride=
 
     world = dist.get_world_size(group)
     gks, oms, acs, sls = [], [], [], []
+    stream = _consumer_stream(device)
     for slot in range(n_slots):
-        info = solver.roots_device(slot)
+        info = solver.roots_device(slot, stream=stream)
         n = info["n"]
         if not n:
             continue

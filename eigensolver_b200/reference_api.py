@@ -132,11 +132,11 @@ class ReferenceScript:
     """One reference solver script: its equilibrium, profile and settings, on the GPU.
 
     `script` is a key of SCRIPTS (for the two density kinds the plain kind name, as before).
-    Overrides: medium=, profile=, width= (Gaussian profiles), tol=, and any DispersionSolver
-    keyword (n_steps, scheme, coordinate, ext_wavelengths, s_end, device ...)."""
+    Overrides: medium=, profile=, width= (Gaussian profiles), tol=, rule= ("reference" | "converged"),
+    and any DispersionSolver keyword (n_steps, scheme, coordinate, ext_wavelengths, s_end, device ...)."""
 
     def __init__(self, script="cylinder_density", medium=None, width=None, x0=0.0, tol=None, device=0,
-                 profile=None, accept=None, kind=None, **solver_kw):
+                 profile=None, accept=None, kind=None, rule="reference", **solver_kw):
         if kind is not None:            # older spelling: ReferenceScript(kind="slab_density")
             script = kind
         if script not in SCRIPTS:
@@ -157,6 +157,14 @@ class ReferenceScript:
         kw = dict(spec.get("solver", {}))
         kw.update(solver_kw)
         self.solver = DispersionSolver(self.kind, self.medium, profile, device=device, **kw)
+        # rule="reference": the script's own scan / bisection rule, point for point (the point sets its
+        # pickles hold); "converged": one machine-precision root per sign change
+        self.rule = rule
+        if self.accept == "ext" and rule == "reference":
+            # ..._kink_slow.py divides the mismatch by |xi_e| alone (:586): the library's reference rule uses
+            # max(|ext|, |int|); that script is served by the converged rule + its own test in _modes_of
+            self.rule = "converged"
+        self.solver.set_accept_rule(self.rule)
 
     # -- the reference's worker signature -------------------------------
     def _modes_of(self, tab):

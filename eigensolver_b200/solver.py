@@ -473,8 +473,9 @@ class DispersionSolver:
         return n.value, nb.value
 
     def sweep_resident_multi(self, modes, tol_percent=1.0):
-        """One fused scan for all `modes`, then brackets + refinement per mode.  Returns the
-        per-mode root counts; table m stays on the device in slot m."""
+        """One fused scan for all `modes` (up to 4), then the brackets and the refinement of all of them
+        in single launches.  Returns the per-mode table sizes; table m stays on the device in slot m
+        (the refinement may still be running: every accessor orders itself after it)."""
         md = np.array([self._mode(m) for m in modes], dtype=np.int32)
         n = np.zeros(md.size, np.int32)
         nb = np.zeros(md.size, np.int32)
@@ -482,6 +483,15 @@ class DispersionSolver:
                 self.lib.esb_sweep_resident_multi(self.ctx, md.size, _iptr(md), float(tol_percent), _iptr(n),
                                                   _iptr(nb)), "esb_sweep_resident_multi")
         return [int(x) for x in n]
+
+    def set_accept_rule(self, rule):
+        """"converged" (default): adjacent-point brackets refined to machine precision, one entry per
+        bracket; "reference": the scripts' own scan / bisection rule point for point (header:
+        esb_accept_rule) - what their pickles hold."""
+        L.check(self.lib, self.ctx,
+                self.lib.esb_set_accept_rule(self.ctx, {"converged": L.ACCEPT_CONVERGED,
+                                                        "reference": L.ACCEPT_REFERENCE}[rule]),
+                "esb_set_accept_rule")
 
     def find_roots_multi(self, modes, k, w, layout="phase_speed", tol_percent=1.0, pinned=False):
         """Host arrays in, one RootTable per mode out (one fused scan).  pinned=True: the tables are
@@ -517,9 +527,14 @@ class DispersionSolver:
                 "esb_download_roots_slot")
         return RootTable(ki, wi, self._k_host, om, ex, iq, ac, it, n)
 
-    def roots_device(self, slot=0):
+    def roots_device(self, slot=0, stream=None):
         """Device pointers of the root table of mode slot `slot` (valid until the next sweep):
-        dict name -> (pointer, numpy dtype string), plus 'n'.  Used for device-side gathers."""
+        dict name -> (pointer, numpy dtype string), plus 'n'.  Used for device-side gathers.
+        stream: the cudaStream_t (integer) that will read them - it is made to wait for the sweep on the
+        device; None: this call blocks until the tables are complete (esb_tables_wait)."""
+        L.check(self.lib, self.ctx,
+                self.lib.esb_tables_wait(self.ctx, C.c_void_p(int(stream)) if stream else None),
+                "esb_tables_wait")
         out = L.esb_roots()
         n = C.c_int32(0)
         L.check(self.lib, self.ctx, self.lib.esb_roots_device(self.ctx, int(slot), C.byref(out), C.byref(n)),

@@ -36,7 +36,8 @@ extern "C" {
 #endif
 
 #define ESB_VERSION 120   /* 1.1: esb_model grew the mesh_* fields; pinned tables, schedules
-                             1.2: ESB_RK8N (normal-form Nystrom scheme, needs the profile's second derivative) */
+                             1.2: ESB_RK8N (normal-form Nystrom scheme, needs the profile's second derivative);
+                                  up to 4 fused modes; esb_set_accept_rule; esb_tables_wait */
 
 typedef struct esb_context esb_context;
 
@@ -172,15 +173,38 @@ int esb_find_roots(esb_context* ctx, int32_t mode, const double* k, int32_t nk, 
  *   esb_upload_axes     H2D copy of k[] and w[] into context-owned buffers
  *   esb_sweep_resident  grid -> brackets -> refinement, root table left on the device
  *   esb_download_roots  D2H copy of the root table (synchronises the stream)
- *   esb_roots_device    device pointers of the root table (valid until the next sweep) */
+ *   esb_roots_device    device pointers of the root table (valid until the next sweep; see esb_tables_wait) */
 int esb_upload_axes(esb_context* ctx, const double* k, int32_t nk, const double* w, int32_t nw,
                     int32_t omega_layout);
 int esb_sweep_resident(esb_context* ctx, int32_t mode, double tol_percent, int32_t* n_roots,
                        int32_t* n_brackets);
 int esb_download_roots(esb_context* ctx, esb_roots* out, int32_t max_roots);
 int esb_roots_device(esb_context* ctx, int32_t slot, esb_roots* out, int32_t* n_roots);
+/* A sweep returns with its refinement still in flight on the context's stream.  The download calls order
+ * themselves after it; a consumer of esb_roots_device pointers calls esb_tables_wait first: `stream` (a
+ * cudaStream_t) is made to wait on the device, NULL blocks the calling host thread until the tables are
+ * complete. */
+int esb_tables_wait(esb_context* ctx, void* stream);
 
-/* Several modes in ONE fused scan (n_modes <= 3): cylinder orders share the staged
+/* What a sweep reports (esb_set_accept_rule; default ESB_ACCEPT_CONVERGED).
+ *   ESB_ACCEPT_CONVERGED  sign changes of D between ADJACENT evaluated grid points, every bracket refined to
+ *                         2 eps |omega| (Brent on the pole-free G = D Y), accepted = the reference's test
+ *                         at the converged root.  One entry per bracket.
+ *   ESB_ACCEPT_REFERENCE  the scripts' own rule, point for point (Density_cylinder.py:803-821 and
+ *                         locate_kink :548-686): walking the evaluated points of a row in order, (i) a grid
+ *                         point whose mismatch is below tol_percent is a solution as it stands (w_index ==
+ *                         its index, iterations 0) and restarts the count of points seen; (ii) a sign change
+ *                         against the previous EVALUATED point (skipped m_e < 0 points in between do not
+ *                         matter) is bisected only if more than two points have been seen since the last
+ *                         restart; (iii) the bisection evaluates the middle of the pair, takes the first
+ *                         point inside the band as THE solution (no further refinement) and otherwise
+ *                         follows a sign change in the UPPER half only, as the scripts' recursion does
+ *                         (accepted = 0 where it gives up).  This reproduces the point sets the scripts
+ *                         pickle; omega is then a dyadic point of the frequency grid, not a converged root. */
+enum esb_accept_rule { ESB_ACCEPT_CONVERGED = 0, ESB_ACCEPT_REFERENCE = 1 };
+int esb_set_accept_rule(esb_context* ctx, int32_t rule);
+
+/* Several modes in ONE fused scan (n_modes <= 4): cylinder orders share the staged
  * coefficient evaluation and the Bessel sets, the slab's sausage and kink share the whole
  * integration.  Grids are mode-slot major: ext[(slot*nk + i)*nw + j].  The sweep keeps one
  * root table per mode slot on the device. */
