@@ -17,7 +17,7 @@ SLAB_DENSITY, CYLINDER_DENSITY, SLAB_FLOW, CYLINDER_ROTATION, CYLINDER_FLOW = 0,
 RK4, RK8, RK8N = 0, 1, 2
 OMEGA_SHARED, OMEGA_PHASE_SPEED, OMEGA_PER_K = 0, 1, 2
 MESH_CLUSTERED, MESH_UNIFORM, MESH_GRADED = 0, 1, 2
-ACCEPT_CONVERGED, ACCEPT_REFERENCE = 0, 1
+ACCEPT_CONVERGED, ACCEPT_REFERENCE, ACCEPT_REFERENCE_SLAB = 0, 1, 2
 
 
 class EsbError(RuntimeError):
@@ -42,6 +42,16 @@ class esb_roots(C.Structure):
         ("omega", C.POINTER(C.c_double)), ("ext", C.POINTER(C.c_double)),
         ("intq", C.POINTER(C.c_double)), ("accepted", C.POINTER(C.c_int32)),
         ("iterations", C.POINTER(C.c_int32)),
+    ]
+
+
+class esb_scan_result(C.Structure):
+    _fields_ = [
+        ("n_entries", C.c_int32),
+        ("model", C.POINTER(C.c_int32)), ("slot", C.POINTER(C.c_int32)), ("k_index", C.POINTER(C.c_int32)),
+        ("w_index", C.POINTER(C.c_int32)), ("accepted", C.POINTER(C.c_int32)),
+        ("iterations", C.POINTER(C.c_int32)),
+        ("omega", C.POINTER(C.c_double)), ("ext", C.POINTER(C.c_double)), ("intq", C.POINTER(C.c_double)),
     ]
 
 
@@ -78,6 +88,8 @@ SYMBOLS = {
                                             _dp, _dp]),
     "esb_sweep_resident_multi": (C.c_int, [_ctx, C.c_int32, _ip, C.c_double, _ip, _ip]),
     "esb_download_roots_slot": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), C.c_int32]),
+    "esb_scan_models": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_model), C.POINTER(_dp), C.c_int32, C.c_int32, _dp,
+                                  C.c_int32, _ip, C.c_double, C.c_int32, _ip, C.POINTER(esb_scan_result)]),
     "esb_roots_pinned": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), _ip]),
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "esb_tables_wait": (C.c_int, [_ctx, C.c_void_p]),

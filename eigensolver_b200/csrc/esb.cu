@@ -247,6 +247,9 @@ __global__ void bracket_reference_kernel(SweepDev sw, int fill) {
     const double* e = S.gext + (size_t)row * sw.nw;
     const double* q = S.gint + (size_t)row * sw.nw;
     const int base = fill ? sw.seg_offset[item] - sw.slot_begin[sl] : 0;
+    // the cylinder scripts bisect after MORE THAN TWO points seen (Density_cylinder.py:815), the slab ones
+    // after more than one (..._coronal.py:614)
+    const int min_seen = sw.rule == ESB_ACCEPT_REFERENCE_SLAB ? 1 : 2;
     int count = 0, seen = 0, prev_j = -1;
     double prev_d = 0.0;                     // xi_diff_check = [0]: the first product is with 0
     for (int j0 = 0; j0 < sw.nw; j0 += 32) {
@@ -272,7 +275,7 @@ __global__ void bracket_reference_kernel(SweepDev sw, int fill) {
             if ((accept_m >> b) & 1u) {
                 lo = hi = jj;                                    // a solution as it stands
                 seen = 0;
-            } else if (sgn * psgn < 0 && seen > 2) {
+            } else if (sgn * psgn < 0 && seen > min_seen) {
                 lo = prev_j; hi = jj;
                 seen = 0;
             }
@@ -503,7 +506,8 @@ __device__ __forceinline__ void brent_feed(Brent& S, double en, double in_, doub
 // drop-in reproduces it.  lo and hi were evaluated by the caller and are outside the band: one new
 // evaluation (the middle) per level.
 struct RefBisect {
-    double a, b, db;        // bracket, D at its upper end
+    double a, b, da, db;    // bracket, D at its ends
+    bool both_halves;       // the slab scripts test the lower half too (len(loop_ws) > 1, ..._coronal.py:510)
     double mid, em, im;     // last trial and (ext, int) there
     int level;
     bool found;
@@ -521,8 +525,11 @@ __device__ __forceinline__ void refbisect_feed(RefBisect& S, double en, double i
     const double dm = en - in_;
     if (mismatch_pct(en, in_) < tol_percent) {
         S.found = true;
+    } else if (S.both_halves && isfinite(dm) && dm * S.da < 0.0) {
+        S.b = S.mid; S.db = dm;
+        ++S.level;
     } else if (isfinite(dm) && dm * S.db < 0.0) {
-        S.a = S.mid;
+        S.a = S.mid; S.da = dm;
         ++S.level;
     } else {
         S.level = -1 - S.level;             // not followed: the reference stops here without a solution
@@ -559,7 +566,7 @@ __device__ __forceinline__ int refine_pickup(const RefineArgs& r, int tq, int pa
     P.t = tq - sw.slot_begin[P.sl];
     if (P.t >= L.capacity) return PICK_SKIP;
     P.mode = L.mode;
-    P.reference = sw.rule == ESB_ACCEPT_REFERENCE;
+    P.reference = sw.rule != ESB_ACCEPT_CONVERGED;
     const int ik = L.bk[P.t], jlo = L.bw[P.t], jhi = L.bw2[P.t];
     P.k = r.k[ik];
     const size_t o = (size_t)ik * sw.nw + jlo, o2 = (size_t)ik * sw.nw + jhi;
@@ -574,7 +581,8 @@ __device__ __forceinline__ int refine_pickup(const RefineArgs& r, int tq, int pa
     const double b = omega_at(r.k, r.w, r.layout, sw.nw, ik, jhi);
     if (P.reference) {
         if (pass != 0) return PICK_SKIP;
-        B.a = a; B.b = b; B.db = L.gext[o2] - L.gint[o2];
+        B.a = a; B.b = b; B.da = L.gext[o] - L.gint[o]; B.db = L.gext[o2] - L.gint[o2];
+        B.both_halves = sw.rule == ESB_ACCEPT_REFERENCE_SLAB;
         B.mid = b; B.em = L.gext[o2]; B.im = L.gint[o2];
         B.level = 0; B.found = false;
         return PICK_WORK;
@@ -698,6 +706,44 @@ __global__ void __launch_bounds__(128) refine_warp_kernel(RefineArgs r) {
     }
 }
 
+// ---- parameter scans: tables of many equilibria compacted into one ------------------------------
+struct ScanOut {
+    int *model, *slot, *k_index, *w_index, *accepted, *iters;
+    double *omega, *ext, *intq;
+};
+
+// counts[t] = entries stored for table t = (model, slot): min(brackets found, capacity)
+__global__ void scan_counts_kernel(const int* __restrict__ slot_begin_all, int n_models, int n_modes, int cap,
+                                   int* __restrict__ counts, int* __restrict__ found) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_models * n_modes) return;
+    const int i = t / n_modes, m = t - i * n_modes;
+    const int* sb = slot_begin_all + (size_t)i * (ESB_MAX_MODES + 1);
+    const int n = sb[m + 1] - sb[m];
+    found[t] = n;
+    counts[t] = n < cap ? n : cap;
+}
+
+// one CTA per table: its entries to their place in the compact table
+__global__ void scan_compact_kernel(const char* __restrict__ base, size_t table_bytes, int cap, int n_modes,
+                                    const int* __restrict__ counts, const int* __restrict__ offsets, ScanOut out) {
+    const int t = blockIdx.x;
+    const int n = counts[t], o = offsets[t];
+    const double* d = reinterpret_cast<const double*>(base + (size_t)t * table_bytes);
+    const int* q = reinterpret_cast<const int*>(d + 3 * (size_t)cap);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        out.omega[o + j] = d[j];
+        out.ext[o + j] = d[cap + j];
+        out.intq[o + j] = d[2 * (size_t)cap + j];
+        out.k_index[o + j] = q[j];
+        out.w_index[o + j] = q[cap + j];
+        out.accepted[o + j] = q[2 * (size_t)cap + j];
+        out.iters[o + j] = q[3 * (size_t)cap + j];
+        out.model[o + j] = t / n_modes;
+        out.slot[o + j] = t - (t / n_modes) * n_modes;
+    }
+}
+
 // ============================================================ host side ====
 
 struct esb_context {
@@ -732,6 +778,19 @@ struct esb_context {
     int* d_slot_begin = nullptr;
     int* h_counts = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_counts = nullptr, ev_done = nullptr;
+    // parameter scans (esb_scan_models): tables of all equilibria, their root tables, the compact result
+    double* d_bank = nullptr;
+    size_t cap_bank = 0;
+    char* d_scan_roots = nullptr;
+    size_t cap_scan_roots = 0;
+    int* d_scan_ints = nullptr;    // [n_models][ESB_MAX_MODES + 1] slot_begin | counts | found | offsets
+    size_t cap_scan_ints = 0;
+    int* h_scan_ints = nullptr;    // page-locked: found[n_tables], counts[n_tables], total
+    size_t cap_h_scan_ints = 0;
+    char* d_compact = nullptr;
+    size_t cap_compact = 0;
+    char* h_compact = nullptr;     // page-locked mirror handed to the caller
+    size_t cap_h_compact = 0;
     bool tables_pending = false;   // a sweep's refinement may still be running: consumers wait on ev_done
     int n_sm = 148;
     int accept_rule = ESB_ACCEPT_CONVERGED;
@@ -892,7 +951,9 @@ extern "C" int esb_destroy(esb_context* c) {
     if (!c) return ESB_OK;
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_tab, c->d_k, c->d_w, c->d_ext, c->d_int, c->d_den, c->d_rowcount, c->d_rowoff, c->d_counter,
-                    c->d_slot_begin};
+                    c->d_slot_begin, c->d_bank, c->d_scan_roots, c->d_scan_ints, c->d_compact};
+    if (c->h_scan_ints) cudaFreeHost(c->h_scan_ints);
+    if (c->h_compact) cudaFreeHost(c->h_compact);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -1159,8 +1220,10 @@ static int bracket_segments(int nw) {
 
 // count pass + scan over all slots of `sw` (segment offsets in c->d_rowoff, slot_begin in c->d_slot_begin),
 // then the asynchronous copy of slot_begin[] to the page-locked c->h_counts, marked by c->ev_counts
-static int brackets_count(esb_context* c, SweepDev& sw, cudaStream_t s) {
-    const bool ref = sw.rule == ESB_ACCEPT_REFERENCE;
+static int brackets_count(esb_context* c, SweepDev& sw, cudaStream_t s, int* d_slot_begin = nullptr) {
+    const bool to_host = d_slot_begin == nullptr;      // the sweep reads the counts; a batch keeps them on the device
+    if (!d_slot_begin) d_slot_begin = c->d_slot_begin;
+    const bool ref = sw.rule != ESB_ACCEPT_CONVERGED;
     sw.nseg = ref ? 1 : bracket_segments(sw.nw);
     const size_t per_slot = (size_t)sw.nk * sw.nseg, items = per_slot * sw.n_slots;
     int rc;
@@ -1168,17 +1231,19 @@ static int brackets_count(esb_context* c, SweepDev& sw, cudaStream_t s) {
     if ((rc = ensure(c, c->d_rowoff, c->cap_rowoff, items + 1))) return rc;
     sw.seg_count = c->d_rowcount;
     sw.seg_offset = c->d_rowoff;
-    sw.slot_begin = c->d_slot_begin;
+    sw.slot_begin = d_slot_begin;
     const int threads = 128, per_block = threads / 32;
     const int blocks = (int)((items + per_block - 1) / per_block);
     if (ref) bracket_reference_kernel<<<blocks, threads, 0, s>>>(sw, 0);
     else bracket_kernel<<<blocks, threads, 0, s>>>(sw, 0);
     CUDA_TRY(c, cudaGetLastError());
-    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, c->d_rowoff, (int)items, (int)per_slot, c->d_slot_begin);
+    scan_kernel<<<1, 1024, 0, s>>>(c->d_rowcount, c->d_rowoff, (int)items, (int)per_slot, d_slot_begin);
     CUDA_TRY(c, cudaGetLastError());
     c->launches += 2;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_counts, c->d_slot_begin, (sw.n_slots + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(c, cudaEventRecord(c->ev_counts, s));
+    if (to_host) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_counts, d_slot_begin, (sw.n_slots + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaEventRecord(c->ev_counts, s));
+    }
     return ESB_OK;
 }
 
@@ -1186,7 +1251,7 @@ static int brackets_fill(esb_context* c, const SweepDev& sw, cudaStream_t s) {
     const size_t items = (size_t)sw.nk * sw.nseg * sw.n_slots;
     const int threads = 128, per_block = threads / 32;
     const int blocks = (int)((items + per_block - 1) / per_block);
-    if (sw.rule == ESB_ACCEPT_REFERENCE) bracket_reference_kernel<<<blocks, threads, 0, s>>>(sw, 1);
+    if (sw.rule != ESB_ACCEPT_CONVERGED) bracket_reference_kernel<<<blocks, threads, 0, s>>>(sw, 1);
     else bracket_kernel<<<blocks, threads, 0, s>>>(sw, 1);
     CUDA_TRY(c, cudaGetLastError());
     c->launches += 1;
@@ -1417,6 +1482,180 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     return ESB_OK;
 }
 
+template <class T>
+static int ensure_pinned(esb_context* c, T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return ESB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    CUDA_TRY(c, cudaHostAlloc((void**)&p, need * sizeof(T), cudaHostAllocDefault));
+    cap = need;
+    return ESB_OK;
+}
+
+// A parameter scan as ONE batched job (BASELINE configs[4]; the reference has no scan driver - a user
+// edits the speeds / profile constants of a script and reruns it): n_models equilibria of the same kind
+// and discretisation over the axes resident in HBM.  All tables are built on the host and uploaded in
+// one copy; per equilibrium the five launches of a sweep (scan, count, prefix, fill, refine) are
+// enqueued back to back with NO host synchronisation - the bracket counts stay on the device, the
+// refinement reads them there, every root table has room for `capacity_per_table` entries; at the end
+// the tables are compacted on the device into one (model, slot, k_index, w_index, omega, ext, int,
+// accepted, iterations) table and copied to page-locked memory in one piece.
+extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model* models,
+                               const double* const* fields, int32_t n_fields, int32_t n_nodes,
+                               const double* boundary, int32_t n_modes, const int32_t* modes, double tol_percent,
+                               int32_t capacity_per_table, int32_t* n_brackets, esb_scan_result* out) {
+    if (!c) return ESB_ERR_ARG;
+    if (n_models < 1 || !models || !fields || !boundary || !out) return fail(c, ESB_ERR_ARG, "bad scan arguments");
+    if (c->ax_nk <= 0 || c->ax_nw <= 1) return fail(c, ESB_ERR_ARG, "axes not uploaded (need nw >= 2)");
+    const int nk = c->ax_nk, nw = c->ax_nw, layout = c->ax_layout;
+    const size_t plane = (size_t)nk * nw;
+    // ---- host: every model's constants and staged table
+    std::vector<HostModel> hm(n_models);
+    std::string err;
+    for (int i = 0; i < n_models; ++i) {
+        int rc = build_host_model(&models[i], fields + (size_t)i * n_fields, n_fields, n_nodes, boundary + i, 1,
+                                  hm[i], err);
+        if (rc) return fail(c, rc, err.c_str());
+        if (hm[i].dm.kind != hm[0].dm.kind || hm[i].dm.scheme != hm[0].dm.scheme ||
+            hm[i].tab.size() != hm[0].tab.size())
+            return fail(c, ESB_ERR_ARG, "the models of a scan share kind, scheme and mesh size");
+    }
+    const esb_model model_keep = c->model;
+    c->model = models[0];                      // check_modes reads the kind
+    const int bad_modes = check_modes(c, n_modes, modes);
+    c->model = model_keep;
+    if (bad_modes) return fail(c, ESB_ERR_ARG, "bad modes");
+    const size_t tab_doubles = hm[0].tab.size();
+    const int n_tables = n_models * n_modes;
+    const int cap = capacity_per_table > 0 ? capacity_per_table
+                                           : (int)std::max<size_t>(4096, plane / 24);
+    const size_t table_bytes = slot_bytes((size_t)cap);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = cur_stream(c);
+    int rc;
+    if ((rc = ensure(c, c->d_bank, c->cap_bank, tab_doubles * n_models))) return rc;
+    if ((rc = ensure(c, c->d_scan_roots, c->cap_scan_roots, table_bytes * n_tables))) return rc;
+    const size_t n_ints = (size_t)n_models * (ESB_MAX_MODES + 1) + 3 * (size_t)n_tables + 2;
+    if ((rc = ensure(c, c->d_scan_ints, c->cap_scan_ints, n_ints))) return rc;
+    if ((rc = ensure_pinned(c, c->h_scan_ints, c->cap_h_scan_ints, 2 * (size_t)n_tables + 2))) return rc;
+    if ((rc = ensure_grid(c, plane * n_modes))) return rc;
+    if ((rc = ensure(c, c->d_den, c->cap_den, plane * n_modes))) return rc;
+    int* d_sb = c->d_scan_ints;
+    int* d_counts = d_sb + (size_t)n_models * (ESB_MAX_MODES + 1);
+    int* d_found = d_counts + n_tables;
+    int* d_offsets = d_found + n_tables;       // [n_tables + 1]
+    {
+        // one upload of all tables (pageable staging: the copy is synchronous with respect to the host buffer)
+        std::vector<double> bank(tab_doubles * n_models);
+        for (int i = 0; i < n_models; ++i) memcpy(&bank[tab_doubles * i], hm[i].tab.data(), tab_doubles * sizeof(double));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_bank, bank.data(), bank.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+    }
+    const int kind = hm[0].dm.kind;
+    const double* tab_keep = c->d_tab;
+    const int tabd_keep = c->tab_doubles;
+    const DevModel dm_keep = c->dm;
+    const bool set_keep = c->model_set;
+    for (int i = 0; i < n_models; ++i) {
+        // the context's launch helpers read (dm, d_tab): point them at equilibrium i of the bank
+        c->dm = hm[i].dm;
+        c->d_tab = c->d_bank + tab_doubles * i;
+        c->tab_doubles = (int)tab_doubles;
+        c->model_set = true;
+        rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s, c->d_den);
+        if (!rc) {
+            SweepDev sw{};
+            sw.n_slots = n_modes; sw.nk = nk; sw.nw = nw;
+            sw.rule = c->accept_rule;
+            sw.tol_percent = tol_percent;
+            for (int m = 0; m < n_modes; ++m) {
+                esb_context::RootBuf rb;
+                slot_carve(rb, c->d_scan_roots + table_bytes * ((size_t)i * n_modes + m), (size_t)cap, nullptr);
+                SlotDev& q = sw.slot[m];
+                q.gext = c->d_ext + m * plane; q.gint = c->d_int + m * plane; q.gden = c->d_den + m * plane;
+                q.bk = rb.bk; q.bw = rb.bw; q.bw2 = rb.bw2;
+                q.omega = rb.om; q.ext = rb.e; q.intq = rb.i; q.accepted = rb.acc; q.iters = rb.it;
+                q.mode = modes[m];
+                q.capacity = cap;
+            }
+            rc = brackets_count(c, sw, s, d_sb + (size_t)i * (ESB_MAX_MODES + 1));
+            if (!rc) rc = brackets_fill(c, sw, s);
+            if (!rc && cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(int), s) != cudaSuccess) rc = ESB_ERR_CUDA;
+            if (!rc) {
+                RefineArgs r;
+                r.M = c->dm;
+                r.tab = c->d_tab;
+                r.tab_doubles = c->tab_doubles;
+                r.k = c->d_k; r.w = c->d_w; r.layout = layout;
+                r.sw = sw;
+                r.counter = c->d_counter;
+                // the bracket count is on the device only: a full persistent launch, schedule by grid size
+                const bool warp_path = c->schedule == 2 || (c->schedule == 0 && plane * n_modes <= 200000);
+                const int n_launch = (int)std::min<size_t>(plane, (size_t)1 << 30);
+                const cudaError_t e = dispatch_kind(kind, hm[0].dm.scheme, [&](auto kd, auto scheme) {
+                    if (warp_path)
+                        return launch_refine_warp<decltype(kd)::value, decltype(scheme)::value>(r, s, n_launch, c->n_sm);
+                    return launch_refine<decltype(kd)::value, decltype(scheme)::value>(r, s, n_launch, c->n_sm);
+                });
+                if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = ESB_ERR_CUDA; }
+                c->launches += 1;
+            }
+        }
+        if (rc) break;
+    }
+    // the context keeps the model it had before the scan
+    c->dm = dm_keep;
+    c->d_tab = const_cast<double*>(tab_keep);
+    c->tab_doubles = tabd_keep;
+    c->model_set = set_keep;
+    for (int m = 0; m < ESB_MAX_MODES; ++m) c->slots[m].n = 0;
+    if (rc) return rc;
+    // ---- counts of all tables -> host (the only wait on the scan itself)
+    scan_counts_kernel<<<(n_tables + 127) / 128, 128, 0, s>>>(d_sb, n_models, n_modes, cap, d_counts, d_found);
+    CUDA_TRY(c, cudaGetLastError());
+    scan_kernel<<<1, 1024, 0, s>>>(d_counts, d_offsets, n_tables, 0, nullptr);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches += 2;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scan_ints, d_found, (size_t)n_tables * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scan_ints + n_tables, d_offsets, ((size_t)n_tables + 1) * sizeof(int),
+                                cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    bool overflow = false;
+    for (int t = 0; t < n_tables; ++t) {
+        if (n_brackets) n_brackets[t] = c->h_scan_ints[t];
+        overflow = overflow || c->h_scan_ints[t] > cap;
+    }
+    const size_t total = (size_t)c->h_scan_ints[2 * n_tables];
+    // ---- compact table: [omega | ext | int] doubles, [model | slot | k | w | accepted | iterations] ints
+    const size_t entry = 3 * sizeof(double) + 6 * sizeof(int);
+    const size_t cap_e = (total + 1) & ~(size_t)1;
+    if ((rc = ensure(c, c->d_compact, c->cap_compact, cap_e * entry + 64))) return rc;
+    if ((rc = ensure_pinned(c, c->h_compact, c->cap_h_compact, cap_e * entry + 64))) return rc;
+    auto carve = [&](char* base, esb_scan_result& r) {
+        double* d = (double*)base;
+        int* q = (int*)(d + 3 * cap_e);
+        r.omega = d; r.ext = d + cap_e; r.intq = d + 2 * cap_e;
+        r.model = q; r.slot = q + cap_e; r.k_index = q + 2 * cap_e; r.w_index = q + 3 * cap_e;
+        r.accepted = q + 4 * cap_e; r.iterations = q + 5 * cap_e;
+    };
+    esb_scan_result dv{}, hv{};
+    carve(c->d_compact, dv);
+    carve(c->h_compact, hv);
+    if (total > 0) {
+        ScanOut so{dv.model, dv.slot, dv.k_index, dv.w_index, dv.accepted, dv.iterations, dv.omega, dv.ext, dv.intq};
+        scan_compact_kernel<<<n_tables, 256, 0, s>>>(c->d_scan_roots, table_bytes, cap, n_modes, d_counts, d_offsets, so);
+        CUDA_TRY(c, cudaGetLastError());
+        c->launches += 1;
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_compact, c->d_compact, cap_e * entry, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+    }
+    hv.n_entries = (int32_t)total;
+    *out = hv;
+    if (overflow) return fail(c, ESB_ERR_CAPACITY, "capacity_per_table too small (n_brackets holds the sizes found)");
+    return ESB_OK;
+}
+
 extern "C" int esb_sweep_resident(esb_context* c, int32_t mode, double tol_percent, int32_t* n_roots,
                                   int32_t* n_brackets) {
     return esb_sweep_resident_multi(c, 1, &mode, tol_percent, n_roots, n_brackets);
@@ -1505,7 +1744,7 @@ extern "C" int esb_tables_wait(esb_context* c, void* stream) {
 }
 
 extern "C" int esb_set_accept_rule(esb_context* c, int32_t rule) {
-    if (!c || (rule != ESB_ACCEPT_CONVERGED && rule != ESB_ACCEPT_REFERENCE)) return ESB_ERR_ARG;
+    if (!c || rule < ESB_ACCEPT_CONVERGED || rule > ESB_ACCEPT_REFERENCE_SLAB) return ESB_ERR_ARG;
     c->accept_rule = rule;
     return ESB_OK;
 }

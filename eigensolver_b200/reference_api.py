@@ -160,6 +160,8 @@ class ReferenceScript:
         # rule="reference": the script's own scan / bisection rule, point for point (the point sets its
         # pickles hold); "converged": one machine-precision root per sign change
         self.rule = rule
+        if rule == "reference" and self.kind.startswith("slab"):
+            self.rule = "reference_slab"   # bisects after two points seen, follows both halves
         if self.accept == "ext" and rule == "reference":
             # ..._kink_slow.py divides the mismatch by |xi_e| alone (:586): the library's reference rule uses
             # max(|ext|, |int|); that script is served by the converged rule + its own test in _modes_of

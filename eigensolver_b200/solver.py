@@ -490,7 +490,8 @@ class DispersionSolver:
         esb_accept_rule) - what their pickles hold."""
         L.check(self.lib, self.ctx,
                 self.lib.esb_set_accept_rule(self.ctx, {"converged": L.ACCEPT_CONVERGED,
-                                                        "reference": L.ACCEPT_REFERENCE}[rule]),
+                                                        "reference": L.ACCEPT_REFERENCE,
+                                                        "reference_slab": L.ACCEPT_REFERENCE_SLAB}[rule]),
                 "esb_set_accept_rule")
 
     def find_roots_multi(self, modes, k, w, layout="phase_speed", tol_percent=1.0, pinned=False):
@@ -526,6 +527,40 @@ class DispersionSolver:
         L.check(self.lib, self.ctx, self.lib.esb_download_roots_slot(self.ctx, int(slot), C.byref(out), n),
                 "esb_download_roots_slot")
         return RootTable(ki, wi, self._k_host, om, ex, iq, ac, it, n)
+
+    def scan_models(self, points, modes, tol_percent=1.0, capacity_per_table=0):
+        """A parameter scan as ONE batched job (esb_scan_models): every equilibrium in `points` (dicts
+        with optional 'medium' and 'profile', on this solver's mesh) swept over the uploaded axes with no
+        host synchronisation in between.  Returns (table, n_brackets): `table` = dict of numpy VIEWS of
+        page-locked buffers owned by the context (model, slot, k_index, w_index, omega, ext, intq,
+        accepted, iterations; valid until the next scan), n_brackets[model][mode]."""
+        import copy
+        md = np.array([self._mode(m) for m in modes], dtype=np.int32)
+        specs = []
+        for p in points:
+            sp = copy.copy(self.spec)
+            sp.model = type(self.spec.model).from_buffer_copy(self.spec.model)
+            sp.replace(p.get("medium"), p.get("profile"))
+            specs.append(sp)
+        n = len(specs)
+        models = (L.esb_model * n)(*[sp.model for sp in specs])
+        sampled = [sp.sampled() for sp in specs]
+        nf = self.spec.n_fields
+        fptr = (C.POINTER(C.c_double) * (n * nf))(*[_dptr(f) for fields, _ in sampled for f in fields])
+        boundary = np.ascontiguousarray([b[0] for _, b in sampled], dtype=np.float64)
+        nb = np.zeros(n * md.size, np.int32)
+        out = L.esb_scan_result()
+        rc = self.lib.esb_scan_models(self.ctx, n, models, fptr, nf, self.spec.nodes.size, _dptr(boundary),
+                                      md.size, _iptr(md), float(tol_percent), int(capacity_per_table), _iptr(nb),
+                                      C.byref(out))
+        L.check(self.lib, self.ctx, rc, "esb_scan_models")
+        ne = out.n_entries
+        names = ("model", "slot", "k_index", "w_index", "accepted", "iterations", "omega", "ext", "intq")
+        if ne == 0:
+            tab = {nm: np.zeros(0, np.float64 if nm in ("omega", "ext", "intq") else np.int32) for nm in names}
+        else:
+            tab = {nm: np.ctypeslib.as_array(getattr(out, nm), shape=(ne,)) for nm in names}
+        return tab, nb.reshape(n, md.size)
 
     def roots_device(self, slot=0, stream=None):
         """Device pointers of the root table of mode slot `slot` (valid until the next sweep):

@@ -200,8 +200,11 @@ int esb_tables_wait(esb_context* ctx, void* stream);
  *                         point inside the band as THE solution (no further refinement) and otherwise
  *                         follows a sign change in the UPPER half only, as the scripts' recursion does
  *                         (accepted = 0 where it gives up).  This reproduces the point sets the scripts
- *                         pickle; omega is then a dyadic point of the frequency grid, not a converged root. */
-enum esb_accept_rule { ESB_ACCEPT_CONVERGED = 0, ESB_ACCEPT_REFERENCE = 1 };
+ *                         pickle; omega is then a dyadic point of the frequency grid, not a converged root.
+ *   ESB_ACCEPT_REFERENCE_SLAB  the slab scripts' variant of the same rule (..._method_coronal.py:606-624,
+ *                         :502-518): a sign change is bisected after more than ONE point seen, and the
+ *                         bisection follows the lower half too. */
+enum esb_accept_rule { ESB_ACCEPT_CONVERGED = 0, ESB_ACCEPT_REFERENCE = 1, ESB_ACCEPT_REFERENCE_SLAB = 2 };
 int esb_set_accept_rule(esb_context* ctx, int32_t rule);
 
 /* Several modes in ONE fused scan (n_modes <= 4): cylinder orders share the staged
@@ -215,6 +218,31 @@ int esb_sweep_resident_multi(esb_context* ctx, int32_t n_modes, const int32_t* m
                              double tol_percent, int32_t* n_roots /* [n_modes] */,
                              int32_t* n_brackets /* [n_modes] */);
 int esb_download_roots_slot(esb_context* ctx, int32_t slot, esb_roots* out, int32_t max_roots);
+
+/* A parameter scan as ONE batched job (BASELINE configs[4]): n_models equilibria of the same kind, scheme
+ * and mesh size, swept over the axes uploaded with esb_upload_axes.  fields[i * n_fields + f] = field f of
+ * model i at ITS esb_mesh_nodes(), boundary[i] = its first field at s_start.  Every (model, mode) root
+ * table has room for capacity_per_table entries (0: one per 24 grid points); n_brackets[i * n_modes + m]
+ * receives the sizes found.  No host synchronisation between the equilibria; the result is ONE compact
+ * table in page-locked memory owned by the context (valid until the next scan or esb_destroy), ordered by
+ * (model, mode slot, k index, omega index).  ESB_ERR_CAPACITY: some table outgrew its room (the result
+ * holds the first capacity_per_table entries of it). */
+typedef struct esb_scan_result {
+    int32_t n_entries;
+    int32_t* model;       /* index into models[]                       */
+    int32_t* slot;        /* index into modes[]                        */
+    int32_t* k_index;
+    int32_t* w_index;
+    int32_t* accepted;
+    int32_t* iterations;
+    double* omega;
+    double* ext;
+    double* intq;
+} esb_scan_result;
+int esb_scan_models(esb_context* ctx, int32_t n_models, const esb_model* models, const double* const* fields,
+                    int32_t n_fields, int32_t n_nodes, const double* boundary, int32_t n_modes,
+                    const int32_t* modes, double tol_percent, int32_t capacity_per_table,
+                    int32_t* n_brackets /* [n_models * n_modes] */, esb_scan_result* out);
 
 /* D2H copy of the root table of `slot` into page-locked host buffers OWNED BY THE CONTEXT; *out
  * receives their addresses, *n_roots the entry count.  One packed copy at full PCIe rate, no

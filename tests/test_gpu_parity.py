@@ -197,43 +197,138 @@ def test_shipped_root_tables(golden_dir):
         assert total > 300 and inside / total > 0.85, (name, inside, total)
 
 
-def test_reference_api_drop_in(golden_dir):
-    """sausage()/kink() keep the reference's signature and reproduce its own scan result."""
+#: the assignment-line edits of tests/golden/make_scan_golden.py, as ReferenceScript keywords
+DROPIN_OVERRIDES = {
+    "cylinder_density": {}, "cylinder_density_photospheric": {}, "slab_density": {},
+    "slab_density_photospheric": dict(width=0.9), "slab_flow": dict(width=1.0), "slab_flow_photospheric": {},
+    "cylinder_flow": dict(medium=esb.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=0.35), width=1.0),
+    "rotation_sausage": {}, "rotation_kink": dict(profile=esb.PowerLawRotation(0.15, 1.25)),
+}
 
-    class Q:
-        def __init__(self):
-            self.items = []
 
-        def put(self, x):
-            self.items.append(x)
+class _Q:
+    def __init__(self):
+        self.items = []
 
-    # (script preset, fixture, overrides matching the run that produced the fixture, its tolerance)
-    for script_name, fixture, kw, tol in (
-            ("cylinder_density", "cylinder_density_coronal", {}, 1.0),
-            ("slab_density", "slab_density_coronal", {}, 1.0),
-            ("cylinder_flow", "cylinder_flow_coronal",
-             dict(medium=esb.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=0.35), width=1.0), 6.0),
-            ("slab_flow", "slab_flow_coronal", dict(width=1.0), 1.0)):
-        g = np.load(os.path.join(golden_dir, "ref_scan_%s.npz" % fixture))
-        with esb.ReferenceScript(script_name, **kw) as script:
-            assert script.tol == tol
-            n = found = 0
-            while "scan%d_k" % n in g.files:
-                mode = int(g["scan%d_mode" % n][0]); k = float(g["scan%d_k" % n][0])
-                freq = g["scan%d_freq" % n]; ws_ref = g["scan%d_sol_ws" % n]
-                ws, ks = Q(), Q()
-                (script.kink if mode == 1 else script.sausage)(k, ws, ks, freq)
-                assert len(ws.items) == 1 and len(ks.items) == 1 and len(ws.items[0]) == len(ks.items[0])
-                assert all(kk == k for kk in ks.items[0])
-                for w in ws_ref:        # the reference stops bisecting once inside its acceptance band
-                    assert min(abs(np.array(ws.items[0]) - w)) < 1e-2 * tol * abs(w), (script_name, mode, k, w)
-                    found += 1
-                n += 1
-            assert found >= 1
-    with esb.ReferenceScript("cylinder_density") as script:
+    def put(self, x):
+        self.items.append(x)
+
+
+def test_reference_rule_reproduces_the_scripts_scan(golden_dir):
+    """sausage()/kink() keep the reference's signature and, under the "reference" accept rule, reproduce
+    the reference's OWN scan + bisection output: tests/golden/ref_scans.npz holds sol_omegas of 48 calls
+    of the unmodified scripts (9 scripts, both modes, windows with and without modes; most windows that
+    contain a mode return nothing - the scripts' recursion follows the upper half only).  A solution of
+    the scripts is a point of the dyadic refinement of the frequency grid, so agreement is to ROUNDING.
+
+    Measured: 37 of 48 calls identical (same count, same points to 1e-9).  The other 11, by cause:
+      * the scripts' bisection keeps module-global state (`loop_ws`, `xi_diff_loop_check`) from one bracket
+        of a call to the next, which sometimes lets a later bracket recurse into its lower half
+        (cylinder k = 3.5, photospheric cylinder k = 1.5, flow slab): not emulated;
+      * flow_multiprocessor.py asks for a mismatch below 1e-6 %, which its own odeint noise cannot reach:
+        it returns nothing where the converged D does reach it;
+      * the rotational kink script evaluates the second-order form, noisy where C3 ~ 0: a few
+        grid points are inside the 2.5 % band for the converged D and not for the script.
+    For those calls both directions are checked in the weaker sense: every solution of the script lies
+    within one grid interval of a root of the converged rule, and every solution reported here passes
+    the script's own acceptance test by construction."""
+    g = np.load(os.path.join(golden_dir, "ref_scans.npz"))
+    n_cases = n_sols = exact = 0
+    scripts = {}
+    try:
+        n = 0
+        while "c%d_script" % n in g.files:
+            name = str(g["c%d_script" % n])
+            if name not in scripts:
+                scripts[name] = esb.ReferenceScript(name, **DROPIN_OVERRIDES[name])
+            script = scripts[name]
+            mode = int(g["c%d_mode" % n][0]); k = float(g["c%d_k" % n][0])
+            freq = g["c%d_freq" % n]; ws_ref = np.sort(g["c%d_sol_ws" % n])
+            ws, ks = _Q(), _Q()
+            (script.kink if mode == 1 else script.sausage)(k, ws, ks, freq)
+            assert len(ws.items) == 1 and len(ks.items) == 1 and len(ws.items[0]) == len(ks.items[0])
+            assert all(kk == k for kk in ks.items[0])
+            got = np.sort(np.array(ws.items[0], dtype=np.float64))
+            n_cases += 1
+            n_sols += len(ws_ref)
+            if len(got) == len(ws_ref) and np.allclose(got, ws_ref, rtol=1e-9, atol=0):
+                exact += 1
+            else:
+                script.solver.set_accept_rule("converged")
+                conv = script.solver.find_roots(mode, [k], freq, layout="shared", tol_percent=script.tol)
+                script.solver.set_accept_rule(script.rule)
+                dw = abs(freq[1] - freq[0])
+                for w in ws_ref:
+                    assert len(conv.omega) and np.min(np.abs(conv.omega - w)) <= dw, (name, mode, k, w)
+                if len(got):
+                    e, q = script.solver.dispersion_grid(mode, [k], got, layout="shared")
+                    assert np.all(np.abs(e - q) * 100 / np.maximum(np.abs(e), np.abs(q)) < script.tol)
+            n += 1
+    finally:
+        for sc in scripts.values():
+            sc.close()
+    assert n_cases >= 40 and n_sols >= 12
+    assert exact >= 0.75 * n_cases, (exact, n_cases)
+
+
+def test_reference_api_driver_loop():
+    with esb.ReferenceScript("cylinder_density", rule="converged") as script:
         out = script.run(np.linspace(0.5, 4.0, 8), speeds=[2.95, 4.0, 4.95], n_freq=40)
     assert len(out) == 4 and len(out[0]) == len(out[1]) and len(out[2]) == len(out[3])
     assert len(out[2]) >= 4 and np.all(out[2] / out[3] > 2.9) and np.all(out[2] / out[3] < 5.0)
+    # the reference rule returns a subset of the branches' points (it gives up on lower-half roots) plus
+    # the grid points inside the band; all of them pass the acceptance test
+    with esb.ReferenceScript("cylinder_density") as script:
+        ref = script.run(np.linspace(0.5, 4.0, 8), speeds=[2.95, 4.0, 4.95], n_freq=40)
+        assert len(ref) == 4 and len(ref[2]) == len(ref[3])
+        if len(ref[2]):
+            e, q = script.solver.dispersion_grid(1, ref[3], np.asarray(ref[2])[:, None], layout="per_k")
+            assert np.all(np.abs(e - q) * 100 / np.maximum(np.abs(e), np.abs(q)) < 1.0)
+
+
+def test_scan_models_equals_single_sweeps():
+    """esb_scan_models (configs[4]: every equilibrium enqueued back to back, no host synchronisation,
+    one compact table) returns what one sweep per equilibrium returns, and its values match the C
+    oracle of each equilibrium."""
+    from eigensolver_b200.scan import density_flow_grid
+    dens, flow = density_flow_grid([0.15, 0.2055, 0.3], [0.2, 0.5, 0.9])
+    k = np.linspace(0.4, 4.0, 12)
+    for kind, pts, modes, W in (("cylinder_density", dens, [0, 1, 2], np.linspace(0.55, 4.5, 300)),
+                                ("slab_flow", flow, [0, 1], np.linspace(1.25, 2.45, 200))):
+        with esb.DispersionSolver(kind) as s:
+            s.upload_axes(k, W)
+            s.set_schedule("lane")
+            tab, nb = s.scan_models(pts, modes)
+            tab = {name: np.array(v) for name, v in tab.items()}
+            assert nb.shape == (len(pts), len(modes)) and nb.sum() == len(tab["omega"]) > 0
+            # ordered by (model, slot, k index, omega index)
+            key = ((tab["model"].astype(np.int64) * 8 + tab["slot"]) * len(k) + tab["k_index"]) * len(W) + tab["w_index"]
+            assert np.all(np.diff(key) > 0)
+            for i, p in enumerate(pts):
+                s.reconfigure(medium=p["medium"], profile=p["profile"])
+                singles = s.find_roots_multi(modes, k, W)
+                for slot, t in enumerate(singles):
+                    sel = (tab["model"] == i) & (tab["slot"] == slot)
+                    assert sel.sum() == nb[i, slot] == len(t.omega)
+                    assert np.array_equal(tab["k_index"][sel], t.k_index) and np.array_equal(tab["w_index"][sel], t.w_index)
+                    assert np.array_equal(tab["omega"][sel], t.omega, equal_nan=True)
+                    assert np.array_equal(tab["accepted"][sel], t.accepted)
+            # a table that outgrows its room is reported, not silently truncated
+            with pytest.raises(esb.EsbError, match="capacity"):
+                s.scan_models(pts, modes, capacity_per_table=2)
+    # against the oracle: one accepted mode of every density equilibrium
+    with esb.DispersionSolver("cylinder_density") as s:
+        Wr = np.linspace(2.95, 4.95, 120)
+        s.upload_axes(k, Wr)
+        tab, nb = s.scan_models(dens, [1])
+        for i, p in enumerate(dens):
+            model = ork.make_model("cylinder_density", medium=p["medium"], width=p["profile"].width)
+            sel = np.nonzero((tab["model"] == i) & (tab["accepted"] == 1))[0]
+            assert len(sel) >= 3
+            for j in sel[:: max(1, len(sel) // 6)]:
+                kk = k[tab["k_index"][j]]
+                r, _, _ = ork.refine(model, 1, kk, kk * Wr[tab["w_index"][j]], kk * Wr[tab["w_index"][j] + 1])
+                assert abs(tab["omega"][j] - r) <= ROOT_TOL * abs(r), (i, kk, r, tab["omega"][j])
 
 
 def test_edge_cases(solvers):
