@@ -203,6 +203,109 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(sm), "source": self.source}
 
 
+def cylinder_continua(medium, profile, margin=0.02):
+    """Phase-speed intervals of the bench equilibrium in which an Alfven or cusp resonance sits inside
+    the layer (the noise floor): [min, max] of vA(r) and cT(r) over the layer, +- margin."""
+    r = np.linspace(-1.0, -0.001, 4001)
+    rho = profile(medium, r)[0]
+    beta = medium.vA_i0**2 * medium.rho_i0
+    alpha = medium.rho_e * (medium.c_e**2 + 0.5 * medium.gamma * medium.vA_e**2) - 0.5 * medium.gamma * beta
+    vA2, c2 = beta / rho, alpha / rho
+    cT2 = c2 * vA2 / (c2 + vA2)
+    return [(np.sqrt(v.min()) - margin, np.sqrt(v.max()) + margin) for v in (vA2, cT2)]
+
+
+def other_configs(esb, local):
+    """BASELINE configs[0], [2], [3] at full size on one GPU (scan + brackets + refinement, axes resident):
+    evaluations per second, time of the scan kernel and its share - the driver-run counterpart of
+    profiles/r01u_configs_throughput.jsonl."""
+    import torch
+    out = []
+    cases = [
+        ("configs[0] slab non-uniform density, sausage+kink, 200 k x 2000 omega", "slab_density", {}, [0, 1],
+         np.linspace(0.001, 0.75, 200), np.linspace(0.41, 2.95, 2000), 20),
+        ("configs[2] slab sheared flow U0(x), backward+forward branches, 2000 k x 20000 omega", "slab_flow",
+         dict(medium=esb.FlowMedium(U_i0=0.35), profile=esb.GaussianFlow(1.0)), [0, 1],
+         np.linspace(0.01, 4.5, 2000), np.linspace(-2.7, 2.7, 20000), 3),
+        ("configs[3] cylinder rotational flow Omega(r), n = 0..3, 2000 k x 20000 omega", "cylinder_rotation",
+         dict(profile=esb.PowerLawRotation(0.15, 1.25), s_end=0.01), [0, 1, 2, 3],
+         np.linspace(0.25, 4.0, 2000), np.linspace(0.40, 1.6, 20000), 2),
+    ]
+    for name, kind, kw, modes, k, W, steps in cases:
+        with esb.DispersionSolver(kind, device=local, **kw) as s:
+            s.upload_axes(k, W)
+            s.sweep_resident_multi(modes)
+            s.lib.esb_tables_wait(s.ctx, None)
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            kms = []
+            for _ in range(steps):
+                ns = s.sweep_resident_multi(modes)
+                kms.append(s.last_kernel_ms())
+            s.lib.esb_tables_wait(s.ctx, None)
+            dt = (time.perf_counter() - t) / steps
+            evals = len(modes) * k.size * W.size
+            out.append({"config": name, "scheme": s.spec.scheme, "n_steps": int(s.model.n_steps), "modes": modes,
+                        "evals_per_step": evals, "ms_per_step": 1e3 * dt, "evals_per_sec": evals / dt,
+                        "kernel_ms": float(np.mean(kms)), "kernel_share": float(np.mean(kms)) / (1e3 * dt),
+                        "brackets": int(sum(ns))})
+    return out
+
+
+SCAN_CONTRASTS = 20
+SCAN_AMPLITUDES = 20
+
+
+def strong_scaling_job(esb, local, dev, rank, world, steps=2):
+    """BASELINE configs[4] as stated: a parameter scan of 1e9 D evaluations - 20 density contrasts x
+    (n = 0, 1, 2) of the cylinder and 20 flow amplitudes x (sausage, kink) of the slab, each on a
+    1000 k x 10000 omega grid - as a FIXED-SIZE job split over the GPUs: every rank sweeps all 40
+    equilibria on its strided share of the wavenumbers (eigensolver_b200.scan), the accepted modes are
+    gathered.  Host tables in, compact root tables in page-locked memory out, gather included."""
+    import torch
+    import torch.distributed as dist
+    from eigensolver_b200.scan import density_flow_grid, gather_scan_modes, parameter_scan
+    dens, flow = density_flow_grid(np.linspace(0.1, 0.4, SCAN_CONTRASTS), np.linspace(0.05, 0.9, SCAN_AMPLITUDES))
+    k = np.linspace(K_RANGE[0], K_RANGE[1], NK)
+    Wd = np.linspace(W_RANGE[0], W_RANGE[1], NW)
+    Wf = np.linspace(-2.7, 2.7, NW)
+    evals = (len(dens) * 3 + len(flow) * 2) * NK * NW
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with esb.DispersionSolver("cylinder_density", device=local) as sd, \
+            esb.DispersionSolver("slab_flow", device=local) as sf:
+        def job():
+            n = 0
+            for solver, pts, W, modes in ((sd, dens, Wd, [0, 1, 2]), (sf, flow, Wf, [0, 1])):
+                res = parameter_scan(solver, pts, k, W, modes, rank=rank, world=world)
+                if world > 1:
+                    n += gather_scan_modes(res, dev).shape[0]
+                else:
+                    n += int(np.asarray(res.table["accepted"]).sum())
+            return n
+        job()                                   # warm-up: allocations, capacities
+        sync()
+        t = time.perf_counter()
+        for _ in range(steps):
+            n_modes = job()
+        sync()
+        dt = (time.perf_counter() - t) / steps
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    return {"workload": "configs[4]: %d density contrasts x n=0,1,2 (cylinder) + %d flow amplitudes x sausage,kink "
+                        "(slab), 1000 k x 10000 omega each; every rank sweeps all equilibria on k[rank::N]"
+                        % (SCAN_CONTRASTS, SCAN_AMPLITUDES),
+            "evals": evals, "seconds": dt, "evals_per_sec": evals / dt, "n_gpus": world, "steps": steps,
+            "modes_gathered": int(n_modes), "scaling": "strong"}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -312,6 +415,20 @@ def run_gpu_arm(args):
     sampler.stop.set()
     sampler.join()
 
+    # ---- brackets of rank 0 outside the continua (the region parity is claimed for), after the timing
+    n_regular = None
+    if rank == 0:
+        iv = cylinder_continua(solver.medium, solver.profile)
+        solver.upload_axes(k, W)
+        ns = solver.sweep_resident_multi(MODES)
+        n_regular = 0
+        for slot, nn in enumerate(ns):
+            tab = solver.download_roots(nn, slot)
+            ok = np.ones(nn, bool)
+            for lo, hi in iv:
+                for Wp in (W[tab.w_index], W[tab.w_index + 1]):
+                    ok &= (Wp < lo) | (Wp > hi)
+            n_regular += int(ok.sum())
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,6 +437,9 @@ def run_gpu_arm(args):
     value = evals_per_step * args.steps / (ms * 1e-3)
     e2e = evals_per_step * args.steps / (ms_e2e * 1e-3)
 
+    solver.close()
+    strong = None if args.no_extras else strong_scaling_job(esb, local, dev, rank, world)
+    configs = other_configs(esb, local) if (world == 1 and not args.no_extras) else None
     if rank == 0:
         kms = float(np.mean(kernel_ms))                      # one fused launch = 3 modes x NK*NW evals
         achieved = FLOPS_FUSED_LAUNCH / (kms * 1e-3) * 1e-12
@@ -343,6 +463,8 @@ def run_gpu_arm(args):
                        "n_steps": N_STEPS, "mesh": "graded", "scheme": "rk8n", "profile": "inverted Gaussian, width 0.95",
                        "l2": "working set 720 MB of (ext, int, Y) written per step > 126 MB L2; inputs are 88 KB"},
             "roots_per_sec": n_brackets * world * args.steps / (ms * 1e-3),
+            "roots_per_sec_regular": n_regular * world * args.steps / (ms * 1e-3),
+            "brackets_regular_rank0": n_regular,
             "modes_found": n_modes, "brackets_rank0": n_brackets,
             "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -360,8 +482,11 @@ def run_gpu_arm(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if strong:
+            line["strong_scaling"] = strong
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line))
-    solver.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -373,6 +498,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the configs[0,2,3] record and the configs[4] strong-scaling job")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -99,3 +99,40 @@ def test_gather_handles_empty_rank(tmp_path):
         assert list(gk) == [5, 7] and list(gw) == [1.5, 2.5] and list(ga) == [1, 0]
     finally:
         dist.destroy_process_group()
+
+
+def _scan_worker(rank, world, port, out):
+    """two ranks, each with the compact scan table of its strided wavenumbers (synthetic tables here:
+    the gather is host-side logic)"""
+    import torch.distributed as dist
+    from eigensolver_b200.scan import ScanResult, gather_scan_modes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7 + rank)
+        n = 5 + 3 * rank                     # uneven shares; rank 1 also has unaccepted entries
+        table = {"model": rng.integers(0, 3, n).astype(np.int32), "slot": rng.integers(0, 2, n).astype(np.int32),
+                 "k_index": rng.integers(0, 4, n).astype(np.int32), "omega": rng.uniform(1, 2, n),
+                 "accepted": (np.arange(n) % (2 if rank else 1) == 0).astype(np.int32)}
+        res = ScanResult([], table, np.zeros(4), rank, world)
+        g = gather_scan_modes(res, "cpu").numpy()
+        mine = table["accepted"] == 1
+        want = np.stack([table["model"][mine], table["slot"][mine], table["k_index"][mine] * world + rank,
+                         table["omega"][mine]], axis=1)
+        np.savez(out % rank, gathered=g, mine=want)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gather_of_scan_modes(tmp_path):
+    """gather_scan_modes: the accepted modes of every rank, global rows = k_offset + k_index * k_stride,
+    concatenated in rank order; every rank receives the same table."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "scan%d.npz")
+    mp.spawn(_scan_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    g0, g1 = np.load(out % 0), np.load(out % 1)
+    assert np.array_equal(g0["gathered"], g1["gathered"])
+    assert np.array_equal(g0["gathered"], np.concatenate([g0["mine"], g1["mine"]]))
+    assert len(g1["mine"]) < 8            # the unaccepted entries of rank 1 were left out

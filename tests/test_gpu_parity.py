@@ -318,7 +318,7 @@ def test_scan_models_equals_single_sweeps():
                 s.scan_models(pts, modes, capacity_per_table=2)
     # against the oracle: one accepted mode of every density equilibrium
     with esb.DispersionSolver("cylinder_density") as s:
-        Wr = np.linspace(2.95, 4.95, 120)
+        Wr = np.linspace(3.3, 4.95, 120)          # above the Alfven continuum of every contrast (edge <= 3.05)
         s.upload_axes(k, Wr)
         tab, nb = s.scan_models(dens, [1])
         for i, p in enumerate(dens):
@@ -756,23 +756,36 @@ def test_device_side_gather_equals_host_table(solvers):
 
 
 def test_parameter_scan_matches_fresh_solvers():
-    """configs[4]-style scan: reconfiguring one context per equilibrium gives what a freshly
-    built solver gives, and sharding the list over ranks covers it exactly once."""
+    """configs[4]-style scan through eigensolver_b200.scan: the batched job gives what a freshly built
+    solver gives for every equilibrium, and sharding the WAVENUMBERS (strided) over ranks covers the
+    scan exactly once."""
     from eigensolver_b200.scan import density_flow_grid, parameter_scan
     dens, flow = density_flow_grid([0.15, 0.2055, 0.3], [0.2, 0.5, 0.9])
     k = np.linspace(0.4, 4.0, 12)
     for kind, pts, modes, W in (("cylinder_density", dens, [0, 1, 2], np.linspace(0.55, 4.5, 300)),
                                 ("slab_flow", flow, [0, 1], np.linspace(1.25, 2.45, 200))):
         with esb.DispersionSolver(kind) as s:
+            s.set_schedule("lane")
             res = parameter_scan(s, pts, k, W, modes, keep_tables=True)
-            halves = [parameter_scan(s, pts, k, W, modes, rank=r, world=2) for r in range(2)]
-        assert [p.label for p in halves[0] + halves[1]] == [p.label for p in res]
-        assert [p.n_brackets for p in halves[0] + halves[1]] == [p.n_brackets for p in res]
-        for p, r in zip(pts, res):
+            halves = [parameter_scan(s, pts, k, W, modes, rank=r, world=2, keep_tables=True) for r in range(2)]
+        assert [p.label for p in res.points] == [p["label"] for p in pts]
+        for i in range(len(pts)):
+            for m in range(len(modes)):
+                assert halves[0].points[i].n_brackets[m] + halves[1].points[i].n_brackets[m] == res.points[i].n_brackets[m]
+                # rank r owns rows r, r+2, ...: the union of the two shards is the single-rank table
+                rows = np.concatenate([h.points[i].tables[m]["k_index"] * h.k_stride + h.k_offset for h in halves])
+                om = np.concatenate([h.points[i].tables[m]["omega"] for h in halves])
+                full = res.points[i].tables[m]
+                order = np.lexsort((om, rows))
+                order_full = np.lexsort((full["omega"], full["k_index"]))
+                assert np.array_equal(rows[order], full["k_index"][order_full])
+                assert np.array_equal(om[order], full["omega"][order_full], equal_nan=True)
+        for p, r in zip(pts, res.points):
             with esb.DispersionSolver(kind, medium=p["medium"], profile=p["profile"]) as fresh:
+                fresh.set_schedule("lane")
                 tabs = fresh.find_roots_multi(modes, k, W)
             for a, b in zip(tabs, r.tables):
-                assert np.array_equal(a.k_index, b.k_index) and np.array_equal(a.omega, b.omega, equal_nan=True)
+                assert np.array_equal(a.k_index, b["k_index"]) and np.array_equal(a.omega, b["omega"], equal_nan=True)
             assert sum(r.n_modes) > 0
     # the contrast helper reproduces the reference's own rho_e for its own vA_e
     from eigensolver_b200.scan import medium_for_density_contrast
