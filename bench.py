@@ -264,7 +264,7 @@ def strong_scaling_job(esb, local, dev, rank, world, steps=2):
     gathered.  Host tables in, compact root tables in page-locked memory out, gather included."""
     import torch
     import torch.distributed as dist
-    from eigensolver_b200.scan import density_flow_grid, gather_scan_modes, parameter_scan
+    from eigensolver_b200.scan import density_flow_grid, gather_scan_modes_device, parameter_scan
     dens, flow = density_flow_grid(np.linspace(0.1, 0.4, SCAN_CONTRASTS), np.linspace(0.05, 0.9, SCAN_AMPLITUDES))
     k = np.linspace(K_RANGE[0], K_RANGE[1], NK)
     Wd = np.linspace(W_RANGE[0], W_RANGE[1], NW)
@@ -279,13 +279,25 @@ def strong_scaling_job(esb, local, dev, rank, world, steps=2):
 
     with esb.DispersionSolver("cylinder_density", device=local) as sd, \
             esb.DispersionSolver("slab_flow", device=local) as sf:
+        host = {}
+
         def job():
+            """host tables in -> (model, mode, k row, omega) of every accepted mode in page-locked memory on
+            rank 0 (N > 1: gathered over NCCL from the device buffers)"""
             n = 0
             for solver, pts, W, modes in ((sd, dens, Wd, [0, 1, 2]), (sf, flow, Wf, [0, 1])):
-                res = parameter_scan(solver, pts, k, W, modes, rank=rank, world=world)
                 if world > 1:
-                    n += gather_scan_modes(res, dev).shape[0]
+                    res = parameter_scan(solver, pts, k, W, modes, rank=rank, world=world, download=False)
+                    g = gather_scan_modes_device(solver, res, dev)
+                    if rank == 0:
+                        if host.get("cap", 0) < g.shape[0]:
+                            host["cap"] = int(g.shape[0] * 1.25) + 1024
+                            host["buf"] = torch.empty((host["cap"], 4), dtype=torch.float64).pin_memory()
+                        host["buf"][: g.shape[0]].copy_(g, non_blocking=True)
+                        torch.cuda.current_stream(dev).synchronize()
+                    n += g.shape[0]
                 else:
+                    res = parameter_scan(solver, pts, k, W, modes)
                     n += int(np.asarray(res.table["accepted"]).sum())
             return n
         job()                                   # warm-up: allocations, capacities

@@ -89,7 +89,9 @@ SYMBOLS = {
     "esb_sweep_resident_multi": (C.c_int, [_ctx, C.c_int32, _ip, C.c_double, _ip, _ip]),
     "esb_download_roots_slot": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), C.c_int32]),
     "esb_scan_models": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_model), C.POINTER(_dp), C.c_int32, C.c_int32, _dp,
-                                  C.c_int32, _ip, C.c_double, C.c_int32, _ip, C.POINTER(esb_scan_result)]),
+                                  C.c_int32, _ip, C.c_double, C.c_int32, C.c_int32, _ip,
+                                  C.POINTER(esb_scan_result)]),
+    "esb_scan_device": (C.c_int, [_ctx, C.POINTER(esb_scan_result)]),
     "esb_roots_pinned": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), _ip]),
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "esb_tables_wait": (C.c_int, [_ctx, C.c_void_p]),

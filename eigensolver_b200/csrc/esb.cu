@@ -662,6 +662,9 @@ __global__ void __launch_bounds__(128, MINB) refine_kernel(RefineArgs r) {
             wq = P.reference ? B.mid : S.b;
             pending = true;
         }
+        // (Handing the last few iterating lanes of a warp to the warp-cooperative evaluation once the
+        // queue is drained was tried: 3.97 -> 3.88 ms on the bench sweep, and the tables are then no longer
+        // bit-reproducible - which lanes switch depends on the order the queue was served in.  Not kept.)
         if (!__any_sync(0xffffffffu, pending)) break;
         double en, in_, yn;
         eval_point<KIND, SCHEME, false, true>(r.M, stab, P.k, wq, P.mode, en, in_, yn);
@@ -790,6 +793,7 @@ struct esb_context {
     char* d_compact = nullptr;
     size_t cap_compact = 0;
     char* h_compact = nullptr;     // page-locked mirror handed to the caller
+    esb_scan_result scan_dev{};    // the same table, device pointers
     size_t cap_h_compact = 0;
     bool tables_pending = false;   // a sweep's refinement may still be running: consumers wait on ev_done
     int n_sm = 148;
@@ -1482,6 +1486,13 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     return ESB_OK;
 }
 
+// device pointers of the compact table of the last esb_scan_models (valid until the next scan)
+extern "C" int esb_scan_device(esb_context* c, esb_scan_result* out) {
+    if (!c || !out) return ESB_ERR_ARG;
+    *out = c->scan_dev;
+    return ESB_OK;
+}
+
 template <class T>
 static int ensure_pinned(esb_context* c, T*& p, size_t& cap, size_t need) {
     if (need <= cap && p) return ESB_OK;
@@ -1504,7 +1515,8 @@ static int ensure_pinned(esb_context* c, T*& p, size_t& cap, size_t need) {
 extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model* models,
                                const double* const* fields, int32_t n_fields, int32_t n_nodes,
                                const double* boundary, int32_t n_modes, const int32_t* modes, double tol_percent,
-                               int32_t capacity_per_table, int32_t* n_brackets, esb_scan_result* out) {
+                               int32_t capacity_per_table, int32_t download, int32_t* n_brackets,
+                               esb_scan_result* out) {
     if (!c) return ESB_ERR_ARG;
     if (n_models < 1 || !models || !fields || !boundary || !out) return fail(c, ESB_ERR_ARG, "bad scan arguments");
     if (c->ax_nk <= 0 || c->ax_nw <= 1) return fail(c, ESB_ERR_ARG, "axes not uploaded (need nw >= 2)");
@@ -1528,8 +1540,9 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
     if (bad_modes) return fail(c, ESB_ERR_ARG, "bad modes");
     const size_t tab_doubles = hm[0].tab.size();
     const int n_tables = n_models * n_modes;
-    const int cap = capacity_per_table > 0 ? capacity_per_table
-                                           : (int)std::max<size_t>(4096, plane / 24);
+    // even: every table of the packed allocation then starts 8-byte aligned
+    const int cap = ((capacity_per_table > 0 ? capacity_per_table
+                                             : (int)std::max<size_t>(4096, plane / 24)) + 1) & ~1;
     const size_t table_bytes = slot_bytes((size_t)cap);
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t s = cur_stream(c);
@@ -1590,8 +1603,13 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
                 r.k = c->d_k; r.w = c->d_w; r.layout = layout;
                 r.sw = sw;
                 r.counter = c->d_counter;
-                // the bracket count is on the device only: a full persistent launch, schedule by grid size
-                const bool warp_path = c->schedule == 2 || (c->schedule == 0 && plane * n_modes <= 200000);
+                // the bracket count is on the device only: a full persistent launch, the schedule from an
+                // estimate (one bracket per 64 grid points: the bench sweep has one per 107) against the
+                // measured crossovers of esb_sweep_resident_multi
+                const size_t n_est = plane * n_modes / 64;
+                const size_t limit = (kind == KIND_CYL_DENSITY || kind == KIND_CYL_FLOW) ? 24000
+                                     : kind == KIND_CYL_ROTATION ? 100000 : 250000;
+                const bool warp_path = c->schedule == 2 || (c->schedule == 0 && n_est <= limit);
                 const int n_launch = (int)std::min<size_t>(plane, (size_t)1 << 30);
                 const cudaError_t e = dispatch_kind(kind, hm[0].dm.scheme, [&](auto kd, auto scheme) {
                     if (warp_path)
@@ -1631,7 +1649,7 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
     const size_t entry = 3 * sizeof(double) + 6 * sizeof(int);
     const size_t cap_e = (total + 1) & ~(size_t)1;
     if ((rc = ensure(c, c->d_compact, c->cap_compact, cap_e * entry + 64))) return rc;
-    if ((rc = ensure_pinned(c, c->h_compact, c->cap_h_compact, cap_e * entry + 64))) return rc;
+    if (download && (rc = ensure_pinned(c, c->h_compact, c->cap_h_compact, cap_e * entry + 64))) return rc;
     auto carve = [&](char* base, esb_scan_result& r) {
         double* d = (double*)base;
         int* q = (int*)(d + 3 * cap_e);
@@ -1641,15 +1659,21 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
     };
     esb_scan_result dv{}, hv{};
     carve(c->d_compact, dv);
-    carve(c->h_compact, hv);
+    if (download) carve(c->h_compact, hv);
+    dv.n_entries = (int32_t)total;
+    c->scan_dev = dv;
     if (total > 0) {
         ScanOut so{dv.model, dv.slot, dv.k_index, dv.w_index, dv.accepted, dv.iterations, dv.omega, dv.ext, dv.intq};
         scan_compact_kernel<<<n_tables, 256, 0, s>>>(c->d_scan_roots, table_bytes, cap, n_modes, d_counts, d_offsets, so);
         CUDA_TRY(c, cudaGetLastError());
         c->launches += 1;
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_compact, c->d_compact, cap_e * entry, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (download) {
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_compact, c->d_compact, cap_e * entry, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
     }
+    CUDA_TRY(c, cudaEventRecord(c->ev_done, s));
+    c->tables_pending = true;
     hv.n_entries = (int32_t)total;
     *out = hv;
     if (overflow) return fail(c, ESB_ERR_CAPACITY, "capacity_per_table too small (n_brackets holds the sizes found)");

@@ -50,12 +50,17 @@ class ScanResult:
 
 
 def parameter_scan(solver: DispersionSolver, points, k, W, modes, layout="phase_speed", tol_percent=1.0,
-                   rank=0, world=1, keep_tables=False, capacity_per_table=0) -> ScanResult:
+                   rank=0, world=1, keep_tables=False, capacity_per_table=0, download=True) -> ScanResult:
     """Sweep every equilibrium in `points` (list of dicts with optional keys 'medium', 'profile' and
-    a free-form 'label') over the (k, W) grid: this rank's rows are k[rank::world], all equilibria."""
+    a free-form 'label') over the (k, W) grid: this rank's rows are k[rank::world], all equilibria.
+    download=False: the compact table stays on the device (result.table is None; gather_scan_modes_device
+    reads it in place)."""
     k_loc, k_off, k_stride = shard_k(np.asarray(k, dtype=np.float64), rank, world, layout="strided")
     solver.upload_axes(k_loc, W, layout)
-    tab, nb = solver.scan_models(points, modes, tol_percent, capacity_per_table)
+    tab, nb = solver.scan_models(points, modes, tol_percent, capacity_per_table, download=download)
+    if tab is None:
+        pts = [ScanPoint(p.get("label", {}), [int(x) for x in nb[i]], None) for i, p in enumerate(points)]
+        return ScanResult(pts, None, k_loc, k_off, k_stride)
     out = []
     n_slots = len(list(modes))
     # entries of (model i, slot m) are contiguous and in this order
@@ -96,6 +101,36 @@ def gather_scan_modes(result: ScanResult, device, group=None):
     bufs = [torch.zeros_like(pay) for _ in range(world)]
     dist.all_gather(bufs, pay, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def gather_scan_modes_device(solver: DispersionSolver, result: ScanResult, device, group=None):
+    """The same gather straight from the library's device buffers (no host round trip): NCCL over NVLink
+    moves (model, mode slot, global k row, omega) of the accepted modes of every rank."""
+    import torch
+    import torch.distributed as dist
+    from .distributed import _DevArray, _consumer_stream
+
+    world = dist.get_world_size(group)
+    info = solver.scan_table_device(stream=_consumer_stream(device))
+    n = info["n"]
+    if n:
+        col = lambda name: torch.as_tensor(_DevArray(info[name][0], n, info[name][1]), device=device)
+        m = col("accepted") == 1
+        mine = torch.stack((col("model")[m].to(torch.float64), col("slot")[m].to(torch.float64),
+                            col("k_index")[m].to(torch.float64) * float(result.k_stride) + float(result.k_offset),
+                            col("omega")[m]), dim=1)
+    else:
+        mine = torch.zeros((0, 4), dtype=torch.float64, device=device)
+    cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device=device)
+    counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts = counts.tolist()
+    cap = max(max(counts), 1)
+    pay = torch.zeros((cap, 4), dtype=torch.float64, device=device)
+    pay[: mine.shape[0]] = mine
+    out = torch.empty((world * cap, 4), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, pay, group=group)
+    return torch.cat([out[r * cap: r * cap + c] for r, c in enumerate(counts)], dim=0)
 
 
 def density_flow_grid(contrasts, flow_amplitudes, base_density: Medium = None, base_flow: FlowMedium = None,

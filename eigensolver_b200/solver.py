@@ -528,12 +528,13 @@ class DispersionSolver:
                 "esb_download_roots_slot")
         return RootTable(ki, wi, self._k_host, om, ex, iq, ac, it, n)
 
-    def scan_models(self, points, modes, tol_percent=1.0, capacity_per_table=0):
+    def scan_models(self, points, modes, tol_percent=1.0, capacity_per_table=0, download=True):
         """A parameter scan as ONE batched job (esb_scan_models): every equilibrium in `points` (dicts
         with optional 'medium' and 'profile', on this solver's mesh) swept over the uploaded axes with no
         host synchronisation in between.  Returns (table, n_brackets): `table` = dict of numpy VIEWS of
         page-locked buffers owned by the context (model, slot, k_index, w_index, omega, ext, intq,
-        accepted, iterations; valid until the next scan), n_brackets[model][mode]."""
+        accepted, iterations; valid until the next scan), n_brackets[model][mode].
+        download=False: the table stays on the device (table = None; see scan_table_device)."""
         import copy
         md = np.array([self._mode(m) for m in modes], dtype=np.int32)
         specs = []
@@ -551,9 +552,11 @@ class DispersionSolver:
         nb = np.zeros(n * md.size, np.int32)
         out = L.esb_scan_result()
         rc = self.lib.esb_scan_models(self.ctx, n, models, fptr, nf, self.spec.nodes.size, _dptr(boundary),
-                                      md.size, _iptr(md), float(tol_percent), int(capacity_per_table), _iptr(nb),
-                                      C.byref(out))
+                                      md.size, _iptr(md), float(tol_percent), int(capacity_per_table),
+                                      1 if download else 0, _iptr(nb), C.byref(out))
         L.check(self.lib, self.ctx, rc, "esb_scan_models")
+        if not download:
+            return None, nb.reshape(n, md.size)
         ne = out.n_entries
         names = ("model", "slot", "k_index", "w_index", "accepted", "iterations", "omega", "ext", "intq")
         if ne == 0:
@@ -561,6 +564,20 @@ class DispersionSolver:
         else:
             tab = {nm: np.ctypeslib.as_array(getattr(out, nm), shape=(ne,)) for nm in names}
         return tab, nb.reshape(n, md.size)
+
+    def scan_table_device(self, stream=None):
+        """Device pointers of the compact table of the last scan_models: dict name -> (pointer, numpy
+        dtype string), plus 'n'.  `stream` as in roots_device."""
+        L.check(self.lib, self.ctx,
+                self.lib.esb_tables_wait(self.ctx, C.c_void_p(int(stream)) if stream else None),
+                "esb_tables_wait")
+        out = L.esb_scan_result()
+        L.check(self.lib, self.ctx, self.lib.esb_scan_device(self.ctx, C.byref(out)), "esb_scan_device")
+        addr = lambda p: C.cast(p, C.c_void_p).value or 0
+        tab = {nm: (addr(getattr(out, nm)), "<f8" if nm in ("omega", "ext", "intq") else "<i4")
+               for nm in ("model", "slot", "k_index", "w_index", "accepted", "iterations", "omega", "ext", "intq")}
+        tab["n"] = out.n_entries
+        return tab
 
     def roots_device(self, slot=0, stream=None):
         """Device pointers of the root table of mode slot `slot` (valid until the next sweep):

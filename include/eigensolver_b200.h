@@ -241,8 +241,12 @@ typedef struct esb_scan_result {
 } esb_scan_result;
 int esb_scan_models(esb_context* ctx, int32_t n_models, const esb_model* models, const double* const* fields,
                     int32_t n_fields, int32_t n_nodes, const double* boundary, int32_t n_modes,
-                    const int32_t* modes, double tol_percent, int32_t capacity_per_table,
+                    const int32_t* modes, double tol_percent, int32_t capacity_per_table, int32_t download,
                     int32_t* n_brackets /* [n_models * n_modes] */, esb_scan_result* out);
+/* download = 0 leaves the compact table on the device (out->n_entries is set, its pointers are NULL):
+ * esb_scan_device hands out the device pointers (multi-GPU gathers read them in place; order the consumer
+ * with esb_tables_wait). */
+int esb_scan_device(esb_context* ctx, esb_scan_result* out);
 
 /* D2H copy of the root table of `slot` into page-locked host buffers OWNED BY THE CONTEXT; *out
  * receives their addresses, *n_roots the entry count.  One packed copy at full PCIe rate, no

@@ -751,6 +751,17 @@ def test_device_side_gather_equals_host_table(solvers):
                                          np.full(int((h.accepted == 1).sum()), float(slot))], axis=1)
                                for slot, h in enumerate(hosts)])
         assert np.array_equal(allm, want)
+        # a parameter scan left on the device and gathered from there == the downloaded compact table
+        from eigensolver_b200.scan import density_flow_grid, gather_scan_modes_device, parameter_scan
+        dens, _ = density_flow_grid([0.15, 0.3], [0.5])
+        with esb.DispersionSolver("cylinder_density") as sc:
+            host = parameter_scan(sc, dens, k, W, [0, 1])
+            acc = np.asarray(host.table["accepted"]) == 1
+            want = np.stack([np.asarray(host.table[c])[acc].astype(np.float64) for c in ("model", "slot", "k_index", "omega")], axis=1)
+            res = parameter_scan(sc, dens, k, W, [0, 1], download=False)
+            assert res.table is None
+            got = gather_scan_modes_device(sc, res, dev).cpu().numpy()
+        assert len(want) > 0 and np.array_equal(got, want)
     finally:
         dist.destroy_process_group()
 
