@@ -73,7 +73,7 @@ def test_grid_brackets_and_roots_match_c_oracle(solvers, name):
         # refined roots (accepted modes) vs the oracle's own refinement of the same bracket
         idx = np.nonzero(sel_g & (tab.accepted == 1))[0]
         assert len(idx) >= 3
-        for j in idx[:: max(1, len(idx) // 12)]:
+        for j in idx:                       # EVERY accepted root above the noise floor
             kk = k[tab.k_index[j]]
             r, er, ir = ork.refine(model, mode, kk, kk * W[tab.w_index[j]], kk * W[tab.w_index[j] + 1])
             assert abs(tab.omega[j] - r) <= ROOT_TOL * abs(r), (mode, kk, r, tab.omega[j])
@@ -585,6 +585,66 @@ def test_rk4_and_rk8_agree():
             eb, ib = b.dispersion_grid(1, k, W)
         assert np.array_equal(ea, eb, equal_nan=True)
         assert np.nanmax(np.abs(ia - ib) / np.abs(ia)) < 1e-6, kind           # 4th order at 2048 steps
+
+
+#: BASELINE.json configs[0..3]: (case, modes, k axis, W axis) at full size
+BASELINE_GRIDS = {
+    "configs[0]": ("slab_density", [0, 1], np.linspace(0.001, 0.75, 200), np.linspace(0.41, 2.95, 2000)),
+    "configs[1]": ("cylinder_density", [0, 1, 2, 3], np.linspace(0.01, 4.5, 1000), np.linspace(0.5, 5.0, 10000)),
+    "configs[2]": ("slab_flow", [0, 1], np.linspace(0.01, 4.5, 2000), np.linspace(-2.7, 2.7, 20000)),
+    "configs[3]": ("cylinder_rotation", [0, 1, 2, 3], np.linspace(0.25, 4.0, 2000), np.linspace(0.40, 1.6, 20000)),
+}
+
+
+@pytest.mark.parametrize("config", list(BASELINE_GRIDS))
+def test_oracle_samples_on_baseline_grids(solvers, config):
+    """The oracle ON the BASELINE coordinates: 40 rows of the full-size k axis (the smallest wavenumbers
+    0.01 <= k < 0.05 included, where the exterior starts at |r| = 1885) x 400 columns of the full-size
+    omega axis, evaluated by the throughput kernel (one thread per point, every mode fused, n = 3
+    included), every point above the noise floor compared with the C oracle: > 2000 points per mode."""
+    name, modes, k_full, W_full = BASELINE_GRIDS[config]
+    case, s = CASES[name], solvers[name]
+    rng = np.random.default_rng(2024)
+    small = np.nonzero(k_full < 0.05)[0]
+    rows = np.unique(np.concatenate([small[:: max(1, len(small) // 8)][:8] if len(small) else [0],
+                                     rng.choice(len(k_full), 34, replace=False)]))
+    cols = np.sort(rng.choice(len(W_full), 400, replace=False))
+    k, W = k_full[rows], W_full[cols]
+    model = case.c_model()
+    s.set_schedule("lane")
+    try:
+        fused = modes[:3]
+        E, I = s.dispersion_grid_multi(fused, k, W)
+        grids = {m: (E[j], I[j]) for j, m in enumerate(fused)}
+        for m in modes[3:]:
+            grids[m] = s.dispersion_grid(m, k, W)
+    finally:
+        s.set_schedule("auto")
+    for m in modes:
+        e, i = grids[m]
+        e0, i0 = ork.grid(model, m, k, W)
+        fin = np.isfinite(e0) & np.isfinite(i0)
+        assert np.array_equal(np.isfinite(e) & np.isfinite(i), fin)
+        ok = case.regular(k, W, m) & fin
+        assert ok.sum() > 2000, (config, m, ok.sum())
+        dev = (np.abs((e - i) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0)))[ok]
+        # 99.9 % within 1e-10, every point within D_TOL except the grid points next to a pole of D (Y -> 0:
+        # int = N/Y amplifies the 1e-10 error of Y), which stay within 2e-8
+        assert np.quantile(dev, 0.999) < 2e-10, (config, m, np.quantile(dev, 0.999))
+        assert (dev > D_TOL).sum() <= 2 and dev.max() < 2e-8, (config, m, dev.max(), (dev > D_TOL).sum())
+        if len(small):
+            lo = ok & (k[:, None] < 0.05)
+            assert lo.sum() > 300 and (np.abs((e - i) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0)))[lo].max() < D_TOL
+        # the brackets of these rows: identical index sets above the noise floor, every accepted root checked
+        tab = s.find_roots(m, k, W)
+        ok_iv = ok[:, :-1] & ok[:, 1:]
+        ok_, ow_ = ork.brackets(e0 - i0)
+        sel_o, sel_g = ok_iv[ok_, ow_], ok_iv[tab.k_index, tab.w_index]
+        assert np.array_equal(ok_[sel_o], tab.k_index[sel_g]) and np.array_equal(ow_[sel_o], tab.w_index[sel_g])
+        for j in np.nonzero(sel_g & (tab.accepted == 1))[0]:
+            kk = k[tab.k_index[j]]
+            r, _, _ = ork.refine(model, m, kk, kk * W[tab.w_index[j]], kk * W[tab.w_index[j] + 1])
+            assert abs(tab.omega[j] - r) <= ROOT_TOL * abs(r), (config, m, kk, r, tab.omega[j])
 
 
 def test_full_size_properties(solvers):

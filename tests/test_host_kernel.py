@@ -45,6 +45,32 @@ def test_host_build_matches_c_oracle(name):
         assert np.nanmax(dev[ok]) < D_TOL, (mode, np.nanmax(dev[ok]))
 
 
+@pytest.mark.parametrize("name,kmin,kmax,modes", [("cylinder_density", 0.01, 4.5, [0, 1, 2, 3]),
+                                                  ("slab_density", 0.001, 0.75, [0, 1]),
+                                                  ("slab_flow", 0.01, 4.5, [0, 1]),
+                                                  ("cylinder_rotation", 0.25, 4.0, [0, 1, 2, 3]),
+                                                  ("cylinder_flow", 0.01, 4.0, [0, 1, 2, 3])])
+def test_host_build_on_baseline_coordinates(name, kmin, kmax, modes):
+    """Random (k, omega) from the BASELINE k ranges - 40 % of them in the lowest decade of k, where the
+    exterior solution starts thousands of radii out - and every azimuthal order up to n = 3."""
+    case = CASES[name]
+    model = case.c_model()
+    rng = np.random.default_rng(11)
+    k = np.concatenate([rng.uniform(kmin, min(5 * kmin, kmax), 160), rng.uniform(kmin, kmax, 240)])
+    W = rng.uniform(case.W[0], case.W[1], k.size)
+    sp = spec_of(case)
+    for mode in modes:
+        e, i, _ = hk.evaluate(sp, [mode], k, k * W)
+        ref = np.array([ork.point(model, mode, kk, kk * ww) for kk, ww in zip(k, W)])
+        e0, i0 = ref[:, 0], ref[:, 1]
+        fin = np.isfinite(e0) & np.isfinite(i0)
+        assert np.array_equal(np.isfinite(e[0]) & np.isfinite(i[0]), fin)
+        ok = fin & np.array([case.regular(kk, np.array([ww]), mode)[0, 0] for kk, ww in zip(k, W)])
+        assert ok.sum() > 100
+        dev = np.abs((e[0] - i[0]) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+        assert dev[ok].max() < D_TOL, (mode, dev[ok].max())
+
+
 @pytest.mark.parametrize("kind", ["cylinder_density", "cylinder_flow", "slab_density"])
 def test_normal_form_and_first_derivative_form_agree(kind):
     """ESB_RK8N (u = sqrt|F| y, Nystrom form) and ESB_RK8 ((y, h y') variables) are two discretisations of
