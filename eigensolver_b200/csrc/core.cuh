@@ -1028,23 +1028,27 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
                 den_q[s] = P[0];
                 xi_b = Pb * X[0] / P[0];
             } else {
-                // kink (:308): P(axis end) = c = -(B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1), xi(axis end) free:
-                // the two fundamental solutions (1, 0), (0, 1) from there; P(1) = c P1 + alpha P2 = P_e
-                double P[2] = {1.0, 0.0}, X[2] = {0.0, 1.0};
+                // kink (:308): P(axis end) = c = -(B_phi(1)^2 - rho(1) v_phi(1)^2) xi_e(1), xi(axis end) free.
+                // ONE solution suffices here too: the system matrix has trace m11 + m22 = -1/r, so the
+                // Wronskian of any two solutions obeys r W(r) = const (Abel).  With y = (P, xi) the wanted
+                // solution and (P2, X2) the one started from (0, 1) at the axis end,
+                //     P X2 - P2 xi = c r_axis / r      =>   xi(1) = (P_e X2(1) - c r_axis/s_start) / P2(1)
+                // (the same value the superposition c (P1, X1) + alpha (P2, X2) with P(1) = P_e gives, without
+                // integrating (P1, X1)).
+                double P[1] = {0.0}, X[1] = {1.0};
 #ifdef __CUDA_ARCH__
                 if constexpr (WARP) {
                     double T[4];
                     warp_transfer(0, M.n_steps, [&](int i0, int i1, double (&u)[2], double (&v)[2]) {
                         integrate_rotation<2, true>(M, pt, mm, tab, u, v, i0, i1);
                     }, T);
-                    P[0] = T[0]; P[1] = T[1]; X[0] = T[2]; X[1] = T[3];
+                    P[0] = T[1]; X[0] = T[3];
                 } else
 #endif
-                integrate_rotation<2>(M, pt, mm, tab, P, X);
+                integrate_rotation<1>(M, pt, mm, tab, P, X);
                 const double c = M.rho_vb2 * xi_e;
-                const double alpha = (Pb - c * P[0]) / P[1];
-                den_q[s] = P[1];
-                xi_b = fma(c, X[0], alpha * X[1]);
+                den_q[s] = P[0];
+                xi_b = fma(Pb, X[0], -c * (M.r_axis / M.s_start)) / P[0];
             }
             ext_q[s] = xi_e;
             int_q[s] = xi_b;      // xi_i(1) = (C1 P + D P')/C3 at r = 1   (:314)

@@ -92,6 +92,22 @@ POINTS["cylinder_rotation_kink_p1"] = dict(
     solver="cylinder_rotation_kink", overrides={"v_twist": 0.1, "power": 1.0},
     ks=[0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.55, 0.8, 0.97, 1.1, 1.2, 1.3, 1.45, 0.49, 1.6])
 
+# the kink scripts at their OWN shipped rotation laws (power 0.8: the Doppler shift m v_phi/r grows towards
+# the axis, so part of every scan crosses a resonance near the axis; "regular_only" keeps the candidate
+# points at which neither D nor C3 changes sign inside the layer - tests/helpers.py::rotation_regular -
+# plus the skipped ones, because the reference needs minutes per point across a resonance)
+POINTS["cylinder_rotation_kink_p08"] = dict(
+    solver="cylinder_rotation_kink", overrides={}, regular_only=(0.25, 0.8, 0.001),
+    ks=[0.25, 0.31, 0.37, 0.6, 1.0, 1.5, 2.0, 2.5, 3.0, 3.5, 4.0],
+    Ws=[0.97, 1.05, 1.1, 1.2, 1.28, 1.33, 1.37, 1.39, 1.45, 0.49, 1.6])
+# the sausage script with the same law (its own layer end, r = 0.01)
+POINTS["cylinder_rotation_sausage_p08"] = dict(
+    solver="cylinder_rotation_sausage", overrides={"v_twist": 0.25, "power": 0.8}, regular_only=(0.25, 0.8, 0.01),
+    ks=[0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.55, 0.8, 0.97, 1.1, 1.2, 1.3, 1.45, 0.49, 1.6])
+POINTS["cylinder_rotation_kink_slow_p08"] = dict(
+    solver="cylinder_rotation_kink_slow", overrides={}, regular_only=(0.1, 0.8, 0.001),
+    ks=[0.05, 0.2, 0.5, 1.0, 2.0, 3.0, 4.0], Ws=[0.95, 1.02, 1.08, 1.15, 1.19, 1.3, 1.45, 0.49, 1.6])
+
 SCANS = {
     # (mode, k, W_lo, W_hi, n)  - intervals that contain a mode
     "cylinder_density_coronal": [("kink", 1.0, 2.95, 4.9, 30), ("sausage", 2.0, 2.95, 4.9, 30),
@@ -122,6 +138,22 @@ PICKLES = {
 }
 
 
+def _rotation_point_ok(law, mode, k, W, margin=0.03):
+    """skipped by the reference (m_e < 0), or regular: no resonance inside the layer at W and W +- margin"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import helpers
+    from oracle import reference_path as rp
+    md = rp.CYL_PHOTOSPHERIC
+    if md.m_e(k, W * k) < 0:
+        return True
+    vt, pw, s_end = law
+    ok = helpers.regular_mask(np.array([W]), helpers.rotation_continua(md, vt, pw, s_end, mode, k), margin)[0]
+    for dW in (-margin, 0.0, margin):
+        ok = ok and helpers.rotation_regular(md, vt, pw, s_end, mode, k, np.array([W + dW]))[0]
+    return bool(ok)
+
+
 def main():
     only = sys.argv[1:]
     for name, spec in POINTS.items():
@@ -135,6 +167,8 @@ def main():
                 continue
             for k in spec["ks"]:
                 for W in spec["Ws"]:
+                    if spec.get("regular_only") and not _rotation_point_ok(spec["regular_only"], mode_id, k, W):
+                        continue
                     rows.append((mode_id, k, W * k, ref.D(mode, k, W * k)))
         a = np.array(rows)
         np.savez(os.path.join(HERE, "ref_D_%s.npz" % name), mode=a[:, 0].astype(np.int32), k=a[:, 1],
@@ -166,17 +200,20 @@ def main():
             roots[key + "_sausage_k"] = np.real(np.asarray(sk)).astype(np.float64)
             roots[key + "_kink_w"] = np.real(np.asarray(kw)).astype(np.float64)
             roots[key + "_kink_k"] = np.real(np.asarray(kk)).astype(np.float64)
-    # rotational flow: [omega, k] per file; regular regime (power >= 1) only
-    rot = "Cylinder/Rotational flow/Photospheric/Example data/Cylindrical_photospheric_vtwist%s_power%s_%s.pickle"
-    for vt, pw, kind in (("01", "1", "sausage_fast"), ("01", "125", "sausage_fast"), ("015", "1", "sausage_fast"),
-                         ("01", "1", "fund_kink"), ("01", "125", "fund_kink"), ("015", "1", "fund_kink")):
-        with open(os.path.join(REF_ROOT, rot % (vt, pw, kind)), "rb") as fh:
+    # rotational flow: [omega, k] per file, every shipped table (54: four rotation amplitudes x powers
+    # 0.8, 0.9, 1, 1.25 x the sausage / kink, fast / slow scripts); key rot_v<amp>_p<power>_<file suffix>
+    rot_dir = os.path.join(REF_ROOT, "Cylinder/Rotational flow/Photospheric/Example data")
+    for path in sorted(glob.glob(os.path.join(rot_dir, "Cylindrical_photospheric_vtwist*_power*_*.pickle"))):
+        stem = os.path.basename(path)[len("Cylindrical_photospheric_vtwist"):-len(".pickle")]
+        vt, rest = stem.split("_power", 1)
+        pw, kind = rest.split("_", 1)
+        with open(path, "rb") as fh:
             w, k = pickle.load(fh, encoding="latin1")
-        key = "rot_v%s_p%s_%s" % (vt, pw, "sausage" if "sausage" in kind else "kink")
+        key = "rot_v%s_p%s_%s" % (vt, pw, kind)
         roots[key + "_w"] = np.real(np.asarray(w)).astype(np.float64)
         roots[key + "_k"] = np.real(np.asarray(k)).astype(np.float64)
     np.savez(os.path.join(HERE, "ref_roots.npz"), **roots)
-    print("ref_roots.npz:", len(roots) // 5, "tables")
+    print("ref_roots.npz:", len(roots), "arrays")
 
 
 if __name__ == "__main__":

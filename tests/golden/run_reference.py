@@ -60,6 +60,11 @@ SOLVERS = {
         "wavenumber = np.linspace(0.25,0.37,20)",
         {"kink": ("kink", "xi_diff_check")},
     ),
+    "cylinder_rotation_kink_slow": (
+        "Cylinder/Rotational flow/Photospheric/Solvers/Twisted_photospheric_nonlinear_flow_kink_slow.py",
+        "wavenumber = np.linspace(0.01,0.5,60)",
+        {"kink": ("kink", "xi_diff_check")},
+    ),
     "cylinder_rotation_sausage": (
         "Cylinder/Rotational flow/Photospheric/Solvers/Twisted_photospheric_flow_sausage.py",
         "wavenumber = np.linspace(0.75,4.,110.)",

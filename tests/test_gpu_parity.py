@@ -55,7 +55,7 @@ def test_grid_brackets_and_roots_match_c_oracle(solvers, name):
         ok = reg & np.isfinite(e0) & np.isfinite(i0)
         e0 = np.where(np.isfinite(e0) & np.isfinite(i0), e0, np.nan)
         i0 = np.where(np.isfinite(e0), i0, np.nan)
-        assert ok.sum() > 0.25 * ok.size
+        assert ok.sum() > case.min_regular * ok.size
         dev = np.abs((ext - inq) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
         assert np.nanmax(dev[ok]) < D_TOL, (mode, np.nanmax(dev[ok]))
         assert np.nanmax(np.abs(ext - e0)[ok] / np.abs(e0)[ok]) < 1e-10     # closed-form exterior

@@ -157,11 +157,13 @@ def test_c_oracle_equals_converged_scipy_path(name):
 
 @pytest.mark.parametrize("fixture,mode,v_twist,power", [
     ("cylinder_rotation_sausage", 0, 0.15, 1.25), ("cylinder_rotation_kink", 1, 0.15, 1.25),
-    ("cylinder_rotation_sausage_p1", 0, 0.1, 1.0), ("cylinder_rotation_kink_p1", 1, 0.1, 1.0)])
+    ("cylinder_rotation_sausage_p1", 0, 0.1, 1.0), ("cylinder_rotation_kink_p1", 1, 0.1, 1.0),
+    ("cylinder_rotation_kink_p08", 1, 0.25, 0.8), ("cylinder_rotation_kink_slow_p08", 1, 0.1, 0.8)])
 def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode, v_twist, power):
     """Rotational-flow cylinder: D from the reference's own sausage()/kink() (scipy defaults, sympy
-    coefficients rebuilt per point) vs the restatement (sympy coefficients built once), for the two
-    rotation laws v_phi = 0.15 r^1.25 and v_phi = 0.1 r."""
+    coefficients rebuilt per point) vs the restatement (sympy coefficients built once), for the
+    rotation laws v_phi = 0.15 r^1.25, v_phi = 0.1 r and - the two kink scripts exactly as shipped -
+    v_phi = 0.25 r^0.8 (..._kink_fast.py:176-177) and 0.1 r^0.8 (..._kink_slow.py:176-177)."""
     import helpers
     md = rp.CYL_PHOTOSPHERIC
     s_end = 0.01 if mode == 0 else 0.001
@@ -176,8 +178,17 @@ def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode, v_
             ok = ok and helpers.rotation_regular(md, v_twist, power, s_end, mode, k, np.array([W + dW]))[0]
         return ok
 
+    # power < 1, layer down to r = 0.001: LSODA at its default 1.5e-8 tolerance is amplified by the
+    # 1/r^2 growth of the coefficients towards the axis, so two evaluations of the SAME formulation at the
+    # reference's settings (fsolve vs two linear shots) already differ by 1e-3..5e-2 of the scale, and the
+    # reference's value sits 2-14 % off the converged one (same sign) - its usual amplitude error
+    # (DESIGN.md).  The port reproduces the executed reference to within that same noise (1e-10 at most
+    # points, up to 6e-2 where fsolve's termination decides), and the C oracle the
+    # converged value (< 1e-10).
+    steep = power < 1.0
+    skip_tol, agree_tol, stride = (0.1, 0.1, 1) if steep else (1e-4, 2e-3, 2)
     n_checked = n_skipped = 0
-    for k, w, Dref in list(zip(g["k"], g["w"], g["D"]))[::2]:
+    for k, w, Dref in list(zip(g["k"], g["w"], g["D"]))[::stride]:
         Dor = rp.D(model, k, w)
         if np.isnan(Dref):
             assert np.isnan(Dor)
@@ -186,38 +197,67 @@ def test_rotation_oracle_equals_executed_reference(golden_dir, fixture, mode, v_
         if not regular(k, w / k):
             continue
         el, il = rp.dispersion(model, k, w, shoot="linear")
-        if abs((el - il) - Dor) > 1e-4 * max(abs(el), abs(il)):
+        if abs((el - il) - Dor) > skip_tol * max(abs(el), abs(il)):
             continue                      # reference fsolve stopped short of convergence
         # coefficients evaluated in a different floating-point order (sympy cse once vs per point)
         # steer LSODA through different step sequences: agreement at its 1e-8 tolerance amplified
         # by the 1/r^2 growth towards the axis, not at rounding level
-        assert abs(Dor - Dref) <= 2e-3 * max(abs(el), abs(il)), (k, w, Dref, Dor)
+        assert abs(Dor - Dref) <= agree_tol * max(abs(el), abs(il)), (k, w, Dref, Dor)
         # and the C restatement (first-order system, no coefficient derivatives) agrees with the converged path
         e2, i2 = ork.point(c_model, mode, k, w)
         et, it_ = rp.dispersion(model, k, w, **TIGHT)
         assert abs((e2 - i2) - (et - it_)) <= 1e-7 * max(abs(et), abs(it_)), (k, w)
+        # the reference's own value: the converged one with its amplitude error, never another sign
+        # (where D is not a small difference of ext and int, i.e. away from a root)
+        if abs(et - it_) > 1e-2 * max(abs(et), abs(it_)):
+            assert 0.5 < Dref / (et - it_) < 1.6, (k, w, Dref, et - it_)
         n_checked += 1
-    assert n_checked >= 6 and n_skipped >= 2
+    assert n_checked >= (12 if steep else 6) and n_skipped >= 2
+
+
+ROT_AMPLITUDES = {"005": 0.05, "01": 0.1, "015": 0.15, "025": 0.25}
+ROT_POWERS = {"08": 0.8, "09": 0.9, "1": 1.0, "125": 1.25}
+
+
+def rotation_tables(g):
+    """(key, v_twist, power, mode, s_end) of every shipped rotational root table in ref_roots.npz"""
+    out = []
+    for f in sorted(g.files):
+        if not (f.startswith("rot_v") and f.endswith("_k")):
+            continue
+        key = f[:-2]
+        vt, pw, kind = key[len("rot_v"):].split("_", 2)
+        mode = 0 if "sausage" in kind else 1
+        out.append((key, ROT_AMPLITUDES[vt], ROT_POWERS[pw[1:]], mode, 0.01 if mode == 0 else 0.001))
+    return out
 
 
 def test_rotation_shipped_root_tables(golden_dir):
-    """Example data of the rotational-flow solvers (regular regime, power >= 1).  Those scripts
-    accept at 1.5-4.5 % (their xi_tol / P_tol), and the kink files were produced with end points
-    and tolerances that changed between runs, so the band checked here is 5 %."""
+    """Example data of the rotational-flow solvers: ALL 54 shipped tables - four rotation amplitudes,
+    powers 0.8, 0.9, 1, 1.25, the sausage and the kink scripts (22 + 32 tables).  The scripts accept at
+    1.5-4.5 % (their xi_tol / P_tol) and the kink files were produced with end points and tolerances that
+    changed between runs, so the band checked here is 5 %.  Every table, power 0.8 and kink included, has
+    >= 85 % of its regular points inside the band under the C oracle, and >= 65 % of the sampled points of every
+    table are regular (no resonance inside the layer): the shipped rotational results lie where parity
+    with the reference is defined."""
+    import helpers
     g = np.load(os.path.join(golden_dir, "ref_roots.npz"))
-    case = CASES["cylinder_rotation"]
-    md = case.rp_medium()
+    md = rp.CYL_PHOTOSPHERIC
+    tables = rotation_tables(g)
+    assert len(tables) == 54 and sum(t[3] for t in tables) == 32
     total = inside = 0
-    for key, vt, pw, mode, s_end in (("rot_v01_p1_sausage", 0.1, 1.0, 0, 0.01),
-                                     ("rot_v01_p125_sausage", 0.1, 1.25, 0, 0.01),
-                                     ("rot_v015_p1_sausage", 0.15, 1.0, 0, 0.01)):
+    for key, vt, pw, mode, s_end in tables:
         k, w = g[key + "_k"][::3], g[key + "_w"][::3]
         model = ork.make_model("cylinder_rotation", medium=md, v_twist=vt, power=pw, s_end=s_end)
         pct = np.array([rp.mismatch_percent(*ork.point(model, mode, a, b)) for a, b in zip(k, w)])
-        pct = pct[np.isfinite(pct)]
-        total += len(pct)
-        inside += int((pct < 5.0).sum())
-    assert total > 120 and inside / total > 0.85, (inside, total)
+        reg = np.array([helpers.rotation_regular(md, vt, pw, s_end, mode, a, np.array([b / a]))[0]
+                        for a, b in zip(k, w)])
+        ok = np.isfinite(pct) & reg
+        assert ok.sum() >= 0.65 * len(k), (key, int(ok.sum()), len(k))
+        assert (pct[ok] < 5.0).mean() > 0.85, (key, float((pct[ok] < 5.0).mean()))
+        total += int(ok.sum())
+        inside += int((pct[ok] < 5.0).sum())
+    assert total > 2000 and inside / total > 0.95, (inside, total)
 
 
 def test_fsolve_and_linear_shooting_agree():
