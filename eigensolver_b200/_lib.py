@@ -55,6 +55,14 @@ class esb_scan_result(C.Structure):
     ]
 
 
+class esb_guard_report(C.Structure):
+    _fields_ = [
+        ("worst", C.c_double), ("threshold", C.c_double),
+        ("slot", C.c_int32), ("k_index", C.c_int32), ("w_index", C.c_int32), ("stride", C.c_int32),
+        ("n_checked", C.c_int64), ("n_above", C.c_int64),
+    ]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _ctx = C.c_void_p
@@ -96,10 +104,17 @@ SYMBOLS = {
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "esb_tables_wait": (C.c_int, [_ctx, C.c_void_p]),
     "esb_set_accept_rule": (C.c_int, [_ctx, C.c_int32]),
+    "esb_set_guard_fields": (C.c_int, [_ctx, C.POINTER(esb_model), C.POINTER(_dp), C.c_int32, C.c_int32, _dp,
+                                       C.c_int32, C.c_int32, C.c_double]),
+    "esb_guard_result": (C.c_int, [_ctx, C.POINTER(esb_guard_report)]),
     "esb_set_schedule": (C.c_int, [_ctx, C.c_int32]),
     "esb_fp64_peak": (C.c_int, [_ctx, _dp]),
     "esb_rk_selftest": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _dp]),
     "esb_bessel_ik_scaled": (C.c_int, [C.c_int32, C.c_double, _dp]),
+    "esb_bessel_jy": (C.c_int, [C.c_int32, C.c_double, _dp]),
+    "esb_bessel_jy_dev": (C.c_int, [_ctx, C.c_int32, _dp, C.c_int32, _dp]),
+    "esb_exterior_leaky": (C.c_int, [C.POINTER(esb_model), C.c_int32, C.c_double, C.c_double, _dp]),
+    "esb_exterior_leaky_dev": (C.c_int, [_ctx, C.c_int32, _dp, _dp, C.c_int32, _dp]),
     "esb_last_kernel_ms": (C.c_double, [_ctx]),
     "esb_launch_count": (C.c_int64, [_ctx]),
 }

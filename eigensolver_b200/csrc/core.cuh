@@ -1143,6 +1143,57 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
     }
 }
 
+// --------------------------------------------------------- noise-floor test ----
+// true where no resonance of the ODE sits inside the layer (with a relative margin on the resonant
+// quantity), i.e. where the integration converges as the mesh is refined: the points the
+// discretisation guard (esb.cu guard_kernel) may judge.  Inside the continua (a singular point in the
+// layer) ANY step count returns solver noise, as the reference's odeint does.
+//   density kinds   rho(x) w^2 = k^2 {beta, tau} (Alfven, cusp; slab also alpha: the sound point of F)
+//   flow kinds      (w - k U)^2 = k^2 {vA^2 (cylinder), cT^2, c^2 (slab)}, slab also w = k U
+//   rotation        D or C3 changes sign between staged nodes (C3 = 0 is singular for the reference's
+//                   second-order form only, but the reference output there is noise all the same)
+ESB_HD bool outside_range(double v, double lo, double hi, double margin) {
+    const double pad = margin * fmax(fabs(lo), fabs(hi));
+    return v < lo - pad || v > hi + pad;
+}
+
+template <int KIND>
+ESB_HD bool resonance_free(const DevModel& M, const Point& pt, double mode, const double* __restrict__ tab,
+                           double margin) {
+    if constexpr (KIND == KIND_CYL_DENSITY || KIND == KIND_SLAB_DENSITY) {
+        const double A = pt.A > 1e-280 ? pt.A : 1e-280;
+        bool ok = outside_range(pt.Kbeta / A, M.f_lo, M.f_hi, margin) &&
+                  outside_range(pt.Ktau / A, M.f_lo, M.f_hi, margin);
+        if (KIND == KIND_SLAB_DENSITY) ok = ok && outside_range(pt.Kalpha / A, M.f_lo, M.f_hi, margin);
+        return ok;
+    } else if constexpr (KIND == KIND_CYL_FLOW || KIND == KIND_SLAB_FLOW) {
+        const double Oa = fma(-pt.k, M.f_lo, pt.w), Ob = fma(-pt.k, M.f_hi, pt.w);
+        const double a2 = Oa * Oa, b2 = Ob * Ob;
+        const bool through_zero = Oa * Ob <= 0.0;
+        const double hi = fmax(a2, b2), lo = through_zero ? 0.0 : fmin(a2, b2);
+        bool ok = outside_range(pt.K * M.cTi2, lo, hi, margin);
+        if (KIND == KIND_CYL_FLOW) ok = ok && outside_range(pt.K * M.vAi2, lo, hi, margin);
+        else ok = ok && outside_range(pt.K * M.ci2, lo, hi, margin) && !through_zero &&
+                  fmin(a2, b2) > margin * margin * pt.A;
+        return ok;
+    } else {
+        // at w and at w (1 +- margin): a point NEXT to a resonance converges slowly too
+        for (int j = -1; j <= 1; ++j) {
+            Point q = pt;
+            q.w = pt.w * (1.0 + j * margin);
+            q.A = q.w * q.w;
+            bool pos_d = false, neg_d = false, pos_c = false, neg_c = false;
+            for (int i = 0; i < M.n_nodes; ++i) {
+                const RotCoef c = node_rot(M, q, mode, tab + (size_t)i * ROT_FIELDS);
+                pos_d = pos_d || c.invD > 0.0; neg_d = neg_d || !(c.invD > 0.0);
+                pos_c = pos_c || c.C3 > 0.0; neg_c = neg_c || !(c.C3 > 0.0);
+            }
+            if ((pos_d && neg_d) || (pos_c && neg_c)) return false;
+        }
+        return true;
+    }
+}
+
 template <int KIND, int SCHEME, bool WARP = false, bool YFORM = false>
 ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
                        double& ext_q, double& int_q, double& den_q) {

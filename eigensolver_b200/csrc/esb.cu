@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -26,6 +27,7 @@
 
 #include "../../include/eigensolver_b200.h"
 #include "core.cuh"
+#include "bessel_jy.cuh"
 #include "model_host.h"
 
 using namespace esb;
@@ -709,6 +711,117 @@ __global__ void __launch_bounds__(128) refine_warp_kernel(RefineArgs r) {
     }
 }
 
+// ---- J_n / Y_n on the device (the leaky side, bessel_jy.cuh) ------------------------------------------
+// out[4 i .. 4 i + 3] = {J_n, J_n', Y_n, Y_n'}(x[i])
+__global__ void bessel_jy_kernel(int n, const double* __restrict__ x, int count, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    BesselJY b;
+    bessel_jy(n, x[i], b);
+    double J, dJ, Y, dY;
+    bessel_jy_order(b, n, x[i], J, dJ, Y, dY);
+    out[4 * i] = J; out[4 * i + 1] = dJ; out[4 * i + 2] = Y; out[4 * i + 3] = dY;
+}
+
+// out[2 i], out[2 i + 1] = (P, dP/dr) at |r| = 1 of the leaky exterior at (k[i], w[i]); NaN where m_e >= 0
+__global__ void exterior_leaky_kernel(DevModel M, int n, const double* __restrict__ k, const double* __restrict__ w,
+                                      int count, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double me = m_e2(M, k[i] * k[i], w[i] * w[i]);
+    double yb = nan(""), ypb = nan("");
+    if (me < 0.0) exterior_cyl_leaky(M.ic_v, M.ic_s, M.r_sign, M.ext_len, k[i], me, n, yb, ypb);
+    out[2 * i] = yb; out[2 * i + 1] = ypb;
+}
+
+// ---- discretisation guard --------------------------------------------------------------------------
+// The integrator is fixed-step where the reference's odeint adapts.  With a guard model set
+// (esb_set_guard_fields: the same equilibrium on a finer mesh, normally 2 x n_steps), every sweep
+// re-evaluates every stride-th (point, mode) of its scan with the fine table and keeps the worst
+// deviation.  8th order: doubling the steps divides the error by ~256, so the deviation IS the
+// discretisation error of the sweep at that point.  Judged on the pole-free function G = D Y
+// (Y = the denominator of int, stored by the scan), relative to |ext Y| + |int Y|: next to a pole of D
+// (Y -> 0) int = N/Y amplifies the error of Y without bound while G stays regular.  Points inside the
+// resonant continua (resonance_free) are not judged: no step count converges there.
+// One lane per sample, one 32-sample tile per warp; runs on a side stream next to the bracket passes.
+struct GuardRecord {
+    unsigned long long key;        // high 32 bits of the worst deviation (a positive double) | sample id
+    unsigned long long n_checked;
+    unsigned long long n_above;    // samples above the threshold
+};
+
+struct GuardArgs {
+    DevModel M;                    // the FINE model
+    const double* tab;
+    int tab_doubles;
+    const double* k;
+    const double* w;
+    int nk, nw, layout;
+    int n_modes;
+    int modes[4];
+    const double* ext;             // the planes of the sweep being judged
+    const double* intq;
+    const double* den;
+    int stride;
+    unsigned n_per_mode;           // samples per mode slot
+    double threshold, margin;
+    GuardRecord* out;
+};
+
+__host__ __device__ __forceinline__ size_t guard_point(unsigned j, int stride) {
+    // a slowly sliding offset inside the stride, so that a row length that is a multiple of the stride
+    // does not put every sample into the same omega column
+    return (size_t)j * stride + (j % (unsigned)stride);
+}
+
+template <int KIND, int SCHEME>
+__global__ void __launch_bounds__(128) guard_kernel(GuardArgs g) {
+    extern __shared__ __align__(16) double stab[];
+    stage_table(g.tab, stab, g.tab_doubles);
+    const int lane = threadIdx.x & 31;
+    const size_t plane = (size_t)g.nk * g.nw;
+    const unsigned sample = (blockIdx.x * blockDim.x + threadIdx.x);
+    unsigned long long key = 0ULL;
+    unsigned checked = 0, above = 0;
+    if (sample < g.n_per_mode * (unsigned)g.n_modes) {
+        const int slot = (int)(sample / g.n_per_mode);
+        const unsigned j = sample - (unsigned)slot * g.n_per_mode;
+        const size_t p = guard_point(j, g.stride);
+        if (p < plane) {
+            const int ik = (int)(p / g.nw), iw = (int)(p - (size_t)ik * g.nw);
+            const double e0 = g.ext[slot * plane + p], i0 = g.intq[slot * plane + p], d0 = g.den[slot * plane + p];
+            if (isfinite(e0) && isfinite(i0) && isfinite(d0)) {
+                const double k = g.k[ik];
+                const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
+                const Point pt = make_point(g.M, k, w);
+                if (resonance_free<KIND>(g.M, pt, double(g.modes[slot]), stab, g.margin)) {
+                    double e, i, d;
+                    eval_point<KIND, SCHEME>(g.M, stab, k, w, g.modes[slot], e, i, d);
+                    const double scale = fabs(e * d) + fabs(i * d);
+                    const double dev = fabs((e0 - i0) * d0 - (e - i) * d) / scale;
+                    if (isfinite(dev)) {
+                        checked = 1;
+                        above = dev > g.threshold ? 1 : 0;
+                        key = ((unsigned long long)__double_as_longlong(dev) & 0xffffffff00000000ULL) | sample;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, key, off);
+        key = o > key ? o : key;
+        checked += __shfl_down_sync(0xffffffffu, checked, off);
+        above += __shfl_down_sync(0xffffffffu, above, off);
+    }
+    if (lane == 0 && checked) {
+        atomicMax(&g.out->key, key);
+        atomicAdd(&g.out->n_checked, (unsigned long long)checked);
+        if (above) atomicAdd(&g.out->n_above, (unsigned long long)above);
+    }
+}
+
 // ---- parameter scans: tables of many equilibria compacted into one ------------------------------
 struct ScanOut {
     int *model, *slot, *k_index, *w_index, *accepted, *iters;
@@ -795,6 +908,21 @@ struct esb_context {
     char* h_compact = nullptr;     // page-locked mirror handed to the caller
     esb_scan_result scan_dev{};    // the same table, device pointers
     size_t cap_h_compact = 0;
+    // discretisation guard (esb_set_guard_fields): fine model + table, side stream, device / pinned record
+    bool guard_set = false;
+    DevModel g_dm{};
+    double* d_gtab = nullptr;
+    size_t cap_gtab = 0;
+    int g_tab_doubles = 0;
+    int guard_stride = 0;
+    double guard_threshold = 1e-9;
+    cudaStream_t guard_stream = nullptr;
+    cudaEvent_t ev_scan = nullptr, ev_guard = nullptr;
+    GuardRecord* d_guard = nullptr;
+    GuardRecord* h_guard = nullptr;
+    bool guard_pending = false;    // a record of the last sweep is (being) written
+    int guard_n_modes = 0, guard_nw = 0;
+    unsigned guard_n_per_mode = 0;
     bool tables_pending = false;   // a sweep's refinement may still be running: consumers wait on ev_done
     int n_sm = 148;
     int accept_rule = ESB_ACCEPT_CONVERGED;
@@ -964,6 +1092,12 @@ extern "C" int esb_destroy(esb_context* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->d_gtab) cudaFree(c->d_gtab);
+    if (c->d_guard) cudaFree(c->d_guard);
+    if (c->h_guard) cudaFreeHost(c->h_guard);
+    if (c->ev_scan) cudaEventDestroy(c->ev_scan);
+    if (c->ev_guard) cudaEventDestroy(c->ev_guard);
+    if (c->guard_stream) cudaStreamDestroy(c->guard_stream);
     if (c->ev_counts) cudaEventDestroy(c->ev_counts);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (auto& sl : c->slots) {
@@ -1017,6 +1151,8 @@ extern "C" int esb_set_model_fields(esb_context* c, const esb_model* m, const do
     c->tab_doubles = (int)hm.tab.size();
     c->model = *m;
     c->model_set = true;
+    c->guard_set = false;          // the guard belongs to the previous equilibrium
+    c->guard_pending = false;
     return ESB_OK;
 }
 
@@ -1165,6 +1301,120 @@ static cudaError_t dispatch_kind(int kind, int scheme, F&& f) {
     }
 #undef ESB_KIND_CASE
 #undef ESB_KIND_CASE_N
+}
+
+
+// ---- discretisation guard: set-up, launch, report ---------------------------------------------
+extern "C" int esb_set_guard_fields(esb_context* c, const esb_model* fine, const double* const* fields,
+                                    int32_t n_fields, int32_t n_nodes, const double* boundary,
+                                    int32_t n_boundary, int32_t stride, double threshold) {
+    if (!c) return ESB_ERR_ARG;
+    if (stride <= 0) {                       // switch the guard off
+        c->guard_set = false;
+        c->guard_stride = 0;
+        return ESB_OK;
+    }
+    if (!c->model_set) return fail(c, ESB_ERR_ARG, "set the model before its guard");
+    if (!fine || fine->kind != c->model.kind) return fail(c, ESB_ERR_ARG, "guard model of another kind");
+    if (!(threshold > 0.0)) return fail(c, ESB_ERR_ARG, "guard threshold");
+    HostModel hm;
+    std::string err;
+    int rc = build_host_model(fine, fields, n_fields, n_nodes, boundary, n_boundary, hm, err);
+    if (rc) return fail(c, rc, err.c_str());
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->guard_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->guard_stream, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_scan, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_guard, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_guard, sizeof(GuardRecord)));
+        CUDA_TRY(c, cudaHostAlloc((void**)&c->h_guard, sizeof(GuardRecord), cudaHostAllocDefault));
+    }
+    // the old table may still be read by a guard kernel in flight
+    CUDA_TRY(c, cudaStreamSynchronize(c->guard_stream));
+    c->guard_set = false;
+    if ((rc = ensure(c, c->d_gtab, c->cap_gtab, hm.tab.size()))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_gtab, hm.tab.data(), hm.tab.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                c->guard_stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->guard_stream));       // `tab` is a pageable buffer
+    c->g_dm = hm.dm;
+    c->g_tab_doubles = (int)hm.tab.size();
+    c->guard_stride = stride;
+    c->guard_threshold = threshold;
+    c->guard_set = true;
+    c->guard_pending = false;
+    return ESB_OK;
+}
+
+template <int KIND, int SCHEME>
+static cudaError_t launch_guard(const GuardArgs& g, cudaStream_t s) {
+    const size_t smem = (size_t)g.tab_doubles * sizeof(double);
+    static bool done[MAX_DEVICES] = {};
+    cudaError_t e = configure_once(guard_kernel<KIND, SCHEME>, done);
+    if (e != cudaSuccess) return e;
+    const unsigned total = g.n_per_mode * (unsigned)g.n_modes;
+    guard_kernel<KIND, SCHEME><<<(total + 127) / 128, 128, smem, s>>>(g);
+    return cudaGetLastError();
+}
+
+// after the scan of a sweep has been enqueued on `s`: the guard pass on the side stream
+static int guard_launch(esb_context* c, int n_modes, const int32_t* modes, int nk, int nw, int layout,
+                        cudaStream_t s) {
+    const size_t plane = (size_t)nk * nw;
+    GuardArgs g;
+    g.M = c->g_dm;
+    g.tab = c->d_gtab;
+    g.tab_doubles = c->g_tab_doubles;
+    g.k = c->d_k; g.w = c->d_w; g.nk = nk; g.nw = nw; g.layout = layout;
+    g.n_modes = n_modes;
+    for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
+    g.ext = c->d_ext; g.intq = c->d_int; g.den = c->d_den;
+    g.stride = c->guard_stride;
+    g.n_per_mode = (unsigned)((plane + c->guard_stride - 1) / c->guard_stride);
+    g.threshold = c->guard_threshold;
+    g.margin = 0.05;
+    g.out = c->d_guard;
+    CUDA_TRY(c, cudaEventRecord(c->ev_scan, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->guard_stream, c->ev_scan, 0));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(GuardRecord), c->guard_stream));
+    const cudaError_t e = dispatch_kind(c->g_dm.kind, c->g_dm.scheme, [&](auto kind, auto scheme) {
+        return launch_guard<decltype(kind)::value, decltype(scheme)::value>(g, c->guard_stream);
+    });
+    CUDA_TRY(c, e);
+    c->launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(GuardRecord), cudaMemcpyDeviceToHost, c->guard_stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_guard, c->guard_stream));
+    c->guard_pending = true;
+    c->guard_n_modes = n_modes;
+    c->guard_nw = nw;
+    c->guard_n_per_mode = g.n_per_mode;
+    return ESB_OK;
+}
+
+extern "C" int esb_guard_result(esb_context* c, esb_guard_report* out) {
+    if (!c || !out) return ESB_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    out->slot = out->k_index = out->w_index = -1;
+    out->threshold = c->guard_threshold;
+    out->stride = c->guard_set ? c->guard_stride : 0;
+    if (!c->guard_set || !c->guard_pending) return ESB_OK;        // no guard, or no sweep since it was set
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_guard));
+    const GuardRecord r = *c->h_guard;
+    out->n_checked = (int64_t)r.n_checked;
+    out->n_above = (int64_t)r.n_above;
+    if (r.n_checked) {
+        const unsigned long long bits = r.key & 0xffffffff00000000ULL;
+        double worst;
+        memcpy(&worst, &bits, sizeof(worst));
+        out->worst = worst;
+        const unsigned sample = (unsigned)(r.key & 0xffffffffULL);
+        const int slot = (int)(sample / c->guard_n_per_mode);
+        const size_t p = guard_point(sample - (unsigned)slot * c->guard_n_per_mode, c->guard_stride);
+        out->slot = slot;
+        out->k_index = (int32_t)(p / c->guard_nw);
+        out->w_index = (int32_t)(p - (size_t)out->k_index * c->guard_nw);
+    }
+    return ESB_OK;
 }
 
 static int check_mode(const esb_context* c, int mode) {
@@ -1428,6 +1678,11 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
     if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s,
                              c->d_den)))
         return rc;
+    // (worker-sized sweeps - the warp-per-point regime - are latency bound and are not sampled)
+    c->guard_pending = false;
+    if (c->guard_set && plane * n_modes > GRID_WARP_MAX_POINTS &&
+        (rc = guard_launch(c, n_modes, modes, nk, nw, layout, s)))
+        return rc;
     // first sweep of a context: room for one bracket per 64 grid points (grown on demand below)
     for (int m = 0; m < n_modes; ++m)
         if (!c->slots[m].base && (rc = ensure_slot(c, c->slots[m], std::max<size_t>(1024, plane / 64)))) return rc;
@@ -1484,6 +1739,8 @@ extern "C" int esb_sweep_resident_multi(esb_context* c, int32_t n_modes, const i
         CUDA_TRY(c, e);
         c->launches += 1;
     }
+    // the next sweep overwrites the planes the guard pass reads: the sweep is complete when both are
+    if (c->guard_pending) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_guard, 0));
     CUDA_TRY(c, cudaEventRecord(c->ev_done, s));
     c->tables_pending = true;
     return ESB_OK;
@@ -1859,6 +2116,74 @@ extern "C" int esb_rk_selftest(int32_t scheme, int32_t n_steps, double T, double
     out[0] = y[0];
     out[1] = yp[0];
     return ESB_OK;
+}
+
+extern "C" int esb_bessel_jy(int32_t n, double x, double out[4]) {
+    if (n < 0 || n > ESB_MAX_ORDER || !(x > 0.0) || !out) return ESB_ERR_ARG;
+    BesselJY b;
+    bessel_jy(n, x, b);
+    bessel_jy_order(b, n, x, out[0], out[1], out[2], out[3]);
+    return ESB_OK;
+}
+
+// host arrays in and out, evaluated by the DEVICE build of the evaluators
+static int dev_map(esb_context* c, const double* a, const double* b, int32_t count, int n_out, double* out,
+                   const std::function<cudaError_t(const double*, const double*, double*, cudaStream_t)>& launch) {
+    if (!c || !a || !out || count <= 0) return ESB_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = cur_stream(c);
+    double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+    int rc = ESB_OK;
+    auto done = [&](int code) {
+        cudaFree(d_a); cudaFree(d_b); cudaFree(d_o);
+        return code;
+    };
+    if (cudaMalloc((void**)&d_a, sizeof(double) * count) != cudaSuccess ||
+        (b && cudaMalloc((void**)&d_b, sizeof(double) * count) != cudaSuccess) ||
+        cudaMalloc((void**)&d_o, sizeof(double) * count * n_out) != cudaSuccess)
+        return done(fail(c, ESB_ERR_ALLOC, "device allocation"));
+    if (cudaMemcpyAsync(d_a, a, sizeof(double) * count, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        (b && cudaMemcpyAsync(d_b, b, sizeof(double) * count, cudaMemcpyHostToDevice, s) != cudaSuccess))
+        return done(fail(c, ESB_ERR_CUDA, "upload"));
+    if (launch(d_a, d_b, d_o, s) != cudaSuccess) return done(fail(c, ESB_ERR_CUDA, "launch"));
+    c->launches += 1;
+    if (cudaMemcpyAsync(out, d_o, sizeof(double) * count * n_out, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return done(fail(c, ESB_ERR_CUDA, "download"));
+    return done(rc);
+}
+
+extern "C" int esb_bessel_jy_dev(esb_context* c, int32_t n, const double* x, int32_t count, double* out) {
+    if (n < 0 || n > ESB_MAX_ORDER) return ESB_ERR_ARG;
+    return dev_map(c, x, nullptr, count, 4, out, [&](const double* dx, const double*, double* d_o, cudaStream_t s) {
+        bessel_jy_kernel<<<(count + 127) / 128, 128, 0, s>>>(n, dx, count, d_o);
+        return cudaGetLastError();
+    });
+}
+
+// (P, dP/dr) at |r| = 1 of the exterior solution where m_e < 0, for the exterior medium and the initial
+// values of `m`: host build, and the same through the device build
+extern "C" int esb_exterior_leaky(const esb_model* m, int32_t n, double k, double w, double out[2]) {
+    if (check_model(m) || n < 0 || n > ESB_MAX_ORDER || !(k > 0.0) || !out) return ESB_ERR_ARG;
+    const double vAe2 = m->vA_e * m->vA_e, ce2 = m->c_e * m->c_e, se2 = vAe2 + ce2, cTe2 = ce2 * vAe2 / se2;
+    const double K = k * k, A = w * w;
+    const double me = ((K * vAe2 - A) * (K * ce2 - A)) / (se2 * (K * cTe2 - A));
+    out[0] = out[1] = nan("");
+    if (!(me < 0.0)) return ESB_OK;           // not on the leaky side: the regular exterior applies
+    exterior_cyl_leaky(m->ext_ic_value, m->ext_ic_slope, m->r_sign >= 0 ? 1.0 : -1.0,
+                       m->ext_wavelengths * 2.0 * M_PI, k, me, n, out[0], out[1]);
+    return ESB_OK;
+}
+
+extern "C" int esb_exterior_leaky_dev(esb_context* c, int32_t n, const double* k, const double* w, int32_t count,
+                                      double* out) {
+    if (!c || !c->model_set) return ESB_ERR_ARG;
+    if (n < 0 || n > ESB_MAX_ORDER || !w) return ESB_ERR_ARG;
+    const DevModel M = c->dm;
+    return dev_map(c, k, w, count, 2, out, [&](const double* dk, const double* dw, double* d_o, cudaStream_t s) {
+        exterior_leaky_kernel<<<(count + 127) / 128, 128, 0, s>>>(M, n, dk, dw, count, d_o);
+        return cudaGetLastError();
+    });
 }
 
 extern "C" int esb_bessel_ik_scaled(int32_t n, double z, double out[4]) {

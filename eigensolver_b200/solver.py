@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import warnings
 
 import numpy as np
 
@@ -329,12 +330,22 @@ class ModelSpec:
                     coordinate="positive" if (self.kind == "cylinder_density" and m.r_sign > 0) else "negative")
 
 
+class DiscretisationWarning(UserWarning):
+    """The fixed-step integration lost digits on this profile: raise n_steps (DispersionSolver.guard_report)."""
+
+
+#: default sampling of the discretisation guard: every 256th (grid point, mode) of a sweep is re-evaluated
+#: at twice the steps (< 1 % of the scan's arithmetic, on a side stream)
+GUARD_STRIDE = 256
+GUARD_THRESHOLD = 1e-9
+
+
 class DispersionSolver:
     """One GPU context evaluating D(omega,k) for one equilibrium model."""
 
     def __init__(self, kind, medium=None, profile=None, n_steps=None, scheme=None, mesh=None,
                  device=0, rho_A=1.0, ext_ic=None, ext_wavelengths=3.0, coordinate="negative", s_end=None,
-                 mesh_params=None):
+                 mesh_params=None, guard=GUARD_STRIDE, guard_threshold=GUARD_THRESHOLD):
         """kind: "cylinder_density" | "slab_density" | "slab_flow" | "cylinder_rotation" |
         "cylinder_flow".
         profile: callable (medium, x) -> (rho, rho', rho'') for the density kinds, (U, U', U'') for
@@ -344,9 +355,14 @@ class DispersionSolver:
         scheme: "rk8n" (normal form, default where the kind has one) | "rk8" | "rk4".
         s_end: far end of the layer (the rotational sausage script stops at r = 0.01, the kink one at 0.001).
         coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
-        layer 1 -> 0.001, exterior slope given as dP/dr)."""
+        layer 1 -> 0.001, exterior slope given as dP/dr).
+        guard: stride of the built-in discretisation guard (every guard-th (point, mode) of a sweep is
+        re-evaluated at 2 x n_steps; a host-returning root search warns - DiscretisationWarning - when the
+        worst deviation exceeds guard_threshold; guard_report() reads it); 0 / None switches it off."""
         self.spec = ModelSpec(kind, medium, profile, n_steps, scheme, mesh, rho_A, ext_ic, ext_wavelengths,
                               coordinate, s_end, mesh_params)
+        self.guard_stride = int(guard or 0)
+        self.guard_threshold = float(guard_threshold)
         self.lib = self.spec.lib
         self.kind = kind
         self.ctx = L._ctx()
@@ -366,6 +382,50 @@ class DispersionSolver:
     def _upload_model(self):
         L.check(self.lib, self.ctx, self.lib.esb_set_model_fields(self.ctx, *self.spec.abi_args()),
                 "esb_set_model_fields")
+        self._upload_guard()
+
+    def _fine_spec(self, factor=2):
+        """The same equilibrium at `factor` x the steps (None if its table cannot be staged)."""
+        kw = self.spec.solver_kwargs()
+        kw["n_steps"] = int(self.spec.model.n_steps) * int(factor)
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > 900:
+            kw["scheme"] = "rk8"          # the six-field table of that many steps exceeds shared memory
+        if kw["n_steps"] > 1400:
+            return None
+        return ModelSpec(**kw)
+
+    def _upload_guard(self):
+        self._guard_on = False
+        if self.guard_stride <= 0:
+            return
+        fine = self._fine_spec()
+        if fine is None:
+            return
+        L.check(self.lib, self.ctx,
+                self.lib.esb_set_guard_fields(self.ctx, *fine.abi_args(), self.guard_stride, self.guard_threshold),
+                "esb_set_guard_fields")
+        self._guard_on = True
+
+    def guard_report(self):
+        """Discretisation guard of the LAST sweep (waits for it): dict with `worst` (largest deviation of
+        the pole-free function G = D Y between n_steps and 2 n_steps over the sampled points outside the
+        resonant continua - the discretisation error of the sweep), where it occurred (`slot`, `k_index`,
+        `w_index`), `n_checked`, `n_above` (samples above `threshold`), `stride` (0: guard off)."""
+        rep = L.esb_guard_report()
+        L.check(self.lib, self.ctx, self.lib.esb_guard_result(self.ctx, C.byref(rep)), "esb_guard_result")
+        return {f: getattr(rep, f) for f, _ in L.esb_guard_report._fields_}
+
+    def _warn_guard(self):
+        """called by the host-returning root searches (they wait for the sweep anyway)"""
+        if not getattr(self, "_guard_on", False):
+            return
+        rep = self.guard_report()
+        if rep["n_checked"] and rep["worst"] > rep["threshold"]:
+            warnings.warn("discretisation error %.1e > %.0e at n_steps = %d (%d of %d sampled points above; worst "
+                          "at mode slot %d, k index %d, omega index %d): raise n_steps"
+                          % (rep["worst"], rep["threshold"], int(self.spec.model.n_steps), rep["n_above"],
+                             rep["n_checked"], rep["slot"], rep["k_index"], rep["w_index"]),
+                          DiscretisationWarning, stacklevel=3)
 
     def reconfigure(self, medium=None, profile=None):
         """Swap the equilibrium (speeds and/or profile) on the same context and mesh: one small
@@ -454,6 +514,7 @@ class DispersionSolver:
         n, nb = self.sweep_resident(mode, tol_percent)
         tab = self.download_roots(n)
         tab.n_brackets = nb
+        self._warn_guard()
         return tab
 
     # -- the same pipeline in three steps (axes stay resident in HBM) -----
@@ -500,8 +561,11 @@ class DispersionSolver:
         self.upload_axes(k, w, layout)
         ns = self.sweep_resident_multi(modes, tol_percent)
         if pinned:
-            return [self.download_roots_pinned(slot) for slot in range(len(ns))]
-        return [self.download_roots(n, slot) for slot, n in enumerate(ns)]
+            tabs = [self.download_roots_pinned(slot) for slot in range(len(ns))]
+        else:
+            tabs = [self.download_roots(n, slot) for slot, n in enumerate(ns)]
+        self._warn_guard()
+        return tabs
 
     def download_roots_pinned(self, slot=0):
         """Root table of mode slot `slot` copied into page-locked host buffers owned by the context
@@ -615,7 +679,7 @@ class DispersionSolver:
         kw["n_steps"] = int(m.n_steps) * int(factor)
         if kw["scheme"] == "rk8n" and kw["n_steps"] > 900:
             kw["scheme"] = "rk8"          # the six-field table of that many steps exceeds shared memory
-        with DispersionSolver(**kw) as fine:
+        with DispersionSolver(guard=0, **kw) as fine:
             e1, i1 = fine.dispersion_grid_multi(modes, k, w, layout)
         ok = np.isfinite(e0) & np.isfinite(i0) & np.isfinite(e1) & np.isfinite(i1)
         dev = np.where(ok, np.abs((e0 - i0) - (e1 - i1)) / np.maximum(np.abs(e1), np.abs(i1)), 0.0)
@@ -631,6 +695,26 @@ class DispersionSolver:
                 self.lib.esb_set_schedule(self.ctx, {"auto": 0, "lane": 1, "warp": 2}[mode]),
                 "esb_set_schedule")
 
+    def bessel_jy_device(self, n, x):
+        """(count, 4) array {J_n, J_n', Y_n, Y_n'}(x) evaluated ON THE DEVICE (esb_bessel_jy_dev)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        out = np.empty((x.size, 4))
+        L.check(self.lib, self.ctx, self.lib.esb_bessel_jy_dev(self.ctx, int(n), _dptr(x), x.size, _dptr(out)),
+                "esb_bessel_jy_dev")
+        return out
+
+    def exterior_leaky_device(self, n, k, w):
+        """(count, 2) array (P, dP/dr) at |r| = 1 of the exterior solution where m_e < 0 - the points the
+        reference and the sweeps skip - in closed form with J_n, Y_n, on the device; NaN where m_e >= 0."""
+        k = np.ascontiguousarray(k, dtype=np.float64).ravel()
+        w = np.ascontiguousarray(w, dtype=np.float64).ravel()
+        assert k.size == w.size
+        out = np.empty((k.size, 2))
+        L.check(self.lib, self.ctx,
+                self.lib.esb_exterior_leaky_dev(self.ctx, int(n), _dptr(k), _dptr(w), k.size, _dptr(out)),
+                "esb_exterior_leaky_dev")
+        return out
+
     def fp64_peak_tflops(self):
         v = C.c_double(0.0)
         L.check(self.lib, self.ctx, self.lib.esb_fp64_peak(self.ctx, C.byref(v)), "esb_fp64_peak")
@@ -642,6 +726,16 @@ class DispersionSolver:
 
     def launch_count(self):
         return int(self.lib.esb_launch_count(self.ctx))
+
+
+def bessel_jy(n, x):
+    """Host helper: (J_n, J_n', Y_n, Y_n') from the library's evaluators (the leaky side, m_e < 0)."""
+    lib = L.load()
+    out = (C.c_double * 4)()
+    rc = lib.esb_bessel_jy(int(n), float(x), out)
+    if rc != L.ESB_OK:
+        raise L.EsbError("esb_bessel_jy: bad argument")
+    return tuple(out)
 
 
 def bessel_ik_scaled(n, z):

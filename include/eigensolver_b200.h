@@ -35,9 +35,11 @@
 extern "C" {
 #endif
 
-#define ESB_VERSION 120   /* 1.1: esb_model grew the mesh_* fields; pinned tables, schedules
+#define ESB_VERSION 130   /* 1.1: esb_model grew the mesh_* fields; pinned tables, schedules
                              1.2: ESB_RK8N (normal-form Nystrom scheme, needs the profile's second derivative);
-                                  up to 4 fused modes; esb_set_accept_rule; esb_tables_wait */
+                                  up to 4 fused modes; esb_set_accept_rule; esb_tables_wait
+                             1.3: esb_set_guard_fields / esb_guard_result (discretisation guard);
+                                  esb_bessel_jy[_dev], esb_exterior_leaky[_dev] (J_n, Y_n: the leaky side) */
 
 typedef struct esb_context esb_context;
 
@@ -186,6 +188,31 @@ int esb_roots_device(esb_context* ctx, int32_t slot, esb_roots* out, int32_t* n_
  * complete. */
 int esb_tables_wait(esb_context* ctx, void* stream);
 
+/* Discretisation guard.  The integrator is fixed-step where the reference's odeint adapts (Density_cylinder.py
+ * :768-790): a profile sharper than the shipped ones silently loses digits.  esb_set_guard_fields takes the
+ * SAME equilibrium on a finer mesh - `fine` = the model with (normally) 2 x n_steps, the fields sampled at ITS
+ * esb_mesh_nodes() - and from then on every esb_sweep_resident[_multi] re-evaluates every stride-th
+ * (grid point, mode) of its scan with the fine table, on a side stream next to the bracket passes (~2/stride of
+ * the scan's arithmetic).  esb_guard_result waits for that pass and reports the worst deviation - judged on the
+ * pole-free function G = D Y relative to |ext Y| + |int Y| - over the sampled points outside the resonant
+ * continua, where it occurred, and how many samples exceeded `threshold`.  8th order: halving the step divides
+ * the error by ~256, so the value is (to 0.4 %) the discretisation error of the sweep itself.  stride <= 0
+ * switches the guard off; it must be set again after every esb_set_model[_fields].  Sweeps of at most 8192
+ * (point, mode) pairs - the latency-bound worker-sized calls - and esb_scan_models are not sampled
+ * (n_checked = 0). */
+typedef struct esb_guard_report {
+    double worst;        /* largest deviation over the judged samples (0 if none) */
+    double threshold;
+    int32_t slot, k_index, w_index;   /* where (-1: none) */
+    int32_t stride;      /* 0: no guard set */
+    int64_t n_checked;   /* samples judged (evaluated, outside the continua) */
+    int64_t n_above;     /* ... of them above the threshold */
+} esb_guard_report;
+int esb_set_guard_fields(esb_context* ctx, const esb_model* fine, const double* const* fields, int32_t n_fields,
+                         int32_t n_nodes, const double* boundary, int32_t n_boundary, int32_t stride,
+                         double threshold);
+int esb_guard_result(esb_context* ctx, esb_guard_report* out);
+
 /* What a sweep reports (esb_set_accept_rule; default ESB_ACCEPT_CONVERGED).
  *   ESB_ACCEPT_CONVERGED  sign changes of D between ADJACENT evaluated grid points, every bracket refined to
  *                         2 eps |omega| (Brent on the pole-free G = D Y), accepted = the reference's test
@@ -285,6 +312,20 @@ int esb_brackets_dev(esb_context* ctx, const double* d_ext, const double* d_intq
 /* Host-side helper (no GPU needed): scaled modified Bessel functions used by the
  * exterior solution, out = {e^-z I_n, d/dz, e^z K_n, d/dz}.  For unit tests. */
 int esb_bessel_ik_scaled(int32_t n, double z, double out[4]);
+
+/* Bessel functions J_n, Y_n (n <= 3): the oscillatory (leaky, m_e < 0) side of the exterior solution, which the
+ * reference's scan loop skips (Density_cylinder.py:760) and the sweeps therefore report as "no value".
+ *   esb_bessel_jy            host build: out = {J_n, J_n', Y_n, Y_n'}(x), x > 0
+ *   esb_bessel_jy_dev        the same evaluators run on the device: x[count] in, out[4 * count]
+ *   esb_exterior_leaky       closed form of the reference's own exterior initial-value problem
+ *                            (:765-770) where m_e < 0: out = (P, dP/dr) at |r| = 1 for azimuthal order n,
+ *                            the exterior medium and initial values of `m` (NaN where m_e >= 0)
+ *   esb_exterior_leaky_dev   the same on the device for k[count], w[count] and the context's model */
+int esb_bessel_jy(int32_t n, double x, double out[4]);
+int esb_bessel_jy_dev(esb_context* ctx, int32_t n, const double* x, int32_t count, double* out);
+int esb_exterior_leaky(const esb_model* m, int32_t n, double k, double w, double out[2]);
+int esb_exterior_leaky_dev(esb_context* ctx, int32_t n, const double* k, const double* w, int32_t count,
+                           double* out);
 
 /* Host-side helper (no GPU needed): integrates y'' = sin(t) y' - (1+t^2) y, y(0)=1, y'(0)=0.3
  * over [0,T] in n_steps uniform steps with the SAME step functions the kernels use; out =

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_defaults():
     lib = esb.load()
-    assert lib.esb_version() == 120
+    assert lib.esb_version() == 130
     assert lib.esb_sizeof_model() == C.sizeof(L.esb_model)        # the ctypes mirror of the struct
     m = L.esb_model()
     assert lib.esb_model_defaults(L.CYLINDER_DENSITY, C.byref(m)) == 0
@@ -105,6 +105,55 @@ def test_bessel_helper_matches_scipy():
         esb.bessel_ik_scaled(4, 1.0)
     with pytest.raises(esb.EsbError):
         esb.bessel_ik_scaled(0, 0.0)
+
+
+def test_bessel_jy_matches_scipy():
+    """J_n, Y_n and their derivatives (the leaky side the reference skips): error relative to the local
+    amplitude sqrt(J^2 + Y^2) - relative accuracy is meaningless next to a zero of an oscillating function."""
+    worst = 0.0
+    xs = list(np.geomspace(1e-3, 5.0, 150)) + list(np.linspace(4.9, 8.1, 200)) + list(np.geomspace(8.0, 5e3, 300)) + \
+        [4.9999, 5.0, 5.0001, 7.9999, 8.0, 8.0001]
+    for n in range(4):
+        for x in xs:
+            J, dJ, Y, dY = esb.bessel_jy(n, x)
+            want = (sp.jv(n, x), sp.jvp(n, x), sp.yv(n, x), sp.yvp(n, x))
+            amp, damp = np.hypot(want[0], want[2]), np.hypot(want[1], want[3])
+            worst = max(worst, abs(J - want[0]) / amp, abs(Y - want[2]) / amp, abs(dJ - want[1]) / damp,
+                        abs(dY - want[3]) / damp)
+    assert worst < 5e-15, worst
+    with pytest.raises(esb.EsbError):
+        esb.bessel_jy(4, 1.0)
+    with pytest.raises(esb.EsbError):
+        esb.bessel_jy(0, 0.0)
+
+
+def test_leaky_exterior_closed_form_matches_integration():
+    """esb_exterior_leaky = the reference's exterior initial-value problem (Density_cylinder.py:765-770:
+    P'' + P'/r - (m_e + n^2/r^2) P = 0 from r = -3*2pi/k with P0 = [1e-8, 1e-15]) where m_e < 0 - the points
+    its scan loop skips - against a tight numerical integration of the same problem."""
+    from scipy.integrate import solve_ivp
+    lib = esb.load()
+    m = L.esb_model()
+    lib.esb_model_defaults(L.CYLINDER_DENSITY, C.byref(m))
+    out = (C.c_double * 2)()
+    vAe2, ce2 = m.vA_e**2, m.c_e**2
+    cTe2 = ce2 * vAe2 / (ce2 + vAe2)
+    n_checked = 0
+    for n in range(4):
+        for k, W in ((0.5, 5.3), (1.0, 6.0), (2.5, 5.05), (1.5, 0.499), (3.0, 0.4985)):   # above vA_e; in (cT_e, c_e) = (0.4975, 0.5)
+            w = k * W
+            me = (k * k * vAe2 - w * w) * (k * k * ce2 - w * w) / ((vAe2 + ce2) * (k * k * cTe2 - w * w))
+            assert me < 0
+            assert lib.esb_exterior_leaky(C.byref(m), n, k, w, out) == 0
+            r0 = -3.0 * 2.0 * np.pi / k
+            sol = solve_ivp(lambda r, y: [y[1], -y[1] / r + (me + n * n / (r * r)) * y[0]], (r0, -1.0),
+                            [m.ext_ic_value, m.ext_ic_slope], method="DOP853", rtol=1e-12, atol=1e-30)
+            P, dP = sol.y[0, -1], sol.y[1, -1]
+            amp = np.hypot(P, dP / np.sqrt(-me))
+            assert abs(out[0] - P) < 1e-9 * amp and abs(out[1] - dP) < 1e-9 * amp * np.sqrt(-me), (n, k, W)
+            n_checked += 1
+    assert n_checked == 20
+    assert lib.esb_exterior_leaky(C.byref(m), 0, 1.0, 3.0, out) == 0 and np.isnan(out[0])     # m_e >= 0 there
 
 
 def _no_gpu():

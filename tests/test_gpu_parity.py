@@ -518,6 +518,74 @@ def test_convergence_check_flags_sharp_profiles():
     assert err_fine < 1e-3 * err_default      # ... and 4x the steps (8th order) cure it
 
 
+def test_discretisation_guard_flags_sharp_profiles():
+    """The guard built into every sweep (esb_set_guard_fields: every 256th (point, mode) re-evaluated at
+    2 x n_steps on a side stream) reports the discretisation error without anyone calling
+    convergence_check: below 1e-9 for every shipped equilibrium, visible - and warned about by the
+    host-returning root search - for the sharp shell, silent again with enough steps."""
+    import warnings as _w
+    k = np.linspace(0.5, 4.5, 64); W = np.linspace(0.5, 5.0, 512)       # the bench window, continua included
+    for name, case in CASES.items():
+        kk = np.linspace(0.25, 4.0, 64) if case.kind == "cylinder_rotation" else k
+        WW = np.linspace(case.W[0], case.W[1], 512)
+        with case.gpu_solver(esb) as s:
+            with _w.catch_warnings():
+                _w.simplefilter("error", esb.DiscretisationWarning)
+                s.find_roots_multi(list(case.modes)[:2], kk, WW)
+            rep = s.guard_report()
+            assert rep["stride"] == 256 and rep["n_checked"] >= 20, (name, rep)
+            assert rep["worst"] < 1e-9 and rep["n_above"] == 0, (name, rep)
+    sharp = esb.GaussianDensity(0.05, x0=-0.5)
+    W2 = np.linspace(4.6, 4.95, 512)          # above the Alfven continuum (vA = 4.41 outside the shell)
+    with esb.DispersionSolver("cylinder_density", profile=sharp) as s:
+        with pytest.warns(esb.DiscretisationWarning):
+            s.find_roots_multi([0, 1], k, W2)
+        rep = s.guard_report()
+        err, _ = s.convergence_check([0, 1], k, W2)
+        assert rep["worst"] > 1e-9 and rep["n_above"] > 0
+        assert 0.05 * err < rep["worst"] <= 2.0 * err          # the same quantity the explicit check measures
+    with esb.DispersionSolver("cylinder_density", profile=sharp, n_steps=576) as s:
+        with _w.catch_warnings():
+            _w.simplefilter("error", esb.DiscretisationWarning)
+            s.find_roots_multi([0, 1], k, W2)
+        assert s.guard_report()["worst"] < 1e-9
+    # worker-sized sweeps are not sampled; a solver built without the guard reports stride 0
+    with esb.DispersionSolver("cylinder_density") as s:
+        s.find_roots("kink", k[:1], W2[:90])
+        assert s.guard_report()["n_checked"] == 0
+    with esb.DispersionSolver("cylinder_density", guard=0) as s:
+        s.find_roots_multi([0, 1], k, W2)
+        assert s.guard_report()["stride"] == 0
+
+
+def test_bessel_jy_and_leaky_exterior_on_the_device(solvers):
+    """The J_n / Y_n evaluators and the closed-form leaky exterior as the DEVICE build computes them
+    (esb_bessel_jy_dev, esb_exterior_leaky_dev) against scipy and against the host build."""
+    import ctypes as C
+    from scipy import special as sp
+    s = solvers["cylinder_density"]
+    x = np.concatenate([np.geomspace(1e-3, 5.0, 400), np.linspace(4.9, 8.1, 400), np.geomspace(8.0, 5e3, 800)])
+    for n in range(4):
+        got = s.bessel_jy_device(n, x)
+        J, dJ, Y, dY = sp.jv(n, x), sp.jvp(n, x), sp.yv(n, x), sp.yvp(n, x)
+        amp, damp = np.hypot(J, Y), np.hypot(dJ, dY)
+        assert np.max(np.abs(got[:, 0] - J) / amp) < 5e-15 and np.max(np.abs(got[:, 2] - Y) / amp) < 5e-15
+        assert np.max(np.abs(got[:, 1] - dJ) / damp) < 5e-15 and np.max(np.abs(got[:, 3] - dY) / damp) < 5e-15
+    rng = np.random.default_rng(3)
+    k = rng.uniform(0.05, 4.5, 2000)
+    W = np.where(rng.random(2000) < 0.7, rng.uniform(5.001, 9.0, 2000), rng.uniform(0.4976, 0.4999, 2000))
+    out = (C.c_double * 2)()
+    for n in range(4):
+        dev = s.exterior_leaky_device(n, k, k * W)
+        assert np.isfinite(dev).all()
+        for j in range(0, 2000, 40):
+            assert s.lib.esb_exterior_leaky(C.byref(s.model), n, k[j], k[j] * W[j], out) == 0
+            amp = np.hypot(out[0], out[1])
+            assert abs(dev[j, 0] - out[0]) < 1e-12 * amp and abs(dev[j, 1] - out[1]) < 1e-12 * amp
+    # the regular side is not theirs
+    assert np.isnan(s.exterior_leaky_device(1, np.array([1.0]), np.array([3.0]))).all()
+
+
 def test_device_pointer_entry_points(solvers):
     """esb_dispersion_grid_dev / esb_brackets_dev on caller-owned device buffers (torch tensors) and a
     caller-owned stream: the same grids and the same sorted bracket list as the host entry points."""
