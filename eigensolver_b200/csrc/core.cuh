@@ -1153,8 +1153,8 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
 //   rotation        D or C3 changes sign between staged nodes (C3 = 0 is singular for the reference's
 //                   second-order form only, but the reference output there is noise all the same)
 ESB_HD bool outside_range(double v, double lo, double hi, double margin) {
-    const double pad = margin * fmax(fabs(lo), fabs(hi));
-    return v < lo - pad || v > hi + pad;
+    // lo, hi >= 0 (densities, squared frequencies): a relative margin on either bound
+    return v < lo * (1.0 - margin) || v > hi * (1.0 + margin);
 }
 
 template <int KIND>
@@ -1177,20 +1177,20 @@ ESB_HD bool resonance_free(const DevModel& M, const Point& pt, double mode, cons
                   fmin(a2, b2) > margin * margin * pt.A;
         return ok;
     } else {
-        // at w and at w (1 +- margin): a point NEXT to a resonance converges slowly too
+        // D = 0 and C3 = 0 only at a resonance: the signs of D and C3 must be the same at every node AND at
+        // w (1 - margin), w, w (1 + margin) - a point NEXT to a resonance converges slowly too
+        bool pos_d = false, neg_d = false, pos_c = false, neg_c = false;
         for (int j = -1; j <= 1; ++j) {
             Point q = pt;
             q.w = pt.w * (1.0 + j * margin);
             q.A = q.w * q.w;
-            bool pos_d = false, neg_d = false, pos_c = false, neg_c = false;
             for (int i = 0; i < M.n_nodes; ++i) {
                 const RotCoef c = node_rot(M, q, mode, tab + (size_t)i * ROT_FIELDS);
                 pos_d = pos_d || c.invD > 0.0; neg_d = neg_d || !(c.invD > 0.0);
                 pos_c = pos_c || c.C3 > 0.0; neg_c = neg_c || !(c.C3 > 0.0);
             }
-            if ((pos_d && neg_d) || (pos_c && neg_c)) return false;
         }
-        return true;
+        return !(pos_d && neg_d) && !(pos_c && neg_c);
     }
 }
 

@@ -768,14 +768,17 @@ struct GuardArgs {
     GuardRecord* out;
 };
 
+// sample j -> grid point: tiles of 32 CONSECUTIVE omega points (one warp: coalesced reads of the planes and
+// lanes that take the same branch of the per-point scheme switch), one tile per 32 * stride points, its
+// offset sliding through that window so that a row length that is a multiple of it does not put every tile
+// into the same omega columns
 __host__ __device__ __forceinline__ size_t guard_point(unsigned j, int stride) {
-    // a slowly sliding offset inside the stride, so that a row length that is a multiple of the stride
-    // does not put every sample into the same omega column
-    return (size_t)j * stride + (j % (unsigned)stride);
+    const unsigned tile = j >> 5, lane = j & 31u;
+    return (size_t)tile * 32u * (unsigned)stride + 32u * (tile % (unsigned)stride) + lane;
 }
 
 template <int KIND, int SCHEME>
-__global__ void __launch_bounds__(128) guard_kernel(GuardArgs g) {
+__global__ void __launch_bounds__(256) guard_kernel(GuardArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
     const int lane = threadIdx.x & 31;
@@ -921,7 +924,7 @@ struct esb_context {
     GuardRecord* d_guard = nullptr;
     GuardRecord* h_guard = nullptr;
     bool guard_pending = false;    // a record of the last sweep is (being) written
-    int guard_n_modes = 0, guard_nw = 0;
+    int guard_n_modes = 0, guard_nw = 0, guard_last_stride = 0;
     unsigned guard_n_per_mode = 0;
     bool tables_pending = false;   // a sweep's refinement may still be running: consumers wait on ev_done
     int n_sm = 148;
@@ -1309,7 +1312,7 @@ extern "C" int esb_set_guard_fields(esb_context* c, const esb_model* fine, const
                                     int32_t n_fields, int32_t n_nodes, const double* boundary,
                                     int32_t n_boundary, int32_t stride, double threshold) {
     if (!c) return ESB_ERR_ARG;
-    if (stride <= 0) {                       // switch the guard off
+    if (stride == 0 || stride < ESB_GUARD_AUTO) {                       // switch the guard off
         c->guard_set = false;
         c->guard_stride = 0;
         return ESB_OK;
@@ -1352,7 +1355,7 @@ static cudaError_t launch_guard(const GuardArgs& g, cudaStream_t s) {
     cudaError_t e = configure_once(guard_kernel<KIND, SCHEME>, done);
     if (e != cudaSuccess) return e;
     const unsigned total = g.n_per_mode * (unsigned)g.n_modes;
-    guard_kernel<KIND, SCHEME><<<(total + 127) / 128, 128, smem, s>>>(g);
+    guard_kernel<KIND, SCHEME><<<(total + 255) / 256, 256, smem, s>>>(g);
     return cudaGetLastError();
 }
 
@@ -1368,8 +1371,14 @@ static int guard_launch(esb_context* c, int n_modes, const int32_t* modes, int n
     g.n_modes = n_modes;
     for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
     g.ext = c->d_ext; g.intq = c->d_int; g.den = c->d_den;
-    g.stride = c->guard_stride;
-    g.n_per_mode = (unsigned)((plane + c->guard_stride - 1) / c->guard_stride);
+    // ESB_GUARD_AUTO: about 32 k samples per sweep whatever its size, at least every 64th point
+    int stride = c->guard_stride;
+    if (stride == ESB_GUARD_AUTO) {
+        stride = 64;
+        while (stride < 4096 && plane * n_modes / stride > 32768) stride *= 2;
+    }
+    g.stride = stride;
+    g.n_per_mode = 32u * (unsigned)((plane + 32 * (size_t)stride - 1) / (32 * (size_t)stride));
     g.threshold = c->guard_threshold;
     g.margin = 0.05;
     g.out = c->d_guard;
@@ -1387,6 +1396,7 @@ static int guard_launch(esb_context* c, int n_modes, const int32_t* modes, int n
     c->guard_n_modes = n_modes;
     c->guard_nw = nw;
     c->guard_n_per_mode = g.n_per_mode;
+    c->guard_last_stride = stride;
     return ESB_OK;
 }
 
@@ -1397,6 +1407,7 @@ extern "C" int esb_guard_result(esb_context* c, esb_guard_report* out) {
     out->threshold = c->guard_threshold;
     out->stride = c->guard_set ? c->guard_stride : 0;
     if (!c->guard_set || !c->guard_pending) return ESB_OK;        // no guard, or no sweep since it was set
+    out->stride = c->guard_last_stride;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventSynchronize(c->ev_guard));
     const GuardRecord r = *c->h_guard;
@@ -1409,7 +1420,7 @@ extern "C" int esb_guard_result(esb_context* c, esb_guard_report* out) {
         out->worst = worst;
         const unsigned sample = (unsigned)(r.key & 0xffffffffULL);
         const int slot = (int)(sample / c->guard_n_per_mode);
-        const size_t p = guard_point(sample - (unsigned)slot * c->guard_n_per_mode, c->guard_stride);
+        const size_t p = guard_point(sample - (unsigned)slot * c->guard_n_per_mode, c->guard_last_stride);
         out->slot = slot;
         out->k_index = (int32_t)(p / c->guard_nw);
         out->w_index = (int32_t)(p - (size_t)out->k_index * c->guard_nw);

@@ -334,9 +334,9 @@ class DiscretisationWarning(UserWarning):
     """The fixed-step integration lost digits on this profile: raise n_steps (DispersionSolver.guard_report)."""
 
 
-#: default sampling of the discretisation guard: every 256th (grid point, mode) of a sweep is re-evaluated
-#: at twice the steps (< 1 % of the scan's arithmetic, on a side stream)
-GUARD_STRIDE = 256
+#: default sampling of the discretisation guard (ESB_GUARD_AUTO): every sweep re-evaluates about 32 k of its
+#: (grid point, mode) pairs at twice the steps, on a side stream - 0.5 % of a 3e7-point sweep
+GUARD_STRIDE = -1
 GUARD_THRESHOLD = 1e-9
 
 
@@ -356,9 +356,10 @@ class DispersionSolver:
         s_end: far end of the layer (the rotational sausage script stops at r = 0.01, the kink one at 0.001).
         coordinate="positive": the cylinder scripts written in r > 0 (photospheric set:
         layer 1 -> 0.001, exterior slope given as dP/dr).
-        guard: stride of the built-in discretisation guard (every guard-th (point, mode) of a sweep is
-        re-evaluated at 2 x n_steps; a host-returning root search warns - DiscretisationWarning - when the
-        worst deviation exceeds guard_threshold; guard_report() reads it); 0 / None switches it off."""
+        guard: stride of the built-in discretisation guard (one 32-point tile per 32 * guard grid points of
+        a sweep is re-evaluated at 2 x n_steps; -1 = chosen per sweep, about 32 k samples; a host-returning
+        root search warns - DiscretisationWarning - when the worst deviation exceeds guard_threshold;
+        guard_report() reads it); 0 / None switches it off."""
         self.spec = ModelSpec(kind, medium, profile, n_steps, scheme, mesh, rho_A, ext_ic, ext_wavelengths,
                               coordinate, s_end, mesh_params)
         self.guard_stride = int(guard or 0)
@@ -396,7 +397,7 @@ class DispersionSolver:
 
     def _upload_guard(self):
         self._guard_on = False
-        if self.guard_stride <= 0:
+        if self.guard_stride == 0:
             return
         fine = self._fine_spec()
         if fine is None:

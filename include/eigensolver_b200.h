@@ -196,15 +196,19 @@ int esb_tables_wait(esb_context* ctx, void* stream);
  * the scan's arithmetic).  esb_guard_result waits for that pass and reports the worst deviation - judged on the
  * pole-free function G = D Y relative to |ext Y| + |int Y| - over the sampled points outside the resonant
  * continua, where it occurred, and how many samples exceeded `threshold`.  8th order: halving the step divides
- * the error by ~256, so the value is (to 0.4 %) the discretisation error of the sweep itself.  stride <= 0
- * switches the guard off; it must be set again after every esb_set_model[_fields].  Sweeps of at most 8192
+ * the error by ~256, so the value is (to 0.4 %) the discretisation error of the sweep itself.  The samples are
+ * tiles of 32 consecutive omega points, one tile per 32 * stride grid points; stride = ESB_GUARD_AUTO lets every
+ * sweep pick the stride that judges about 32 k samples (64 <= stride <= 4096: 0.5 % of a 3e7-point sweep, 3 % of
+ * a 1e5-point one); stride = 0 switches the guard off; it must be set again after every
+ * esb_set_model[_fields].  Sweeps of at most 8192
  * (point, mode) pairs - the latency-bound worker-sized calls - and esb_scan_models are not sampled
  * (n_checked = 0). */
+#define ESB_GUARD_AUTO (-1)
 typedef struct esb_guard_report {
     double worst;        /* largest deviation over the judged samples (0 if none) */
     double threshold;
     int32_t slot, k_index, w_index;   /* where (-1: none) */
-    int32_t stride;      /* 0: no guard set */
+    int32_t stride;      /* the stride the last sweep used; 0: no guard set */
     int64_t n_checked;   /* samples judged (evaluated, outside the continua) */
     int64_t n_above;     /* ... of them above the threshold */
 } esb_guard_report;

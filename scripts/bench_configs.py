@@ -65,5 +65,5 @@ with esb.DispersionSolver("cylinder_density") as sd, esb.DispersionSolver("slab_
 rec = {"config": "configs[4] parameter scan: 25 density contrasts (cylinder, 3 modes) + 25 flow amplitudes (slab, 2 modes), "
                  "500 k x 2000 omega each, incl. per-point table upload and root-table download",
        "evals": tot, "s_total": dt, "evals_per_sec": tot / dt,
-       "modes_found": int(sum(sum(p.n_modes) for p in r1 + r2))}
+       "modes_found": int(np.asarray(r1.table["accepted"]).sum() + np.asarray(r2.table["accepted"]).sum())}
 print(json.dumps(rec), flush=True)
