@@ -62,13 +62,26 @@ def _cpu_init():
 
 
 def _cpu_eval(args):
-    """One D evaluation through the oracle port of the reference's scipy path."""
+    """One D evaluation through the oracle port of the reference's scipy path (coefficients in closed form:
+    the per-point sympy / lambdify rebuild of Density_cylinder.py:705-757 hoisted out)."""
     import warnings
     warnings.filterwarnings("ignore")
     from oracle import reference_path as rp
     mode, k, w = args
     prof = rp.GaussianDensity(rp.CYL_CORONAL, width=0.95, const_B=True)
     e, i = rp.dispersion(rp.CylinderDensity(prof, mode), k, w)      # scipy defaults, fsolve
+    return e - i
+
+
+def _cpu_eval_unhoisted(args):
+    """The same evaluation with the reference's own cost structure: sympy re-derives and lambdifies the six
+    coefficient functions at every (k, omega), as the script's scan loop does."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import reference_path as rp
+    mode, k, w = args
+    prof = rp.GaussianDensity(rp.CYL_CORONAL, width=0.95, const_B=True)
+    e, i = rp.dispersion(rp.CylinderDensityPerPoint(prof, mode), k, w)
     return e - i
 
 
@@ -80,12 +93,22 @@ def cpu_sample(nk, nw, seed=0):
     return [(m, k, k * W) for m in MODES for k in ks for W in Ws]
 
 
-def time_cpu(pool, cores, nk, nw, seed):
+def time_cpu(pool, cores, nk, nw, seed, fn=_cpu_eval):
     pts = cpu_sample(nk, nw, seed)
     t = time.perf_counter()
-    pool.map(_cpu_eval, pts, chunksize=max(1, len(pts) // (cores * 8)))
+    pool.map(fn, pts, chunksize=max(1, len(pts) // (cores * 8)))
     dt = time.perf_counter() - t
     return len(pts), dt
+
+
+def unhoisted_rate(pool, cores):
+    """evaluations/s of the per-point-sympy variant on a small sample (~10 s on all cores)"""
+    time_cpu(pool, cores, 1, cores, 2, _cpu_eval_unhoisted)          # sympy import, caches
+    nk, nw = 4, max(4, cores)
+    n, dt = time_cpu(pool, cores, nk, nw, 7, _cpu_eval_unhoisted)
+    return {"value": n / dt, "unit": "evals/s",
+            "sample": "%d k x %d omega x 3 modes (%.0f s): coefficients re-derived with sympy and lambdified at "
+                      "every point, as Density_cylinder.py:705-757 does" % (nk, nw, dt)}
 
 
 def run_reference_arm(args):
@@ -102,6 +125,7 @@ def run_reference_arm(args):
             n, dt = time_cpu(pool, cores, nk, nw, 100 + s)
             tot_n += n
             tot_t += dt
+        unhoisted = unhoisted_rate(pool, cores)
     value = tot_n / tot_t
     sample = "%d k x %d omega x 3 modes per step (uniform random in the workload's k/omega box)" % (nk, nw)
     line = {
@@ -109,12 +133,17 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample,
+                   "sampled": "the CPU arm times a uniform random SAMPLE of the workload's (k, omega) box per step "
+                              "(the full 3e7-point grid takes ~27 h on these cores); rates are per evaluation"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample,
+                         "unhoisted": unhoisted},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle/reference_path.py = the reference's numpy/scipy path (odeint + fsolve at scipy "
-                "defaults) with the sympy/lambdify coefficient rebuild hoisted out; the reference scripts "
-                "themselves need /root/reference, matplotlib and numpy<1.18 and cannot travel",
+                "defaults) with the sympy/lambdify coefficient rebuild hoisted out (value: the faster, conservative "
+                "rate); cpu_baseline.unhoisted = the same with the rebuild per point, the reference's own cost "
+                "structure; the reference scripts themselves need /root/reference, matplotlib and numpy<1.18 and "
+                "cannot travel",
     }
     print(json.dumps(line))
 
@@ -449,6 +478,7 @@ def run_gpu_arm(args):
     value = evals_per_step * args.steps / (ms * 1e-3)
     e2e = evals_per_step * args.steps / (ms_e2e * 1e-3)
 
+    guard = solver.guard_report()          # of the last sweep: the discretisation error the run carried
     solver.close()
     strong = None if args.no_extras else strong_scaling_job(esb, local, dev, rank, world)
     configs = other_configs(esb, local) if (world == 1 and not args.no_extras) else None
@@ -462,7 +492,8 @@ def run_gpu_arm(args):
             with mp.get_context("fork").Pool(cores, initializer=_cpu_init) as pool:
                 time_cpu(pool, cores, 2, cores, 1)
                 n, dt = time_cpu(pool, cores, 16, max(8, 8 * cores), 5)      # ~15 s on all cores
-            cpu = {"value": n / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                unhoisted = unhoisted_rate(pool, cores)
+            cpu = {"value": n / dt, "unit": "evals/s", "cores": cores, "kind": "port", "unhoisted": unhoisted,
                    "sample": "16 k x %d omega x 3 modes, uniform random in the workload's box (%.0f s); oracle/"
                              "reference_path.py (scipy odeint + fsolve, the reference's algorithm)"
                              % (max(8, 8 * cores), dt)}
@@ -491,6 +522,10 @@ def run_gpu_arm(args):
                                         "(nominal 148 SM x 64 FMA/clk x 1.965 GHz = %.1f TFLOP/s)" % nominal,
                          "kernel_share_of_step": kms / (ms / args.steps)},
             "clocks": sampler.summary(),
+            "guard": {"worst_deviation": guard["worst"], "samples_judged": guard["n_checked"],
+                      "above_1e-9": guard["n_above"], "stride": guard["stride"],
+                      "what": "built-in discretisation guard, inside the timed sweeps: (point, mode) samples "
+                              "re-evaluated at 2 x n_steps on a side stream, outside the resonant continua"},
         }
         if cpu:
             line["cpu_baseline"] = cpu

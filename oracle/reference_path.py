@@ -320,6 +320,66 @@ class CylinderDensity(_Base):
         return slope / (rho * (w * w - k * k * vA2))
 
 
+class CylinderDensityPerPoint(CylinderDensity):
+    """The same model with the reference's own per-point cost structure: Density_cylinder.py:705-757
+    re-derives D, Q, T, C1, C2, C3, F = r D/C3, dF = diff(F, r) and g = -diff(r C1/C3, r) - r (C2 - C1^2/C3)/D
+    with sympy and lambdifies six functions at EVERY (k, omega) of the scan loop, before the two odeint /
+    fsolve stages.  `prepare(k, w)` restates exactly that (with v_phi = B_phi = v_z = 0, B_i = B_0 as the
+    script sets them, :97-108); the hoisted class above evaluates the collapsed closed forms instead.
+    Used by bench.py's CPU legs to report the reference's true per-evaluation rate next to the hoisted
+    (faster, conservative) one, and pinned to the hoisted path in tests/test_oracle_pinned.py."""
+
+    def prepare(self, k, w):
+        import sympy as sym
+        md, pf = self.medium, self.profile
+        rr = sym.symbols("r")
+        m, v_phi, B_phi, v_z = self.m, 0.0, 0.0, 0.0                                       # :97-108
+        B_0 = md.B_0
+        rho_e, c_e, vA_e, gamma = md.rho_e, md.c_e, md.vA_e, md.gamma
+
+        def rho_i(r):                                                                      # :135-146
+            if isinstance(pf, EpsteinDensity):
+                return pf.rho_A * ((md.rho_i0 - rho_e) / (sym.cosh((r - pf.x0) / pf.width) ** 4) ** 2 + rho_e)
+            return pf.rho_A * (rho_e + (md.rho_i0 - rho_e) * sym.exp(-(r - pf.x0) ** 2 / pf.width**2))
+
+        B_i = lambda r: B_0                                                                # :196
+        vA_i = lambda r: (B_i(r) + B_phi) / sym.sqrt(rho_i(r))                             # :188
+        c_i = lambda r: sym.sqrt(rho_e * (c_e**2 + 0.5 * gamma * vA_e**2) / rho_i(r) - 0.5 * gamma * vA_i(r) ** 2)  # :210
+        shift = lambda r: w - (m * v_phi / r) + k * v_z                                    # :705
+        alfven = lambda r: (m * B_phi / r) + (k * B_i(r)) / sym.sqrt(rho_i(r))             # :708
+        cusp = lambda r: alfven(r) * c_i(r) / sym.sqrt(c_i(r) ** 2 + vA_i(r) ** 2)         # :711
+        D = lambda r: rho_i(r) * (c_i(r) ** 2 + vA_i(r) ** 2) * (shift(r) ** 2 - alfven(r) ** 2) * (
+            shift(r) ** 2 - cusp(r) ** 2)                                                  # :714
+        Q = lambda r: (-(shift(r) ** 2 - alfven(r) ** 2) * rho_i(r) * v_phi**2 / r) + (
+            2 * shift(r) ** 2 * B_phi**2 / r) + (
+            2 * shift(r) * B_phi * v_phi * ((m * B_phi / r) + (k * B_i(r))) / r)           # :719
+        T = lambda r: (((m * B_phi / r) + (k * B_i(r))) * B_phi) + rho_i(r) * v_phi * shift(r)   # :722
+        C1 = lambda r: (Q(r) * shift(r)) - (2 * m * (c_i(r) ** 2 + vA_i(r) ** 2) * (
+            shift(r) ** 2 - cusp(r) ** 2) * T(r) / r**2)                                   # :725
+        C2 = lambda r: shift(r) ** 4 - ((c_i(r) ** 2 + vA_i(r) ** 2) * (m**2 / r**2 + k**2) * (
+            shift(r) ** 2 - cusp(r) ** 2))                                                 # :730
+        C3_diff = lambda r: (B_phi / r) ** 2 - (rho_i(r) * (v_phi / r) ** 2)               # :733
+        C3 = lambda r: (D(r) * (rho_i(r) * (shift(r) ** 2 - alfven(r) ** 2) + (r * sym.diff(C3_diff(r), r)))) + (
+            Q(r) ** 2 - (4 * (c_i(r) ** 2 + vA_i(r) ** 2) * (shift(r) ** 2 - cusp(r) ** 2) * T(r) ** 2 / r**2))  # :736
+        F = lambda r: (r * D(r)) / C3(r)                                                   # :741
+        dF = lambda r: sym.diff(F(r), r)                                                   # :746
+        g = lambda r: -(sym.diff((r * C1(r) / C3(r)), r)) - (r * (C2(r) - (C1(r) ** 2 / C3(r))) / D(r))   # :752
+        self._D = sym.lambdify(rr, D(rr), "numpy")                                         # :717
+        self._C1 = sym.lambdify(rr, C1(rr), "numpy")                                       # :728
+        self._C3 = sym.lambdify(rr, C3(rr), "numpy")                                       # :739
+        self._F = sym.lambdify(rr, F(rr), "numpy")                                         # :744
+        self._dF = sym.lambdify(rr, dF(rr), "numpy")                                       # :749
+        self._g = sym.lambdify(rr, g(rr), "numpy")                                         # :755
+
+    def coeffs(self, r, k, w):
+        F = self._F(r)
+        return -self._dF(r) / F, self._g(r) / F                                            # dP_dr_i :782
+
+    def int_match(self, k, w, y0, slope):
+        r = self.s0
+        return (self._C1(r) * y0 + self._D(r) * slope) / self._C3(r)                       # :798
+
+
 @dataclasses.dataclass
 class FlowMedium:
     """Speeds of the slab flow script (flow_multiprocessor_coronal.py:47-56): uniform density
@@ -602,6 +662,8 @@ def exterior(model, k, w, rtol=None, atol=None):
 def dispersion(model, k, w, rtol=None, atol=None, xtol=None, shoot="fsolve"):
     """Steps 1-4 for one (k, w).  Returns (exterior quantity, interior quantity);
     D = ext - int.  (nan, nan) where the reference skips the point."""
+    if hasattr(model, "prepare"):
+        model.prepare(k, w)                  # the reference rebuilds its coefficients before the m_e test (:705-757)
     yb = exterior(model, k, w, rtol, atol)
     if yb is None:
         return float("nan"), float("nan")

@@ -66,6 +66,29 @@ def test_oracle_equals_executed_reference(golden_dir, name, tol, stride):
     assert n_checked >= 6 and n_skipped >= 2
 
 
+def test_per_point_sympy_variant_is_the_same_function(golden_dir):
+    """CylinderDensityPerPoint rebuilds D, C1, C2, C3, F, dF, g with sympy and lambdifies six functions at every
+    (k, omega), as Density_cylinder.py:705-757 does (the cost structure bench.py's `unhoisted` CPU rate
+    times): same values as the executed reference and as the hoisted closed forms."""
+    case = CASES["cylinder_density"]
+    g = np.load(os.path.join(golden_dir, "ref_D_%s.npz" % case.fixture))
+    prof = rp.GaussianDensity(rp.CYL_CORONAL, width=0.95, const_B=True)
+    n = 0
+    for mode in (0, 1):
+        hoisted, per_point = rp.CylinderDensity(prof, mode), rp.CylinderDensityPerPoint(prof, mode)
+        for j in np.nonzero(g["mode"] == mode)[0][4::13]:
+            k, w, Dref = g["k"][j], g["w"][j], g["D"][j]
+            Dp = rp.D(per_point, k, w)
+            if np.isnan(Dref):
+                assert np.isnan(Dp)
+                continue
+            e, i = rp.dispersion(hoisted, k, w)
+            assert abs(Dp - (e - i)) <= 1e-7 * max(abs(e), abs(i)), (mode, k, w)
+            assert abs(Dp - Dref) <= 1e-7 * max(abs(e), abs(i)), (mode, k, w)
+            n += 1
+    assert n >= 8
+
+
 @pytest.mark.parametrize("name", ["cylinder_density", "slab_density", "cylinder_flow", "slab_flow"])
 def test_reference_scan_and_bisection(golden_dir, name):
     """The reference's own scan+bisection output (sol_ks/sol_omegas) over a few intervals:
