@@ -103,6 +103,7 @@ SYMBOLS = {
     "esb_roots_pinned": (C.c_int, [_ctx, C.c_int32, C.POINTER(esb_roots), _ip]),
     "esb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "esb_tables_wait": (C.c_int, [_ctx, C.c_void_p]),
+    "esb_pack_modes_dev": (C.c_int, [_ctx, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p]),
     "esb_set_accept_rule": (C.c_int, [_ctx, C.c_int32]),
     "esb_set_guard_fields": (C.c_int, [_ctx, C.POINTER(esb_model), C.POINTER(_dp), C.c_int32, C.c_int32, _dp,
                                        C.c_int32, C.c_int32, C.c_double]),

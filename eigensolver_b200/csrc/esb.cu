@@ -734,6 +734,84 @@ __global__ void exterior_leaky_kernel(DevModel M, int n, const double* __restric
     out[2 * i] = yb; out[2 * i + 1] = ypb;
 }
 
+// ---- accepted modes of all slots packed into one payload (multi-GPU gather) ---------------------------
+// rows 1.. of `out` = (global k row, omega, slot) of every accepted mode, slots in order, each slot in table
+// order (k index, omega index): deterministic.  Row 0 = (count, entries scanned, capacity exceeded ? 1 : 0).
+// Two launches over the same block partition of the concatenated tables: count, then prefix + write.
+struct PackArgs {
+    const int* accepted[ESB_MAX_MODES];
+    const int* k_index[ESB_MAX_MODES];
+    const double* omega[ESB_MAX_MODES];
+    int begin[ESB_MAX_MODES + 1];      // first concatenated index of every slot; [n_slots] = total
+    int n_slots;
+    double k_offset, k_stride;
+    int* block_count;                  // [gridDim.x]
+    double* out;                       // [capacity + 1][3]
+    int capacity;
+};
+
+constexpr int PACK_THREADS = 256, PACK_PER_BLOCK = 2048;
+
+__global__ void __launch_bounds__(PACK_THREADS) pack_modes_kernel(PackArgs a, int write) {
+    __shared__ int warp_sum[PACK_THREADS / 32];
+    __shared__ int base_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = a.begin[a.n_slots];
+    const int lo = blockIdx.x * PACK_PER_BLOCK;
+    const int hi = lo + PACK_PER_BLOCK < total ? lo + PACK_PER_BLOCK : total;
+    int base = 0;
+    if (write) {
+        if (threadIdx.x == 0) {
+            int b = 0, all = 0;
+            for (int i = 0; i < (int)gridDim.x; ++i) {
+                if (i == (int)blockIdx.x) b = all;
+                all += a.block_count[i];
+            }
+            base_sh = b;
+            if (blockIdx.x == 0) {
+                a.out[0] = (double)(all < a.capacity ? all : a.capacity);
+                a.out[1] = (double)total;
+                a.out[2] = all > a.capacity ? 1.0 : 0.0;
+            }
+        }
+        __syncthreads();
+        base = base_sh;
+    }
+    int running = 0;
+    for (int c0 = lo; c0 < hi; c0 += PACK_THREADS) {
+        const int g = c0 + threadIdx.x;
+        int sl = 0, acc = 0;
+        if (g < hi) {
+#pragma unroll
+            for (int q = 1; q < ESB_MAX_MODES; ++q)
+                if (q < a.n_slots && g >= a.begin[q]) sl = q;
+            acc = a.accepted[sl][g - a.begin[sl]] == 1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, acc);
+        if (lane == 0) warp_sum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, chunk = 0;
+#pragma unroll
+        for (int q = 0; q < PACK_THREADS / 32; ++q) {
+            before += q < warp ? warp_sum[q] : 0;
+            chunk += warp_sum[q];
+        }
+        if (write && acc) {
+            const int row = base + running + before + __popc(bal & ((1u << lane) - 1u));
+            if (row < a.capacity) {
+                const int t = g - a.begin[sl];
+                double* o = a.out + 3 * (size_t)(row + 1);
+                o[0] = fma((double)a.k_index[sl][t], a.k_stride, a.k_offset);
+                o[1] = a.omega[sl][t];
+                o[2] = (double)sl;
+            }
+        }
+        running += chunk;
+        __syncthreads();
+    }
+    if (!write && threadIdx.x == 0) a.block_count[blockIdx.x] = running;
+}
+
 // ---- discretisation guard --------------------------------------------------------------------------
 // The integrator is fixed-step where the reference's odeint adapts.  With a guard model set
 // (esb_set_guard_fields: the same equilibrium on a finer mesh, normally 2 x n_steps), every sweep
@@ -893,6 +971,8 @@ struct esb_context {
     // queue heads: ints [0], [1] = the two passes of the refinement, bytes 8..15 = the scan's tile counter;
     // d_slot_begin[ESB_MAX_MODES + 1] = first work index of every slot (written by scan_kernel), h_counts =
     // its page-locked host copy
+    int* d_pack_counts = nullptr;
+    size_t cap_pack_counts = 0;
     int* d_counter = nullptr;
     int* d_slot_begin = nullptr;
     int* h_counts = nullptr;
@@ -1096,6 +1176,7 @@ extern "C" int esb_destroy(esb_context* c) {
         if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->d_gtab) cudaFree(c->d_gtab);
+    if (c->d_pack_counts) cudaFree(c->d_pack_counts);
     if (c->d_guard) cudaFree(c->d_guard);
     if (c->h_guard) cudaFreeHost(c->h_guard);
     if (c->ev_scan) cudaEventDestroy(c->ev_scan);
@@ -2019,6 +2100,45 @@ extern "C" int esb_roots_device(esb_context* c, int32_t slot, esb_roots* out, in
     out->k_index = sl.bk; out->w_index = sl.bw; out->omega = sl.om; out->ext = sl.e;
     out->intq = sl.i; out->accepted = sl.acc; out->iterations = sl.it;
     if (n_roots) *n_roots = sl.n;
+    return ESB_OK;
+}
+
+
+// Accepted modes of the first n_slots mode slots of the last sweep, packed on the device into the caller's
+// buffer d_out[(capacity + 1) * 3] (doubles): row 0 = (rows written, table entries scanned, 1 if more modes
+// than `capacity` were found), rows 1.. = (k_offset + k_stride * k_index, omega, slot) in (slot, k index,
+// omega index) order.  Asynchronous on the context's stream, ordered after the sweep; consumer_stream (a
+// cudaStream_t, may be NULL) is made to wait for it.  The payload of a multi-GPU gather (one fixed-size
+// all-gather, no count exchange, no host synchronisation).
+extern "C" int esb_pack_modes_dev(esb_context* c, int32_t n_slots, double k_offset, double k_stride, double* d_out,
+                                  int32_t capacity, void* consumer_stream) {
+    if (!c || !d_out || n_slots < 1 || n_slots > ESB_MAX_MODES || capacity < 0) return ESB_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = cur_stream(c);
+    PackArgs a{};
+    a.n_slots = n_slots;
+    a.begin[0] = 0;
+    for (int m = 0; m < n_slots; ++m) {
+        const esb_context::RootBuf& sl = c->slots[m];
+        a.accepted[m] = sl.acc; a.k_index[m] = sl.bk; a.omega[m] = sl.om;
+        a.begin[m + 1] = a.begin[m] + sl.n;
+    }
+    a.k_offset = k_offset; a.k_stride = k_stride;
+    a.out = d_out; a.capacity = capacity;
+    const int total = a.begin[n_slots];
+    const int blocks = total > 0 ? (total + PACK_PER_BLOCK - 1) / PACK_PER_BLOCK : 1;
+    int rc;
+    if ((rc = ensure(c, c->d_pack_counts, c->cap_pack_counts, (size_t)blocks))) return rc;
+    a.block_count = c->d_pack_counts;
+    pack_modes_kernel<<<blocks, PACK_THREADS, 0, s>>>(a, 0);
+    CUDA_TRY(c, cudaGetLastError());
+    pack_modes_kernel<<<blocks, PACK_THREADS, 0, s>>>(a, 1);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches += 2;
+    if (consumer_stream && (cudaStream_t)consumer_stream != s) {      // the reader's stream waits for the payload
+        CUDA_TRY(c, cudaEventRecord(c->ev_counts, s));
+        CUDA_TRY(c, cudaStreamWaitEvent((cudaStream_t)consumer_stream, c->ev_counts, 0));
+    }
     return ESB_OK;
 }
 

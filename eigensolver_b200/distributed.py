@@ -144,38 +144,52 @@ def gather_modes_device(solver, n_slots, k_offset, device, group=None, k_stride=
     reference's sol_ks / sol_omegas lists of every rank, read straight from the solver's device
     buffers.  Returns a float64 tensor [total, 3] = (global k row, omega, slot) on `device`, ordered
     by rank (like the reference's queue output, which is in process order) or, with sort=True, by
-    (slot, global k row, omega).  One mask compaction, one count exchange, one payload exchange."""
+    (slot, global k row, omega).
+
+    The payload is packed by the library (esb_pack_modes_dev: two small launches, deterministic order,
+    row 0 = the count) into a buffer of a capacity all ranks share, so a step is ONE fixed-size
+    all_gather_into_tensor - no count exchange, no boolean-mask compaction, no host synchronisation before
+    the collective is enqueued.  The capacity is negotiated once (all_reduce MAX of the table sizes) and
+    again only when some rank reports that it was exceeded."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
+    from . import _lib as L
 
     world = dist.get_world_size(group)
-    gks, oms, acs, sls = [], [], [], []
     stream = _consumer_stream(device)
-    for slot in range(n_slots):
-        info = solver.roots_device(slot, stream=stream)
-        n = info["n"]
-        if not n:
-            continue
-        ki = torch.as_tensor(_DevArray(info["k_index"][0], n, "<i4"), device=device)
-        gks.append(ki.to(torch.float64) * float(k_stride) + float(k_offset))
-        oms.append(torch.as_tensor(_DevArray(info["omega"][0], n, "<f8"), device=device))
-        acs.append(torch.as_tensor(_DevArray(info["accepted"][0], n, "<i4"), device=device))
-        sls.append(torch.full((n,), float(slot), dtype=torch.float64, device=device))
-    if gks:
-        m = torch.cat(acs) == 1
-        mine = torch.stack((torch.cat(gks)[m], torch.cat(oms)[m], torch.cat(sls)[m]), dim=1)
-    else:
-        mine = torch.zeros((0, 3), dtype=torch.float64, device=device)
-    cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device=device)
-    counts = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, cnt, group=group)
-    counts = counts.tolist()
-    cap = max(max(counts), 1)
-    pay = torch.zeros((cap, 3), dtype=torch.float64, device=device)
-    pay[: mine.shape[0]] = mine
-    out = torch.empty((world * cap, 3), dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(out, pay, group=group)
-    full = torch.cat([out[r * cap: r * cap + c] for r, c in enumerate(counts)], dim=0)
+    st = solver.__dict__.setdefault("_gather_state", {})
+
+    def negotiate(minimum):
+        out, n = L.esb_roots(), C.c_int32(0)
+        bound = 0
+        for slot in range(n_slots):           # table sizes are host knowledge of the sweep call: no wait
+            L.check(solver.lib, solver.ctx, solver.lib.esb_roots_device(solver.ctx, slot, C.byref(out), C.byref(n)),
+                    "esb_roots_device")
+            bound += n.value
+        want = torch.tensor([max(bound, minimum)], dtype=torch.int64, device=device)
+        dist.all_reduce(want, op=dist.ReduceOp.MAX, group=group)
+        cap = int(want.item() * 1.25) + 1024
+        st.update(cap=cap, n_slots=n_slots, world=world,
+                  pay=torch.zeros((cap + 1, 3), dtype=torch.float64, device=device),
+                  out=torch.empty((world, cap + 1, 3), dtype=torch.float64, device=device))
+
+    if st.get("n_slots") != n_slots or st.get("world") != world or st["pay"].device != torch.device(device):
+        negotiate(0)
+    while True:
+        L.check(solver.lib, solver.ctx,
+                solver.lib.esb_pack_modes_dev(solver.ctx, int(n_slots), float(k_offset), float(k_stride),
+                                              C.c_void_p(st["pay"].data_ptr()), st["cap"],
+                                              C.c_void_p(int(stream)) if stream else None),
+                "esb_pack_modes_dev")
+        # (stream None = torch on the legacy default stream: it orders itself after the context's blocking
+        #  stream without an event)
+        dist.all_gather_into_tensor(st["out"].view(-1, 3), st["pay"], group=group)
+        head = st["out"][:, 0, :].tolist()       # the one host wait of the step, after the collective
+        if not any(h[2] for h in head):
+            break
+        negotiate(int(max(h[1] for h in head)))  # some rank found more modes than the shared capacity
+    full = torch.cat([st["out"][r, 1: 1 + int(h[0])] for r, h in enumerate(head)], dim=0)
     if sort and full.shape[0]:
         for col in (1, 0, 2):            # stable sorts, least significant key first
             full = full[torch.argsort(full[:, col], stable=True)]

@@ -39,7 +39,7 @@ extern "C" {
                              1.2: ESB_RK8N (normal-form Nystrom scheme, needs the profile's second derivative);
                                   up to 4 fused modes; esb_set_accept_rule; esb_tables_wait
                              1.3: esb_set_guard_fields / esb_guard_result (discretisation guard);
-                                  esb_bessel_jy[_dev], esb_exterior_leaky[_dev] (J_n, Y_n: the leaky side) */
+                                  esb_bessel_jy[_dev], esb_exterior_leaky[_dev] (J_n, Y_n: the leaky side); esb_pack_modes_dev */
 
 typedef struct esb_context esb_context;
 
@@ -216,6 +216,16 @@ int esb_set_guard_fields(esb_context* ctx, const esb_model* fine, const double* 
                          int32_t n_nodes, const double* boundary, int32_t n_boundary, int32_t stride,
                          double threshold);
 int esb_guard_result(esb_context* ctx, esb_guard_report* out);
+
+/* Accepted modes of mode slots 0..n_slots-1 of the last sweep, packed ON THE DEVICE into the caller's device
+ * buffer d_out[(capacity + 1) * 3] (doubles): row 0 = (rows written, table entries scanned, 1 if more than
+ * `capacity` modes were found), rows 1.. = (k_offset + k_stride * k_index, omega, slot), ordered by (slot,
+ * k index, omega index).  Asynchronous on the context's stream, after the sweep; `consumer_stream` (a
+ * cudaStream_t that will read d_out, may be NULL) is made to wait for it.  This is the payload of the
+ * multi-GPU gather (what the reference's parent process collects from its workers' queues,
+ * Density_cylinder.py:1150-1170): one fixed-size all-gather, no count exchange, no host synchronisation. */
+int esb_pack_modes_dev(esb_context* ctx, int32_t n_slots, double k_offset, double k_stride, double* d_out,
+                       int32_t capacity, void* consumer_stream);
 
 /* What a sweep reports (esb_set_accept_rule; default ESB_ACCEPT_CONVERGED).
  *   ESB_ACCEPT_CONVERGED  sign changes of D between ADJACENT evaluated grid points, every bracket refined to
