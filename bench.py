@@ -50,8 +50,9 @@ N_STEPS = 152                  # the cylinder kind's default: normal-form scheme
 FLOPS_PER_EVAL = 201 * N_STEPS + 700
 FLOPS_FUSED_LAUNCH = ((74 + 3 * 127) * N_STEPS + 3 * 500) * NK * NW
 # FP64-pipe instructions of the same launch, from the SASS of the step loop (tools/sass_loop_count.py:
-# 291 per step for three modes) - the pipe-utilisation view of the same roofline
-FP64_INSTR_FUSED_LAUNCH = (291 * N_STEPS + 3 * 300) * NK * NW
+# 281 per step for three modes: 194 DFMA, 74 DMUL, 12 DADD, 1 MUFU.RCP64H - one reciprocal serves the four
+# new stage nodes of a step) - the pipe-utilisation view of the same roofline
+FP64_INSTR_FUSED_LAUNCH = (281 * N_STEPS + 3 * 300) * NK * NW
 WORKLOAD = "cylinder non-uniform density, n=0,1,2, 1000 k x 10000 omega per GPU"
 
 
@@ -104,7 +105,7 @@ def time_cpu(pool, cores, nk, nw, seed, fn=_cpu_eval):
 def unhoisted_rate(pool, cores):
     """evaluations/s of the per-point-sympy variant on a small sample (~10 s on all cores)"""
     time_cpu(pool, cores, 1, cores, 2, _cpu_eval_unhoisted)          # sympy import, caches
-    nk, nw = 4, max(4, cores)
+    nk, nw = 4, max(4, 4 * cores)
     n, dt = time_cpu(pool, cores, nk, nw, 7, _cpu_eval_unhoisted)
     return {"value": n / dt, "unit": "evals/s",
             "sample": "%d k x %d omega x 3 modes (%.0f s): coefficients re-derived with sympy and lambdified at "

@@ -128,6 +128,21 @@ ESB_HD Point make_point(const DevModel& M, double k, double w) {
     return p;
 }
 
+// Four reciprocals for the price of one: a double-precision division costs ~8 FP64-pipe instructions (and
+// a slow-path check), and every step needs one per new stage node.  1/(p1 p2 p3 p4) and nine products give
+// all four to ~3 ulp.  The arguments are products of two O(1)..O(1e32) factors (the w -> 0 clamps below keep
+// the product of all four inside the double range); one of them vanishing or overflowing (a resonance
+// exactly on a node: inside a continuum) spoils the four, which are noise there anyway.
+ESB_HD void reciprocal4(const double (&p)[4], double (&inv)[4]) {
+    const double p01 = p[0] * p[1], p23 = p[2] * p[3];
+    const double r = 1.0 / (p01 * p23);
+    const double i01 = r * p23, i23 = r * p01;
+    inv[0] = i01 * p[1];
+    inv[1] = i01 * p[0];
+    inv[2] = i23 * p[3];
+    inv[3] = i23 * p[2];
+}
+
 // y'' = a y' + b y  at one staged node (4 doubles f[0..3]).
 //   cylinder: f = {1/r, 1/r^2, rho, rho'}
 //       a = -1/r + rho' w^2/(rho w^2 - k^2 beta)
@@ -140,66 +155,86 @@ ESB_HD Point make_point(const DevModel& M, double k, double w) {
 //     (..._coronal.py:222-230.)
 // `b` excludes the azimuthal term; `bm` is its factor: b_total = b + m^2 * bm (bm = 1/r^2 for the
 // cylinder, 0 for the slab), so that several azimuthal orders share one coefficient evaluation.
+// node_coeffs in two halves around its one division, so that the four new stage nodes of a step share ONE
+// reciprocal (reciprocal4 below): `pre` returns the product to invert and keeps what the second half needs.
+struct CoefPre { double u, X, Y, Om, O2, t, sc, va, st; };
+
 template <int KIND>
-ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, double& a, double& b,
-                        double& bm) {
+ESB_HD double node_coeffs_pre(const DevModel& M, const Point& p, const double* f, CoefPre& c) {
     if (KIND == KIND_CYL_DENSITY) {
-        const double invr = f[0], invr2 = f[1], rho = f[2], drho = f[3];
-        const double u = rho * p.A;
-        const double X = u - p.Kbeta;
-        const double Y = fma(M.S, u, -p.SKtau);
-        const double inv = 1.0 / (X * Y);
-        a = fma(drho * p.A * Y, inv, -invr);
-        b = fma(-(u * u) * X, inv, p.K);
-        bm = invr2;
+        c.u = f[2] * p.A;
+        c.X = c.u - p.Kbeta;
+        c.Y = fma(M.S, c.u, -p.SKtau);
+        return c.X * c.Y;
+    } else if (KIND == KIND_CYL_FLOW) {
+        c.Om = fma(-p.k, f[2], p.w);
+        c.O2 = c.Om * c.Om;
+        c.X = fma(-p.K, M.vAi2, c.O2);
+        c.Y = M.si * fma(-p.K, M.cTi2, c.O2);
+        return c.X * c.Y;
+    } else if (KIND == KIND_SLAB_FLOW) {
+        c.Om = fma(-p.k, f[0], p.w);
+        c.O2 = c.Om * c.Om;
+        c.t = fma(-p.K, M.cTi2, c.O2);
+        c.sc = fma(-p.K, M.ci2, c.O2);          // Om^2 - k^2 c^2
+        c.va = fma(-p.K, M.vAi2, c.O2);         // Om^2 - k^2 vA^2
+        c.st = M.si * c.t;
+        c.X = c.Om * c.sc;
+        return c.st * c.X;
+    } else {
+        c.u = f[0] * p.A;
+        c.X = p.Kalpha - c.u;                   // p1
+        c.Y = p.Ktau - c.u;                     // p3
+        return c.X * c.Y;
+    }
+}
+
+template <int KIND>
+ESB_HD void node_coeffs_fin(const DevModel& M, const Point& p, const double* f, const CoefPre& c, double inv,
+                            double& a, double& b, double& bm) {
+    if (KIND == KIND_CYL_DENSITY) {
+        a = fma(f[3] * p.A * c.Y, inv, -f[0]);
+        b = fma(-(c.u * c.u) * c.X, inv, p.K);
+        bm = f[1];
     } else if (KIND == KIND_CYL_FLOW) {
         // f = {1/r, 1/r^2, v_z, v_z'}.  Cylinder_method_flow_testing.py:711-762 with v_phi = B_phi = 0
         // and uniform rho, c, vA:  Om = w - k v_z,  Q = T = C1 = 0,  C3 = D rho (Om^2 - wA^2),
         //   F = r D/C3 = r/(rho (Om^2 - k^2 vA^2)),   g = -r C2/D
         //   a = -F'/F = -1/r - 2 k v_z' Om/(Om^2 - k^2 vA^2)
         //   b = g/F   = m^2/r^2 + k^2 - Om^4/(s (Om^2 - k^2 cT^2))
-        const double invr = f[0], invr2 = f[1], vz = f[2], dvz = f[3];
-        const double Om = fma(-p.k, vz, p.w);
-        const double O2 = Om * Om;
-        const double X = fma(-p.K, M.vAi2, O2);
-        const double Y = M.si * fma(-p.K, M.cTi2, O2);
-        const double inv = 1.0 / (X * Y);
-        a = fma(-2.0 * p.k * dvz * Om * Y, inv, -invr);
-        b = fma(-(O2 * O2) * X, inv, p.K);
-        bm = invr2;
+        a = fma(-2.0 * p.k * f[3] * c.Om * c.Y, inv, -f[0]);
+        b = fma(-(c.O2 * c.O2) * c.X, inv, p.K);
+        bm = f[1];
     } else if (KIND == KIND_SLAB_FLOW) {
         // f = {U, U', U''}.  vx'' = -D vx' - coeff vx  (flow_multiprocessor_coronal.py:211-219,297):
         //   Om = w - k U,  t = Om^2 - k^2 cT^2
         //   m0 = (k^2 c^2 - Om^2)(k^2 vA^2 - Om^2)/(s (k^2 cT^2 - Om^2))
         //   D  = 2 k U' (t + k^4 cT^2 c^2/(s t)) / (Om (Om^2 - k^2 c^2))
         //   a = -D,  b = m0 - k U''/Om - k U' D/Om
-        const double U = f[0], dU = f[1], ddU = f[2];
-        const double Om = fma(-p.k, U, p.w);
-        const double O2 = Om * Om;
-        const double t = fma(-p.K, M.cTi2, O2);
-        const double sc = fma(-p.K, M.ci2, O2);          // Om^2 - k^2 c^2
-        const double va = fma(-p.K, M.vAi2, O2);         // Om^2 - k^2 vA^2
-        const double st = M.si * t;
         // one reciprocal for 1/(s t), 1/(Om sc): inv = 1/(st * Om * sc)
-        const double inv = 1.0 / (st * Om * sc);
-        const double inv_st = inv * (Om * sc);
-        const double inv_osc = inv * st;                 // 1/(Om sc)
-        const double m0 = -(sc * va) * inv_st;           // (Kc^2-O2)(KvA^2-O2)/(s(KcT^2-O2)) = -(sc va)/(s t)
-        const double kdU = p.k * dU;
-        const double Dx = 2.0 * kdU * fma(p.K * p.K * M.cTi2 * M.ci2, inv_st, t) * inv_osc;
-        const double invOm = inv_osc * sc;               // 1/Om
+        const double inv_st = inv * c.X;
+        const double inv_osc = inv * c.st;               // 1/(Om sc)
+        const double m0 = -(c.sc * c.va) * inv_st;       // (Kc^2-O2)(KvA^2-O2)/(s(KcT^2-O2)) = -(sc va)/(s t)
+        const double kdU = p.k * f[1];
+        const double Dx = 2.0 * kdU * fma(p.K * p.K * M.cTi2 * M.ci2, inv_st, c.t) * inv_osc;
+        const double invOm = inv_osc * c.sc;             // 1/Om
         a = -Dx;
-        b = m0 - (p.k * ddU + kdU * Dx) * invOm;
+        b = m0 - (p.k * f[2] + kdU * Dx) * invOm;
         bm = 0.0;
     } else {
-        const double rho = f[0], drho = f[1];
-        const double u = rho * p.A;
-        const double p1 = p.Kalpha - u, p2 = p.Kbeta - u, p3 = p.Ktau - u;
-        const double inv = 1.0 / (p1 * p3);
-        a = p.AKc * drho * inv;
-        b = (p1 * p1) * p2 * inv * M.invS;
+        const double p2 = p.Kbeta - c.u;
+        a = p.AKc * f[1] * inv;
+        b = (c.X * c.X) * p2 * inv * M.invS;
         bm = 0.0;
     }
+}
+
+template <int KIND>
+ESB_HD void node_coeffs(const DevModel& M, const Point& p, const double* f, double& a, double& b,
+                        double& bm) {
+    CoefPre c;
+    const double prod = node_coeffs_pre<KIND>(M, p, f, c);
+    node_coeffs_fin<KIND>(M, p, f, c, 1.0 / prod, a, b, bm);
 }
 
 // ------------------------------------------------------------- integrator ----
@@ -331,8 +366,19 @@ ESB_HD void integrate_layer(const DevModel& M, const Point& pt, const double* __
         const double h = hs[i];
         double ca[NN], cb[NN], bm[NN], cbs[NS][NN];
         ca[0] = a0; cb[0] = b0; bm[0] = bm0;
+        if constexpr (NN == 5) {                 // one reciprocal for the four new stage nodes
+            CoefPre pre[4];
+            double prod[4], inv[4];
 #pragma unroll
-        for (int n = 1; n < NN; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n], bm[n]);
+            for (int n = 0; n < 4; ++n) prod[n] = node_coeffs_pre<KIND>(M, pt, f + (n + 1) * TAB_FIELDS, pre[n]);
+            reciprocal4(prod, inv);
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                node_coeffs_fin<KIND>(M, pt, f + (n + 1) * TAB_FIELDS, pre[n], inv[n], ca[n + 1], cb[n + 1], bm[n + 1]);
+        } else {
+#pragma unroll
+            for (int n = 1; n < NN; ++n) node_coeffs<KIND>(M, pt, f + n * TAB_FIELDS, ca[n], cb[n], bm[n]);
+        }
         a0 = ca[NN - 1]; b0 = cb[NN - 1]; bm0 = bm[NN - 1];       // unscaled, carried to the next step
         if constexpr (SCHEME == SCHEME_RK8) {
             // fold the step into the node coefficients (shared by all solutions): h a, h^2 b
@@ -381,8 +427,9 @@ template <int KIND>
 ESB_HD ScaledPoint make_scaled_point(const DevModel& M, const Point& pt) {
     ScaledPoint sp{};
     if constexpr (KIND == KIND_CYL_DENSITY) {
-        // w = 0: q, p -> 1e280-ish, X Y overflows to +inf, 1/(X Y) = 0 and a = -1/r, b = k^2, the w -> 0 limit
-        const double A = pt.A > 1e-280 ? pt.A : 1e-280;
+        // w -> 0: q, p -> 1e30-ish, 1/(X Y) vanishes against the O(1) terms and a = -1/r, b = k^2, the w -> 0
+        // limit (the clamp keeps the product of FOUR node denominators inside the double range: reciprocal4)
+        const double A = pt.A > 1e-30 ? pt.A : 1e-30;
         sp.q = pt.Kbeta / A;
         sp.p = pt.Ktau / A;
         sp.AS = A / M.S;
@@ -396,38 +443,55 @@ ESB_HD ScaledPoint make_scaled_point(const DevModel& M, const Point& pt) {
 // NFTAB: the node is read from the normal-form table (NF_FIELDS doubles: {-h/(2r) | h^2, h^2/r^2, field,
 // h field', ...}) instead of the 4-field pre-scaled one - the normal-form scheme integrates the points
 // next to a resonance in these variables (shoot_layer) from its own table.
-template <int KIND, bool NFTAB = false>
-ESB_HD void node_coeffs_scaled(const DevModel& M, const Point& pt, const ScaledPoint& sp, double c1, double h2K,
-                               const double* f, double& ha, double& h2b, double& h2bm) {
+// (in two halves around the division, like node_coeffs: `pre` returns the product to invert)
+template <int KIND>
+ESB_HD double node_scaled_pre(const DevModel& M, const Point& pt, const ScaledPoint& sp, const double* f, CoefPre& c) {
+    if constexpr (KIND == KIND_SLAB_DENSITY) {
+        c.u = f[2] * pt.A;
+        c.X = pt.Kalpha - c.u;                  // p1
+        c.Y = pt.Ktau - c.u;                    // p3
+    } else if constexpr (KIND == KIND_CYL_DENSITY) {
+        c.X = f[2] - sp.q;
+        c.Y = f[2] - sp.p;
+    } else {
+        c.Om = fma(-pt.k, f[2], pt.w);
+        c.O2 = c.Om * c.Om;
+        c.X = fma(-pt.K, M.vAi2, c.O2);
+        c.Y = fma(-pt.K, M.cTi2, c.O2);
+    }
+    return c.X * c.Y;
+}
+
+template <int KIND, bool NFTAB>
+ESB_HD void node_scaled_fin(const DevModel& M, const Point& pt, const ScaledPoint& sp, double c1, double h2K,
+                            const double* f, const CoefPre& c, double inv, double& ha, double& h2b, double& h2bm) {
     if constexpr (KIND == KIND_SLAB_DENSITY) {
         // f = {h^2, -, rho, h rho'} (normal-form table only)
-        const double u = f[2] * pt.A;
-        const double p1 = pt.Kalpha - u, p2 = pt.Kbeta - u, p3 = pt.Ktau - u;
-        const double inv = 1.0 / (p1 * p3);
+        const double p2 = pt.Kbeta - c.u;
         ha = (pt.AKc * f[3]) * inv;
-        h2b = ((p1 * p1) * p2) * (inv * c1);                  // c1 = h^2/S
+        h2b = ((c.X * c.X) * p2) * (inv * c1);                // c1 = h^2/S
         h2bm = 0.0;
     } else {
         const double nhinvr = NFTAB ? f[0] + f[0] : -f[0];    // -h/r
         h2bm = f[1];
         if constexpr (KIND == KIND_CYL_DENSITY) {
             const double rho = f[2], hdrho = f[3];
-            const double X = rho - sp.q;
-            const double Y = rho - sp.p;
-            const double inv = 1.0 / (X * Y);
-            ha = fma(hdrho * Y, inv, nhinvr);
-            h2b = fma(-((rho * rho) * X) * c1, inv, h2K);         // c1 = h^2 w^2/S
+            ha = fma(hdrho * c.Y, inv, nhinvr);
+            h2b = fma(-((rho * rho) * c.X) * c1, inv, h2K);       // c1 = h^2 w^2/S
         } else {
-            const double vz = f[2], hdvz = f[3];
-            const double Om = fma(-pt.k, vz, pt.w);
-            const double O2 = Om * Om;
-            const double X = fma(-pt.K, M.vAi2, O2);
-            const double Y = fma(-pt.K, M.cTi2, O2);
-            const double inv = 1.0 / (X * Y);
-            ha = fma((sp.m2k * hdvz) * Om * Y, inv, nhinvr);
-            h2b = fma(-((O2 * O2) * X) * c1, inv, h2K);           // c1 = h^2/s
+            const double hdvz = f[3];
+            ha = fma((sp.m2k * hdvz) * c.Om * c.Y, inv, nhinvr);
+            h2b = fma(-((c.O2 * c.O2) * c.X) * c1, inv, h2K);     // c1 = h^2/s
         }
     }
+}
+
+template <int KIND, bool NFTAB = false>
+ESB_HD void node_coeffs_scaled(const DevModel& M, const Point& pt, const ScaledPoint& sp, double c1, double h2K,
+                               const double* f, double& ha, double& h2b, double& h2bm) {
+    CoefPre c;
+    const double prod = node_scaled_pre<KIND>(M, pt, sp, f, c);
+    node_scaled_fin<KIND, NFTAB>(M, pt, sp, c1, h2K, f, c, 1.0 / prod, ha, h2b, h2bm);
 }
 
 template <int KIND, int NS, bool RANGE = false, bool NFTAB = false>
@@ -464,9 +528,17 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
         const double c1 = h2 * cc, h2K = h2 * pt.K;
         double ha[5], h2b[5], h2bm[5], h2bs[NS][5];
         ha[0] = ha0; h2b[0] = h2b0; h2bm[0] = h2bm0;
+        {                                        // one reciprocal for the four new stage nodes
+            CoefPre pre[4];
+            double prod[4], inv[4];
 #pragma unroll
-        for (int n = 1; n < 5; ++n)
-            node_coeffs_scaled<KIND, NFTAB>(M, pt, sp, c1, h2K, f + n * TF, ha[n], h2b[n], h2bm[n]);
+            for (int n = 0; n < 4; ++n) prod[n] = node_scaled_pre<KIND>(M, pt, sp, f + (n + 1) * TF, pre[n]);
+            reciprocal4(prod, inv);
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                node_scaled_fin<KIND, NFTAB>(M, pt, sp, c1, h2K, f + (n + 1) * TF, pre[n], inv[n], ha[n + 1],
+                                             h2b[n + 1], h2bm[n + 1]);
+        }
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -522,9 +594,10 @@ ESB_HD NPoint make_npoint(const DevModel& M, const Point& pt) {
         sp.m2k = -2.0 * pt.k;
         sp.inv_s = 1.0 / M.si;
     } else {
-        // w = 0: the ratios -> 1e280-ish, the products overflow to +inf, their reciprocal is 0 and
-        // q = k^2 (+ the azimuthal term), the w -> 0 limit
-        const double A = pt.A > 1e-280 ? pt.A : 1e-280;
+        // w -> 0: the ratios -> 1e30-ish, the reciprocals of their products vanish against the O(1) terms and
+        // q = k^2 (+ the azimuthal term), the w -> 0 limit (the clamp keeps the product of FOUR node
+        // denominators inside the double range: reciprocal4)
+        const double A = pt.A > 1e-30 ? pt.A : 1e-30;
         sp.q = pt.Kbeta / A;
         sp.p = pt.Ktau / A;
         sp.t = pt.Kalpha / A;
@@ -534,17 +607,33 @@ ESB_HD NPoint make_npoint(const DevModel& M, const Point& pt) {
     return sp;
 }
 
-// h^2 q (without the azimuthal term) and its azimuthal factor h^2/r^2 at one staged node.
-// c1 = h^2 w^2/S (density), h^2/s (flow); h2K = h^2 k^2.
+// The two factors whose product a node's coefficients divide by (and, flow kinds, the Doppler-shifted
+// frequency they are built from): first half of node_q / node_coeffs_scaled, before the reciprocal.
+struct NodeDen { double X, Y, Om, O2; };
+
 template <int KIND>
-ESB_HD void node_q(const DevModel& M, const Point& pt, const NPoint& sp, double c1, double h2K, const double* f,
-                   double& h2q, double& h2m) {
+ESB_HD double node_den(const DevModel& M, const Point& pt, const NPoint& sp, const double* f, NodeDen& d) {
     if constexpr (KIND == KIND_CYL_DENSITY) {
-        const double rho = f[2];
-        const double X = rho - sp.q;
-        const double Y = rho - sp.p;
-        const double inv = 1.0 / (X * Y);
-        const double iX = inv * Y, iY = inv * X;
+        d.X = f[2] - sp.q;
+        d.Y = f[2] - sp.p;
+    } else if constexpr (KIND == KIND_CYL_FLOW) {
+        d.Om = fma(-pt.k, f[2], pt.w);
+        d.O2 = d.Om * d.Om;
+        d.X = fma(-pt.K, M.vAi2, d.O2);
+        d.Y = fma(-pt.K, M.cTi2, d.O2);
+    } else {
+        d.X = sp.t - f[2];                 // P1
+        d.Y = sp.p - f[2];                 // P3
+    }
+    return d.X * d.Y;
+}
+
+// second half: h^2 q and h^2/r^2 from the factors and inv = 1/(X Y)
+template <int KIND>
+ESB_HD void node_q_fin(const DevModel& M, const Point& pt, const NPoint& sp, double c1, double h2K, const double* f,
+                       const NodeDen& d, double inv, double& h2q, double& h2m) {
+    if constexpr (KIND == KIND_CYL_DENSITY) {
+        const double iX = inv * d.Y, iY = inv * d.X;
         const double L = f[3] * iX;
         double acc = fma(-(sp.AS * f[5]), iY, h2K);
         acc = fma(f[4], iX, acc);
@@ -553,34 +642,38 @@ ESB_HD void node_q(const DevModel& M, const Point& pt, const NPoint& sp, double 
         h2m = f[1];
     } else if constexpr (KIND == KIND_CYL_FLOW) {
         const double hdv = f[3];
-        const double Om = fma(-pt.k, f[2], pt.w);
-        const double O2 = Om * Om;
-        const double X = fma(-pt.K, M.vAi2, O2);
-        const double Y = fma(-pt.K, M.cTi2, O2);
-        const double inv = 1.0 / (X * Y);
-        const double iX = inv * Y, iY = inv * X;
-        const double kO = sp.m2k * Om;                         // -2 k Om
+        const double iX = inv * d.Y, iY = inv * d.X;
+        const double kO = sp.m2k * d.Om;                       // -2 k Om
         const double L = (kO * hdv) * iX;                      // h X'/X
         const double W = fma(pt.K * hdv, hdv, -kO * f[4]);     // h^2 X''/2 = k^2 (h v')^2 - k Om h^2 v''
-        double acc = fma(-((O2 * O2) * c1), iY, h2K);
+        double acc = fma(-((d.O2 * d.O2) * c1), iY, h2K);
         acc = fma(-W, iX, acc);
         acc = fma(0.75 * L, L, acc);
         h2q = fma(L, f[0], acc);
         h2m = f[1];
     } else {
-        const double rho = f[2], hdr = f[3];
-        const double P1 = sp.t - rho, P2 = sp.q - rho, P3 = sp.p - rho;
-        const double I = 1.0 / (P1 * P3);
-        const double i3 = I * P1;
-        const double d = I * sp.dd;                            // i3 - i1
-        const double sm = I * (P1 + P3);                       // i3 + i1
-        const double E = hdr * d;                              // h a
+        const double hdr = f[3];
+        const double P1 = d.X, P3 = d.Y, P2 = sp.q - f[2];
+        const double i3 = inv * P1;
+        const double dd = inv * sp.dd;                         // i3 - i1
+        const double sm = inv * (P1 + P3);                     // i3 + i1
+        const double E = hdr * dd;                             // h a
         double acc = ((c1 * P1) * P2) * i3;                    // h^2 b, c1 = h^2 w^2/S
-        acc = fma(f[4], d, acc);
+        acc = fma(f[4], dd, acc);
         acc = fma(-0.5 * (E * hdr), sm, acc);
         h2q = fma(0.25 * E, E, acc);
         h2m = 0.0;
     }
+}
+
+// h^2 q (without the azimuthal term) and its azimuthal factor h^2/r^2 at one staged node.
+// c1 = h^2 w^2/S (density), h^2/s (flow); h2K = h^2 k^2.
+template <int KIND>
+ESB_HD void node_q(const DevModel& M, const Point& pt, const NPoint& sp, double c1, double h2K, const double* f,
+                   double& h2q, double& h2m) {
+    NodeDen d;
+    const double prod = node_den<KIND>(M, pt, sp, f, d);
+    node_q_fin<KIND>(M, pt, sp, c1, h2K, f, d, 1.0 / prod, h2q, h2m);
 }
 
 // h a (h = the step the node is stored in) and the varying factor of F at a node:
@@ -669,8 +762,16 @@ ESB_HD void integrate_layer_nform(const DevModel& M, const Point& pt, const NPoi
         const double c1 = h2 * cc, h2K = h2 * pt.K;
         double q[5], bm[5], qs[NS][5];
         q[0] = q0; bm[0] = bm0;
+        {
+            NodeDen den[4];
+            double prod[4], inv[4];
 #pragma unroll
-        for (int n = 1; n < 5; ++n) node_q<KIND>(M, pt, sp, c1, h2K, f + n * NF_FIELDS, q[n], bm[n]);
+            for (int n = 0; n < 4; ++n) prod[n] = node_den<KIND>(M, pt, sp, f + (n + 1) * NF_FIELDS, den[n]);
+            reciprocal4(prod, inv);
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                node_q_fin<KIND>(M, pt, sp, c1, h2K, f + (n + 1) * NF_FIELDS, den[n], inv[n], q[n + 1], bm[n + 1]);
+        }
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -714,8 +815,10 @@ ESB_HD void nform_end_values(const DevModel& M, const Point& pt, const NPoint& s
 constexpr int ROT_FIELDS = 8;
 
 // unscaled pieces of the system matrix: m11 = -C1/D, m12 = C3/D, m21 = -C2/D, m22 = C1/D - 1/r
-struct RotCoef { double C1, C2, C3, invD, invr; };
+struct RotCoef { double C1, C2, C3, invD, invr, Dd; };
 
+// INVERT = false leaves invD to the caller (integrate_rotation inverts the four new nodes of a step together)
+template <bool INVERT = true>
 ESB_HD RotCoef node_rot(const DevModel& M, const Point& p, double m, const double* f) {
     const double invr = f[0], invr2 = f[1], vr = f[2], s = f[3], c2 = f[4], rv = f[5], q0 = f[6], f2 = f[7];
     const double Om = fma(-m, vr, p.w);
@@ -732,7 +835,8 @@ ESB_HD RotCoef node_rot(const DevModel& M, const Point& p, double m, const doubl
     c.C1 = fma(Q, O2, -2.0 * m * TA);
     c.C2 = fma(O2, O2, -A2 * fma(m * m, invr2, p.K));
     c.C3 = fma(Dd, ra1 + f2, fma(Q, Q, -4.0 * TA * T));
-    c.invD = 1.0 / Dd;
+    c.Dd = Dd;
+    if (INVERT) c.invD = 1.0 / Dd;
     c.invr = invr;
     return c;
 }
@@ -759,10 +863,21 @@ ESB_HD void integrate_rotation(const DevModel& M, const Point& pt, double m, con
         const double h = hs[i];
         double m11[5], m12[5], m21[5], m22[5];
         rot_scaled(c0, h, m11[0], m12[0], m21[0], m22[0]);
+        {                                        // one reciprocal for the four new stage nodes
+            RotCoef cn[4];
+            double prod[4], inv[4];
 #pragma unroll
-        for (int n = 1; n < 5; ++n) {
-            c0 = node_rot(M, pt, m, f + n * ROT_FIELDS);
-            rot_scaled(c0, h, m11[n], m12[n], m21[n], m22[n]);
+            for (int n = 0; n < 4; ++n) {
+                cn[n] = node_rot<false>(M, pt, m, f + (n + 1) * ROT_FIELDS);
+                prod[n] = cn[n].Dd;
+            }
+            reciprocal4(prod, inv);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                cn[n].invD = inv[n];
+                rot_scaled(cn[n], h, m11[n + 1], m12[n + 1], m21[n + 1], m22[n + 1]);
+            }
+            c0 = cn[3];
         }
         const RhsSystem rhs{m11, m12, m21, m22};
         rk8_generic<NS>(P, X, rhs);
