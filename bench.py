@@ -50,9 +50,9 @@ N_STEPS = 152                  # the cylinder kind's default: normal-form scheme
 FLOPS_PER_EVAL = 201 * N_STEPS + 700
 FLOPS_FUSED_LAUNCH = ((74 + 3 * 127) * N_STEPS + 3 * 500) * NK * NW
 # FP64-pipe instructions of the same launch, from the SASS of the step loop (tools/sass_loop_count.py:
-# 281 per step for three modes: 194 DFMA, 74 DMUL, 12 DADD, 1 MUFU.RCP64H - one reciprocal serves the four
+# 275 per step for three modes: 195 DFMA, 68 DMUL, 11 DADD, 1 MUFU.RCP64H - one reciprocal serves the four
 # new stage nodes of a step) - the pipe-utilisation view of the same roofline
-FP64_INSTR_FUSED_LAUNCH = (281 * N_STEPS + 3 * 300) * NK * NW
+FP64_INSTR_FUSED_LAUNCH = (275 * N_STEPS + 3 * 300) * NK * NW
 WORKLOAD = "cylinder non-uniform density, n=0,1,2, 1000 k x 10000 omega per GPU"
 
 

@@ -51,7 +51,8 @@ enum { SCHEME_RK4 = 0, SCHEME_RK8 = 1, SCHEME_RK8N = 2 };
 enum { OMEGA_SHARED = 0, OMEGA_PHASE_SPEED = 1, OMEGA_PER_K = 2 };
 
 constexpr int TAB_FIELDS = 4;   // doubles per node in the staged table
-constexpr int NF_FIELDS = 6;    // ... for the normal-form scheme (SCHEME_RK8N)
+constexpr int NF_FIELDS = 8;    // ... for the normal-form scheme (SCHEME_RK8N)
+constexpr double NF_SQRT34 = 0.86602540378443864676;   // sqrt(3/4): see model_host.h
 
 struct DevModel {
     int kind, scheme, n_steps, n_nodes;
@@ -472,14 +473,14 @@ ESB_HD void node_scaled_fin(const DevModel& M, const Point& pt, const ScaledPoin
         h2b = ((c.X * c.X) * p2) * (inv * c1);                // c1 = h^2/S
         h2bm = 0.0;
     } else {
-        const double nhinvr = NFTAB ? f[0] + f[0] : -f[0];    // -h/r
+        const double nhinvr = NFTAB ? f[6] + f[6] : -f[0];    // -h/r
         h2bm = f[1];
         if constexpr (KIND == KIND_CYL_DENSITY) {
-            const double rho = f[2], hdrho = f[3];
+            const double rho = f[2], hdrho = NFTAB ? f[7] : f[3];
             ha = fma(hdrho * c.Y, inv, nhinvr);
             h2b = fma(-((rho * rho) * c.X) * c1, inv, h2K);       // c1 = h^2 w^2/S
         } else {
-            const double hdvz = f[3];
+            const double hdvz = NFTAB ? f[7] : f[3];
             ha = fma((sp.m2k * hdvz) * c.Om * c.Y, inv, nhinvr);
             h2b = fma(-((c.O2 * c.O2) * c.X) * c1, inv, h2K);     // c1 = h^2/s
         }
@@ -504,6 +505,8 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
     const int iend = RANGE ? r1 : M.n_steps;
     const double* hs = tab + (size_t)M.n_nodes * TF;
     const double* gs = hs + M.n_steps;
+    const double* hs2 = gs + M.n_steps;          // h^2, (h'/h)^2: staged
+    const double* gs2 = hs2 + M.n_steps;
     const ScaledPoint sp = make_scaled_point<KIND>(M, pt);
     const double cc = (KIND == KIND_CYL_DENSITY) ? sp.AS : (KIND == KIND_SLAB_DENSITY) ? M.invS : sp.inv_s;
     double ha0, h2b0, h2bm0;
@@ -524,7 +527,7 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
     }
     for (int i = i0; i < iend; ++i) {
         const double* f = tab + (size_t)(i * 4) * TF;
-        const double h = hs[i], h2 = h * h;
+        const double h2 = hs2[i];
         const double c1 = h2 * cc, h2K = h2 * pt.K;
         double ha[5], h2b[5], h2bm[5], h2bs[NS][5];
         ha[0] = ha0; h2b[0] = h2b0; h2bm[0] = h2bm0;
@@ -545,7 +548,7 @@ ESB_HD void integrate_layer_prescaled(const DevModel& M, const Point& pt, const 
             for (int n = 0; n < 5; ++n)
                 h2bs[s][n] = is_cyl_second_order<KIND> ? fma(m2[s], h2bm[n], h2b[n]) : h2b[n];
         rk8_step<NS>(y, yp, ha, h2bs);
-        const double g = gs[i], g2 = g * g;
+        const double g = gs[i], g2 = gs2[i];
         ha0 = ha[4] * g; h2b0 = h2b[4] * g2; h2bm0 = h2bm[4] * g2;        // the shared node, in the next step's scale
 #pragma unroll
         for (int s = 0; s < NS; ++s) yp[s] *= g;
@@ -583,6 +586,7 @@ struct NPoint {
     double dd;           // slab: (alpha - tau) k^2/w^2
     double m2k;          // flow: -2 k
     double inv_s;        // flow: 1/(c^2 + vA^2)
+    double K43;          // flow: k^2 / (3/4)  (the staged first derivative carries a factor sqrt(3/4))
 };
 
 template <int KIND>
@@ -593,6 +597,7 @@ ESB_HD NPoint make_npoint(const DevModel& M, const Point& pt) {
     if constexpr (KIND == KIND_CYL_FLOW) {
         sp.m2k = -2.0 * pt.k;
         sp.inv_s = 1.0 / M.si;
+        sp.K43 = pt.K * (4.0 / 3.0);
     } else {
         // w -> 0: the ratios -> 1e30-ish, the reciprocals of their products vanish against the O(1) terms and
         // q = k^2 (+ the azimuthal term), the w -> 0 limit (the clamp keeps the product of FOUR node
@@ -633,22 +638,23 @@ template <int KIND>
 ESB_HD void node_q_fin(const DevModel& M, const Point& pt, const NPoint& sp, double c1, double h2K, const double* f,
                        const NodeDen& d, double inv, double& h2q, double& h2m) {
     if constexpr (KIND == KIND_CYL_DENSITY) {
+        // f[3] = c h rho', f[0] = -h/(2r)/c, c = sqrt(3/4):  3/4 L^2 - L h/(2r) = L'^2 + L' f[0],  L' = c L
         const double iX = inv * d.Y, iY = inv * d.X;
         const double L = f[3] * iX;
         double acc = fma(-(sp.AS * f[5]), iY, h2K);
         acc = fma(f[4], iX, acc);
-        acc = fma(0.75 * L, L, acc);
+        acc = fma(L, L, acc);
         h2q = fma(L, f[0], acc);
         h2m = f[1];
     } else if constexpr (KIND == KIND_CYL_FLOW) {
-        const double hdv = f[3];
+        const double hdv = f[3];                               // c h v'
         const double iX = inv * d.Y, iY = inv * d.X;
         const double kO = sp.m2k * d.Om;                       // -2 k Om
-        const double L = (kO * hdv) * iX;                      // h X'/X
-        const double W = fma(pt.K * hdv, hdv, -kO * f[4]);     // h^2 X''/2 = k^2 (h v')^2 - k Om h^2 v''
+        const double L = (kO * hdv) * iX;                      // c h X'/X
+        const double W = fma(sp.K43 * hdv, hdv, -kO * f[4]);   // h^2 X''/2 = k^2 (h v')^2 - k Om h^2 v''
         double acc = fma(-((d.O2 * d.O2) * c1), iY, h2K);
         acc = fma(-W, iX, acc);
-        acc = fma(0.75 * L, L, acc);
+        acc = fma(L, L, acc);
         h2q = fma(L, f[0], acc);
         h2m = f[1];
     } else {
@@ -682,12 +688,12 @@ template <int KIND>
 ESB_HD void nform_edge(const DevModel& M, const Point& pt, const NPoint& sp, const double* f, double& ha, double& Xf) {
     if constexpr (KIND == KIND_CYL_DENSITY) {
         const double X = f[2] - sp.q;
-        ha = fma(f[3], 1.0 / X, 2.0 * f[0]);
+        ha = fma(f[7], 1.0 / X, 2.0 * f[6]);
         Xf = X;
     } else if constexpr (KIND == KIND_CYL_FLOW) {
         const double Om = fma(-pt.k, f[2], pt.w);
         const double X = fma(-pt.K, M.vAi2, Om * Om);
-        ha = fma((sp.m2k * Om) * f[3], 1.0 / X, 2.0 * f[0]);
+        ha = fma((sp.m2k * Om) * f[7], 1.0 / X, 2.0 * f[6]);
         Xf = X;
     } else {
         const double P1 = sp.t - f[2], P3 = sp.p - f[2];
@@ -740,6 +746,8 @@ ESB_HD void integrate_layer_nform(const DevModel& M, const Point& pt, const NPoi
     const int iend = RANGE ? r1 : M.n_steps;
     const double* hs = tab + (size_t)M.n_nodes * NF_FIELDS;
     const double* gs = hs + M.n_steps;
+    const double* hs2 = gs + M.n_steps;          // h^2, (h'/h)^2: staged, not recomputed every step
+    const double* gs2 = hs2 + M.n_steps;
     const double cc = (KIND == KIND_CYL_FLOW) ? sp.inv_s : sp.AS;
     double q0, bm0;
     if (!RANGE || i0 == 0) {
@@ -758,7 +766,7 @@ ESB_HD void integrate_layer_nform(const DevModel& M, const Point& pt, const NPoi
     }
     for (int i = i0; i < iend; ++i) {
         const double* f = tab + (size_t)(i * 4) * NF_FIELDS;
-        const double h = hs[i], h2 = h * h;
+        const double h2 = hs2[i];
         const double c1 = h2 * cc, h2K = h2 * pt.K;
         double q[5], bm[5], qs[NS][5];
         q[0] = q0; bm[0] = bm0;
@@ -777,7 +785,7 @@ ESB_HD void integrate_layer_nform(const DevModel& M, const Point& pt, const NPoi
 #pragma unroll
             for (int n = 0; n < 5; ++n) qs[s][n] = CYL ? fma(m2[s], bm[n], q[n]) : q[n];
         rkn8_step<NS>(u, up, qs);
-        const double g = gs[i], g2 = g * g;
+        const double g = gs[i], g2 = gs2[i];
         q0 = q[4] * g2; bm0 = bm[4] * g2;                      // the shared node, in the next step's scale
 #pragma unroll
         for (int s = 0; s < NS; ++s) up[s] *= g;

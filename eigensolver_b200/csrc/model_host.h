@@ -186,7 +186,7 @@ struct HostModel {
 };
 
 // Everything esb_set_model_fields uploads, built on the host: the device model constants and the
-// staged table [n_nodes][fields per node], h[N], g[N] = h[i+1]/h[i] (last: 1/h[N-1]).
+// staged table [n_nodes][fields per node], h[N], g[N] = h[i+1]/h[i] (last: 1/h[N-1]), h^2[N], g^2[N].
 // fields[f][node]: density kinds {rho, rho'} (+ rho'' for ESB_RK8N); slab flow {U, U', U''};
 // rotation {v_phi, v_phi', c_i^2}; axial flow {v_z, v_z'} (+ v_z'').  boundary[0] = first field at s_start.
 static inline int build_host_model(const esb_model* m, const double* const* fields, int32_t n_fields,
@@ -203,7 +203,7 @@ static inline int build_host_model(const esb_model* m, const double* const* fiel
     const int N = m->n_steps, nps = nodes_per_step(m->scheme);
     const int tf = model_tab_fields(m);
     std::vector<double>& tab = out.tab;
-    tab.assign((size_t)need * tf + 2 * (size_t)N, 0.0);
+    tab.assign((size_t)need * tf + 4 * (size_t)N, 0.0);
     // step a node belongs to (the step-end node is stored in the scale of the step it ends and is
     // shared with the next step, which rescales the carried coefficients)
     auto step_h = [&](int i) {
@@ -214,20 +214,26 @@ static inline int build_host_model(const esb_model* m, const double* const* fiel
         double* f = &tab[(size_t)i * tf];
         if (m->scheme == ESB_RK8N) {
             // normal form u'' = q u (core.cuh integrate_layer_nform), everything pre-scaled by the step:
-            //   cylinder: {-h/(2r), h^2/r^2, field, h field', -h^2 field''/2, h^2 field^2 (density)}
-            //   slab:     {h^2, -, rho, h rho', -h^2 rho''/2, -}
+            //   cylinder: {-h/(2r)/c, h^2/r^2, field, c h field', -h^2 field''/2, h^2 field^2 (density),
+            //              -h/(2r), h field'},  c = sqrt(3/4): q contains 3/4 L^2 - L/(2r) with L = h field'/X,
+            //              and with the first derivative stored times c both terms are single FMAs of L' = c L
+            //              (fields 6, 7: the unscaled pair for the (y, h y') variables and the end conversion)
+            //   slab:     {h^2, -, rho, h rho', -h^2 rho''/2, -, h^2, h rho'}
             const double h = step_h(i), h2 = h * h;
             const double v = fields[0][i], dv = fields[1][i], ddv = fields[2][i];
             if (m->kind == ESB_SLAB_DENSITY) {
-                f[0] = h2;
+                f[0] = f[6] = h2;
                 f[1] = 0.0;
+                f[3] = f[7] = h * dv;
             } else {
                 const double r = nodes[i];
-                f[0] = -0.5 * h / r;
+                f[6] = -0.5 * h / r;
+                f[7] = h * dv;
+                f[0] = f[6] / NF_SQRT34;
+                f[3] = f[7] * NF_SQRT34;
                 f[1] = h2 / (r * r);
             }
             f[2] = v;
-            f[3] = h * dv;
             f[4] = -0.5 * h2 * ddv;
             f[5] = h2 * v * v;
         } else if (m->kind == ESB_CYLINDER_DENSITY || m->kind == ESB_CYLINDER_FLOW) {
@@ -264,6 +270,8 @@ static inline int build_host_model(const esb_model* m, const double* const* fiel
         double* hs = &tab[(size_t)need * tf];
         for (int i = 0; i < N; ++i) hs[i] = nodes[(i + 1) * nps] - nodes[i * nps];
         for (int i = 0; i < N; ++i) hs[N + i] = (i + 1 < N) ? hs[i + 1] / hs[i] : 1.0 / hs[i];
+        for (int i = 0; i < N; ++i) hs[2 * N + i] = hs[i] * hs[i];             // h^2
+        for (int i = 0; i < N; ++i) hs[3 * N + i] = hs[N + i] * hs[N + i];     // (h'/h)^2
     }
 
     DevModel& d = out.dm;

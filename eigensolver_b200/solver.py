@@ -389,9 +389,9 @@ class DispersionSolver:
         """The same equilibrium at `factor` x the steps (None if its table cannot be staged)."""
         kw = self.spec.solver_kwargs()
         kw["n_steps"] = int(self.spec.model.n_steps) * int(factor)
-        if kw["scheme"] == "rk8n" and kw["n_steps"] > 900:
-            kw["scheme"] = "rk8"          # the six-field table of that many steps exceeds shared memory
-        if kw["n_steps"] > 1400:
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > 680:
+            kw["scheme"] = "rk8"          # the eight-field table of that many steps exceeds shared memory
+        if kw["n_steps"] > 1350:
             return None
         return ModelSpec(**kw)
 
@@ -678,8 +678,8 @@ class DispersionSolver:
         m = self.model
         kw = self.spec.solver_kwargs()
         kw["n_steps"] = int(m.n_steps) * int(factor)
-        if kw["scheme"] == "rk8n" and kw["n_steps"] > 900:
-            kw["scheme"] = "rk8"          # the six-field table of that many steps exceeds shared memory
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > 680:
+            kw["scheme"] = "rk8"          # the eight-field table of that many steps exceeds shared memory
         with DispersionSolver(guard=0, **kw) as fine:
             e1, i1 = fine.dispersion_grid_multi(modes, k, w, layout)
         ok = np.isfinite(e0) & np.isfinite(i0) & np.isfinite(e1) & np.isfinite(i1)
