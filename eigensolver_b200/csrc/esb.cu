@@ -47,6 +47,7 @@ struct GridArgs {
     double* den;            // optional [n_modes][nk][nw]: denominator of intq (sweep path; see refine_kernel)
     int schedule;           // 0 = by size, 1 = one thread per point, 2 = one warp per point
     unsigned long long* tile_counter;   // work queue head of the persistent scan kernel (zeroed before launch)
+    int threads;            // CTA size of the persistent scan (0: ESB_GRID_THREADS, the most the registers allow)
 };
 
 __device__ __forceinline__ double omega_at(const double* __restrict__ k, const double* __restrict__ w,
@@ -1004,6 +1005,13 @@ struct esb_context {
     // its page-locked host copy
     int* d_pack_counts = nullptr;
     size_t cap_pack_counts = 0;
+    // esb_scan_models pipeline: the refinement of equilibrium i runs on its own stream beside the scan of
+    // equilibrium i + 1 (second set of planes, scan CTAs two thirds of their usual size)
+    cudaStream_t refine_stream = nullptr;
+    cudaEvent_t ev_fill[2] = {nullptr, nullptr}, ev_refine[2] = {nullptr, nullptr};
+    double *d_ext2 = nullptr, *d_int2 = nullptr, *d_den2 = nullptr;
+    size_t cap_grid2 = 0;
+    int scan_threads = 0;          // CTA size override of the persistent scan kernel (0: default)
     int* d_counter = nullptr;
     int* d_slot_begin = nullptr;
     int* h_counts = nullptr;
@@ -1208,6 +1216,14 @@ extern "C" int esb_destroy(esb_context* c) {
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->d_gtab) cudaFree(c->d_gtab);
     if (c->d_pack_counts) cudaFree(c->d_pack_counts);
+    if (c->d_ext2) cudaFree(c->d_ext2);
+    if (c->d_int2) cudaFree(c->d_int2);
+    if (c->d_den2) cudaFree(c->d_den2);
+    for (int b = 0; b < 2; ++b) {
+        if (c->ev_fill[b]) cudaEventDestroy(c->ev_fill[b]);
+        if (c->ev_refine[b]) cudaEventDestroy(c->ev_refine[b]);
+    }
+    if (c->refine_stream) cudaStreamDestroy(c->refine_stream);
     if (c->d_seg_tmp) cudaFree(c->d_seg_tmp);
     if (c->d_guard) cudaFree(c->d_guard);
     if (c->h_guard) cudaFreeHost(c->h_guard);
@@ -1309,7 +1325,9 @@ static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s, int n_sm) {
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(g.tile_counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    constexpr int threads = ESB_GRID_THREADS(SCHEME);
+    // fewer warps than the launch bound leave registers for a refinement CTA of the previous equilibrium
+    // beside it (esb_scan_models)
+    const int threads = (g.threads > 0 && g.threads < ESB_GRID_THREADS(SCHEME)) ? g.threads : ESB_GRID_THREADS(SCHEME);
     const long long n_tiles = (long long)g.nk * ((g.nw + 31) / 32);
     long long blocks = (n_tiles + threads / 32 - 1) / (threads / 32);
     // one CTA per SM; a grid with fewer tiles than warp slots spreads its tiles over all SMs
@@ -1571,6 +1589,7 @@ static int grid_dev_multi(esb_context* c, int n_modes, const int32_t* modes, con
     for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
     g.ext = d_ext; g.intq = d_int; g.den = d_den;
     g.schedule = c->schedule;
+    g.threads = c->scan_threads;
     g.tile_counter = reinterpret_cast<unsigned long long*>(c->d_counter + 2);
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, s));
@@ -1960,13 +1979,57 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
     const int tabd_keep = c->tab_doubles;
     const DevModel dm_keep = c->dm;
     const bool set_keep = c->model_set;
+    // Pipeline: the refinement of equilibrium i (latency bound at the end of its queue; on a small grid for
+    // most of its duration) runs on its own stream beside the scan of equilibrium i + 1.  The persistent scan
+    // kernel normally takes the whole register file of an SM; launched with two thirds of its warps it
+    // leaves room for one refinement CTA per SM.  Two sets of planes alternate; the root tables and the
+    // bracket counts are per equilibrium anyway.
+    static const bool overlap_env = [] { const char* e = getenv("ESB_SCAN_OVERLAP"); return !e || atoi(e) != 0; }();
+    // Measured (scripts/gpu_scan_breakdown.py, one rank's share of the configs[4] job on 1 / 2 / 4 / 8 GPUs):
+    // cylinder density family 541 / 284 / 157 / 94 ms without, 549 / 286 / 149 / 84 ms with the pipeline - the
+    // normal-form scan loses more from running on 8 instead of 12 warps than a throughput-bound refinement
+    // gains, so it is pipelined only while the refinement is latency bound (at most ~2 brackets per lane of
+    // one launch); slab flow family 678 / 311 / 159 / 84 -> 661 / 309 / 157 / 82 ms: always.
+    const bool overlap = overlap_env && n_models >= 2 &&
+                         (hm[0].dm.scheme != SCHEME_RK8N || plane * n_modes / 64 <= 131072);
+    if (overlap) {
+        if (!c->refine_stream) {
+            CUDA_TRY(c, cudaStreamCreateWithFlags(&c->refine_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fill[b], cudaEventDisableTiming));
+                CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_refine[b], cudaEventDisableTiming));
+            }
+        }
+        if (c->cap_grid2 < plane * n_modes) {
+            CUDA_TRY(c, cudaStreamSynchronize(c->refine_stream));
+            if (c->d_ext2) cudaFree(c->d_ext2);
+            if (c->d_int2) cudaFree(c->d_int2);
+            if (c->d_den2) cudaFree(c->d_den2);
+            c->d_ext2 = c->d_int2 = c->d_den2 = nullptr;
+            c->cap_grid2 = 0;
+            CUDA_TRY(c, cudaMalloc((void**)&c->d_ext2, plane * n_modes * sizeof(double)));
+            CUDA_TRY(c, cudaMalloc((void**)&c->d_int2, plane * n_modes * sizeof(double)));
+            CUDA_TRY(c, cudaMalloc((void**)&c->d_den2, plane * n_modes * sizeof(double)));
+            c->cap_grid2 = plane * n_modes;
+        }
+    }
+    const int threads_keep = c->scan_threads;
+    if (overlap) c->scan_threads = hm[0].dm.scheme == SCHEME_RK8N ? 256 : 384;
+    bool refined[2] = {false, false};
     for (int i = 0; i < n_models; ++i) {
+        const int b = overlap ? (i & 1) : 0;
+        double* p_ext = b ? c->d_ext2 : c->d_ext;
+        double* p_int = b ? c->d_int2 : c->d_int;
+        double* p_den = b ? c->d_den2 : c->d_den;
+        cudaStream_t rs = overlap ? c->refine_stream : s;
         // the context's launch helpers read (dm, d_tab): point them at equilibrium i of the bank
         c->dm = hm[i].dm;
         c->d_tab = c->d_bank + tab_doubles * i;
         c->tab_doubles = (int)tab_doubles;
         c->model_set = true;
-        rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s, c->d_den);
+        // these planes were read by the refinement of equilibrium i - 2
+        if (overlap && refined[b] && cudaStreamWaitEvent(s, c->ev_refine[b], 0) != cudaSuccess) { rc = ESB_ERR_CUDA; break; }
+        rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, p_ext, p_int, s, p_den);
         if (!rc) {
             SweepDev sw{};
             sw.n_slots = n_modes; sw.nk = nk; sw.nw = nw;
@@ -1976,7 +2039,7 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
                 esb_context::RootBuf rb;
                 slot_carve(rb, c->d_scan_roots + table_bytes * ((size_t)i * n_modes + m), (size_t)cap, nullptr);
                 SlotDev& q = sw.slot[m];
-                q.gext = c->d_ext + m * plane; q.gint = c->d_int + m * plane; q.gden = c->d_den + m * plane;
+                q.gext = p_ext + m * plane; q.gint = p_int + m * plane; q.gden = p_den + m * plane;
                 q.bk = rb.bk; q.bw = rb.bw; q.bw2 = rb.bw2;
                 q.omega = rb.om; q.ext = rb.e; q.intq = rb.i; q.accepted = rb.acc; q.iters = rb.it;
                 q.mode = modes[m];
@@ -1984,7 +2047,12 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
             }
             rc = brackets_count(c, sw, s, d_sb + (size_t)i * (ESB_MAX_MODES + 1));
             if (!rc) rc = brackets_fill(c, sw, s);
-            if (!rc && cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(int), s) != cudaSuccess) rc = ESB_ERR_CUDA;
+            if (!rc && overlap) {
+                if (cudaEventRecord(c->ev_fill[b], s) != cudaSuccess ||
+                    cudaStreamWaitEvent(rs, c->ev_fill[b], 0) != cudaSuccess)
+                    rc = ESB_ERR_CUDA;
+            }
+            if (!rc && cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(int), rs) != cudaSuccess) rc = ESB_ERR_CUDA;
             if (!rc) {
                 RefineArgs r;
                 r.M = c->dm;
@@ -2003,15 +2071,23 @@ extern "C" int esb_scan_models(esb_context* c, int32_t n_models, const esb_model
                 const int n_launch = (int)std::min<size_t>(plane, (size_t)1 << 30);
                 const cudaError_t e = dispatch_kind(kind, hm[0].dm.scheme, [&](auto kd, auto scheme) {
                     if (warp_path)
-                        return launch_refine_warp<decltype(kd)::value, decltype(scheme)::value>(r, s, n_launch, c->n_sm);
-                    return launch_refine<decltype(kd)::value, decltype(scheme)::value>(r, s, n_launch, c->n_sm);
+                        return launch_refine_warp<decltype(kd)::value, decltype(scheme)::value>(r, rs, n_launch, c->n_sm);
+                    return launch_refine<decltype(kd)::value, decltype(scheme)::value>(r, rs, n_launch, c->n_sm);
                 });
                 if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = ESB_ERR_CUDA; }
                 c->launches += 1;
+                if (!rc && overlap) {
+                    if (cudaEventRecord(c->ev_refine[b], rs) != cudaSuccess) rc = ESB_ERR_CUDA;
+                    refined[b] = true;
+                }
             }
         }
         if (rc) break;
     }
+    c->scan_threads = threads_keep;
+    if (overlap)                                 // the compaction below reads every root table
+        for (int b = 0; b < 2; ++b)
+            if (refined[b] && cudaStreamWaitEvent(s, c->ev_refine[b], 0) != cudaSuccess && !rc) rc = ESB_ERR_CUDA;
     // the context keeps the model it had before the scan
     c->dm = dm_keep;
     c->d_tab = const_cast<double*>(tab_keep);

@@ -544,6 +544,7 @@ class DispersionSolver:
         L.check(self.lib, self.ctx,
                 self.lib.esb_sweep_resident_multi(self.ctx, md.size, _iptr(md), float(tol_percent), _iptr(n),
                                                   _iptr(nb)), "esb_sweep_resident_multi")
+        self.last_n_brackets = [int(x) for x in nb]     # per mode slot: brackets found (>= table entries stored)
         return [int(x) for x in n]
 
     def set_accept_rule(self, rule):
@@ -565,6 +566,8 @@ class DispersionSolver:
             tabs = [self.download_roots_pinned(slot) for slot in range(len(ns))]
         else:
             tabs = [self.download_roots(n, slot) for slot, n in enumerate(ns)]
+        for tab, nb in zip(tabs, self.last_n_brackets):
+            tab.n_brackets = nb
         self._warn_guard()
         return tabs
 
