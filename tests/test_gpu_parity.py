@@ -880,6 +880,20 @@ def test_device_side_gather_equals_host_table(solvers):
                                          np.full(int((h.accepted == 1).sum()), float(slot))], axis=1)
                                for slot, h in enumerate(hosts)])
         assert np.array_equal(allm, want)
+        # the payload itself (esb_pack_modes_dev): header row = (rows, entries scanned, overflow flag); a
+        # capacity that is too small is reported, not overrun
+        import ctypes as C
+        n_acc = len(want)
+        for cap in (n_acc + 5, n_acc, max(n_acc - 7, 1)):
+            buf = torch.full((cap + 3, 3), -1.0, dtype=torch.float64, device=dev)
+            rc = s.lib.esb_pack_modes_dev(s.ctx, len(ns), 3.0, 8.0, C.c_void_p(buf.data_ptr()), cap, None)
+            assert rc == 0
+            s.lib.esb_tables_wait(s.ctx, None)
+            torch.cuda.synchronize()
+            b = buf.cpu().numpy()
+            assert b[0, 0] == min(n_acc, cap) and b[0, 1] == sum(ns) and b[0, 2] == (1.0 if n_acc > cap else 0.0)
+            assert np.array_equal(b[1: 1 + min(n_acc, cap)], want[: min(n_acc, cap)])
+            assert (b[1 + cap:] == -1.0).all()                       # nothing written past the capacity
         # a parameter scan left on the device and gathered from there == the downloaded compact table
         from eigensolver_b200.scan import density_flow_grid, gather_scan_modes_device, parameter_scan
         dens, _ = density_flow_grid([0.15, 0.3], [0.5])
