@@ -391,7 +391,7 @@ class DispersionSolver:
         kw["n_steps"] = int(self.spec.model.n_steps) * int(factor)
         if kw["scheme"] == "rk8n" and kw["n_steps"] > 680:
             kw["scheme"] = "rk8"          # the eight-field table of that many steps exceeds shared memory
-        if kw["n_steps"] > 1350:
+        if kw["n_steps"] > 1270 or (self.kind == "cylinder_rotation" and kw["n_steps"] > 700):
             return None
         return ModelSpec(**kw)
 
