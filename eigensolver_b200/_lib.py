@@ -116,6 +116,8 @@ SYMBOLS = {
     "esb_bessel_jy_dev": (C.c_int, [_ctx, C.c_int32, _dp, C.c_int32, _dp]),
     "esb_exterior_leaky": (C.c_int, [C.POINTER(esb_model), C.c_int32, C.c_double, C.c_double, _dp]),
     "esb_exterior_leaky_dev": (C.c_int, [_ctx, C.c_int32, _dp, _dp, C.c_int32, _dp]),
+    "esb_dispersion_grid_leaky": (C.c_int, [_ctx, C.c_int32, _ip, _dp, C.c_int32, _dp, C.c_int32, C.c_int32,
+                                            _dp, _dp]),
     "esb_last_kernel_ms": (C.c_double, [_ctx]),
     "esb_launch_count": (C.c_int64, [_ctx]),
 }

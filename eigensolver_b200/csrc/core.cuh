@@ -18,6 +18,7 @@
 //     (rho, rho') at fixed Runge-Kutta stage nodes, staged in shared memory.
 #pragma once
 #include "bessel.cuh"
+#include "bessel_jy.cuh"
 
 namespace esb {
 #define ESB_RKN_ENUM
@@ -901,8 +902,18 @@ ESB_HD double m_e2(const DevModel& M, double K, double A) {
 // Exact solution at x = -1 of the reference's exterior initial-value problem, slab.
 ESB_HD void exterior_slab(const DevModel& M, double k, double me, double& yb, double& ypb) {
     // vx'' = m_e vx   (..._coronal.py:245), from -x0 to -1
-    const double kap = sqrt(me);
     const double L = M.ext_len / k - 1.0;
+    if (me < 0.0) {
+        // the leaky side (only reached by the opt-in leaky evaluation: the reference skips m_e < 0): the
+        // same initial-value problem has the oscillatory solution
+        const double q = sqrt(-me);
+        double sn, cs;
+        sincos(q * L, &sn, &cs);
+        yb = fma(M.ic_v, cs, (M.ic_s / q) * sn);
+        ypb = fma(-M.ic_v * q, sn, M.ic_s * cs);
+        return;
+    }
+    const double kap = sqrt(me);
     if (kap * L < 1e-8) {
         yb = fma(M.ic_s, L, M.ic_v) + 0.5 * me * L * L * M.ic_v;
         ypb = M.ic_s + me * L * M.ic_v;
@@ -1098,7 +1109,10 @@ ESB_HD void shoot_layer(const DevModel& M, const Point& pt, const double* __rest
 // has the roots of D and no such poles; the refinement iterates on G (esb.cu refine_kernel).
 // WARP (device only, NM = 1, all 32 lanes of the warp call it with the same arguments): the layer is
 // integrated cooperatively (warp_transfer); every lane returns the same values.
-template <int KIND, int SCHEME, int NM, bool WARP = false, bool YFORM = false>
+// LEAKY (opt-in, esb_dispersion_grid_leaky): points with m_e < 0 are NOT skipped - their exterior is the
+// oscillatory solution of the same initial-value problem (J_n, Y_n / cos, sin: bessel_jy.cuh), what the
+// reference's odeint would return without its "if m_e < 0: pass".  The default (false) is the reference's rule.
+template <int KIND, int SCHEME, int NM, bool WARP = false, bool YFORM = false, bool LEAKY = false>
 ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, double k, double w,
                              const int (&modes)[NM], double (&ext_q)[NM], double (&int_q)[NM],
                              double (&den_q)[NM]) {
@@ -1109,7 +1123,8 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
     const double We = (KIND == KIND_SLAB_FLOW) ? fma(-k, M.U_e, w) : w;
     const double Ae = (KIND == KIND_SLAB_FLOW) ? We * We : pt.A;
     const double me = m_e2(M, pt.K, Ae);
-    if (!(me >= 0.0)) {                       // "if m_e < 0: pass"  (Density_cylinder.py:760)
+    const bool leaky = LEAKY && me < 0.0;
+    if (!(me >= 0.0) && !leaky) {             // "if m_e < 0: pass"  (Density_cylinder.py:760)
 #pragma unroll
         for (int s = 0; s < NM; ++s) { ext_q[s] = nanv; int_q[s] = nanv; den_q[s] = nanv; }
         return;
@@ -1119,12 +1134,13 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
 #pragma unroll
         for (int s = 0; s < NM; ++s) nmax = modes[s] > nmax ? modes[s] : nmax;
         ExtCyl E;
-        exterior_cyl_prepare(M, k, me, nmax, E);
+        if (!leaky) exterior_cyl_prepare(M, k, me, nmax, E);
         const double xi_e_const = -1.0 / (M.rho_e * (pt.K * M.vAe2 - pt.A));        // :263
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
             double Pb, ypb;
-            exterior_cyl_order(M, E, modes[s], Pb, ypb);
+            if (LEAKY && leaky) exterior_cyl_leaky(M.ic_v, M.ic_s, M.r_sign, M.ext_len, k, me, modes[s], Pb, ypb);
+            else exterior_cyl_order(M, E, modes[s], Pb, ypb);
             const double xi_e = xi_e_const * ypb;
             // The layer is integrated from the axis end (where the scripts impose their end condition)
             // out to the boundary r = s_start, where P = P_e fixes the scale.
@@ -1181,14 +1197,15 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
 #pragma unroll
         for (int s = 0; s < NM; ++s) nmax = modes[s] > nmax ? modes[s] : nmax;
         ExtCyl E;
-        exterior_cyl_prepare(M, k, me, nmax, E);
+        if (!leaky) exterior_cyl_prepare(M, k, me, nmax, E);
         double yb[NM], y[NM], yp[NM], m2[NM];
         // xi_e = -P'/(rho_e (k^2 vA_e^2 - w^2))      (Density_cylinder.py:702,773)
         const double xi_e_const = -1.0 / (M.rho_e * (pt.K * M.vAe2 - pt.A));
 #pragma unroll
         for (int s = 0; s < NM; ++s) {
             double ypb;
-            exterior_cyl_order(M, E, modes[s], yb[s], ypb);
+            if (LEAKY && leaky) exterior_cyl_leaky(M.ic_v, M.ic_s, M.r_sign, M.ext_len, k, me, modes[s], yb[s], ypb);
+            else exterior_cyl_order(M, E, modes[s], yb[s], ypb);
             ext_q[s] = xi_e_const * ypb;
             // interior from the axis outwards: sausage P'(axis)=0 (:1084), kink/fluting P(axis)=0 (:787)
             y[s] = modes[s] == 0 ? 1.0 : 0.0;
@@ -1317,12 +1334,12 @@ ESB_HD bool resonance_free(const DevModel& M, const Point& pt, double mode, cons
     }
 }
 
-template <int KIND, int SCHEME, bool WARP = false, bool YFORM = false>
+template <int KIND, int SCHEME, bool WARP = false, bool YFORM = false, bool LEAKY = false>
 ESB_HD void eval_point(const DevModel& M, const double* __restrict__ tab, double k, double w, int mode,
                        double& ext_q, double& int_q, double& den_q) {
     const int modes[1] = {mode};
     double e[1], i[1], d[1];
-    eval_point_multi<KIND, SCHEME, 1, WARP, YFORM>(M, tab, k, w, modes, e, i, d);
+    eval_point_multi<KIND, SCHEME, 1, WARP, YFORM, LEAKY>(M, tab, k, w, modes, e, i, d);
     ext_q = e[0];
     int_q = i[0];
     den_q = d[0];

@@ -27,7 +27,6 @@
 
 #include "../../include/eigensolver_b200.h"
 #include "core.cuh"
-#include "bessel_jy.cuh"
 #include "model_host.h"
 
 using namespace esb;
@@ -146,6 +145,29 @@ __global__ void __launch_bounds__(128) grid_warp_kernel(GridArgs g) {
             g.intq[p] = fin ? i : nan("");
             if (g.den) g.den[p] = d;
         }
+    }
+}
+
+// Opt-in evaluation over the WHOLE grid, leaky side included (core.cuh eval_point_multi<..., LEAKY>): one thread
+// per (mode, k, omega), grid-stride.  Not on the reference path (it skips m_e < 0), hence not tuned: the
+// throughput kernels above stay free of the extra exterior branch.
+template <int KIND, int SCHEME>
+__global__ void __launch_bounds__(128) grid_leaky_kernel(GridArgs g) {
+    extern __shared__ __align__(16) double stab[];
+    stage_table(g.tab, stab, g.tab_doubles);
+    const size_t plane = (size_t)g.nk * g.nw;
+    const size_t total = plane * g.n_modes;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(p / plane);
+        const size_t o = p - slot * plane;
+        const int ik = (int)(o / g.nw), iw = (int)(o - (size_t)ik * g.nw);
+        const double k = g.k[ik];
+        const double w = omega_at(g.k, g.w, g.layout, g.nw, ik, iw);
+        double e, i, d;
+        eval_point<KIND, SCHEME, false, false, true>(g.M, stab, k, w, g.modes[slot], e, i, d);
+        const bool fin = isfinite(e) && isfinite(i);
+        g.ext[p] = fin ? e : nan("");
+        g.intq[p] = fin ? i : nan("");
     }
 }
 
@@ -1724,6 +1746,54 @@ extern "C" int esb_dispersion_grid_multi(esb_context* c, int32_t n_modes, const 
     cudaStream_t s = cur_stream(c);
     if ((rc = grid_dev_multi(c, n_modes, modes, c->d_k, nk, c->d_w, nw, layout, c->d_ext, c->d_int, s)))
         return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(ext, c->d_ext, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(intq, c->d_int, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    return ESB_OK;
+}
+
+template <int KIND, int SCHEME>
+static cudaError_t launch_grid_leaky(const GridArgs& g, cudaStream_t s, int n_sm) {
+    const size_t smem = (size_t)g.tab_doubles * sizeof(double);
+    static bool done[MAX_DEVICES] = {};
+    cudaError_t e = configure_once(grid_leaky_kernel<KIND, SCHEME>, done);
+    if (e != cudaSuccess) return e;
+    const size_t total = (size_t)g.nk * g.nw * g.n_modes;
+    size_t blocks = (total + 127) / 128;
+    if (blocks > (size_t)n_sm * 8) blocks = (size_t)n_sm * 8;
+    grid_leaky_kernel<KIND, SCHEME><<<(int)blocks, 128, smem, s>>>(g);
+    return cudaGetLastError();
+}
+
+// D over the whole grid, the leaky side (m_e < 0) included; same arguments and layout as
+// esb_dispersion_grid_multi.  Where m_e >= 0 the values are those of the regular evaluation.
+extern "C" int esb_dispersion_grid_leaky(esb_context* c, int32_t n_modes, const int32_t* modes, const double* k,
+                                         int32_t nk, const double* w, int32_t nw, int32_t layout, double* ext,
+                                         double* intq) {
+    if (!c) return ESB_ERR_ARG;
+    if (!c->model_set) return fail(c, ESB_ERR_ARG, "model not set");
+    if (!k || !w || !ext || !intq || nk <= 0 || nw <= 0 || layout < 0 || layout > 2 ||
+        check_modes(c, n_modes, modes))
+        return fail(c, ESB_ERR_ARG, "bad grid arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = esb_upload_axes(c, k, nk, w, nw, layout))) return rc;
+    const size_t n = (size_t)nk * nw * n_modes;
+    if ((rc = ensure_grid(c, n))) return rc;
+    cudaStream_t s = cur_stream(c);
+    GridArgs g{};
+    g.M = c->dm;
+    g.tab = c->d_tab;
+    g.tab_doubles = c->tab_doubles;
+    g.k = c->d_k; g.w = c->d_w; g.nk = nk; g.nw = nw; g.layout = layout;
+    g.n_modes = n_modes;
+    for (int i = 0; i < 4; ++i) g.modes[i] = i < n_modes ? modes[i] : 0;
+    g.ext = c->d_ext; g.intq = c->d_int; g.den = nullptr;
+    const cudaError_t e = dispatch_kind(c->dm.kind, c->dm.scheme, [&](auto kind, auto scheme) {
+        return launch_grid_leaky<decltype(kind)::value, decltype(scheme)::value>(g, s, c->n_sm);
+    });
+    CUDA_TRY(c, e);
+    c->launches += 1;
     CUDA_TRY(c, cudaMemcpyAsync(ext, c->d_ext, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(c, cudaMemcpyAsync(intq, c->d_int, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(c, cudaStreamSynchronize(s));

@@ -490,6 +490,19 @@ class DispersionSolver:
         L.check(self.lib, self.ctx, rc, "esb_dispersion_grid_multi")
         return ext, inq
 
+    def dispersion_grid_leaky(self, modes, k, w, layout="phase_speed"):
+        """OPT-IN, beyond the reference: (ext, int) of shape (n_modes, nk, nw) over the WHOLE grid - where
+        m_e < 0 (the points the reference and every sweep skip) the exterior is the oscillatory solution of
+        the same initial-value problem (J_n, Y_n; slab: cos, sin), interior and matching unchanged."""
+        k, w, lay, nw = self._axes(k, w, layout)
+        md = np.array([self._mode(m) for m in modes], dtype=np.int32)
+        ext = np.empty((md.size, k.size, nw), dtype=np.float64)
+        inq = np.empty((md.size, k.size, nw), dtype=np.float64)
+        rc = self.lib.esb_dispersion_grid_leaky(self.ctx, md.size, _iptr(md), _dptr(k), k.size, _dptr(w), nw,
+                                                lay, _dptr(ext), _dptr(inq))
+        L.check(self.lib, self.ctx, rc, "esb_dispersion_grid_leaky")
+        return ext, inq
+
     def D(self, mode, k, w, layout="phase_speed"):
         e, i = self.dispersion_grid(mode, k, w, layout)
         return e - i

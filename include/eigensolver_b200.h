@@ -334,12 +334,21 @@ int esb_bessel_ik_scaled(int32_t n, double z, double out[4]);
  *   esb_exterior_leaky       closed form of the reference's own exterior initial-value problem
  *                            (:765-770) where m_e < 0: out = (P, dP/dr) at |r| = 1 for azimuthal order n,
  *                            the exterior medium and initial values of `m` (NaN where m_e >= 0)
- *   esb_exterior_leaky_dev   the same on the device for k[count], w[count] and the context's model */
+ *   esb_exterior_leaky_dev   the same on the device for k[count], w[count] and the context's model
+ *   esb_dispersion_grid_leaky  OPT-IN: D over the whole grid with the leaky side included - where m_e < 0 the
+ *                            exterior is that closed form (slab: cos / sin) and the interior shooting and the
+ *                            matching are unchanged, i.e. what the reference's scan loop would evaluate without
+ *                            its "if m_e < 0: pass"; where m_e >= 0 the values of esb_dispersion_grid_multi.
+ *                            Same arguments and layout as esb_dispersion_grid_multi.  The sweeps, brackets and
+ *                            root tables keep the reference's skip rule. */
 int esb_bessel_jy(int32_t n, double x, double out[4]);
 int esb_bessel_jy_dev(esb_context* ctx, int32_t n, const double* x, int32_t count, double* out);
 int esb_exterior_leaky(const esb_model* m, int32_t n, double k, double w, double out[2]);
 int esb_exterior_leaky_dev(esb_context* ctx, int32_t n, const double* k, const double* w, int32_t count,
                            double* out);
+int esb_dispersion_grid_leaky(esb_context* ctx, int32_t n_modes, const int32_t* modes, const double* k,
+                              int32_t nk, const double* w, int32_t nw, int32_t omega_layout, double* ext,
+                              double* intq);
 
 /* Host-side helper (no GPU needed): integrates y'' = sin(t) y' - (1+t^2) y, y(0)=1, y'(0)=0.3
  * over [0,T] in n_steps uniform steps with the SAME step functions the kernels use; out =

@@ -36,7 +36,7 @@ typedef struct {
                             4 cylinder axial flow v_z(r) = U_e + (U_i0-U_e) exp(-(r-x0)^2/width^2) */
     int n_ext;           /* exterior steps */
     int n_int;           /* interior steps */
-    int pad;
+    int leaky;           /* 1: do not skip m_e < 0 (test-only extension; 0 = the reference's rule) */
     double c_i0, vA_i0, vA_e, c_e, gamma, rho_i0, rho_A;
     double width, x0;    /* inverted-Gaussian density profile */
     double ic_v, ic_s;   /* exterior initial values */
@@ -299,7 +299,9 @@ int ork_point(const ork_model* m, int mode, double k, double w, double* ext_q, d
     const double We = (m->kind == 2) ? w - k * m->U_e : w;     /* exterior Doppler shift (flow :207) */
     const double Ae = We * We;
     p.m_e = ((p.K * vAe2 - Ae) * (p.K * ce2 - Ae)) / ((vAe2 + ce2) * (p.K * p.cT_e2 - Ae));
-    if (!(p.m_e >= 0.0)) {
+    /* m->leaky (test-only extension, default 0 = the reference's rule): the exterior below is integrated
+     * numerically, so without the skip it simply returns the oscillatory solution of the same problem */
+    if (!(p.m_e >= 0.0) && !(m->leaky == 1 && p.m_e < 0.0)) {
         *ext_q = NAN; *int_q = NAN;
         return 1;
     }

@@ -15,7 +15,7 @@ LIB = os.path.join(_HERE, "_build", "liboracle_rk.so")
 
 
 class ork_model(C.Structure):
-    _fields_ = [("kind", C.c_int), ("n_ext", C.c_int), ("n_int", C.c_int), ("pad", C.c_int),
+    _fields_ = [("kind", C.c_int), ("n_ext", C.c_int), ("n_int", C.c_int), ("leaky", C.c_int),
                 ("c_i0", C.c_double), ("vA_i0", C.c_double), ("vA_e", C.c_double), ("c_e", C.c_double),
                 ("gamma", C.c_double), ("rho_i0", C.c_double), ("rho_A", C.c_double),
                 ("width", C.c_double), ("x0", C.c_double), ("ic_v", C.c_double), ("ic_s", C.c_double),

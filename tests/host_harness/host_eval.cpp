@@ -50,6 +50,16 @@ static void eval_all(const HostModel& hm, int n_modes, const int32_t* modes, int
     for (auto& t : pool) t.join();
 }
 
+// the opt-in leaky evaluation (eval_point<..., LEAKY = true>), one mode at a time
+template <int KIND, int SCHEME>
+static void eval_leaky(const HostModel& hm, int n_modes, const int32_t* modes, int64_t n, const double* k,
+                       const double* w, double* ext, double* intq, double* den) {
+    for (int64_t p = 0; p < n; ++p)
+        for (int s = 0; s < n_modes; ++s)
+            eval_point<KIND, SCHEME, false, false, true>(hm.dm, hm.tab.data(), k[p], w[p], modes[s], ext[s * n + p],
+                                                         intq[s * n + p], den[s * n + p]);
+}
+
 template <int KIND>
 static int by_scheme(const HostModel& hm, int n_modes, const int32_t* modes, int64_t n, const double* k,
                      const double* w, double* ext, double* intq, double* den) {
@@ -82,4 +92,27 @@ extern "C" int esbh_eval_points(const esb_model* m, const double* const* fields,
         case KIND_CYL_FLOW: return by_scheme<KIND_CYL_FLOW>(hm, n_modes, modes, n, k, w, ext, intq, den);
     }
     return ESB_ERR_ARG;
+}
+
+extern "C" int esbh_eval_points_leaky(const esb_model* m, const double* const* fields, int32_t n_fields,
+                                      int32_t n_nodes, const double* boundary, int32_t n_boundary, int32_t n_modes,
+                                      const int32_t* modes, int64_t n, const double* k, const double* w,
+                                      double* ext, double* intq, double* den) {
+    HostModel hm;
+    std::string err;
+    int rc = build_host_model(m, fields, n_fields, n_nodes, boundary, n_boundary, hm, err);
+    if (rc) return rc;
+    if (hm.dm.kind == KIND_CYL_DENSITY && hm.dm.scheme == SCHEME_RK8N)
+        eval_leaky<KIND_CYL_DENSITY, SCHEME_RK8N>(hm, n_modes, modes, n, k, w, ext, intq, den);
+    else if (hm.dm.kind == KIND_SLAB_DENSITY && hm.dm.scheme == SCHEME_RK8N)
+        eval_leaky<KIND_SLAB_DENSITY, SCHEME_RK8N>(hm, n_modes, modes, n, k, w, ext, intq, den);
+    else if (hm.dm.kind == KIND_CYL_ROTATION)
+        eval_leaky<KIND_CYL_ROTATION, SCHEME_RK8>(hm, n_modes, modes, n, k, w, ext, intq, den);
+    else if (hm.dm.kind == KIND_SLAB_FLOW && hm.dm.scheme == SCHEME_RK8)
+        eval_leaky<KIND_SLAB_FLOW, SCHEME_RK8>(hm, n_modes, modes, n, k, w, ext, intq, den);
+    else if (hm.dm.kind == KIND_CYL_FLOW && hm.dm.scheme == SCHEME_RK8N)
+        eval_leaky<KIND_CYL_FLOW, SCHEME_RK8N>(hm, n_modes, modes, n, k, w, ext, intq, den);
+    else
+        return ESB_ERR_ARG;
+    return ESB_OK;
 }

@@ -27,11 +27,13 @@ def lib():
         l.esbh_eval_points.restype = C.c_int
         l.esbh_eval_points.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int32, C.c_int32, dp, C.c_int32, C.c_int32, ip,
                                        C.c_int64, dp, dp, dp, dp, dp]
+        l.esbh_eval_points_leaky.restype = C.c_int
+        l.esbh_eval_points_leaky.argtypes = l.esbh_eval_points.argtypes
         _lib = l
     return _lib
 
 
-def evaluate(spec, modes, k, w):
+def evaluate(spec, modes, k, w, leaky=False):
     """(ext, int, den), each [n_modes, n]: D = ext - int at the points (k[j], w[j]) (w = omega).
     3 or 2 modes take the fused evaluation of the scan kernel, any other count one mode at a time."""
     k = np.ascontiguousarray(np.broadcast_to(np.asarray(k, dtype=np.float64), np.broadcast(k, w).shape).ravel())
@@ -42,11 +44,12 @@ def evaluate(spec, modes, k, w):
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     args = spec.abi_args()
     model_ptr = C.cast(args[0], C.c_void_p)
-    rc = lib().esbh_eval_points(model_ptr, args[1], args[2], args[3], args[4], args[5], md.size,
+    fn = lib().esbh_eval_points_leaky if leaky else lib().esbh_eval_points
+    rc = fn(model_ptr, args[1], args[2], args[3], args[4], args[5], md.size,
                                 md.ctypes.data_as(C.POINTER(C.c_int32)), k.size, dp(k), dp(w), dp(out[0]),
                                 dp(out[1]), dp(out[2]))
     if rc:
-        raise RuntimeError("esbh_eval_points: status %d" % rc)
+        raise RuntimeError("esbh_eval_points%s: status %d" % ("_leaky" if leaky else "", rc))
     return out
 
 

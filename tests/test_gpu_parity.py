@@ -587,6 +587,31 @@ def test_bessel_jy_and_leaky_exterior_on_the_device(solvers):
     assert np.isnan(s.exterior_leaky_device(1, np.array([1.0]), np.array([3.0]))).all()
 
 
+def test_leaky_grid_on_the_device(solvers):
+    """esb_dispersion_grid_leaky: the whole grid, m_e < 0 included, against the C oracle with its skip rule
+    lifted; on the regular side (m_e >= 0) the values of the default evaluation."""
+    for name, windows in (("cylinder_density", [(5.02, 8.0), (0.4976, 0.4999)]), ("slab_flow", [(2.52, 4.0)]),
+                          ("cylinder_rotation", [(1.52, 3.2)])):
+        case = CASES[name]
+        s = solvers[name]
+        model = case.c_model()
+        model.leaky = 1
+        k = np.linspace(0.3, 4.0, 9)
+        W = np.concatenate([np.linspace(a, b, 40) for a, b in windows] + [np.linspace(*case.roots_window, 40)])
+        modes = list(case.modes)[:2]
+        E, I = s.dispersion_grid_leaky(modes, k, W)
+        E0, I0 = s.dispersion_grid_multi(modes, k, W)
+        skipped = np.isnan(E0)
+        assert skipped.any() and (~skipped).any() and np.isfinite(E).all()
+        assert np.allclose(E[~skipped], E0[~skipped], rtol=1e-12) and np.allclose(I[~skipped], I0[~skipped], rtol=1e-9)
+        for slot, mode in enumerate(modes):
+            e0, i0 = ork.grid(model, mode, k, W)
+            reg = case.regular(k, W, mode, margin=0.03) & skipped[slot]
+            assert reg.sum() > 100
+            dev = np.abs((E[slot] - I[slot]) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+            assert np.quantile(dev[reg], 0.9) < 1e-10 and dev[reg].max() < 1e-7, (name, mode, dev[reg].max())
+
+
 def test_device_pointer_entry_points(solvers):
     """esb_dispersion_grid_dev / esb_brackets_dev on caller-owned device buffers (torch tensors) and a
     caller-owned stream: the same grids and the same sorted bracket list as the host entry points."""

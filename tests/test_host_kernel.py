@@ -105,3 +105,40 @@ def test_fused_equals_single_mode_on_host():
         e1, i1, d1 = hk.grid(sp, [m], k, W)
         assert np.allclose(e3[slot], e1[0], rtol=1e-13, equal_nan=True)
         assert np.allclose(i3[slot], i1[0], rtol=1e-11, equal_nan=True)
+
+
+LEAKY_WINDOWS = {
+    # phase speeds with m_e < 0: above max(c_e, vA_e) and inside (cT_e, min(c_e, vA_e))
+    "cylinder_density": [(5.02, 8.0), (0.4976, 0.4999)], "slab_density": [(3.02, 5.0)],
+    "cylinder_flow": [(5.02, 8.0)], "slab_flow": [(2.52, 4.0), (-4.0, -2.52)],
+    "cylinder_rotation": [(1.52, 3.2), (0.475, 0.499)], "cylinder_photospheric": [(1.52, 3.2), (0.475, 0.499)],
+    "slab_photospheric": [(1.32, 2.5)],
+}
+
+
+@pytest.mark.parametrize("name", list(LEAKY_WINDOWS))
+def test_leaky_evaluation_matches_oracle_without_the_skip(name):
+    """The opt-in leaky evaluation (eval_point<..., LEAKY>: closed-form J_n / Y_n or cos / sin exterior where
+    m_e < 0, interior and matching unchanged) against the C oracle with its skip rule lifted - the oracle
+    integrates the exterior numerically, so it needs no new code for that side.  This is what the reference's
+    scan loop would evaluate without `if m_e < 0: pass` (Density_cylinder.py:760)."""
+    case = CASES[name]
+    model = case.c_model()
+    model.leaky = 1
+    sp = spec_of(case)
+    rng = np.random.default_rng(5)
+    W = np.concatenate([rng.uniform(a, b, 120 // len(LEAKY_WINDOWS[name])) for a, b in LEAKY_WINDOWS[name]])
+    k = rng.uniform(0.3, 4.0, W.size)
+    for mode in list(case.modes)[:3]:
+        e, i, _ = hk.evaluate(sp, [mode], k, k * W, leaky=True)
+        ref = np.array([ork.point(model, mode, a, a * b) for a, b in zip(k, W)])
+        e0, i0 = ref[:, 0], ref[:, 1]
+        assert np.isfinite(e0).all() and np.isfinite(e[0]).all()           # nothing is skipped
+        reg = np.array([case.regular(a, np.array([b]), mode, margin=0.03)[0, 0] for a, b in zip(k, W)])
+        assert reg.sum() >= 60
+        assert np.max(np.abs(e[0] - e0)[reg] / np.abs(e0)[reg]) < 1e-9         # the closed-form exterior
+        dev = np.abs((e[0] - i[0]) - (e0 - i0)) / np.maximum(np.abs(e0), np.abs(i0))
+        assert np.quantile(dev[reg], 0.9) < 1e-10 and dev[reg].max() < 1e-7, (mode, dev[reg].max())
+    # and the default evaluation still skips those points
+    e, i, _ = hk.evaluate(sp, [case.modes[0]], k, k * W)
+    assert np.isnan(e).all() and np.isnan(i).all()
