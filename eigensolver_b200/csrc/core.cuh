@@ -994,11 +994,15 @@ __device__ __forceinline__ void warp_transfer(int first, int n_steps, F&& integr
 // a^2/4): a point whose resonance lies just outside the layer - the analytic continuation of the profile
 // reaches the resonant value a little beyond an end of the layer, or the profile comes close to it
 // without reaching it - is integrated less accurately in u than in y on the same mesh (measured: 1e-5
-// instead of 1e-10 at 0.02 in phase speed above the Alfven continuum, equal beyond ~0.1).  Such points
+// instead of 1e-10 at 0.02 in phase speed above the Alfven continuum, equal beyond ~0.1; the band of 8 % in
+// the resonant quantity is ~0.13 in phase speed there, and a narrower one - 4 % - starts to show).  Such points
 // (resonant value within NF_BAND, relative, of the range the profile spans in the layer, but outside
 // it) take the (y, h y') variables on the same table.  Inside the range (a resonance in the layer: the
 // continua, below the noise floor) any form returns noise; they stay on the cheaper one.
-constexpr double NF_BAND = 0.15;
+#ifndef ESB_NF_BAND
+#define ESB_NF_BAND 0.08
+#endif
+constexpr double NF_BAND = ESB_NF_BAND;
 
 ESB_HD bool in_band(double v, double lo, double hi) {
     return (v > hi && v < hi * (1.0 + NF_BAND)) || (v < lo && v > lo * (1.0 - NF_BAND));
