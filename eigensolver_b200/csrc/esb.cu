@@ -78,14 +78,21 @@ __device__ __forceinline__ void stage_table(const double* __restrict__ g, double
 // the loop: 527 instructions, issue-bound: scan 30.5 / 31.6 / 37.2 ms compiled for 3 / 4 / 2 CTAs of
 // 128 threads per SM, scripts/gpu_variants.py); 16 (128 registers) for the first-derivative schemes,
 // as measured in round 1.
+#ifndef ESB_ROT_THREADS
+#define ESB_ROT_THREADS 512
+#endif
+#ifndef ESB_FLOW_THREADS
+#define ESB_FLOW_THREADS 512
+#endif
 #ifndef ESB_GRID_THREADS
-#define ESB_GRID_THREADS(SCHEME) ((SCHEME) == SCHEME_RK8N ? 384 : 512)
+#define ESB_GRID_THREADS(KIND, SCHEME) \
+    ((SCHEME) == SCHEME_RK8N ? 384 : (KIND) == KIND_CYL_ROTATION ? ESB_ROT_THREADS : (KIND) == KIND_SLAB_FLOW ? ESB_FLOW_THREADS : 512)
 #endif
 #ifndef ESB_REFINE_MINB
 #define ESB_REFINE_MINB(SCHEME) ((SCHEME) == SCHEME_RK8N ? 3 : 4)
 #endif
 template <int KIND, int SCHEME, int NM>
-__global__ void __launch_bounds__(ESB_GRID_THREADS(SCHEME), 1) grid_kernel(GridArgs g) {
+__global__ void __launch_bounds__(ESB_GRID_THREADS(KIND, SCHEME), 1) grid_kernel(GridArgs g) {
     extern __shared__ __align__(16) double stab[];
     stage_table(g.tab, stab, g.tab_doubles);
     const int lane = threadIdx.x & 31;
@@ -1349,7 +1356,8 @@ static cudaError_t launch_grid_nm(const GridArgs& g, cudaStream_t s, int n_sm) {
     if (e != cudaSuccess) return e;
     // fewer warps than the launch bound leave registers for a refinement CTA of the previous equilibrium
     // beside it (esb_scan_models)
-    const int threads = (g.threads > 0 && g.threads < ESB_GRID_THREADS(SCHEME)) ? g.threads : ESB_GRID_THREADS(SCHEME);
+    const int threads = (g.threads > 0 && g.threads < ESB_GRID_THREADS(KIND, SCHEME)) ? g.threads
+                                                                                    : ESB_GRID_THREADS(KIND, SCHEME);
     const long long n_tiles = (long long)g.nk * ((g.nw + 31) / 32);
     long long blocks = (n_tiles + threads / 32 - 1) / (threads / 32);
     // one CTA per SM; a grid with fewer tiles than warp slots spreads its tiles over all SMs
