@@ -14,8 +14,12 @@ with NCCL inside the timed region.
   e2e    the same through the public host API: pinned host k/omega in, the root tables of the
          three modes out into page-locked host memory (N > 1: gathered modes on rank 0)
   roofline.bound = "fp64": the kernel is an FP64-pipe kernel (no tensor cores, 24 B of HBM
-         traffic per 4.3e4 flops), so the bound is the FP64 FMA rate, measured in the same
-         process with a DFMA-chain kernel (esb_fp64_peak); traffic = ncu DRAM bytes per launch.
+         traffic per 2.4e4 flops), so the bound is the FP64 FMA rate, measured in the same
+         process with a DFMA-chain kernel (esb_fp64_peak); frac = algorithmic flops (fma = 2) against it,
+         pipe_frac = FP64 instructions issued against its instruction rate; traffic = ncu DRAM bytes per launch.
+  configs / strong_scaling / guard / roots_per_sec_regular: BASELINE configs[0], [2], [3] at full size, the
+         fixed-size configs[4] job, the discretisation guard's report of the timed sweeps, brackets outside
+         the resonant continua.
   cpu_baseline  the oracle port of the reference's scipy path (odeint + fsolve) timed on a
          bounded sample with all host cores.
 """
