@@ -267,7 +267,10 @@ int esb_download_roots_slot(esb_context* ctx, int32_t slot, esb_roots* out, int3
  * receives the sizes found.  No host synchronisation between the equilibria; the result is ONE compact
  * table in page-locked memory owned by the context (valid until the next scan or esb_destroy), ordered by
  * (model, mode slot, k index, omega index).  ESB_ERR_CAPACITY: some table outgrew its room (the result
- * holds the first capacity_per_table entries of it). */
+ * holds the first capacity_per_table entries of it).  Where it pays (always for the first-derivative kinds;
+ * for the normal-form kinds while the refinement of one grid is latency bound) the refinement of equilibrium
+ * i runs on a second stream beside the scan of equilibrium i + 1, on a second set of planes; the results do not
+ * depend on it (environment ESB_SCAN_OVERLAP=0 switches it off). */
 typedef struct esb_scan_result {
     int32_t n_entries;
     int32_t* model;       /* index into models[]                       */
