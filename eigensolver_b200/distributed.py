@@ -160,6 +160,11 @@ def gather_modes_device(solver, n_slots, k_offset, device, group=None, k_stride=
     stream = _consumer_stream(device)
     st = solver.__dict__.setdefault("_gather_state", {})
 
+    def allocate(cap):
+        st.update(cap=cap, n_slots=n_slots, world=world,
+                  pay=torch.zeros((cap + 1, 3), dtype=torch.float64, device=device),
+                  out=torch.empty((world, cap + 1, 3), dtype=torch.float64, device=device))
+
     def negotiate(minimum):
         out, n = L.esb_roots(), C.c_int32(0)
         bound = 0
@@ -169,10 +174,7 @@ def gather_modes_device(solver, n_slots, k_offset, device, group=None, k_stride=
             bound += n.value
         want = torch.tensor([max(bound, minimum)], dtype=torch.int64, device=device)
         dist.all_reduce(want, op=dist.ReduceOp.MAX, group=group)
-        cap = int(want.item() * 1.25) + 1024
-        st.update(cap=cap, n_slots=n_slots, world=world,
-                  pay=torch.zeros((cap + 1, 3), dtype=torch.float64, device=device),
-                  out=torch.empty((world, cap + 1, 3), dtype=torch.float64, device=device))
+        allocate(int(want.item() * 1.25) + 1024)
 
     if st.get("n_slots") != n_slots or st.get("world") != world or st["pay"].device != torch.device(device):
         negotiate(0)
@@ -190,6 +192,11 @@ def gather_modes_device(solver, n_slots, k_offset, device, group=None, k_stride=
             break
         negotiate(int(max(h[1] for h in head)))  # some rank found more modes than the shared capacity
     full = torch.cat([st["out"][r, 1: 1 + int(h[0])] for r, h in enumerate(head)], dim=0)
+    # the first capacity comes from the bracket counts, an upper bound ~2x the modes: every rank sees the same
+    # headers, so all of them can tighten it to what the modes need (half the bytes of the next exchanges)
+    need = int(max(h[0] for h in head) * 1.25) + 1024
+    if st["cap"] > 1.5 * need:
+        allocate(need)
     if sort and full.shape[0]:
         for col in (1, 0, 2):            # stable sorts, least significant key first
             full = full[torch.argsort(full[:, col], stable=True)]
