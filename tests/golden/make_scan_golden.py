@@ -50,6 +50,12 @@ CASES = {
         ("sausage", 1.5, 0.9, 1.49, 40), ("sausage", 2.5, 0.9, 1.49, 40), ("sausage", 3.5, 0.9, 1.49, 40)]),
     "rotation_kink": ("cylinder_rotation_kink", {"v_twist": 0.15, "power": 1.25}, [
         ("kink", 1.0, 0.9, 1.49, 40), ("kink", 2.5, 0.9, 1.49, 40), ("kink", 3.5, 0.9, 1.49, 40)]),
+    # the two kink scripts exactly as shipped (v_phi = 0.25 r^0.8 / 0.1 r^0.8, layer down to r = 0.001), on
+    # windows where no resonance sits next to the axis (tests/helpers.py rotation_regular); "@" = variant tag
+    "rotation_kink@p08": ("cylinder_rotation_kink", {}, [
+        ("kink", 3.0, 1.25, 1.45, 40), ("kink", 3.5, 1.25, 1.45, 40), ("kink", 4.0, 1.22, 1.45, 40)]),
+    "rotation_kink_slow@p08": ("cylinder_rotation_kink_slow", {}, [
+        ("kink", 2.0, 1.12, 1.45, 40), ("kink", 3.0, 1.06, 1.45, 40), ("kink", 4.0, 1.06, 1.45, 40)]),
 }
 
 
@@ -71,11 +77,16 @@ def run_case(args):
 def main():
     jobs = [(script, solver, ov, case) for script, (solver, ov, cases) in CASES.items() for case in cases]
     only = sys.argv[1:]
+    out, first = {}, 0
     if only:
+        # append the named scripts' cases to the existing fixture instead of regenerating all of it
         jobs = [j for j in jobs if j[0] in only]
-    out = {}
+        old = np.load(os.path.join(HERE, "ref_scans.npz"))
+        out = {f: old[f] for f in old.files}
+        while "c%d_script" % first in out:
+            first += 1
     with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1), maxtasksperchild=1) as pool:
-        for n, r in enumerate(pool.imap(run_case, jobs)):
+        for n, r in enumerate(pool.imap(run_case, jobs), start=first):
             for key in ("script", "overrides"):
                 out["c%d_%s" % (n, key)] = np.array(r[key])
             out["c%d_mode" % n] = np.array([r["mode"]])

@@ -203,6 +203,8 @@ DROPIN_OVERRIDES = {
     "slab_density_photospheric": dict(width=0.9), "slab_flow": dict(width=1.0), "slab_flow_photospheric": {},
     "cylinder_flow": dict(medium=esb.AxialFlowMedium(1.0, 2.0, 5.0, 0.5, U_i0=0.35), width=1.0),
     "rotation_sausage": {}, "rotation_kink": dict(profile=esb.PowerLawRotation(0.15, 1.25)),
+    # the two kink scripts exactly as shipped (0.25 r^0.8 / 0.1 r^0.8): fixture names carry a variant tag
+    "rotation_kink@p08": {}, "rotation_kink_slow@p08": {},
 }
 
 
@@ -216,7 +218,7 @@ class _Q:
 
 def test_reference_rule_reproduces_the_scripts_scan(golden_dir):
     """sausage()/kink() keep the reference's signature and, under the "reference" accept rule, reproduce
-    the reference's OWN scan + bisection output: tests/golden/ref_scans.npz holds sol_omegas of 48 calls
+    the reference's OWN scan + bisection output: tests/golden/ref_scans.npz holds sol_omegas of 48 + 6 calls
     of the unmodified scripts (9 scripts, both modes, windows with and without modes; most windows that
     contain a mode return nothing - the scripts' recursion follows the upper half only).  A solution of
     the scripts is a point of the dyadic refinement of the frequency grid, so agreement is to ROUNDING.
@@ -233,14 +235,14 @@ def test_reference_rule_reproduces_the_scripts_scan(golden_dir):
     within one grid interval of a root of the converged rule, and every solution reported here passes
     the script's own acceptance test by construction."""
     g = np.load(os.path.join(golden_dir, "ref_scans.npz"))
-    n_cases = n_sols = exact = 0
+    n_cases = n_sols = exact = n_steep = 0
     scripts = {}
     try:
         n = 0
         while "c%d_script" % n in g.files:
             name = str(g["c%d_script" % n])
             if name not in scripts:
-                scripts[name] = esb.ReferenceScript(name, **DROPIN_OVERRIDES[name])
+                scripts[name] = esb.ReferenceScript(name.split("@")[0], **DROPIN_OVERRIDES[name])
             script = scripts[name]
             mode = int(g["c%d_mode" % n][0]); k = float(g["c%d_k" % n][0])
             freq = g["c%d_freq" % n]; ws_ref = np.sort(g["c%d_sol_ws" % n])
@@ -249,11 +251,19 @@ def test_reference_rule_reproduces_the_scripts_scan(golden_dir):
             assert len(ws.items) == 1 and len(ks.items) == 1 and len(ws.items[0]) == len(ks.items[0])
             assert all(kk == k for kk in ks.items[0])
             got = np.sort(np.array(ws.items[0], dtype=np.float64))
-            n_cases += 1
+            steep = "@" in name
+            # "@p08": the two kink scripts exactly as shipped (0.25 r^0.8 / 0.1 r^0.8).  Their own D is 2-14 %
+            # off in amplitude there (tests/test_oracle_pinned.py), which decides the band test at marginal
+            # grid points: these six calls are held to the two-direction check below only - and the fast
+            # script's solution must be among the GPU's points exactly
+            n_steep += steep
+            n_cases += not steep
             n_sols += len(ws_ref)
-            if len(got) == len(ws_ref) and np.allclose(got, ws_ref, rtol=1e-9, atol=0):
+            if name == "rotation_kink@p08":
+                assert all(np.min(np.abs(got - w)) <= 1e-9 * abs(w) for w in ws_ref), (name, k, got, ws_ref)
+            if not steep and len(got) == len(ws_ref) and np.allclose(got, ws_ref, rtol=1e-9, atol=0):
                 exact += 1
-            else:
+            elif not (len(got) == len(ws_ref) and np.allclose(got, ws_ref, rtol=1e-9, atol=0)):
                 script.solver.set_accept_rule("converged")
                 conv = script.solver.find_roots(mode, [k], freq, layout="shared", tol_percent=script.tol)
                 script.solver.set_accept_rule(script.rule)
@@ -267,7 +277,7 @@ def test_reference_rule_reproduces_the_scripts_scan(golden_dir):
     finally:
         for sc in scripts.values():
             sc.close()
-    assert n_cases >= 40 and n_sols >= 12
+    assert n_cases >= 40 and n_sols >= 12 and n_steep == 6
     assert exact >= 0.75 * n_cases, (exact, n_cases)
 
 
