@@ -1294,8 +1294,9 @@ ESB_HD void eval_point_multi(const DevModel& M, const double* __restrict__ tab, 
 // layer) ANY step count returns solver noise, as the reference's odeint does.
 //   density kinds   rho(x) w^2 = k^2 {beta, tau} (Alfven, cusp; slab also alpha: the sound point of F)
 //   flow kinds      (w - k U)^2 = k^2 {vA^2 (cylinder), cT^2, c^2 (slab)}, slab also w = k U
-//   rotation        D or C3 changes sign between staged nodes (C3 = 0 is singular for the reference's
-//                   second-order form only, but the reference output there is noise all the same)
+//   rotation        D, C3 or the Doppler-shifted frequency w - m v_phi/r changes sign between staged nodes
+//                   (C3 = 0 is singular for the reference's second-order form only, but the reference output
+//                   there is noise all the same)
 ESB_HD bool outside_range(double v, double lo, double hi, double margin) {
     // lo, hi >= 0 (densities, squared frequencies): a relative margin on either bound
     return v < lo * (1.0 - margin) || v > hi * (1.0 + margin);
@@ -1321,20 +1322,25 @@ ESB_HD bool resonance_free(const DevModel& M, const Point& pt, double mode, cons
                   fmin(a2, b2) > margin * margin * pt.A;
         return ok;
     } else {
-        // D = 0 and C3 = 0 only at a resonance: the signs of D and C3 must be the same at every node AND at
-        // w (1 - margin), w, w (1 + margin) - a point NEXT to a resonance converges slowly too
-        bool pos_d = false, neg_d = false, pos_c = false, neg_c = false;
+        // D = 0 and C3 = 0 only at a resonance, and the Doppler-shifted frequency Om = w - m v_phi/r must not
+        // pass through zero inside the layer either (measured: the deviation between N and 2N steps does not
+        // fall with N there): the signs of D, C3 and Om must be the same at every node AND at w (1 - margin),
+        // w, w (1 + margin) - a point NEXT to a resonance converges slowly too
+        bool pos_d = false, neg_d = false, pos_c = false, neg_c = false, pos_o = false, neg_o = false;
         for (int j = -1; j <= 1; ++j) {
             Point q = pt;
             q.w = pt.w * (1.0 + j * margin);
             q.A = q.w * q.w;
             for (int i = 0; i < M.n_nodes; ++i) {
-                const RotCoef c = node_rot(M, q, mode, tab + (size_t)i * ROT_FIELDS);
+                const double* f = tab + (size_t)i * ROT_FIELDS;
+                const RotCoef c = node_rot(M, q, mode, f);
+                const double Om = fma(-mode, f[2], q.w);
                 pos_d = pos_d || c.invD > 0.0; neg_d = neg_d || !(c.invD > 0.0);
                 pos_c = pos_c || c.C3 > 0.0; neg_c = neg_c || !(c.C3 > 0.0);
+                pos_o = pos_o || Om > 0.0; neg_o = neg_o || !(Om > 0.0);
             }
         }
-        return !(pos_d && neg_d) && !(pos_c && neg_c);
+        return !(pos_d && neg_d) && !(pos_c && neg_c) && !(pos_o && neg_o);
     }
 }
 
