@@ -47,20 +47,47 @@ class ScanResult:
     k: np.ndarray             # this rank's wavenumbers; global row = k_offset + k_index * k_stride
     k_offset: int
     k_stride: int
+    guard: list = None        # guard_ends=True: discretisation-guard reports of the first and the last equilibrium
+
+
+def _guard_ends(solver, points, modes, tol_percent):
+    """The batched job carries no discretisation guard (esb_scan_models).  The two ends of the parameter
+    range are swept once more as ordinary sweeps, which do: their reports bound the error of a scan over a
+    one-parameter family.  The solver's own equilibrium is restored afterwards."""
+    import warnings
+    from .solver import DiscretisationWarning
+    keep = (solver.spec.medium, solver.spec.profile)
+    reports = []
+    try:
+        for p in (points[0], points[-1]) if len(points) > 1 else (points[0],):
+            solver.reconfigure(p.get("medium"), p.get("profile"))
+            solver.sweep_resident_multi(modes, tol_percent)
+            rep = solver.guard_report()
+            reports.append(rep)
+            if rep["n_checked"] and rep["worst"] > rep["threshold"]:
+                warnings.warn("parameter scan: discretisation error %.1e > %.0e at %s: raise n_steps"
+                              % (rep["worst"], rep["threshold"], p.get("label", {})), DiscretisationWarning, stacklevel=3)
+    finally:
+        solver.reconfigure(*keep)
+    return reports
 
 
 def parameter_scan(solver: DispersionSolver, points, k, W, modes, layout="phase_speed", tol_percent=1.0,
-                   rank=0, world=1, keep_tables=False, capacity_per_table=0, download=True) -> ScanResult:
+                   rank=0, world=1, keep_tables=False, capacity_per_table=0, download=True,
+                   guard_ends=False) -> ScanResult:
     """Sweep every equilibrium in `points` (list of dicts with optional keys 'medium', 'profile' and
     a free-form 'label') over the (k, W) grid: this rank's rows are k[rank::world], all equilibria.
     download=False: the compact table stays on the device (result.table is None; gather_scan_modes_device
-    reads it in place)."""
+    reads it in place).  guard_ends=True: the first and the last equilibrium are also swept on their own
+    with the discretisation guard (two extra sweeps; result.guard holds the reports, DiscretisationWarning
+    above the threshold)."""
     k_loc, k_off, k_stride = shard_k(np.asarray(k, dtype=np.float64), rank, world, layout="strided")
     solver.upload_axes(k_loc, W, layout)
+    guard = _guard_ends(solver, points, modes, tol_percent) if guard_ends else None
     tab, nb = solver.scan_models(points, modes, tol_percent, capacity_per_table, download=download)
     if tab is None:
         pts = [ScanPoint(p.get("label", {}), [int(x) for x in nb[i]], None) for i, p in enumerate(points)]
-        return ScanResult(pts, None, k_loc, k_off, k_stride)
+        return ScanResult(pts, None, k_loc, k_off, k_stride, guard)
     out = []
     n_slots = len(list(modes))
     # entries of (model i, slot m) are contiguous and in this order
@@ -74,7 +101,7 @@ def parameter_scan(solver: DispersionSolver, points, k, W, modes, layout="phase_
                 tables.append({name: np.array(tab[name][lo:hi]) for name in
                                ("k_index", "w_index", "omega", "ext", "intq", "accepted", "iterations")})
         out.append(ScanPoint(p.get("label", {}), [int(x) for x in nb[i]], n_modes, tables if keep_tables else None))
-    return ScanResult(out, tab, k_loc, k_off, k_stride)
+    return ScanResult(out, tab, k_loc, k_off, k_stride, guard)
 
 
 def gather_scan_modes(result: ScanResult, device, group=None):

@@ -944,6 +944,27 @@ def test_device_side_gather_equals_host_table(solvers):
         dist.destroy_process_group()
 
 
+def test_parameter_scan_guards_the_ends_of_the_range():
+    """The batched scan job is not sampled by the discretisation guard; guard_ends=True sweeps the two ends of
+    the parameter range on their own: clean for a family of shipped-like profile widths, flagged for a family
+    of sharp shells."""
+    import warnings as _w
+    from eigensolver_b200.scan import parameter_scan
+    k = np.linspace(0.5, 4.5, 48); W = np.linspace(4.6, 4.95, 256)      # above the Alfven continuum
+    smooth = [dict(profile=esb.GaussianDensity(w), label={"width": w}) for w in (0.9, 0.95, 1.0)]
+    sharp = [dict(profile=esb.GaussianDensity(w, x0=-0.5), label={"shell width": w}) for w in (0.05, 0.04, 0.03)]
+    with esb.DispersionSolver("cylinder_density") as s:
+        with _w.catch_warnings():
+            _w.simplefilter("error", esb.DiscretisationWarning)
+            res = parameter_scan(s, smooth, k, W, [0, 1], guard_ends=True)
+        assert len(res.guard) == 2 and all(r["n_checked"] > 50 and r["worst"] < 1e-9 for r in res.guard)
+        assert s.spec.profile == esb.GaussianDensity(0.95)          # the solver's own equilibrium is back
+        assert len(res.points) == 3 and res.table is not None
+        with pytest.warns(esb.DiscretisationWarning):
+            res = parameter_scan(s, sharp, k, W, [0, 1], guard_ends=True)
+        assert min(r["worst"] for r in res.guard) > 1e-9
+
+
 def test_parameter_scan_matches_fresh_solvers():
     """configs[4]-style scan through eigensolver_b200.scan: the batched job gives what a freshly built
     solver gives for every equilibrium, and sharding the WAVENUMBERS (strided) over ranks covers the
