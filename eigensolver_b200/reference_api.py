@@ -118,6 +118,50 @@ SCRIPTS = {
 }
 
 
+def pickle_layout(script):
+    """Which of run()'s four arrays a script pickles, in order (`pickle.dump([...], f)` at the end of every
+    solver script): the density / flow scripts all four (Density_cylinder.py:1183), the rotational sausage
+    scripts `[sol_omegas1, sol_ks1]` (Twisted_photospheric_flow_sausage.py:786), the rotational kink scripts
+    `[sol_omegas_kink1, sol_ks_kink1]` (..._kink_fast.py:782)."""
+    if script not in SCRIPTS:
+        raise KeyError("unknown solver script %r" % script)
+    if script.startswith("rotation_sausage"):
+        return (0, 1)
+    if script.startswith("rotation_kink"):
+        return (2, 3)
+    return (0, 1, 2, 3)
+
+
+def write_root_table(path, results, script="cylinder_density"):
+    """The reference's output file: `results` = run()'s [sol_omegas1, sol_ks1, sol_omegas_kink1, sol_ks_kink1]
+    pickled as numpy arrays in the layout THAT script writes (pickle_layout), so that the analysis scripts
+    which read those files (e.g. Eigenfunctions/analysis_compare_coronal_eigenfunctions_coronal.py:364
+    `sol_omegas, sol_ks, sol_omegas_kink, sol_ks_kink = pickle.load(f)`) work on them unchanged."""
+    import pickle
+    if len(results) < 4:
+        raise ValueError("results = [sol_omegas1, sol_ks1, sol_omegas_kink1, sol_ks_kink1]")
+    payload = [np.asarray(results[i], dtype=np.float64) for i in pickle_layout(script)]
+    with open(path, "wb") as fh:
+        pickle.dump(payload, fh)
+    return payload
+
+
+def read_root_table(path, script="cylinder_density"):
+    """Inverse of write_root_table; also reads the reference's own Example data pickles (written by
+    Python 2 numpy: latin1).  Returns [sol_omegas1, sol_ks1, sol_omegas_kink1, sol_ks_kink1], empty
+    arrays for the lists the script does not pickle."""
+    import pickle
+    with open(path, "rb") as fh:
+        data = pickle.load(fh, encoding="latin1")
+    layout = pickle_layout(script)
+    if len(data) != len(layout):
+        raise ValueError("%s holds %d lists, script %r pickles %d" % (path, len(data), script, len(layout)))
+    out = [np.zeros(0) for _ in range(4)]
+    for i, a in zip(layout, data):
+        out[i] = np.real(np.asarray(a)).astype(np.float64)
+    return out
+
+
 class _ListSink:
     """Minimal stand-in for multiprocessing.Queue when the caller has none."""
 
@@ -235,6 +279,12 @@ class ReferenceScript:
             out.append(np.concatenate(ws) if ws else np.zeros(0))
             out.append(np.concatenate(ks) if ks else np.zeros(0))
         return out
+
+    def run_and_pickle(self, path, **kw):
+        """run() and write the script's own output file (write_root_table)."""
+        results = self.run(**kw)
+        write_root_table(path, results, self.script)
+        return results
 
     def close(self):
         self.solver.close()

@@ -96,3 +96,29 @@ def test_worker_signature_on_gpu(name):
     with esb.ReferenceScript(name) as script:
         out = script.run(wavenumber=np.linspace(*sp["wavenumber"][:2], 6), n_freq=40)
         assert len(out) == 4 and len(out[0]) == len(out[1]) and len(out[2]) == len(out[3])
+
+
+def test_root_table_files_have_the_scripts_layout(tmp_path):
+    """The output file of every solver script: four arrays for the density / flow scripts
+    (Density_cylinder.py:1183), two for the rotational ones (Twisted_photospheric_*:782-790), as numpy arrays -
+    what the reference's analysis scripts unpack (analysis_compare_coronal_eigenfunctions_coronal.py:364)."""
+    import pickle
+    from eigensolver_b200 import reference_api as ra
+    res = [np.array([3.0, 3.1]), np.array([1.0, 1.0]), np.array([2.5]), np.array([0.7])]
+    for script in SCRIPTS:
+        path = tmp_path / (script + ".pickle")
+        ra.write_root_table(path, res, script)
+        with open(path, "rb") as fh:
+            raw = pickle.load(fh)
+        layout = ra.pickle_layout(script)
+        assert len(raw) == (2 if script.startswith("rotation_") else 4) == len(layout)
+        assert all(isinstance(a, np.ndarray) and a.dtype == np.float64 for a in raw)
+        back = ra.read_root_table(path, script)
+        for i in range(4):
+            assert np.array_equal(back[i], res[i] if i in layout else np.zeros(0))
+    if len(raw) == 4:                     # the unpacking line of the analysis scripts
+        sol_omegas, sol_ks, sol_omegas_kink, sol_ks_kink = raw
+    with pytest.raises(KeyError):
+        ra.pickle_layout("no_such_script")
+    with pytest.raises(ValueError):
+        ra.read_root_table(path, "rotation_kink" if len(raw) == 4 else "cylinder_density")
