@@ -1302,6 +1302,17 @@ ESB_HD bool outside_range(double v, double lo, double hi, double margin) {
     return v < lo * (1.0 - margin) || v > hi * (1.0 + margin);
 }
 
+// What the discretisation guard judges: g = D Y / (|ext Y| + |int Y|), the acceptance test's relative mismatch
+// made pole-free (int = N / Y: g = (ext Y - N) / (|ext Y| + |N|) stays regular where Y -> 0) AND projective -
+// unchanged when N and Y carry a common factor.  They do: both are built from the solution that dominates
+// towards the axis (r^-n), whose amplitude error cancels in int = N / Y (measured, fluting n = 3 at 152 steps:
+// N and Y each 2.5e-9 off, D 4e-15); G = D Y itself would report that harmless factor as an error of the sweep.
+ESB_HD double guard_deviation(double e0, double i0, double d0, double e, double i, double d) {
+    const double g0 = (e0 - i0) * d0 / (fabs(e0 * d0) + fabs(i0 * d0));
+    const double g = (e - i) * d / (fabs(e * d) + fabs(i * d));
+    return fabs(g0 - g);
+}
+
 template <int KIND>
 ESB_HD bool resonance_free(const DevModel& M, const Point& pt, double mode, const double* __restrict__ tab,
                            double margin) {

@@ -878,9 +878,10 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_modes_kernel(PackArgs a, in
 // (esb_set_guard_fields: the same equilibrium on a finer mesh, normally 2 x n_steps), every sweep
 // re-evaluates every stride-th (point, mode) of its scan with the fine table and keeps the worst
 // deviation.  8th order: doubling the steps divides the error by ~256, so the deviation IS the
-// discretisation error of the sweep at that point.  Judged on the pole-free function G = D Y
-// (Y = the denominator of int, stored by the scan), relative to |ext Y| + |int Y|: next to a pole of D
-// (Y -> 0) int = N/Y amplifies the error of Y without bound while G stays regular.  Points inside the
+// discretisation error of the sweep at that point.  Judged on g = D Y / (|ext Y| + |int Y|) (Y = the
+// denominator of int, stored by the scan; core.cuh guard_deviation): next to a pole of D (Y -> 0) int = N/Y
+// amplifies the error of Y without bound while g stays regular, and a common factor of N and Y - which
+// cancels in D - cancels in g too.  Points inside the
 // resonant continua (resonance_free) are not judged: no step count converges there.
 // One lane per sample, one 32-sample tile per warp; runs on a side stream next to the bracket passes.
 struct GuardRecord {
@@ -939,8 +940,7 @@ __global__ void __launch_bounds__(256) guard_kernel(GuardArgs g) {
                 if (resonance_free<KIND>(g.M, pt, double(g.modes[slot]), stab, g.margin)) {
                     double e, i, d;
                     eval_point<KIND, SCHEME>(g.M, stab, k, w, g.modes[slot], e, i, d);
-                    const double scale = fabs(e * d) + fabs(i * d);
-                    const double dev = fabs((e0 - i0) * d0 - (e - i) * d) / scale;
+                    const double dev = guard_deviation(e0, i0, d0, e, i, d);
                     if (isfinite(dev)) {
                         checked = 1;
                         above = dev > g.threshold ? 1 : 0;

@@ -409,7 +409,9 @@ class DispersionSolver:
 
     def guard_report(self):
         """Discretisation guard of the LAST sweep (waits for it): dict with `worst` (largest deviation of
-        the pole-free function G = D Y between n_steps and 2 n_steps over the sampled points outside the
+        g = D Y / (|ext Y| + |int Y|) - the acceptance test's relative mismatch, regular at the poles of D and
+        blind to a common factor of int's numerator and denominator - between n_steps and 2 n_steps over the
+        sampled points outside the
         resonant continua - the discretisation error of the sweep), where it occurred (`slot`, `k_index`,
         `w_index`), `n_checked`, `n_above` (samples above `threshold`), `stride` (0: guard off)."""
         rep = L.esb_guard_report()
@@ -704,6 +706,78 @@ class DispersionSolver:
         om = ww[j[1], j[2]] if lay == L.OMEGA_PER_K else (kk[j[1]] * ww[j[2]] if lay == L.OMEGA_PHASE_SPEED else ww[j[2]])
         return float(dev[j]), {"mode": modes[j[0]], "k": float(kk[j[1]]), "omega": float(om),
                                "n_steps": int(m.n_steps), "n_steps_fine": int(m.n_steps) * int(factor)}
+
+    #: the most steps whose table fits the 200 KB staged in shared memory, per scheme (esb_set_model_fields
+    #: refuses more); the rotation kind carries more fields per node
+    _STEP_CAP = {"rk8n": 680, "rk8": 1270, "rk4": 1270}
+
+    def _respec(self, n_steps):
+        """This solver's equilibrium at another step count (the normal-form table of > 680 steps does not fit
+        shared memory: such a count runs on the first-derivative scheme)."""
+        kw = self.spec.solver_kwargs()
+        kw["n_steps"] = int(n_steps)
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > self._STEP_CAP["rk8n"]:
+            kw["scheme"] = "rk8"
+        self.spec = ModelSpec(**kw)
+        self._upload_model()
+
+    def resolve_steps(self, modes, k, w, layout="phase_speed", target=None, max_rounds=6, sample=(48, 256)):
+        """Error control for a profile the shipped step counts were not tuned for - the fixed-step counterpart
+        of the adaptivity the reference gets from odeint (Density_cylinder.py:783 `odeint(dP_dr, ...)`, default
+        rtol = atol = 1.49e-8): a `sample` = (rows, columns) grid spanning the caller's (k, w) window in
+        the caller's layout is swept with EVERY point re-evaluated at 2 x n_steps by the built-in guard; while the
+        worst deviation exceeds `target` (default: this solver's guard_threshold, 1e-9) n_steps is raised by the
+        factor the scheme's order predicts ((worst / target)^(1/8) for the eighth-order schemes, 1/4 for
+        "rk4", 15 % margin, at least x 1.25) and the model is uploaded again.  The new step count stays in
+        force for every later call.  Returns {"n_steps", "scheme", "worst", "resolved", "history": [(n_steps,
+        worst), ...]}; resolved = False when the staged table's capacity (guard at twice the steps included)
+        was reached first - a DiscretisationWarning says so."""
+        if self.guard_stride == 0:
+            raise ValueError("resolve_steps needs the discretisation guard (guard != 0)")
+        target = self.guard_threshold if target is None else float(target)
+        kk, ww, lay, nw = self._axes(k, w, layout)
+        # the sample spans the caller's window in the caller's layout, whatever its size (a worker-sized call
+        # of one k and ~90 frequencies is below the 8192 pairs the guard samples at all)
+        ks = np.linspace(kk.min(), kk.max(), int(sample[0]))
+        if lay == L.OMEGA_PER_K:
+            o = np.argsort(kk)
+            lo, hi = np.interp(ks, kk[o], ww[o].min(axis=1)), np.interp(ks, kk[o], ww[o].max(axis=1))
+            ws = lo[:, None] + (hi - lo)[:, None] * np.linspace(0.0, 1.0, int(sample[1]))[None, :]
+        else:
+            ws = np.linspace(ww.min(), ww.max(), int(sample[1]))
+        stride_keep, self.guard_stride = self.guard_stride, 1
+        history = []
+        try:
+            self._upload_guard()
+            # the guard needs the table of 2 x n_steps staged as well
+            cap = (700 if self.kind == "cylinder_rotation" else self._STEP_CAP["rk8"]) // 2
+            for rnd in range(max_rounds):
+                n_now = int(self.spec.model.n_steps)
+                if not self._guard_on:
+                    break
+                self.upload_axes(ks, ws, layout)
+                self.sweep_resident_multi(list(modes))
+                rep = self.guard_report()
+                if rep["n_checked"] == 0:        # the whole window is leaky / inside a continuum: nothing to judge
+                    break
+                worst = float(rep["worst"])
+                history.append((n_now, worst))
+                if worst <= target or n_now >= cap or rnd == max_rounds - 1:
+                    break
+                order = 4.0 if self.spec.scheme == "rk4" else 8.0
+                grow = min(4.0, max(1.25, 1.15 * (worst / target) ** (1.0 / order))) if np.isfinite(worst) else 4.0
+                self._respec(min(int(-(-n_now * grow // 8) * 8), cap))
+        finally:
+            self.guard_stride = stride_keep
+            self._upload_guard()
+        resolved = bool(history) and history[-1][1] <= target
+        if not resolved:
+            warnings.warn("resolve_steps: discretisation error %s at n_steps = %d, target %.0e not reached within the "
+                          "staged table's capacity" % ("%.1e" % history[-1][1] if history else "unknown",
+                                                       int(self.spec.model.n_steps), target),
+                          DiscretisationWarning, stacklevel=2)
+        return {"n_steps": int(self.spec.model.n_steps), "scheme": self.spec.scheme,
+                "worst": history[-1][1] if history else float("nan"), "resolved": resolved, "history": history}
 
     def set_schedule(self, mode):
         """Scan and refinement kernels: "auto" (by size) | "lane" (one lane per point / bracket) |

@@ -193,8 +193,12 @@ int esb_tables_wait(esb_context* ctx, void* stream);
  * SAME equilibrium on a finer mesh - `fine` = the model with (normally) 2 x n_steps, the fields sampled at ITS
  * esb_mesh_nodes() - and from then on every esb_sweep_resident[_multi] re-evaluates every stride-th
  * (grid point, mode) of its scan with the fine table, on a side stream next to the bracket passes (~2/stride of
- * the scan's arithmetic).  esb_guard_result waits for that pass and reports the worst deviation - judged on the
- * pole-free function G = D Y relative to |ext Y| + |int Y| - over the sampled points outside the resonant
+ * the scan's arithmetic).  esb_guard_result waits for that pass and reports the worst deviation - judged on
+ * g = D Y / (|ext Y| + |int Y|), Y = the denominator of int: the acceptance test's relative mismatch, regular at
+ * the poles of D and unchanged by a common factor of int's numerator and denominator, which cancels in D (the
+ * amplitude error of the solution that dominates towards the axis: 2.5e-9 for the fluting order n = 3 at the
+ * default steps, which G = D Y alone - the measure of the first 1.3 builds - reported although D is converged to
+ * 1e-13) - over the sampled points outside the resonant
  * continua, where it occurred, and how many samples exceeded `threshold`.  8th order: halving the step divides
  * the error by ~256, so the value is (to 0.4 %) the discretisation error of the sweep itself.  The samples are
  * tiles of 32 consecutive omega points, one tile per 32 * stride grid points; stride = ESB_GUARD_AUTO lets every

@@ -116,3 +116,62 @@ extern "C" int esbh_eval_points_leaky(const esb_model* m, const double* const* f
         return ESB_ERR_ARG;
     return ESB_OK;
 }
+
+// The discretisation guard's judgement (csrc/esb.cu guard_kernel) at n points: dev[slot][p] = guard_deviation
+// between the COARSE model's (ext, int, den) and the FINE model's, NaN where the guard does not judge the point
+// (skipped / overflowed / inside a resonant continuum within `margin`).  Both models as in esb_set_model_fields.
+template <int KIND, int SCHEME_C, int SCHEME_F>
+static void guard_all(const HostModel& hc, const HostModel& hf, int n_modes, const int32_t* modes, int64_t n,
+                      const double* k, const double* w, double margin, double* dev) {
+    for (int64_t p = 0; p < n; ++p)
+        for (int s = 0; s < n_modes; ++s) {
+            double e0, i0, d0, e, i, d;
+            dev[s * n + p] = nan("");
+            eval_point<KIND, SCHEME_C>(hc.dm, hc.tab.data(), k[p], w[p], modes[s], e0, i0, d0);
+            if (!(std::isfinite(e0) && std::isfinite(i0) && std::isfinite(d0))) continue;
+            const Point pt = make_point(hf.dm, k[p], w[p]);
+            if (!resonance_free<KIND>(hf.dm, pt, double(modes[s]), hf.tab.data(), margin)) continue;
+            eval_point<KIND, SCHEME_F>(hf.dm, hf.tab.data(), k[p], w[p], modes[s], e, i, d);
+            const double v = guard_deviation(e0, i0, d0, e, i, d);
+            if (std::isfinite(v)) dev[s * n + p] = v;
+        }
+}
+
+template <int KIND>
+static int guard_by_scheme(const HostModel& hc, const HostModel& hf, int n_modes, const int32_t* modes, int64_t n,
+                           const double* k, const double* w, double margin, double* dev) {
+    const int sc = hc.dm.scheme, sf = hf.dm.scheme;
+    if (sc == SCHEME_RK8 && sf == SCHEME_RK8)
+        guard_all<KIND, SCHEME_RK8, SCHEME_RK8>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+    else if constexpr (KIND == KIND_CYL_ROTATION || KIND == KIND_SLAB_FLOW)
+        return ESB_ERR_ARG;
+    else if (sc == SCHEME_RK8N && sf == SCHEME_RK8N)
+        guard_all<KIND, SCHEME_RK8N, SCHEME_RK8N>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+    else if (sc == SCHEME_RK8N && sf == SCHEME_RK8)
+        guard_all<KIND, SCHEME_RK8N, SCHEME_RK8>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+    else
+        return ESB_ERR_ARG;
+    return ESB_OK;
+}
+
+extern "C" int esbh_guard_points(const esb_model* mc, const double* const* fields_c, int32_t n_fields_c,
+                                 int32_t n_nodes_c, const double* boundary_c, const esb_model* mf,
+                                 const double* const* fields_f, int32_t n_fields_f, int32_t n_nodes_f,
+                                 const double* boundary_f, int32_t n_boundary, int32_t n_modes, const int32_t* modes, int64_t n, const double* k, const double* w,
+                                 double margin, double* dev) {
+    HostModel hc, hf;
+    std::string err;
+    int rc = build_host_model(mc, fields_c, n_fields_c, n_nodes_c, boundary_c, n_boundary, hc, err);
+    if (rc) return rc;
+    rc = build_host_model(mf, fields_f, n_fields_f, n_nodes_f, boundary_f, n_boundary, hf, err);
+    if (rc) return rc;
+    if (hc.dm.kind != hf.dm.kind) return ESB_ERR_ARG;
+    switch (hc.dm.kind) {
+        case KIND_SLAB_DENSITY: return guard_by_scheme<KIND_SLAB_DENSITY>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+        case KIND_CYL_DENSITY: return guard_by_scheme<KIND_CYL_DENSITY>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+        case KIND_SLAB_FLOW: return guard_by_scheme<KIND_SLAB_FLOW>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+        case KIND_CYL_ROTATION: return guard_by_scheme<KIND_CYL_ROTATION>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+        case KIND_CYL_FLOW: return guard_by_scheme<KIND_CYL_FLOW>(hc, hf, n_modes, modes, n, k, w, margin, dev);
+    }
+    return ESB_ERR_ARG;
+}

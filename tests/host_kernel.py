@@ -29,8 +29,33 @@ def lib():
                                        C.c_int64, dp, dp, dp, dp, dp]
         l.esbh_eval_points_leaky.restype = C.c_int
         l.esbh_eval_points_leaky.argtypes = l.esbh_eval_points.argtypes
+        l.esbh_guard_points.restype = C.c_int
+        l.esbh_guard_points.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int32, C.c_int32, dp,
+                                        C.c_void_p, C.POINTER(dp), C.c_int32, C.c_int32, dp, C.c_int32,
+                                        C.c_int32, ip, C.c_int64, dp, dp, C.c_double, dp]
         _lib = l
     return _lib
+
+
+def guard_grid(spec, fine, modes, k, W, margin=0.15):
+    """The discretisation guard's judgement (csrc/esb.cu guard_kernel: core.cuh guard_deviation behind the
+    resonance_free filter) of `spec` against `fine` on a phase-speed grid: [n_modes, nk, nw], NaN where the guard
+    does not judge the point."""
+    k = np.asarray(k, dtype=np.float64)
+    W = np.asarray(W, dtype=np.float64)
+    kk = np.ascontiguousarray(np.repeat(k, W.size))
+    ww = np.ascontiguousarray((k[:, None] * W[None, :]).ravel())
+    md = np.asarray(list(modes), dtype=np.int32)
+    dev = np.empty((md.size, kk.size))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    a, b = spec.abi_args(), fine.abi_args()
+    rc = lib().esbh_guard_points(C.cast(a[0], C.c_void_p), a[1], a[2], a[3], a[4],
+                                 C.cast(b[0], C.c_void_p), b[1], b[2], b[3], b[4], a[5],
+                                 md.size, md.ctypes.data_as(C.POINTER(C.c_int32)), kk.size, dp(kk), dp(ww),
+                                 float(margin), dp(dev))
+    if rc:
+        raise RuntimeError("esbh_guard_points: status %d" % rc)
+    return dev.reshape(md.size, k.size, W.size)
 
 
 def evaluate(spec, modes, k, w, leaky=False):

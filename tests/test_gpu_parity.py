@@ -1001,3 +1001,41 @@ def test_parameter_scan_matches_fresh_solvers():
     from eigensolver_b200.scan import medium_for_density_contrast
     m = medium_for_density_contrast(esb.CYLINDER_CORONAL, esb.CYLINDER_CORONAL.rho_e)
     assert abs(m.vA_e - 5.0) < 1e-12
+
+
+def test_resolve_steps_restores_the_tolerance_on_a_sharp_profile():
+    """Error control in place of odeint's adaptivity (Density_cylinder.py:783): resolve_steps raises n_steps,
+    by the factor the order predicts from the guard's own measurement, until the discretisation error of the
+    window is below 1e-9 - confirmed independently by convergence_check (D itself, a second context) and by
+    the next root search staying silent; the shipped profile needs nothing; a shell no staged table can
+    resolve is reported, not hidden."""
+    import warnings as _w
+    k = np.linspace(0.5, 4.5, 9); W2 = np.linspace(4.6, 4.95, 60)         # a worker-sized window
+    sharp = esb.GaussianDensity(0.05, x0=-0.5)
+    with esb.DispersionSolver("cylinder_density", profile=sharp) as s:
+        n0 = int(s.model.n_steps)
+        err0, _ = s.convergence_check([0, 1], k, W2)
+        with _w.catch_warnings():
+            _w.simplefilter("error", esb.DiscretisationWarning)
+            out = s.resolve_steps([0, 1], k, W2)
+        assert out["resolved"] and out["n_steps"] == int(s.model.n_steps) > n0, out
+        assert out["history"][0] == (n0, out["history"][0][1]) and out["history"][0][1] > 1e-9, out
+        assert out["worst"] <= 1e-9 and len(out["history"]) <= 3, out
+        err1, where = s.convergence_check([0, 1], k, W2)
+        # (convergence_check takes the maximum of D's own relative deviation over ALL points, the ones next to a
+        # pole of D included, where int = N / Y amplifies any error without bound: it falls by the same factor)
+        assert where["n_steps"] == out["n_steps"] and err1 < 1e-3 * err0, (err0, err1, out)
+        with _w.catch_warnings():
+            _w.simplefilter("error", esb.DiscretisationWarning)
+            tabs = s.find_roots_multi([0, 1], np.linspace(0.5, 4.5, 64), np.linspace(4.6, 4.95, 512))
+        assert s.guard_report()["n_checked"] > 0 and sum(len(t.omega) for t in tabs) > 0
+    with esb.DispersionSolver("cylinder_density") as s:
+        out = s.resolve_steps([0, 1, 2], k, np.linspace(3.0, 4.9, 120))
+        assert out["resolved"] and out["n_steps"] == n0 and len(out["history"]) == 1, out
+    with esb.DispersionSolver("cylinder_density", profile=esb.GaussianDensity(0.004, x0=-0.5)) as s:
+        with pytest.warns(esb.DiscretisationWarning):
+            out = s.resolve_steps([1], k, W2)
+        assert not out["resolved"] and out["n_steps"] == 635 and out["worst"] > 1e-9, out
+    with esb.DispersionSolver("cylinder_density", guard=0) as s:
+        with pytest.raises(ValueError):
+            s.resolve_steps([1], k, W2)

@@ -142,3 +142,51 @@ def test_leaky_evaluation_matches_oracle_without_the_skip(name):
     # and the default evaluation still skips those points
     e, i, _ = hk.evaluate(sp, [case.modes[0]], k, k * W)
     assert np.isnan(e).all() and np.isnan(i).all()
+
+
+def _fine(sp, factor=2):
+    """what DispersionSolver._fine_spec uploads as the guard's model"""
+    kw = sp.solver_kwargs()
+    kw["n_steps"] *= factor
+    if kw["scheme"] == "rk8n" and kw["n_steps"] > 680:
+        kw["scheme"] = "rk8"
+    return esb.ModelSpec(**kw)
+
+
+def test_guard_measure_on_host():
+    """The discretisation guard's own judgement (core.cuh guard_deviation behind resonance_free - the code the
+    device's guard_kernel runs) on the host build: (i) every shipped equilibrium, every azimuthal order up to
+    n = 3, is far below the 1e-9 threshold at its default step count; (ii) the measure is projective: for the
+    fluting n = 3 order the numerator N = int Y and the denominator Y both carry a 2.5e-9 amplitude error of the
+    solution that dominates towards the axis, which cancels in int = N / Y - D is converged to 1e-13 - and which
+    G = D Y alone (the measure of ABI 1.3) reported as an error of the sweep; (iii) the sharp shell is seen,
+    and cured by the step count the order predicts."""
+    for name, case in CASES.items():
+        k = np.linspace(0.25, 4.0, 12) if case.kind == "cylinder_rotation" else np.linspace(0.5, 4.5, 12)
+        W = np.linspace(case.W[0], case.W[1], 120)
+        sp = spec_of(case)
+        modes = list(case.modes) + ([3] if case.kind.startswith("cylinder") else [])
+        dev = hk.guard_grid(sp, _fine(sp), modes, k, W)
+        for m, d in zip(modes, dev):
+            if name == "cylinder_rotation_p08" and m >= 2:
+                continue                                  # (almost) every point next to a resonance: nothing judged
+            assert np.isfinite(d).sum() > 100 and np.nanmax(d) < 5e-11, (name, m, np.nanmax(d), np.isfinite(d).sum())
+    case = CASES["cylinder_density"]
+    sp = spec_of(case)
+    k, W = np.linspace(0.5, 4.5, 12), np.linspace(3.0, 4.9, 60)
+    e0, i0, d0 = hk.grid(sp, [3], k, W)
+    e1, i1, d1 = hk.grid(_fine(sp), [3], k, W)
+    ok = np.isfinite(e0) & np.isfinite(i0)
+    common = (d0 / d1 - 1.0)[ok]
+    assert 1e-9 < np.median(np.abs(common)) < 1e-8                          # Y: a visible factor, point by point ...
+    assert np.median(np.abs((i0 * d0) / (i1 * d1) - 1.0 - (d0 / d1 - 1.0))[ok]) < 1e-12     # ... shared by N ...
+    assert np.median(np.abs((e0 - i0) - (e1 - i1))[ok] / np.maximum(np.abs(e1), np.abs(i1))[ok]) < 1e-13   # ... not in D
+    old = np.abs((e0 - i0) * d0 - (e1 - i1) * d1) / (np.abs(e1 * d1) + np.abs(i1 * d1))
+    new = hk.guard_grid(sp, _fine(sp), [3], k, W)
+    assert np.nanmedian(old[np.isfinite(new)]) > 1e-10 and np.nanmax(new) < 5e-11
+    k, W2 = np.linspace(0.5, 4.5, 12), np.linspace(4.6, 4.95, 80)
+    worst = {}
+    for n in (None, 448):
+        sp = esb.ModelSpec("cylinder_density", profile=esb.GaussianDensity(0.05, x0=-0.5), n_steps=n)
+        worst[n] = np.nanmax(hk.guard_grid(sp, _fine(sp), [0, 1], k, W2))
+    assert worst[None] > 1e-7 and worst[448] < 1e-9, worst
