@@ -75,6 +75,7 @@ SYMBOLS = {
     "esb_mesh_size": (C.c_int, [C.POINTER(esb_model), _ip]),
     "esb_mesh_nodes": (C.c_int, [C.POINTER(esb_model), _dp]),
     "esb_model_n_fields": (C.c_int, [C.POINTER(esb_model), _ip]),
+    "esb_model_max_steps": (C.c_int, [C.POINTER(esb_model), _ip]),
     "esb_create": (C.c_int, [C.c_int32, C.POINTER(_ctx)]),
     "esb_destroy": (C.c_int, [_ctx]),
     "esb_last_error": (C.c_char_p, [_ctx]),

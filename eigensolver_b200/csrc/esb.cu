@@ -1203,6 +1203,15 @@ extern "C" int esb_model_n_fields(const esb_model* m, int32_t* n_fields) {
     return ESB_OK;
 }
 
+extern "C" int esb_model_max_steps(const esb_model* m, int32_t* max_steps) {
+    if (!m || !max_steps) return ESB_ERR_ARG;
+    esb_model t = *m;
+    t.n_steps = 8;                              // any valid count: the answer depends on (kind, scheme) only
+    if (check_model(&t)) return ESB_ERR_ARG;
+    *max_steps = model_max_steps(&t);
+    return ESB_OK;
+}
+
 extern "C" int esb_create(int32_t device, esb_context** out) {
     if (!out) return ESB_ERR_ARG;
     *out = nullptr;
@@ -1327,7 +1336,7 @@ extern "C" int esb_set_model(esb_context* c, const esb_model* m, const double* r
 }
 
 // ---- launches ---------------------------------------------------------------
-constexpr int TABLE_SMEM_MAX = 200 * 1024;       // model_host.h refuses larger tables
+constexpr int TABLE_SMEM_MAX = (int)TABLE_BYTES_MAX;  // model_host.h refuses larger tables
 constexpr int MAX_DEVICES = 64;
 
 // Function attributes are set once per (kernel instantiation, device): the staged table is read-only

@@ -180,6 +180,26 @@ static inline int model_tab_fields(const esb_model* m) {
     return m->scheme == ESB_RK8N ? NF_FIELDS : TAB_FIELDS;
 }
 
+// the staged table lives in the shared memory of every CTA
+constexpr size_t TABLE_BYTES_MAX = 200 * 1024;
+
+// doubles of the staged table: [n_nodes][fields per node], then h, g, h^2, g^2 per step
+static inline size_t model_tab_doubles(const esb_model* m) {
+    return (size_t)mesh_size(m) * model_tab_fields(m) + 4 * (size_t)m->n_steps;
+}
+
+// the largest n_steps whose table can be staged for this (kind, scheme)
+static inline int model_max_steps(const esb_model* m) {
+    esb_model t = *m;
+    int lo = 0, hi = 1 << 20;                   // table(lo) fits, table(hi) does not
+    while (hi - lo > 1) {
+        t.n_steps = lo + (hi - lo) / 2;
+        if (model_tab_doubles(&t) * sizeof(double) <= TABLE_BYTES_MAX) lo = t.n_steps; else hi = t.n_steps;
+    }
+    if ((m->kind == ESB_SLAB_DENSITY || m->kind == ESB_SLAB_FLOW) && (lo % 2)) lo -= 1;     // check_model: even
+    return lo;
+}
+
 struct HostModel {
     DevModel dm;
     std::vector<double> tab;
@@ -203,7 +223,7 @@ static inline int build_host_model(const esb_model* m, const double* const* fiel
     const int N = m->n_steps, nps = nodes_per_step(m->scheme);
     const int tf = model_tab_fields(m);
     std::vector<double>& tab = out.tab;
-    tab.assign((size_t)need * tf + 4 * (size_t)N, 0.0);
+    tab.assign(model_tab_doubles(m), 0.0);
     // step a node belongs to (the step-end node is stored in the scale of the step it ends and is
     // shared with the next step, which rescales the carried coefficients)
     auto step_h = [&](int i) {
@@ -337,7 +357,7 @@ static inline int build_host_model(const esb_model* m, const double* const* fiel
         d.tau = d.alpha * d.beta / d.S;
         d.rho_b = boundary[0];
     }
-    if (tab.size() * sizeof(double) > 200 * 1024) {
+    if (tab.size() * sizeof(double) > TABLE_BYTES_MAX) {
         err = "n_steps too large for the shared-memory table (200 KB)";
         return ESB_ERR_ARG;
     }

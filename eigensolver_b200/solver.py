@@ -300,6 +300,16 @@ class ModelSpec:
     def scheme(self):
         return _SCHEME_NAMES[self.model.scheme]
 
+    def max_steps(self, scheme=None):
+        """The most steps whose table fits the shared memory it is staged in (esb_model_max_steps), for this
+        spec's kind and `scheme` (default: its own)."""
+        m = type(self.model).from_buffer_copy(self.model)
+        if scheme is not None:
+            m.scheme = _SCHEMES[scheme]
+        n = C.c_int32()
+        L.check(self.lib, None, self.lib.esb_model_max_steps(C.byref(m), C.byref(n)), "esb_model_max_steps")
+        return n.value
+
     def sampled(self):
         """-> (fields, boundary): the profile at the mesh nodes, the first field at s_start."""
         scale = self.rho_A if self.kind in ("cylinder_density", "slab_density") else 1.0
@@ -389,9 +399,9 @@ class DispersionSolver:
         """The same equilibrium at `factor` x the steps (None if its table cannot be staged)."""
         kw = self.spec.solver_kwargs()
         kw["n_steps"] = int(self.spec.model.n_steps) * int(factor)
-        if kw["scheme"] == "rk8n" and kw["n_steps"] > 680:
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > self.spec.max_steps():
             kw["scheme"] = "rk8"          # the eight-field table of that many steps exceeds shared memory
-        if kw["n_steps"] > 1270 or (self.kind == "cylinder_rotation" and kw["n_steps"] > 700):
+        if kw["n_steps"] > self.spec.max_steps(kw["scheme"]):
             return None
         return ModelSpec(**kw)
 
@@ -696,7 +706,7 @@ class DispersionSolver:
         m = self.model
         kw = self.spec.solver_kwargs()
         kw["n_steps"] = int(m.n_steps) * int(factor)
-        if kw["scheme"] == "rk8n" and kw["n_steps"] > 680:
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > self.spec.max_steps():
             kw["scheme"] = "rk8"          # the eight-field table of that many steps exceeds shared memory
         with DispersionSolver(guard=0, **kw) as fine:
             e1, i1 = fine.dispersion_grid_multi(modes, k, w, layout)
@@ -707,16 +717,12 @@ class DispersionSolver:
         return float(dev[j]), {"mode": modes[j[0]], "k": float(kk[j[1]]), "omega": float(om),
                                "n_steps": int(m.n_steps), "n_steps_fine": int(m.n_steps) * int(factor)}
 
-    #: the most steps whose table fits the 200 KB staged in shared memory, per scheme (esb_set_model_fields
-    #: refuses more); the rotation kind carries more fields per node
-    _STEP_CAP = {"rk8n": 680, "rk8": 1270, "rk4": 1270}
-
     def _respec(self, n_steps):
-        """This solver's equilibrium at another step count (the normal-form table of > 680 steps does not fit
+        """This solver's equilibrium at another step count (a normal-form table beyond its capacity does not fit
         shared memory: such a count runs on the first-derivative scheme)."""
         kw = self.spec.solver_kwargs()
         kw["n_steps"] = int(n_steps)
-        if kw["scheme"] == "rk8n" and kw["n_steps"] > self._STEP_CAP["rk8n"]:
+        if kw["scheme"] == "rk8n" and kw["n_steps"] > self.spec.max_steps():
             kw["scheme"] = "rk8"
         self.spec = ModelSpec(**kw)
         self._upload_model()
@@ -750,7 +756,8 @@ class DispersionSolver:
         try:
             self._upload_guard()
             # the guard needs the table of 2 x n_steps staged as well
-            cap = (700 if self.kind == "cylinder_rotation" else self._STEP_CAP["rk8"]) // 2
+            cap = self.spec.max_steps("rk4" if self.spec.scheme == "rk4" else "rk8") // 2
+            cap -= cap % 2
             for rnd in range(max_rounds):
                 n_now = int(self.spec.model.n_steps)
                 if not self._guard_on:

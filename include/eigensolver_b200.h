@@ -39,7 +39,8 @@ extern "C" {
                              1.2: ESB_RK8N (normal-form Nystrom scheme, needs the profile's second derivative);
                                   up to 4 fused modes; esb_set_accept_rule; esb_tables_wait
                              1.3: esb_set_guard_fields / esb_guard_result (discretisation guard);
-                                  esb_bessel_jy[_dev], esb_exterior_leaky[_dev] (J_n, Y_n: the leaky side); esb_pack_modes_dev */
+                                  esb_bessel_jy[_dev], esb_exterior_leaky[_dev] (J_n, Y_n: the leaky side); esb_pack_modes_dev;
+                                  esb_model_max_steps; the guard judges the projective mismatch (see esb_set_guard_fields) */
 
 typedef struct esb_context esb_context;
 
@@ -138,6 +139,10 @@ int esb_set_model(esb_context* ctx, const esb_model* m, const double* rho, const
  *   ESB_CYLINDER_FLOW : fields = {v_z, v_z'} (+ v_z'' with ESB_RK8N), boundary = {v_z(s_start)}
  * esb_model_n_fields() returns the count for a model.  A failed call leaves the previous model set. */
 int esb_model_n_fields(const esb_model* m, int32_t* n_fields);
+/* The staged table ([esb_mesh_size() nodes][products per node] + 4 doubles per step) lives in the shared memory
+ * of every CTA (200 KB): the largest n_steps esb_set_model_fields accepts for this model's (kind, scheme) -
+ * 710 for ESB_RK8N and the rotation kind, 1279 for the other first-derivative tables.  Host code, no GPU. */
+int esb_model_max_steps(const esb_model* m, int32_t* max_steps);
 int esb_set_model_fields(esb_context* ctx, const esb_model* m, const double* const* fields,
                          int32_t n_fields, int32_t n_nodes, const double* boundary,
                          int32_t n_boundary);

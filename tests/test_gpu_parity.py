@@ -1035,7 +1035,8 @@ def test_resolve_steps_restores_the_tolerance_on_a_sharp_profile():
     with esb.DispersionSolver("cylinder_density", profile=esb.GaussianDensity(0.004, x0=-0.5)) as s:
         with pytest.warns(esb.DiscretisationWarning):
             out = s.resolve_steps([1], k, W2)
-        assert not out["resolved"] and out["n_steps"] == 635 and out["worst"] > 1e-9, out
+        cap = s.spec.max_steps("rk8") // 2          # the guard's table of twice the steps is staged as well
+        assert not out["resolved"] and out["n_steps"] == cap - cap % 2 and out["worst"] > 1e-9, out
     with esb.DispersionSolver("cylinder_density", guard=0) as s:
         with pytest.raises(ValueError):
             s.resolve_steps([1], k, W2)

@@ -190,3 +190,22 @@ def test_guard_measure_on_host():
         sp = esb.ModelSpec("cylinder_density", profile=esb.GaussianDensity(0.05, x0=-0.5), n_steps=n)
         worst[n] = np.nanmax(hk.guard_grid(sp, _fine(sp), [0, 1], k, W2))
     assert worst[None] > 1e-7 and worst[448] < 1e-9, worst
+
+
+def test_max_steps_is_the_capacity_of_the_staged_table():
+    """esb_model_max_steps (host code of the library): the largest step count whose staged table fits the
+    200 KB of shared memory - the table of that many steps builds, one more step is refused."""
+    expect = {("cylinder_density", "rk8n"): 710, ("cylinder_density", "rk8"): 1279, ("cylinder_rotation", "rk8"): 710,
+              ("slab_density", "rk8n"): 710, ("slab_flow", "rk8"): 1278, ("cylinder_flow", "rk8n"): 710}
+    for (kind, scheme), n_max in expect.items():
+        sp = esb.ModelSpec(kind, scheme=scheme)
+        assert sp.max_steps() == n_max, (kind, scheme, sp.max_steps())
+        step = 2 if kind.startswith("slab") else 1
+        kw = sp.solver_kwargs()
+        mode = [1]
+        kw["n_steps"] = n_max
+        e, i, _ = hk.evaluate(esb.ModelSpec(**kw), mode, [1.0], [1.3 if kind == "cylinder_rotation" else 4.7])
+        kw["n_steps"] = n_max + step
+        with pytest.raises(RuntimeError):
+            hk.evaluate(esb.ModelSpec(**kw), mode, [1.0], [4.7])
+    assert esb.ModelSpec("cylinder_density").max_steps("rk8") == 1279
