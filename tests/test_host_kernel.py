@@ -209,3 +209,52 @@ def test_max_steps_is_the_capacity_of_the_staged_table():
         with pytest.raises(RuntimeError):
             hk.evaluate(esb.ModelSpec(**kw), mode, [1.0], [4.7])
     assert esb.ModelSpec("cylinder_density").max_steps("rk8") == 1279
+
+
+def test_host_build_on_the_scanned_equilibria():
+    """The two families of BASELINE configs[4] (eigensolver_b200.scan.density_flow_grid: cylinder density models
+    over the density contrast, slab flow models over the flow amplitude): the kernels' arithmetic against the C
+    oracle at random (k, omega) outside each equilibrium's own continua, every mode."""
+    from eigensolver_b200.scan import density_flow_grid
+    from helpers import continua, cyl_profile, flow_continua, regular_mask
+    from oracle import reference_path as rp
+    dens, flow = density_flow_grid(np.linspace(0.05, 0.4, 5), np.linspace(0.1, 0.9, 5))
+    rng = np.random.default_rng(5)
+    for p in dens:
+        md = p["medium"]
+        sp = esb.ModelSpec("cylinder_density", medium=md, profile=p["profile"])
+        model = ork.make_model("cylinder_density", medium=md, width=p["profile"].width)
+        iv = continua(cyl_profile(p["profile"].width, rp.Medium(c_i0=md.c_i0, vA_i0=md.vA_i0, vA_e=md.vA_e, c_e=md.c_e)),
+                      -1.0, -0.001, False)
+        k = rng.uniform(0.05, 4.5, 150)
+        W = rng.uniform(0.45, min(md.vA_e, 5.0), k.size)          # the phase speeds of the BASELINE window
+        e, i, _ = hk.evaluate(sp, [0, 1, 2], k, k * W)
+        for slot, mode in enumerate((0, 1, 2)):
+            ref = np.array([ork.point(model, mode, kk, kk * ww) for kk, ww in zip(k, W)])
+            fin = np.isfinite(ref[:, 0]) & np.isfinite(ref[:, 1])
+            assert np.array_equal(np.isfinite(e[slot]) & np.isfinite(i[slot]), fin)
+            ok = fin & regular_mask(W, iv, 0.02)
+            assert ok.sum() > 30, (p["label"], mode, ok.sum())
+            dev = np.abs((e[slot] - i[slot]) - (ref[:, 0] - ref[:, 1])) / np.maximum(np.abs(ref[:, 0]), np.abs(ref[:, 1]))
+            # next to a pole of D (int = N / Y, Y -> 0) the error of Y is amplified: at most one such point
+            assert np.quantile(dev[ok], 0.98) < 2e-10 and (dev[ok] > D_TOL).sum() <= 1 and dev[ok].max() < 2e-8, \
+                (p["label"], mode, dev[ok].max())
+    for p in flow:
+        md = p["medium"]
+        sp = esb.ModelSpec("slab_flow", medium=md, profile=p["profile"])
+        rmd = rp.FlowMedium(width=p["profile"].width, U_i0=md.U_i0)
+        model = ork.make_model("slab_flow", medium=rmd, width=p["profile"].width)
+        iv = flow_continua(rmd)
+        k = rng.uniform(0.05, 4.5, 150)
+        W = rng.uniform(-2.7, 2.7, k.size)
+        e, i, _ = hk.evaluate(sp, [0, 1], k, k * W)
+        for slot, mode in enumerate((0, 1)):
+            ref = np.array([ork.point(model, mode, kk, kk * ww) for kk, ww in zip(k, W)])
+            fin = np.isfinite(ref[:, 0]) & np.isfinite(ref[:, 1])
+            assert np.array_equal(np.isfinite(e[slot]) & np.isfinite(i[slot]), fin)
+            ok = fin & regular_mask(W, iv, 0.02)
+            assert ok.sum() > 30, (p["label"], mode, ok.sum())
+            dev = np.abs((e[slot] - i[slot]) - (ref[:, 0] - ref[:, 1])) / np.maximum(np.abs(ref[:, 0]), np.abs(ref[:, 1]))
+            # next to a pole of D (int = N / Y, Y -> 0) the error of Y is amplified: at most one such point
+            assert np.quantile(dev[ok], 0.98) < 2e-10 and (dev[ok] > D_TOL).sum() <= 1 and dev[ok].max() < 2e-8, \
+                (p["label"], mode, dev[ok].max())
