@@ -339,6 +339,28 @@ def test_scan_models_equals_single_sweeps():
                 kk = k[tab["k_index"][j]]
                 r, _, _ = ork.refine(model, 1, kk, kk * Wr[tab["w_index"][j]], kk * Wr[tab["w_index"][j] + 1])
                 assert abs(tab["omega"][j] - r) <= ROOT_TOL * abs(r), (i, kk, r, tab["omega"][j])
+    # ... and accepted modes of every flow equilibrium, both parities, forward branch (the speeds between the
+    # Doppler-shifted continua and the exterior cut-off)
+    from helpers import flow_continua, regular_mask
+    from oracle import reference_path as rp
+    with esb.DispersionSolver("slab_flow") as s:
+        Wf = np.linspace(1.25, 2.45, 200)
+        s.upload_axes(k, Wf)
+        tab, nb = s.scan_models(flow, [0, 1])
+        for i, p in enumerate(flow):
+            rmd = rp.FlowMedium(width=p["profile"].width, U_i0=p["medium"].U_i0)
+            model = ork.make_model("slab_flow", medium=rmd, width=p["profile"].width)
+            checked = 0
+            for slot in (0, 1):
+                sel = np.nonzero((tab["model"] == i) & (tab["slot"] == slot) & (tab["accepted"] == 1))[0]
+                sel = sel[regular_mask(Wf[tab["w_index"][sel]], flow_continua(rmd), 0.03) &
+                          regular_mask(Wf[tab["w_index"][sel] + 1], flow_continua(rmd), 0.03)]
+                for j in sel[:: max(1, len(sel) // 6)]:
+                    kk = k[tab["k_index"][j]]
+                    r, _, _ = ork.refine(model, slot, kk, kk * Wf[tab["w_index"][j]], kk * Wf[tab["w_index"][j] + 1])
+                    assert abs(tab["omega"][j] - r) <= ROOT_TOL * abs(r), (i, slot, kk, r, tab["omega"][j])
+                    checked += 1
+            assert checked >= 3, (i, checked)
 
 
 def test_edge_cases(solvers):
