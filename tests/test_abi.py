@@ -183,3 +183,19 @@ def test_product_package_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
                 assert "scipy" not in txt, f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/eigensolver_b200.h compiled as strict C99 (-pedantic, warnings are errors) into a program that
+    links libeigensolver_b200.so and calls its host-side entry points; without a GPU esb_create refuses."""
+    import subprocess
+    exe = str(tmp_path / "host_only")
+    libdir = os.path.dirname(esb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_c", "host_only.c"), "-o", exe,
+                           "-L", libdir, "-leigensolver_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode().split()
+    version, n_steps, n_nodes, n_fields, max_steps, rc = (int(v) for v in out)
+    assert (version, n_steps, n_nodes, n_fields, max_steps) == (130, 152, 4 * 152 + 1, 3, 710)
+    import torch
+    assert rc == (0 if torch.cuda.is_available() else L.ESB_ERR_CUDA)
